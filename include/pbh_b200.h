@@ -1,0 +1,224 @@
+/* pbh_b200.h — C ABI of the B200-native batched Plonk-by-hand prover / verifier.
+ *
+ * This is the drop-in boundary for the hot path of adria0/plonk-by-fingers.  The reference has no
+ * FFI of its own: its boundary is the crate's public Rust API.  Each entry point
+ * below names the reference function(s) whose results it reproduces bit for bit (file:line relative
+ * to the reference repository).  The Rust-side binding a maintainer would add is in INTEGRATION.md
+ * and plonk-by-fingers_b200/rust/.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only.  Return 0 on success, a negative pbh_error otherwise; nothing
+ *    aborts or unwinds across this boundary.  A Rust panic of the reference becomes a per-item
+ *    status byte (below), never a process abort.
+ *  - One context drives one CUDA device (one process per GPU under torchrun).  A context may be
+ *    used from one host thread at a time.
+ *  - Batches are structure-of-arrays BYTE PLANES: plane k of an n-item batch is the n bytes at
+ *    base + k*pitch (pitch >= n; pitch is in bytes and lets a shard address a column range of a
+ *    larger batch without repacking).  One byte per field element: F_17 values 0..16, F_101
+ *    values 0..100.
+ *  - Entry points without suffix take HOST pointers and run H2D -> kernels -> D2H on the context's
+ *    streams (chunked and overlapped).  `_dev` variants take DEVICE pointers on the context's
+ *    device and only enqueue kernels on the context's compute stream (use pbh_ctx_sync to wait).
+ *
+ * Encoding of out-of-range bytes.  The reference cannot represent them (`U64Field` values are
+ * only constructible through `From<u64>`/`f17`/`f101`, which reduce): a witness, blinder, challenge
+ * or `u` byte >= 17, or a G1 coordinate byte >= 101, or an infinity-bitmap bit outside the 9 defined
+ * ones, yields status PBH_ST_BAD_ENCODING for that item.  The seven proof evaluations are the one
+ * exception: a byte >= 17 there models a failing `in_field()` (src/plonk.rs:538-547) and yields a
+ * completed verification with verdict false / PBH_VR_NOT_IN_FIELD, after the on-curve check as in
+ * the reference.
+ */
+#ifndef PBH_B200_H
+#define PBH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PBH_ABI_VERSION 1
+
+/* ---- errors (return values) ---------------------------------------------------------------- */
+typedef enum pbh_error {
+  PBH_OK = 0,
+  PBH_ERR_BAD_ARGUMENT = -1,   /* null pointer, pitch < n, unsupported size, ... */
+  PBH_ERR_SETUP_PANIC = -2,    /* the reference's SRS::create / Plonk::new would panic on these inputs */
+  PBH_ERR_CUDA = -3,           /* a CUDA call failed; see pbh_last_error */
+  PBH_ERR_NO_DEVICE = -4,      /* no usable CUDA device: there is NO CPU fallback */
+  PBH_ERR_UNSUPPORTED = -5
+} pbh_error;
+
+/* ---- per-item prover status (mirrors the reference's panic sites in program order) ----------- */
+#define PBH_ST_OK 0            /* proof bytes are valid                                            */
+#define PBH_ST_UNSATISFIED 1   /* src/plonk.rs:199  assert!(constraints.satisfies(assigments))      */
+#define PBH_ST_ACC_DIV0 2      /* src/plonk.rs:297  (dend / dsor).unwrap()                          */
+#define PBH_ST_T_REMAINDER 3   /* src/plonk.rs:370  assert_eq!(rem, Poly::zero())  (Q1)             */
+#define PBH_ST_T_SLICE 4       /* src/plonk.rs:376  t_x.coeffs()[12..18]           (Q5)             */
+#define PBH_ST_SRS_OOB 5       /* src/plonk.rs:56   g1s[n] out of bounds           (Q2)             */
+#define PBH_ST_BAD_ENCODING 32 /* input byte outside the field (not representable in the reference) */
+
+/* ---- per-item verifier result byte ------------------------------------------------------------ */
+#define PBH_VR_ACCEPT 0x01        /* verify() == true                      src/plonk.rs:649         */
+#define PBH_VR_REJECT_PAIRING 0x00 /* verify() == false: e_1 != e_2        src/plonk.rs:649         */
+#define PBH_VR_NOT_ON_CURVE 0x02  /* verify() == false at Step 1           src/plonk.rs:523-534     */
+#define PBH_VR_NOT_IN_FIELD 0x04  /* verify() == false at Step 2           src/plonk.rs:538-547     */
+#define PBH_VR_PANIC_ZH0 0x10     /* verify() panics: Z_H(z) == 0          src/plonk.rs:579         */
+#define PBH_VR_BAD_ENCODING 0x20  /* see "Encoding of out-of-range bytes"                           */
+/* bit 0 of the result byte is the reference's bool whenever bits 4 and 5 are clear. */
+
+/* ---- wire layout (plane indices) ------------------------------------------------------------ */
+/* prover input: src/plonk.rs:191-197 — Assigments (12) + rand[9] + Challange (5) = 26 planes      */
+#define PBH_WIT_PLANES 12   /* a[0..4), b[0..4), c[0..4)          src/constraints.rs:132-136        */
+#define PBH_RAND_PLANES 9   /* b1..b9                             src/plonk.rs:196, 248, 267        */
+#define PBH_CHAL_PLANES 5   /* alpha, beta, gamma, z, v           src/plonk.rs:97-108               */
+/* proof: src/plonk.rs:61-95 — 9 G1 points then 7 F_17 evaluations                                 */
+#define PBH_PROOF_POINTS 9  /* a_s b_s c_s z_s t_lo_s t_mid_s t_hi_s w_z_s w_z_omega_s              */
+#define PBH_PROOF_EVALS 7   /* a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z                    */
+/* planes 0..17: x,y of point k at planes 2k, 2k+1; planes 18,19: `infinite` flags (bit k of plane
+ * 18 for points 0..7, bit 0 of plane 19 for point 8); planes 20..26: the evaluations.            */
+#define PBH_PROOF_PLANES 27
+#define PBH_PROOF_INF_PLANE 18
+#define PBH_PROOF_EVAL_PLANE 20
+/* algorithmic bytes per item: prove 26 in + 27 proof + 1 status = 54;
+ * verify 27 + 5 + 1 in + 1 result = 34                                                            */
+#define PBH_PROVE_BYTES_PER_ITEM 54
+#define PBH_VERIFY_BYTES_PER_ITEM 34
+
+/* ---- circuit description: src/constraints.rs:109-118 (Constrains) ---------------------------- */
+#define PBH_N_GATES 4       /* prove() is hard-wired to 4 gates: src/plonk.rs:376-378              */
+#define PBH_COPY_A 0
+#define PBH_COPY_B 1
+#define PBH_COPY_C 2
+typedef struct pbh_circuit {
+  /* selector vectors, F_17 values: src/constraints.rs:110-114 */
+  uint8_t q_l[PBH_N_GATES], q_r[PBH_N_GATES], q_o[PBH_N_GATES], q_m[PBH_N_GATES], q_c[PBH_N_GATES];
+  /* copy constraints CopyOf::{A,B,C}(n): wire = PBH_COPY_*, index = n (1-based): :67-71, :115-117 */
+  uint8_t c_a_wire[PBH_N_GATES], c_a_index[PBH_N_GATES];
+  uint8_t c_b_wire[PBH_N_GATES], c_b_index[PBH_N_GATES];
+  uint8_t c_c_wire[PBH_N_GATES], c_c_index[PBH_N_GATES];
+} pbh_circuit;
+
+/* algorithm selection for the group operations of the fused kernels (both are bit-exact) */
+#define PBH_ALGO_ARITH 0  /* per-item affine curve arithmetic, Miller loop and final exponentiation */
+#define PBH_ALGO_TABLE 1  /* group-structure tables built at context creation by the ARITH kernels  */
+
+typedef struct pbh_ctx pbh_ctx;
+
+/* The circuit of the reference's only end-to-end test (src/pbh/mod.rs:56-67). */
+void pbh_circuit_pbh_test(pbh_circuit* out);
+
+/* SRS::create(s, srs_n) (src/plonk.rs:35-48) + Plonk::new(srs, omega_pows) (src/plonk.rs:120-175)
+ * + the circuit-constant work the reference redoes on every call (src/plonk.rs:222-243, 328-333,
+ * 506-517, 557-562), computed once and uploaded to `device`.  omega_pows must be 4.
+ * PBH_ERR_SETUP_PANIC when the reference would panic (e.g. s = 0, or G2 * s hitting P + (-P)). */
+int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_n, uint8_t omega_pows,
+                   int device, pbh_ctx** out);
+void pbh_ctx_destroy(pbh_ctx* ctx);
+const char* pbh_last_error(const pbh_ctx* ctx);   /* ctx may be NULL: last global (creation) error */
+int pbh_ctx_set_algo(pbh_ctx* ctx, int algo);     /* PBH_ALGO_* ; default PBH_ALGO_TABLE            */
+int pbh_ctx_get_algo(const pbh_ctx* ctx);
+int pbh_ctx_device(const pbh_ctx* ctx);
+int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */
+/* CUDA stream handle (cudaStream_t) the `_dev` entry points launch on; for event timing. */
+void* pbh_ctx_stream(pbh_ctx* ctx);
+/* number of kernel launches issued through this context so far */
+uint64_t pbh_ctx_launch_count(const pbh_ctx* ctx);
+
+/* Read back setup results (host copies): the SRS of src/plonk.rs:28-32 and the hoisted constants.
+ * g1s_xy_inf: srs_n+1 triples (x,y,infinite); g2: g2_1.a, g2_1.b, g2_s.a, g2_s.b;
+ * selector_commits: q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s as triples. */
+int pbh_ctx_get_srs(const pbh_ctx* ctx, uint8_t* g1s_xy_inf, size_t g1s_capacity_points, uint32_t* n_points,
+                    uint8_t g2[4]);
+int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t selector_commits[24]);
+
+/* Plonk::prove (src/plonk.rs:191-466), n items.
+ *   wit   12 planes, rand 9 planes, chal 5 planes (each with its own pitch)
+ *   proof 27 planes (zeroed for items whose status != PBH_ST_OK), status n bytes */
+int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand,
+                    size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch,
+                    uint8_t* status);
+int pbh_prove_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand,
+                        size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, uint8_t* proof,
+                        size_t proof_pitch, uint8_t* status);
+
+/* Plonk::verify (src/plonk.rs:468-650), n items.
+ *   proof 27 planes, chal 5 planes, u n bytes (rand[0] of :473)
+ *   result n bytes of PBH_VR_*; gt (nullable) 4 planes e_1.a e_1.b e_2.a e_2.b, defined when the
+ *   pairing check was reached (result is ACCEPT or REJECT_PAIRING), zero otherwise. */
+int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                     size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
+int pbh_verify_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                         size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
+
+/* ---- sweep kernels (the per-kernel configs of BASELINE.json), HOST or DEVICE pointers --------- */
+/* `on_device` != 0: pointers are device pointers, kernels are only enqueued.                      */
+
+/* size-4 NTT over F_17, omega = 4: evals[i] = sum_j coeffs[j] * 4^(ij)  (src/fft.rs:66-78, 90-106
+ * with EvaluationDomainGenerator(4, 4)); 4 planes in, 4 planes out. */
+int pbh_ntt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t in_pitch, uint8_t* evals,
+                   size_t out_pitch, int on_device);
+/* inverse: Plonk::interpolate_at_h (src/plonk.rs:177-179) == fft_inv (src/fft.rs:72-78), always 4
+ * coefficients (zero padded; the reference's normalised length is implied by the values). */
+int pbh_intt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* evals, size_t in_pitch, uint8_t* coeffs,
+                    size_t out_pitch, int on_device);
+/* generic power-of-two NTT / iNTT over F_modulus (modulus < 2^16, size in {2,4,...,64}), values as
+ * uint16 planes; reproduces CooleyTurkey::fft / fft_inv (src/fft.rs:66-78) for full-length input. */
+int pbh_ntt_generic_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t omega, uint32_t size, int inverse,
+                          const uint16_t* in, size_t in_pitch_elems, uint16_t* out, size_t out_pitch_elems,
+                          int on_device);
+/* schoolbook product over F_17 (src/poly.rs:205-218): la, lb coefficient planes (zero padded) in,
+ * la+lb-1 planes out (la, lb <= 16). */
+int pbh_poly_mul_batch(pbh_ctx* ctx, size_t n, uint32_t la, uint32_t lb, const uint8_t* a, size_t a_pitch,
+                       const uint8_t* b, size_t b_pitch, uint8_t* out, size_t out_pitch, int on_device);
+/* coefficientwise a + b or a - b over F_17 on len planes (src/poly.rs:165-203 for equal lengths) */
+int pbh_poly_add_batch(pbh_ctx* ctx, size_t n, uint32_t len, int subtract, const uint8_t* a, size_t a_pitch,
+                       const uint8_t* b, size_t b_pitch, uint8_t* out, size_t out_pitch, int on_device);
+/* (q, r) = p / (x^4 - 1) over F_17 (src/poly.rs:230-247 with rhs = Z_H, src/plonk.rs:369):
+ * 22 planes in, 18 quotient planes + 4 remainder planes out. */
+int pbh_poly_div_zh_batch(pbh_ctx* ctx, size_t n, const uint8_t* p, size_t p_pitch, uint8_t* q, size_t q_pitch,
+                          uint8_t* r, size_t r_pitch, int on_device);
+/* G1P * F101 (src/pbh/g1.rs:146-168): planes x, y, inf(0/1), k (0..100) in; x, y, inf out. */
+int pbh_g1_smul_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
+                      int on_device);
+/* G1P + G1P (src/pbh/g1.rs:119-144): planes x1 y1 inf1 x2 y2 inf2 in; x y inf out.  Items for which
+ * the reference would panic ("cannot add": equal x, unequal non-opposite y — unreachable for points
+ * on the curve) get inf = 0xFF. */
+int pbh_g1_add_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
+                     int on_device);
+/* SRS::eval_at_s (src/plonk.rs:51-58): 7 coefficient planes (F_17, zero padded) in; x, y, inf out. */
+int pbh_kzg_commit_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t in_pitch, uint8_t* out,
+                         size_t out_pitch, int on_device);
+/* PBHPairing::pairing (src/pbh/pairing.rs:12-47): planes p.x p.y p.inf q.a q.b in; gt.a gt.b out. */
+int pbh_pairing_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
+                      int on_device);
+
+/* ---- shard summaries for the multi-GPU gather ---------------------------------- */
+/* Pack bit 0 of each result byte into a bitmap (item i -> bit i%8 of byte i/8), device pointers.  */
+int pbh_pack_verdicts_dev(pbh_ctx* ctx, size_t n, const uint8_t* result, uint8_t* bitmap);
+/* Order-independent-within-plane 64-bit digest of `planes` byte planes of n items starting at
+ * global item index `first_index`: sum over items of mix64(global_index, plane, byte), so digests
+ * of disjoint shards add up (mod 2^64) to the digest of the whole batch.  out: one uint64 (device). */
+int pbh_digest_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint32_t planes, const uint8_t* data, size_t pitch,
+                   uint64_t* out);
+
+/* ---- synthetic inputs, device pointers ------------------------------------------ */
+#define PBH_DIST_UNIFORM 0   /* attempt k = 0 only: exercises every status class                    */
+#define PBH_DIST_FULLPATH 1  /* smallest k whose prove succeeds and whose verify reaches the pairing */
+/* Item i of the batch has global index first_index + i; its bytes depend only on (seed, global
+ * index, dist), so any sharding generates the same batch.  Fills wit/rand/chal/u; `attempt`
+ * (nullable, n bytes) receives the accepted k (saturating at 255). */
+int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64_t seed, int dist, uint8_t* wit,
+                            size_t wit_pitch, uint8_t* rand, size_t rand_pitch, uint8_t* chal, size_t chal_pitch,
+                            uint8_t* u, uint8_t* attempt);
+
+/* ---- measurement helpers ------------------------------------------------------------------------ */
+/* Dependent-chain-free IMAD/IADD3 micro-benchmark: integer lane-operations per second the device
+ * sustains (the INT32 roofline denominator).  which: 0 = IMAD, 1 = IADD3/LOP3, 2 = mixed */
+int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PBH_B200_H */

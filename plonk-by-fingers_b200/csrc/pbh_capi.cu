@@ -1,0 +1,567 @@
+// pbh_capi.cu — the extern "C" boundary of include/pbh_b200.h over the sm_100a kernels.
+//
+// There is no CPU fallback anywhere in this file: every entry point that computes launches a CUDA kernel on
+// the context's device, and context creation fails with PBH_ERR_NO_DEVICE when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <mutex>
+#include <string>
+
+#include "pbh_kernels.cuh"
+#include "pbh_setup.hpp"
+
+using namespace pbh;
+
+namespace {
+std::string g_last_error;
+std::mutex g_err_mutex;
+void set_global_error(const std::string& e) { std::lock_guard<std::mutex> l(g_err_mutex); g_last_error = e; }
+}  // namespace
+
+static constexpr size_t kChunk = (size_t)1 << 21;   // items per staged chunk of the host-pointer entry points
+static constexpr int kSlots = 2;                    // double buffering: copy of chunk k+1 overlaps compute of chunk k
+
+struct pbh_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int algo = PBH_ALGO_TABLE;
+  HostSetup hs;
+  Tables* d_tables = nullptr;
+  uint8_t* d_wtab = nullptr;
+  cudaStream_t compute = nullptr;          // `_dev` entry points
+  cudaStream_t slot_stream[kSlots] = {nullptr, nullptr};
+  uint8_t* slot_buf[kSlots] = {nullptr, nullptr};
+  size_t slot_bytes = 0;
+  uint64_t launches = 0;
+  std::string last_error;
+};
+
+#define CTX_CHECK(ctx)                                     \
+  do {                                                     \
+    if (!(ctx)) { set_global_error("null context"); return PBH_ERR_BAD_ARGUMENT; } \
+  } while (0)
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+      return PBH_ERR_CUDA;                                                                       \
+    }                                                                                            \
+  } while (0)
+
+static int fail(pbh_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->last_error = msg; else set_global_error(msg);
+  return code;
+}
+
+static int grid_for(const pbh_ctx* ctx, size_t n, int per_sm) {
+  size_t blocks = (n + kBlock - 1) / kBlock;
+  size_t cap = (size_t)ctx->sm_count * per_sm;   // a multiple of the SM count; blocks loop grid-stride
+  return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+// Every function below is declared extern "C" by include/pbh_b200.h and inherits that linkage.
+
+void pbh_circuit_pbh_test(pbh_circuit* out) {
+  // src/pbh/mod.rs:56-67: three mul gates, one add gate
+  const uint8_t m1 = 16;
+  const uint8_t ql[4] = {0, 0, 0, 1}, qr[4] = {0, 0, 0, 1}, qo[4] = {m1, m1, m1, m1}, qm[4] = {1, 1, 1, 0}, qc[4] = {0, 0, 0, 0};
+  const uint8_t caw[4] = {PBH_COPY_B, PBH_COPY_B, PBH_COPY_B, PBH_COPY_C}, cai[4] = {1, 2, 3, 1};
+  const uint8_t cbw[4] = {PBH_COPY_A, PBH_COPY_A, PBH_COPY_A, PBH_COPY_C}, cbi[4] = {1, 2, 3, 2};
+  const uint8_t ccw[4] = {PBH_COPY_A, PBH_COPY_B, PBH_COPY_C, PBH_COPY_C}, cci[4] = {4, 4, 4, 3};
+  for (int i = 0; i < 4; i++) {
+    out->q_l[i] = ql[i]; out->q_r[i] = qr[i]; out->q_o[i] = qo[i]; out->q_m[i] = qm[i]; out->q_c[i] = qc[i];
+    out->c_a_wire[i] = caw[i]; out->c_a_index[i] = cai[i];
+    out->c_b_wire[i] = cbw[i]; out->c_b_index[i] = cbi[i];
+    out->c_c_wire[i] = ccw[i]; out->c_c_index[i] = cci[i];
+  }
+}
+
+int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_n, uint8_t omega_pows, int device,
+                   pbh_ctx** out) {
+  if (!circuit || !out) return fail(nullptr, PBH_ERR_BAD_ARGUMENT, "null argument");
+  *out = nullptr;
+  pbh_ctx* ctx = new pbh_ctx();
+  std::string err;
+  int rc = host_setup(*circuit, srs_secret, srs_n, omega_pows, ctx->hs, err);
+  if (rc != PBH_OK) { set_global_error(err); delete ctx; return rc; }
+
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    set_global_error(std::string("no usable CUDA device (there is no CPU fallback): ") +
+                     (ce != cudaSuccess ? cudaGetErrorString(ce) : "device index out of range"));
+    delete ctx;
+    return PBH_ERR_NO_DEVICE;
+  }
+  ctx->device = device;
+  auto bail = [&](const char* what, cudaError_t e) {
+    set_global_error(std::string(what) + ": " + cudaGetErrorString(e));
+    pbh_ctx_destroy(ctx);
+    return PBH_ERR_CUDA;
+  };
+  if ((ce = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", ce);
+  cudaDeviceProp prop;
+  if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", ce);
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((ce = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
+  for (int s = 0; s < kSlots; s++)
+    if ((ce = cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
+  if ((ce = cudaMalloc(&ctx->d_tables, sizeof(Tables))) != cudaSuccess) return bail("cudaMalloc(tables)", ce);
+  if ((ce = cudaMemcpy(ctx->d_tables, &ctx->hs.T, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(tables)", ce);
+  // witness table of the synthetic-input generator: solutions of x^2 + y^2 = z^2 in F_17^3, lexicographic
+  uint8_t wtab[289 * 3];
+  int nw = 0;
+  for (int x = 0; x < 17; x++)
+    for (int y = 0; y < 17; y++)
+      for (int z = 0; z < 17; z++)
+        if ((x * x + y * y) % 17 == (z * z) % 17) { wtab[3 * nw] = x; wtab[3 * nw + 1] = y; wtab[3 * nw + 2] = z; nw++; }
+  if ((ce = cudaMalloc(&ctx->d_wtab, sizeof(wtab))) != cudaSuccess) return bail("cudaMalloc(wtab)", ce);
+  if ((ce = cudaMemcpy(ctx->d_wtab, wtab, sizeof(wtab), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(wtab)", ce);
+  *out = ctx;
+  return PBH_OK;
+}
+
+void pbh_ctx_destroy(pbh_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (int s = 0; s < kSlots; s++) {
+    if (ctx->slot_stream[s]) { cudaStreamSynchronize(ctx->slot_stream[s]); cudaStreamDestroy(ctx->slot_stream[s]); }
+    if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
+  }
+  if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); }
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_wtab) cudaFree(ctx->d_wtab);
+  delete ctx;
+}
+
+const char* pbh_last_error(const pbh_ctx* ctx) {
+  if (ctx) return ctx->last_error.c_str();
+  std::lock_guard<std::mutex> l(g_err_mutex);
+  static thread_local std::string copy;
+  copy = g_last_error;
+  return copy.c_str();
+}
+
+int pbh_ctx_set_algo(pbh_ctx* ctx, int algo) {
+  CTX_CHECK(ctx);
+  if (algo != PBH_ALGO_ARITH && algo != PBH_ALGO_TABLE) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "unknown algo");
+  ctx->algo = algo;
+  return PBH_OK;
+}
+int pbh_ctx_get_algo(const pbh_ctx* ctx) { return ctx ? ctx->algo : PBH_ERR_BAD_ARGUMENT; }
+int pbh_ctx_device(const pbh_ctx* ctx) { return ctx ? ctx->device : PBH_ERR_BAD_ARGUMENT; }
+void* pbh_ctx_stream(pbh_ctx* ctx) { return ctx ? (void*)ctx->compute : nullptr; }
+uint64_t pbh_ctx_launch_count(const pbh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pbh_ctx_sync(pbh_ctx* ctx) {
+  CTX_CHECK(ctx);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute));
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
+int pbh_ctx_get_srs(const pbh_ctx* ctx, uint8_t* g1s_xy_inf, size_t cap_points, uint32_t* n_points, uint8_t g2[4]) {
+  if (!ctx) return PBH_ERR_BAD_ARGUMENT;
+  if (n_points) *n_points = (uint32_t)ctx->hs.g1s.size();
+  if (g1s_xy_inf) {
+    for (size_t i = 0; i < ctx->hs.g1s.size() && i < cap_points; i++) {
+      g1s_xy_inf[3 * i] = (uint8_t)ctx->hs.g1s[i].x; g1s_xy_inf[3 * i + 1] = (uint8_t)ctx->hs.g1s[i].y;
+      g1s_xy_inf[3 * i + 2] = (uint8_t)ctx->hs.g1s[i].inf;
+    }
+  }
+  if (g2) { g2[0] = (uint8_t)ctx->hs.g2_1[0]; g2[1] = (uint8_t)ctx->hs.g2_1[1]; g2[2] = (uint8_t)ctx->hs.g2_s[0]; g2[3] = (uint8_t)ctx->hs.g2_s[1]; }
+  return PBH_OK;
+}
+
+int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
+  if (!ctx || !c) return PBH_ERR_BAD_ARGUMENT;
+  for (int j = 0; j < 8; j++) {
+    c[3 * j] = (uint8_t)ctx->hs.vconst[j].x; c[3 * j + 1] = (uint8_t)ctx->hs.vconst[j].y; c[3 * j + 2] = (uint8_t)ctx->hs.vconst[j].inf;
+  }
+  return PBH_OK;
+}
+
+// ---- device-pointer entry points -----------------------------------------------------------------------
+static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
+  if (A.n == 0) return PBH_OK;
+  int grid = grid_for(ctx, A.n, 8);
+  if (ctx->algo == PBH_ALGO_TABLE) prove_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
+  else prove_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A) {
+  if (A.n == 0) return PBH_OK;
+  int grid = grid_for(ctx, A.n, 8);
+  if (ctx->algo == PBH_ALGO_TABLE) verify_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
+  else verify_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+
+int pbh_prove_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
+                        const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ProveArgs A{wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, proof, proof_pitch, status, n};
+  return launch_prove(ctx, ctx->compute, A);
+}
+
+int pbh_verify_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                         size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  VerifyArgs A{proof, proof_pitch, chal, chal_pitch, u, result, gt, gt_pitch, n};
+  return launch_verify(ctx, ctx->compute, A);
+}
+
+// ---- host-pointer entry points: chunked, double-buffered H2D -> kernel -> D2H ----------------------------
+static int ensure_slots(pbh_ctx* ctx, size_t bytes_per_item) {
+  size_t need = bytes_per_item * kChunk;
+  if (ctx->slot_bytes >= need) return PBH_OK;
+  for (int s = 0; s < kSlots; s++) {
+    if (ctx->slot_buf[s]) { CUDA_TRY(ctx, cudaFree(ctx->slot_buf[s])); ctx->slot_buf[s] = nullptr; }
+  }
+  ctx->slot_bytes = 0;
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaMalloc(&ctx->slot_buf[s], need));
+  ctx->slot_bytes = need;
+  return PBH_OK;
+}
+
+int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
+                    const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_slots(ctx, 26 + 28);
+  if (rc) return rc;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += kChunk, k++) {
+    size_t m = std::min(kChunk, n - lo);
+    int s = (int)(k % kSlots);
+    cudaStream_t st = ctx->slot_stream[s];
+    uint8_t* base = ctx->slot_buf[s];
+    uint8_t *d_wit = base, *d_rnd = base + 12 * kChunk, *d_chal = base + 21 * kChunk, *d_proof = base + 26 * kChunk,
+            *d_status = base + 53 * kChunk;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, kChunk, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, kChunk, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, kChunk, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
+    ProveArgs A{d_wit, kChunk, d_rnd, kChunk, d_chal, kChunk, d_proof, kChunk, d_status, m};
+    rc = launch_prove(ctx, st, A);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, kChunk, m, 27, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
+int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal, size_t chal_pitch,
+                     const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_slots(ctx, 26 + 28);   // one slot size for both directions: 33 + 1 + 4 <= 54
+  if (rc) return rc;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += kChunk, k++) {
+    size_t m = std::min(kChunk, n - lo);
+    int s = (int)(k % kSlots);
+    cudaStream_t st = ctx->slot_stream[s];
+    uint8_t* base = ctx->slot_buf[s];
+    uint8_t *d_proof = base, *d_chal = base + 27 * kChunk, *d_u = base + 32 * kChunk, *d_res = base + 33 * kChunk,
+            *d_gt = base + 34 * kChunk;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, kChunk, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, kChunk, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
+    VerifyArgs A{d_proof, kChunk, d_chal, kChunk, d_u, d_res, gt ? d_gt : nullptr, kChunk, m};
+    rc = launch_verify(ctx, st, A);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
+    if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, kChunk, m, 4, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
+// ---- sweep entry points ---------------------------------------------------------------------------------
+// Host-pointer mode stages whole planes through a temporary device allocation (these are per-kernel test and
+// benchmark entry points; the hot host-pointer path is pbh_prove_batch / pbh_verify_batch above).
+namespace {
+struct Staged {
+  pbh_ctx* ctx;
+  std::vector<void*> allocs;
+  explicit Staged(pbh_ctx* c) : ctx(c) {}
+  ~Staged() { for (void* p : allocs) cudaFree(p); }
+  // returns a device pointer to `planes` planes of pitch n holding a copy of the host planes (or uninitialised)
+  template <class T>
+  T* in(const T* host, size_t pitch, size_t n, size_t planes, cudaError_t& e) {
+    T* d = nullptr;
+    e = cudaMalloc((void**)&d, std::max<size_t>(1, planes * n * sizeof(T)));
+    if (e != cudaSuccess) return nullptr;
+    allocs.push_back(d);
+    if (host) e = cudaMemcpy2DAsync(d, n * sizeof(T), host, pitch * sizeof(T), n * sizeof(T), planes, cudaMemcpyHostToDevice, ctx->compute);
+    return d;
+  }
+  template <class T>
+  cudaError_t out(T* host, size_t pitch, const T* d, size_t n, size_t planes) {
+    return cudaMemcpy2DAsync(host, pitch * sizeof(T), d, n * sizeof(T), n * sizeof(T), planes, cudaMemcpyDeviceToHost, ctx->compute);
+  }
+};
+}  // namespace
+
+#define SWEEP_PROLOGUE(ctx, n)                         \
+  CTX_CHECK(ctx);                                      \
+  if ((n) == 0) return PBH_OK;                         \
+  CUDA_TRY(ctx, cudaSetDevice((ctx)->device));         \
+  cudaError_t ce = cudaSuccess;                        \
+  (void)ce;                                            \
+  Staged stg(ctx)
+
+#define SWEEP_FINISH(ctx)                              \
+  (ctx)->launches++;                                   \
+  CUDA_TRY(ctx, cudaGetLastError())
+
+static int ntt4_impl(pbh_ctx* ctx, bool inverse, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
+                     int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!in || !out || in_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  const uint8_t* d_in = in; uint8_t* d_out = out; size_t ip = in_pitch, op = out_pitch;
+  if (!on_device) {
+    d_in = stg.in(in, in_pitch, n, 4, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint8_t>(nullptr, 0, n, 4, ce); CUDA_TRY(ctx, ce);
+    ip = op = n;
+  }
+  bool vec_ok = ((uintptr_t)d_in % 4 == 0) && ((uintptr_t)d_out % 4 == 0) && (ip % 4 == 0) && (op % 4 == 0);
+  int grid = grid_for(ctx, vec_ok ? (n + 3) / 4 : n, 16);
+  if (inverse) ntt4_kernel<true><<<grid, kBlock, 0, ctx->compute>>>(n, d_in, ip, d_out, op, vec_ok);
+  else ntt4_kernel<false><<<grid, kBlock, 0, ctx->compute>>>(n, d_in, ip, d_out, op, vec_ok);
+  SWEEP_FINISH(ctx);
+  if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, 4)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
+  return PBH_OK;
+}
+int pbh_ntt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t in_pitch, uint8_t* evals, size_t out_pitch, int on_device) {
+  return ntt4_impl(ctx, false, n, coeffs, in_pitch, evals, out_pitch, on_device);
+}
+int pbh_intt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* evals, size_t in_pitch, uint8_t* coeffs, size_t out_pitch, int on_device) {
+  return ntt4_impl(ctx, true, n, evals, in_pitch, coeffs, out_pitch, on_device);
+}
+
+int pbh_ntt_generic_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t omega, uint32_t size, int inverse, const uint16_t* in,
+                          size_t in_pitch, uint16_t* out, size_t out_pitch, int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!in || !out || in_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  if (modulus < 2 || modulus >= 65536 || size < 2 || size > 64 || (size & (size - 1))) return fail(ctx, PBH_ERR_UNSUPPORTED, "modulus < 2^16, size a power of two in [2, 64]");
+  uint32_t log2size = 0;
+  while ((1u << log2size) < size) log2size++;
+  // twiddles omega^i (CooleyTurkey::new, src/fft.rs:52-64) and size^-1 by Fermat (modulus prime, as in the reference's tests)
+  uint16_t tw[64];
+  uint32_t m = 1;
+  for (uint32_t i = 0; i < size; i++) { tw[i] = (uint16_t)m; m = (uint32_t)(((uint64_t)m * (omega % modulus)) % modulus); }
+  uint64_t len_inv = 1, b = size % modulus, e = modulus - 2;
+  while (e) { if (e & 1) len_inv = len_inv * b % modulus; b = b * b % modulus; e >>= 1; }
+  if ((len_inv * (size % modulus)) % modulus != 1) return fail(ctx, PBH_ERR_SETUP_PANIC, "size has no inverse modulo the modulus (F::from(len).inv().unwrap() panics)");
+  uint16_t* d_tw = stg.in(tw, 64, 64, 1, ce); CUDA_TRY(ctx, ce);
+  const uint16_t* d_in = in; uint16_t* d_out = out; size_t ip = in_pitch, op = out_pitch;
+  if (!on_device) {
+    d_in = stg.in(in, in_pitch, n, size, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint16_t>(nullptr, 0, n, size, ce); CUDA_TRY(ctx, ce);
+    ip = op = n;
+  }
+  ntt_generic_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, modulus, size, log2size, (uint32_t)len_inv, inverse, d_tw, d_in, ip, d_out, op);
+  SWEEP_FINISH(ctx);
+  if (!on_device) CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, size));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute));   // d_tw is freed on return
+  return PBH_OK;
+}
+
+int pbh_poly_mul_batch(pbh_ctx* ctx, size_t n, uint32_t la, uint32_t lb, const uint8_t* a, size_t a_pitch, const uint8_t* b,
+                       size_t b_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!a || !b || !out || a_pitch < n || b_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  if (la < 1 || lb < 1 || la > 16 || lb > 16) return fail(ctx, PBH_ERR_UNSUPPORTED, "1 <= la, lb <= 16");
+  const uint8_t *d_a = a, *d_b = b; uint8_t* d_out = out; size_t ap = a_pitch, bp = b_pitch, op = out_pitch;
+  if (!on_device) {
+    d_a = stg.in(a, a_pitch, n, la, ce); CUDA_TRY(ctx, ce);
+    d_b = stg.in(b, b_pitch, n, lb, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint8_t>(nullptr, 0, n, la + lb - 1, ce); CUDA_TRY(ctx, ce);
+    ap = bp = op = n;
+  }
+  poly_mul_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, la, lb, d_a, ap, d_b, bp, d_out, op);
+  SWEEP_FINISH(ctx);
+  if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, la + lb - 1)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
+  return PBH_OK;
+}
+
+int pbh_poly_add_batch(pbh_ctx* ctx, size_t n, uint32_t len, int subtract, const uint8_t* a, size_t a_pitch, const uint8_t* b,
+                       size_t b_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!a || !b || !out || a_pitch < n || b_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  if (len < 1 || len > 64) return fail(ctx, PBH_ERR_UNSUPPORTED, "1 <= len <= 64");
+  const uint8_t *d_a = a, *d_b = b; uint8_t* d_out = out; size_t ap = a_pitch, bp = b_pitch, op = out_pitch;
+  if (!on_device) {
+    d_a = stg.in(a, a_pitch, n, len, ce); CUDA_TRY(ctx, ce);
+    d_b = stg.in(b, b_pitch, n, len, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint8_t>(nullptr, 0, n, len, ce); CUDA_TRY(ctx, ce);
+    ap = bp = op = n;
+  }
+  poly_add_kernel<<<grid_for(ctx, n, 16), kBlock, 0, ctx->compute>>>(n, len, subtract, d_a, ap, d_b, bp, d_out, op);
+  SWEEP_FINISH(ctx);
+  if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, len)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
+  return PBH_OK;
+}
+
+int pbh_poly_div_zh_batch(pbh_ctx* ctx, size_t n, const uint8_t* p, size_t p_pitch, uint8_t* q, size_t q_pitch, uint8_t* r,
+                          size_t r_pitch, int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!p || !q || !r || p_pitch < n || q_pitch < n || r_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  const uint8_t* d_p = p; uint8_t *d_q = q, *d_r = r; size_t pp = p_pitch, qp = q_pitch, rp = r_pitch;
+  if (!on_device) {
+    d_p = stg.in(p, p_pitch, n, 22, ce); CUDA_TRY(ctx, ce);
+    d_q = stg.in<uint8_t>(nullptr, 0, n, 18, ce); CUDA_TRY(ctx, ce);
+    d_r = stg.in<uint8_t>(nullptr, 0, n, 4, ce); CUDA_TRY(ctx, ce);
+    pp = qp = rp = n;
+  }
+  poly_div_zh_kernel<<<grid_for(ctx, n, 16), kBlock, 0, ctx->compute>>>(n, d_p, pp, d_q, qp, d_r, rp);
+  SWEEP_FINISH(ctx);
+  if (!on_device) {
+    CUDA_TRY(ctx, stg.out(q, q_pitch, d_q, n, 18));
+    CUDA_TRY(ctx, stg.out(r, r_pitch, d_r, n, 4));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute));
+  }
+  return PBH_OK;
+}
+
+// common shape: `pin` input planes -> `pout` output planes, kernel(gT, n, in, ip, out, op)
+template <class Launch>
+static int planes_impl(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, size_t pin, uint8_t* out, size_t out_pitch,
+                       size_t pout, int on_device, Launch launch) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!in || !out || in_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  const uint8_t* d_in = in; uint8_t* d_out = out; size_t ip = in_pitch, op = out_pitch;
+  if (!on_device) {
+    d_in = stg.in(in, in_pitch, n, pin, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint8_t>(nullptr, 0, n, pout, ce); CUDA_TRY(ctx, ce);
+    ip = op = n;
+  }
+  launch(grid_for(ctx, n, 8), d_in, ip, d_out, op);
+  SWEEP_FINISH(ctx);
+  if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, pout)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
+  return PBH_OK;
+}
+
+int pbh_g1_smul_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return planes_impl(ctx, n, in, in_pitch, 4, out, out_pitch, 3, on_device, [&](int grid, const uint8_t* di, size_t ip, uint8_t* dout, size_t op) {
+    g1_smul_kernel<<<grid, kBlock, 0, ctx->compute>>>(ctx->d_tables, n, di, ip, dout, op);
+  });
+}
+int pbh_g1_add_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return planes_impl(ctx, n, in, in_pitch, 6, out, out_pitch, 3, on_device, [&](int grid, const uint8_t* di, size_t ip, uint8_t* dout, size_t op) {
+    g1_add_kernel<<<grid, kBlock, 0, ctx->compute>>>(ctx->d_tables, n, di, ip, dout, op);
+  });
+}
+int pbh_kzg_commit_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return planes_impl(ctx, n, coeffs, in_pitch, 7, out, out_pitch, 3, on_device, [&](int grid, const uint8_t* di, size_t ip, uint8_t* dout, size_t op) {
+    if (ctx->algo == PBH_ALGO_TABLE) kzg_commit_kernel<ALGO_TABLE><<<grid, kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, n, di, ip, dout, op);
+    else kzg_commit_kernel<ALGO_ARITH><<<grid, kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, n, di, ip, dout, op);
+  });
+}
+int pbh_pairing_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return planes_impl(ctx, n, in, in_pitch, 5, out, out_pitch, 2, on_device, [&](int grid, const uint8_t* di, size_t ip, uint8_t* dout, size_t op) {
+    pairing_kernel<<<grid, kBlock, 0, ctx->compute>>>(ctx->d_tables, n, di, ip, dout, op);
+  });
+}
+
+// ---- shard summaries, synthetic inputs, measurement --------------------------------------------------------
+int pbh_pack_verdicts_dev(pbh_ctx* ctx, size_t n, const uint8_t* result, uint8_t* bitmap) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!result || !bitmap) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  pack_verdicts_kernel<<<grid_for(ctx, (n + 7) / 8, 8), kBlock, 0, ctx->compute>>>(n, result, bitmap);
+  SWEEP_FINISH(ctx);
+  return PBH_OK;
+}
+
+int pbh_digest_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint32_t planes, const uint8_t* data, size_t pitch, uint64_t* out) {
+  CTX_CHECK(ctx);
+  if (!out) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemsetAsync(out, 0, sizeof(uint64_t), ctx->compute));
+  if (n == 0) return PBH_OK;
+  if (!data || pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  digest_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, first_index, planes, data, pitch, (unsigned long long*)out);
+  SWEEP_FINISH(ctx);
+  return PBH_OK;
+}
+
+int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64_t seed, int dist, uint8_t* wit, size_t wit_pitch,
+                            uint8_t* rnd, size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u, uint8_t* attempt) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !chal || !u) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || chal_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  if (dist != PBH_DIST_UNIFORM && dist != PBH_DIST_FULLPATH) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "unknown distribution");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  GenArgs A{n, first_index, seed, dist, wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, u, attempt, ctx->d_wtab};
+  generate_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, A);
+  SWEEP_FINISH(ctx);
+  return PBH_OK;
+}
+
+int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second) {
+  CTX_CHECK(ctx);
+  if (!lane_ops_per_second || which < 0 || which > 2) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  uint32_t* sink = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&sink, 4));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(ctx, cudaEventCreate(&e0));
+  CUDA_TRY(ctx, cudaEventCreate(&e1));
+  const uint32_t iters = 4096;
+  const int grid = ctx->sm_count * 8;
+  auto launch = [&]() {
+    if (which == 0) int32_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink);
+    else if (which == 1) int32_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink);
+    else int32_peak_kernel<2><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink);
+    ctx->launches++;
+  };
+  for (int w = 0; w < 3; w++) launch();
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, ctx->compute);
+    launch();
+    cudaEventRecord(e1, ctx->compute);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    // per inner repetition: 8 chains x (1 IMAD | 2 ALU ops | 4 IMAD + 8 ALU over the 8 chains)
+    double ops_per_thread = (double)iters * 8.0 * (which == 0 ? 8.0 : (which == 1 ? 16.0 : 12.0));
+    double ops = ops_per_thread * (double)grid * kBlock;
+    if (ms > 0) best = std::max(best, ops / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  CUDA_TRY(ctx, cudaGetLastError());
+  *lane_ops_per_second = best;
+  return PBH_OK;
+}
+

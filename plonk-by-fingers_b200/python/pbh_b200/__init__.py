@@ -1,0 +1,531 @@
+"""pbh_b200 — Python host side of the B200-native batched Plonk-by-hand prover / verifier.
+
+Two layers over the C ABI of include/pbh_b200.h (libpbh_b200.so, hand-written sm_100a kernels):
+
+* `Context` — the batch API: byte-plane numpy arrays (host pointers; H2D/D2H inside the call) or
+  CUDA torch tensors (device pointers; kernels only).
+* the reference's own vocabulary — `f17`, `f101`, `g1f`, `Gate`, `CopyOf`, `Constrains`, `Assigment(s)`,
+  `SRS`, `Challange`, `Proof`, `Plonk.prove / Plonk.verify` — as batch-of-1 wrappers that raise
+  `ReferencePanic` where the Rust crate panics (src/plonk.rs:191-650, src/constraints.rs, src/pbh/mod.rs).
+
+There is NO CPU fallback: without the compiled extension or without a CUDA device every compute call raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_PKG))          # plonk-by-fingers_b200/
+LIB_PATH = os.path.join(_ROOT, "libpbh_b200.so")
+
+u8p = C.POINTER(C.c_uint8)
+u16p = C.POINTER(C.c_uint16)
+
+# status / result codes of include/pbh_b200.h
+ST_OK, ST_UNSATISFIED, ST_ACC_DIV0, ST_T_REMAINDER, ST_T_SLICE, ST_SRS_OOB, ST_BAD_ENCODING = 0, 1, 2, 3, 4, 5, 32
+VR_ACCEPT, VR_REJECT_PAIRING, VR_NOT_ON_CURVE, VR_NOT_IN_FIELD, VR_PANIC_ZH0, VR_BAD_ENCODING = 1, 0, 2, 4, 0x10, 0x20
+ALGO_ARITH, ALGO_TABLE = 0, 1
+DIST_UNIFORM, DIST_FULLPATH = 0, 1
+ERR = {0: "PBH_OK", -1: "PBH_ERR_BAD_ARGUMENT", -2: "PBH_ERR_SETUP_PANIC", -3: "PBH_ERR_CUDA", -4: "PBH_ERR_NO_DEVICE",
+       -5: "PBH_ERR_UNSUPPORTED"}
+PANIC_MESSAGES = {
+    ST_UNSATISFIED: "assertion failed: constraints.satisfies(assigments) (src/plonk.rs:199)",
+    ST_ACC_DIV0: "called `Option::unwrap()` on a `None` value (src/plonk.rs:297)",
+    ST_T_REMAINDER: "assertion failed: `(left == right)` rem != Poly::zero() (src/plonk.rs:370)",
+    ST_T_SLICE: "range end index 18 out of range for slice (src/plonk.rs:376)",
+    ST_SRS_OOB: "index out of bounds: the len is 7 (src/plonk.rs:56)",
+    ST_BAD_ENCODING: "input byte outside the field (not representable in the reference)",
+}
+
+EXPORTS = """pbh_circuit_pbh_test pbh_ctx_create pbh_ctx_destroy pbh_last_error pbh_ctx_set_algo pbh_ctx_get_algo
+pbh_ctx_device pbh_ctx_sync pbh_ctx_stream pbh_ctx_launch_count pbh_ctx_get_srs pbh_ctx_get_verifier_constants
+pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_ntt4_batch pbh_intt4_batch
+pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
+pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
+pbh_measure_int32_peak""".split()
+
+
+class PbhError(RuntimeError):
+    """A negative return code of the C ABI."""
+
+
+class ReferencePanic(RuntimeError):
+    """The reference crate would panic on this input; `.status` is the PBH_ST_* / PBH_VR_* code."""
+
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+class Circuit(C.Structure):
+    """pbh_circuit of include/pbh_b200.h == Constrains of src/constraints.rs:109-118 for 4 gates."""
+    _fields_ = [(name, C.c_uint8 * 4) for name in (
+        "q_l", "q_r", "q_o", "q_m", "q_c", "c_a_wire", "c_a_index", "c_b_wire", "c_b_index", "c_c_wire", "c_c_index")]
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libpbh_b200.so; fails loudly when it has not been built (there is no fallback)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise PbhError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(or `make -C plonk-by-fingers_b200`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        lib.pbh_last_error.restype = C.c_char_p
+        lib.pbh_last_error.argtypes = [C.c_void_p]
+        lib.pbh_ctx_stream.restype = C.c_void_p
+        lib.pbh_ctx_stream.argtypes = [C.c_void_p]
+        lib.pbh_ctx_launch_count.restype = C.c_uint64
+        lib.pbh_ctx_launch_count.argtypes = [C.c_void_p]
+        lib.pbh_ctx_destroy.argtypes = [C.c_void_p]
+        lib.pbh_ctx_destroy.restype = None
+        _LIB = lib
+    return _LIB
+
+
+def pbh_test_circuit():
+    c = Circuit()
+    load_library().pbh_circuit_pbh_test(C.byref(c))
+    return c
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _Planes:
+    """Uniform view of a (planes, n) uint8 batch living on the host (numpy) or the device (torch)."""
+
+    def __init__(self, arr, planes, n=None, name="array"):
+        self.dev = _is_torch(arr)
+        if self.dev:
+            import torch
+            if arr.dtype != torch.uint8 or not arr.is_cuda:
+                raise PbhError(f"{name}: device batches must be CUDA uint8 tensors")
+            if arr.dim() == 1:
+                arr = arr.unsqueeze(0)
+            if arr.stride(-1) != 1:
+                raise PbhError(f"{name}: planes must be contiguous along the item axis")
+            self.arr, self.ptr = arr, arr.data_ptr()
+            self.pitch = arr.stride(0) if arr.shape[0] > 1 else max(arr.shape[1], 1)
+        else:
+            arr = np.asarray(arr)
+            if arr.dtype != np.uint8:
+                raise PbhError(f"{name}: host batches must be uint8 arrays")
+            if arr.ndim == 1:
+                arr = arr.reshape(1, -1)
+            if arr.shape[1] > 0 and arr.strides[1] != 1:
+                arr = np.ascontiguousarray(arr)
+            self.arr, self.ptr = arr, arr.ctypes.data
+            self.pitch = arr.strides[0] if arr.shape[0] > 1 else max(arr.shape[1], 1)
+        if arr.shape[0] != planes:
+            raise PbhError(f"{name}: expected {planes} planes, got {arr.shape[0]}")
+        if n is not None and arr.shape[1] != n:
+            raise PbhError(f"{name}: expected {n} items, got {arr.shape[1]}")
+        self.n = arr.shape[1]
+
+
+class Context:
+    """pbh_ctx: SRS::create + Plonk::new + hoisted circuit constants on one CUDA device."""
+
+    def __init__(self, circuit=None, s=2, srs_n=6, omega_pows=4, device=0, algo="table"):
+        self.lib = load_library()
+        self.circuit = circuit if circuit is not None else pbh_test_circuit()
+        self.s, self.srs_n, self.omega_pows, self.device = s, srs_n, omega_pows, device
+        h = C.c_void_p()
+        rc = self.lib.pbh_ctx_create(C.byref(self.circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), int(device),
+                                     C.byref(h))
+        if rc != 0:
+            msg = self.lib.pbh_last_error(None).decode()
+            if rc == -2:
+                raise ReferencePanic(rc, "setup panics in the reference: " + msg)
+            raise PbhError(f"pbh_ctx_create: {ERR.get(rc, rc)}: {msg}")
+        self.h = h
+        self.set_algo(algo)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pbh_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PbhError(f"{what}: {ERR.get(rc, rc)}: {self.lib.pbh_last_error(self.h).decode()}")
+
+    # ---- context properties ----
+    def set_algo(self, algo):
+        code = {"arith": ALGO_ARITH, "table": ALGO_TABLE}.get(algo, algo)
+        self._check(self.lib.pbh_ctx_set_algo(self.h, int(code)), "pbh_ctx_set_algo")
+        self.algo = "table" if code == ALGO_TABLE else "arith"
+
+    def sync(self):
+        self._check(self.lib.pbh_ctx_sync(self.h), "pbh_ctx_sync")
+
+    @property
+    def stream_ptr(self):
+        return self.lib.pbh_ctx_stream(self.h)
+
+    def torch_stream(self):
+        """The context's compute stream as a torch.cuda.ExternalStream (for CUDA-event timing)."""
+        import torch
+        return torch.cuda.ExternalStream(self.stream_ptr, device=torch.device("cuda", self.device))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pbh_ctx_launch_count(self.h))
+
+    def srs(self):
+        n = C.c_uint32()
+        g1s = np.zeros(3 * (self.srs_n + 1), dtype=np.uint8)
+        g2 = np.zeros(4, dtype=np.uint8)
+        self._check(self.lib.pbh_ctx_get_srs(self.h, g1s.ctypes.data_as(u8p), C.c_size_t(self.srs_n + 1), C.byref(n),
+                                             g2.ctypes.data_as(u8p)), "pbh_ctx_get_srs")
+        return g1s.reshape(-1, 3), g2
+
+    def verifier_constants(self):
+        c = np.zeros(24, dtype=np.uint8)
+        self._check(self.lib.pbh_ctx_get_verifier_constants(self.h, c.ctypes.data_as(u8p)), "pbh_ctx_get_verifier_constants")
+        return c.reshape(8, 3)
+
+    # ---- allocation helpers ----
+    def _empty(self, like_dev, planes, n):
+        if like_dev:
+            import torch
+            return torch.empty((planes, n), dtype=torch.uint8, device=torch.device("cuda", self.device))
+        return np.empty((planes, n), dtype=np.uint8)
+
+    # ---- Plonk::prove / Plonk::verify over batches ----
+    def prove_batch(self, wit, rand, chal, proof=None, status=None):
+        """wit (12,n), rand (9,n), chal (5,n) -> proof (27,n), status (n,).  numpy = host API, torch.cuda = device API."""
+        W = _Planes(wit, 12, name="wit"); n = W.n
+        R = _Planes(rand, 9, n, "rand"); Ch = _Planes(chal, 5, n, "chal")
+        if not (W.dev == R.dev == Ch.dev):
+            raise PbhError("all batches must live on the same side (host or device)")
+        proof = self._empty(W.dev, 27, n) if proof is None else proof
+        status = self._empty(W.dev, 1, n) if status is None else status
+        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status")
+        fn = self.lib.pbh_prove_batch_dev if W.dev else self.lib.pbh_prove_batch
+        rc = fn(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch),
+                C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr))
+        self._check(rc, fn.__name__)
+        return P.arr, S.arr.reshape(-1)
+
+    def verify_batch(self, proof, chal, u, result=None, gt=None, want_gt=False):
+        """proof (27,n), chal (5,n), u (n,) -> result (n,) of PBH_VR_* [, gt (4,n)]."""
+        P = _Planes(proof, 27, name="proof"); n = P.n
+        Ch = _Planes(chal, 5, n, "chal"); U = _Planes(u, 1, n, "u")
+        if not (P.dev == Ch.dev == U.dev):
+            raise PbhError("all batches must live on the same side (host or device)")
+        result = self._empty(P.dev, 1, n) if result is None else result
+        Rs = _Planes(result, 1, n, "result")
+        G = None
+        if want_gt or gt is not None:
+            gt = self._empty(P.dev, 4, n) if gt is None else gt
+            G = _Planes(gt, 4, n, "gt")
+        fn = self.lib.pbh_verify_batch_dev if P.dev else self.lib.pbh_verify_batch
+        rc = fn(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch),
+                C.c_void_p(U.ptr), C.c_void_p(Rs.ptr), C.c_void_p(G.ptr if G else None), C.c_size_t(G.pitch if G else 0))
+        self._check(rc, fn.__name__)
+        res = Rs.arr.reshape(-1)
+        return (res, G.arr) if G else res
+
+    # ---- sweep kernels ----
+    def _sweep(self, fn, arr, pin, pout, *pre):
+        A = _Planes(arr, pin, name="in")
+        out = self._empty(A.dev, pout, A.n)
+        O = _Planes(out, pout, A.n, "out")
+        rc = fn(self.h, *pre, C.c_size_t(A.n), C.c_void_p(A.ptr), C.c_size_t(A.pitch), C.c_void_p(O.ptr), C.c_size_t(O.pitch),
+                int(A.dev))
+        self._check(rc, fn.__name__)
+        return O.arr
+
+    def ntt4_batch(self, coeffs): return self._sweep(self.lib.pbh_ntt4_batch, coeffs, 4, 4)
+    def intt4_batch(self, evals): return self._sweep(self.lib.pbh_intt4_batch, evals, 4, 4)
+    def g1_smul_batch(self, arr): return self._sweep(self.lib.pbh_g1_smul_batch, arr, 4, 3)
+    def g1_add_batch(self, arr): return self._sweep(self.lib.pbh_g1_add_batch, arr, 6, 3)
+    def kzg_commit_batch(self, arr): return self._sweep(self.lib.pbh_kzg_commit_batch, arr, 7, 3)
+    def pairing_batch(self, arr): return self._sweep(self.lib.pbh_pairing_batch, arr, 5, 2)
+
+    def poly_mul_batch(self, a, b):
+        A = _Planes(a, np.shape(a)[0] if not _is_torch(a) else a.shape[0], name="a")
+        B = _Planes(b, np.shape(b)[0] if not _is_torch(b) else b.shape[0], A.n, "b")
+        la, lb = A.arr.shape[0], B.arr.shape[0]
+        out = self._empty(A.dev, la + lb - 1, A.n); O = _Planes(out, la + lb - 1, A.n, "out")
+        rc = self.lib.pbh_poly_mul_batch(self.h, C.c_size_t(A.n), C.c_uint32(la), C.c_uint32(lb), C.c_void_p(A.ptr),
+                                         C.c_size_t(A.pitch), C.c_void_p(B.ptr), C.c_size_t(B.pitch), C.c_void_p(O.ptr),
+                                         C.c_size_t(O.pitch), int(A.dev))
+        self._check(rc, "pbh_poly_mul_batch")
+        return O.arr
+
+    def poly_add_batch(self, a, b, subtract=False):
+        ln = a.shape[0]
+        A = _Planes(a, ln, name="a"); B = _Planes(b, ln, A.n, "b")
+        out = self._empty(A.dev, ln, A.n); O = _Planes(out, ln, A.n, "out")
+        rc = self.lib.pbh_poly_add_batch(self.h, C.c_size_t(A.n), C.c_uint32(ln), int(subtract), C.c_void_p(A.ptr),
+                                         C.c_size_t(A.pitch), C.c_void_p(B.ptr), C.c_size_t(B.pitch), C.c_void_p(O.ptr),
+                                         C.c_size_t(O.pitch), int(A.dev))
+        self._check(rc, "pbh_poly_add_batch")
+        return O.arr
+
+    def poly_div_zh_batch(self, p):
+        P = _Planes(p, 22, name="p")
+        q = self._empty(P.dev, 18, P.n); r = self._empty(P.dev, 4, P.n)
+        Q = _Planes(q, 18, P.n, "q"); R = _Planes(r, 4, P.n, "r")
+        rc = self.lib.pbh_poly_div_zh_batch(self.h, C.c_size_t(P.n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Q.ptr),
+                                            C.c_size_t(Q.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch), int(P.dev))
+        self._check(rc, "pbh_poly_div_zh_batch")
+        return Q.arr, R.arr
+
+    def ntt_generic_batch(self, values, modulus, omega, inverse=False):
+        """values: (size, n) uint16 numpy array (host) -> (size, n) uint16.  CooleyTurkey::fft / fft_inv, src/fft.rs:66-78."""
+        v = np.ascontiguousarray(values, dtype=np.uint16)
+        size, n = v.shape
+        out = np.empty_like(v)
+        rc = self.lib.pbh_ntt_generic_batch(self.h, C.c_size_t(n), C.c_uint32(modulus), C.c_uint32(omega), C.c_uint32(size),
+                                            int(inverse), v.ctypes.data_as(u16p), C.c_size_t(n), out.ctypes.data_as(u16p),
+                                            C.c_size_t(n), 0)
+        self._check(rc, "pbh_ntt_generic_batch")
+        return out
+
+    # ---- device-side helpers (torch) ----
+    def generate_inputs(self, n, first_index=0, seed=0xB200, dist=DIST_FULLPATH, want_attempt=False):
+        """Synthetic batch on the device: returns torch uint8 tensors wit, rand, chal, u[, attempt]."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        wit = torch.empty((12, n), dtype=torch.uint8, device=dev); rand = torch.empty((9, n), dtype=torch.uint8, device=dev)
+        chal = torch.empty((5, n), dtype=torch.uint8, device=dev); u = torch.empty((n,), dtype=torch.uint8, device=dev)
+        att = torch.empty((n,), dtype=torch.uint8, device=dev) if want_attempt else None
+        rc = self.lib.pbh_generate_inputs_dev(self.h, C.c_size_t(n), C.c_uint64(first_index), C.c_uint64(seed), int(dist),
+                                              C.c_void_p(wit.data_ptr()), C.c_size_t(n), C.c_void_p(rand.data_ptr()), C.c_size_t(n),
+                                              C.c_void_p(chal.data_ptr()), C.c_size_t(n), C.c_void_p(u.data_ptr()),
+                                              C.c_void_p(att.data_ptr() if want_attempt else None))
+        self._check(rc, "pbh_generate_inputs_dev")
+        return (wit, rand, chal, u, att) if want_attempt else (wit, rand, chal, u)
+
+    def pack_verdicts(self, result):
+        import torch
+        n = result.numel()
+        out = torch.empty(((n + 7) // 8,), dtype=torch.uint8, device=result.device)
+        self._check(self.lib.pbh_pack_verdicts_dev(self.h, C.c_size_t(n), C.c_void_p(result.data_ptr()), C.c_void_p(out.data_ptr())),
+                    "pbh_pack_verdicts_dev")
+        return out
+
+    def digest(self, data, first_index=0):
+        """64-bit additive digest of a (planes, n) device batch; digests of disjoint shards sum to the whole batch's."""
+        import torch
+        D = _Planes(data, data.shape[0] if data.dim() > 1 else 1, name="data")
+        out = torch.zeros((1,), dtype=torch.int64, device=D.arr.device)
+        rc = self.lib.pbh_digest_dev(self.h, C.c_size_t(D.n), C.c_uint64(first_index), C.c_uint32(D.arr.shape[0]), C.c_void_p(D.ptr),
+                                     C.c_size_t(D.pitch), C.c_void_p(out.data_ptr()))
+        self._check(rc, "pbh_digest_dev")
+        return out
+
+    def measure_int32_peak(self, which=0):
+        v = C.c_double()
+        self._check(self.lib.pbh_measure_int32_peak(self.h, int(which), C.byref(v)), "pbh_measure_int32_peak")
+        return v.value
+
+
+# ================================================================================================
+# The reference's vocabulary (batch-of-1 wrappers)
+# ================================================================================================
+def f17(x):
+    """src/pbh/mod.rs:13-16"""
+    return int(x) % 17
+
+
+def f101(x):
+    """src/pbh/mod.rs:8-11"""
+    return int(x) % 101
+
+
+def g1f(x, y):
+    """src/pbh/g1.rs:11-13 — an affine point; the identity is `None`."""
+    return (f101(x), f101(y))
+
+
+class Gate:
+    """src/constraints.rs:10-64"""
+
+    def __init__(self, q_l, q_r, q_o, q_m, q_c):
+        self.q_l, self.q_r, self.q_o, self.q_m, self.q_c = f17(q_l), f17(q_r), f17(q_o), f17(q_m), f17(q_c)
+
+    @classmethod
+    def sum_a_b(cls): return cls(1, 1, -1, 0, 0)
+    @classmethod
+    def sub_a_b(cls): return cls(1, 1, 1, 0, 0)      # sic: identical signs in the reference (src/constraints.rs:37-45)
+    @classmethod
+    def mul_a_b(cls): return cls(0, 0, -1, 1, 0)
+    @classmethod
+    def bind_a(cls, value): return cls(1, 0, 0, 1, value)
+
+
+class CopyOf:
+    """src/constraints.rs:67-71"""
+
+    def __init__(self, wire, n):
+        self.wire, self.n = wire, n
+
+    @classmethod
+    def A(cls, n): return cls(0, n)
+    @classmethod
+    def B(cls, n): return cls(1, n)
+    @classmethod
+    def C(cls, n): return cls(2, n)
+
+
+class Constrains:
+    """src/constraints.rs:109-153"""
+
+    def __init__(self, gates, copy_constraints):
+        if len(gates) != 4:
+            raise PbhError("this build mirrors the reference's prove(), which is hard-wired to 4 gates (src/plonk.rs:376-378)")
+        self.gates = list(gates)
+        self.c_a, self.c_b, self.c_c = copy_constraints
+
+    def to_circuit(self):
+        c = Circuit()
+        for i, g in enumerate(self.gates):
+            c.q_l[i], c.q_r[i], c.q_o[i], c.q_m[i], c.q_c[i] = g.q_l, g.q_r, g.q_o, g.q_m, g.q_c
+        for name, vec in (("c_a", self.c_a), ("c_b", self.c_b), ("c_c", self.c_c)):
+            for i, cp in enumerate(vec):
+                getattr(c, name + "_wire")[i] = cp.wire
+                getattr(c, name + "_index")[i] = cp.n
+        return c
+
+
+class Assigment:
+    """src/constraints.rs:120-130"""
+
+    def __init__(self, a, b, c):
+        self.a, self.b, self.c = f17(a), f17(b), f17(c)
+
+
+class Assigments:
+    """src/constraints.rs:132-136, 233-244"""
+
+    def __init__(self, assigments):
+        self.a = [v.a for v in assigments]; self.b = [v.b for v in assigments]; self.c = [v.c for v in assigments]
+
+    def __len__(self):
+        return len(self.a)
+
+
+class Challange:
+    """src/plonk.rs:97-108"""
+
+    def __init__(self, alpha, beta, gamma, z, v):
+        self.alpha, self.beta, self.gamma, self.z, self.v = f17(alpha), f17(beta), f17(gamma), f17(z), f17(v)
+
+    def column(self):
+        return np.array([[self.alpha], [self.beta], [self.gamma], [self.z], [self.v]], dtype=np.uint8)
+
+
+POINT_NAMES = "a_s b_s c_s z_s t_lo_s t_mid_s t_hi_s w_z_s w_z_omega_s".split()
+EVAL_NAMES = "a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z".split()
+
+
+class Proof:
+    """src/plonk.rs:61-95.  Points are (x, y) tuples, `None` for the identity."""
+
+    def __init__(self, **kw):
+        for name in POINT_NAMES + EVAL_NAMES:
+            setattr(self, name, kw[name])
+
+    def __eq__(self, other):
+        return all(getattr(self, k) == getattr(other, k) for k in POINT_NAMES + EVAL_NAMES)
+
+    def __repr__(self):
+        return "Proof(" + ", ".join(f"{k}={getattr(self, k)}" for k in POINT_NAMES + EVAL_NAMES) + ")"
+
+    def column(self):
+        col = np.zeros((27, 1), dtype=np.uint8)
+        for k, name in enumerate(POINT_NAMES):
+            p = getattr(self, name)
+            if p is None:
+                p = (0, 0, 1)
+            col[2 * k, 0], col[2 * k + 1, 0] = p[0], p[1]
+            if len(p) > 2 and p[2]:
+                if k < 8:
+                    col[18, 0] |= 1 << k
+                else:
+                    col[19, 0] |= 1
+        for k, name in enumerate(EVAL_NAMES):
+            col[20 + k, 0] = getattr(self, name)
+        return col
+
+    @classmethod
+    def from_column(cls, col):
+        d = {}
+        for k, name in enumerate(POINT_NAMES):
+            inf = (col[18] >> k) & 1 if k < 8 else col[19] & 1
+            x, y = int(col[2 * k]), int(col[2 * k + 1])
+            d[name] = (None if (x == 0 and y == 0) else (x, y, 1)) if inf else (x, y)
+        for k, name in enumerate(EVAL_NAMES):
+            d[name] = int(col[20 + k])
+        return cls(**d)
+
+
+class SRS:
+    """src/plonk.rs:28-48.  `SRS.create(s, n)` records the parameters; the points are computed by the context."""
+
+    def __init__(self, s, n):
+        self.s, self.n = f101(s), int(n)
+
+    @classmethod
+    def create(cls, s, n):
+        return cls(s, n)
+
+
+class Plonk:
+    """src/plonk.rs:110-175, 191-650 — `Plonk.new(srs, omega_pows)`, then prove / verify one item on the GPU."""
+
+    def __init__(self, srs, omega_pows, device=0, algo="table"):
+        self.srs, self.omega_pows, self.device, self.algo = srs, f17(omega_pows), device, algo
+        self._ctx = {}
+
+    @classmethod
+    def new(cls, srs, omega_pows, device=0, algo="table"):
+        return cls(srs, omega_pows, device, algo)
+
+    def _context(self, constraints):
+        key = bytes(constraints.to_circuit())
+        if key not in self._ctx:
+            self._ctx[key] = Context(constraints.to_circuit(), self.srs.s, self.srs.n, self.omega_pows, self.device, self.algo)
+        return self._ctx[key]
+
+    def prove(self, constraints, assigments, challange, rand):
+        ctx = self._context(constraints)
+        wit = np.array([assigments.a + assigments.b + assigments.c], dtype=np.uint8).T.copy()
+        rnd = np.array([[f17(r) for r in rand]], dtype=np.uint8).T.copy()
+        proof, status = ctx.prove_batch(wit, rnd, challange.column())
+        st = int(status[0])
+        if st != ST_OK:
+            raise ReferencePanic(st, PANIC_MESSAGES.get(st, f"status {st}"))
+        return Proof.from_column(proof[:, 0])
+
+    def verify(self, constraints, proof, challange, rand):
+        ctx = self._context(constraints)
+        res = ctx.verify_batch(proof.column(), challange.column(), np.array([f17(rand[0])], dtype=np.uint8))
+        r = int(res[0])
+        if r == VR_PANIC_ZH0:
+            raise ReferencePanic(r, "called `Option::unwrap()` on a `None` value (src/plonk.rs:579)")
+        if r == VR_BAD_ENCODING:
+            raise ReferencePanic(r, "input byte outside the field (not representable in the reference)")
+        return bool(r & 1)

@@ -1,0 +1,131 @@
+// hostemul.cpp — TEST INFRASTRUCTURE.  Compiles the product's __host__ __device__ routines
+// (plonk-by-fingers_b200/csrc/pbh_{arith,prove,verify}.cuh, pbh_setup.hpp) with g++ so that the exact
+// per-item logic the kernels run can be differential-tested against the oracle on a machine without a GPU.
+// It is NOT part of the product and is never loaded by it: the shipped library has no CPU path.
+#include <cstdint>
+#include <cstring>
+#include <string>
+
+#include "../../plonk-by-fingers_b200/csrc/pbh_setup.hpp"
+
+using namespace pbh;
+
+static std::string g_err;
+
+extern "C" {
+
+const char* emul_last_error() { return g_err.c_str(); }
+
+// exhaustive check of the reciprocal constants over their documented ranges; returns the number of mismatches
+uint64_t emul_check_reductions() {
+  uint64_t bad = 0;
+  for (uint32_t x = 0; x < (1u << 28); x++) bad += mod17(x) != x % 17u;
+  for (uint32_t x = 0; x < (1u << 26); x++) bad += mod101(x) != x % 101u;
+  for (uint32_t x = 0; x < (1u << 26); x++) bad += mod102(x) != x % 102u;
+  return bad;
+}
+
+int emul_setup(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t omega_pows, uint8_t* g1s, uint8_t g2[4], uint8_t consts[24],
+               uint8_t* tables_out, size_t tables_cap) {
+  HostSetup hs;
+  int rc = host_setup(*c, s, srs_n, omega_pows, hs, g_err);
+  if (rc) return rc;
+  for (size_t i = 0; i < hs.g1s.size(); i++) { g1s[3 * i] = hs.g1s[i].x; g1s[3 * i + 1] = hs.g1s[i].y; g1s[3 * i + 2] = hs.g1s[i].inf; }
+  g2[0] = hs.g2_1[0]; g2[1] = hs.g2_1[1]; g2[2] = hs.g2_s[0]; g2[3] = hs.g2_s[1];
+  for (int j = 0; j < 8; j++) { consts[3 * j] = hs.vconst[j].x; consts[3 * j + 1] = hs.vconst[j].y; consts[3 * j + 2] = hs.vconst[j].inf; }
+  if (tables_out && tables_cap >= sizeof(Tables)) std::memcpy(tables_out, &hs.T, sizeof(Tables));
+  return 0;
+}
+size_t emul_tables_size() { return sizeof(Tables); }
+
+int emul_prove_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t omega_pows, int algo, size_t n, const uint8_t* wit,
+                     const uint8_t* rnd, const uint8_t* chal, uint8_t* proof, uint8_t* status) {
+  HostSetup hs;
+  int rc = host_setup(*c, s, srs_n, omega_pows, hs, g_err);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    uint32_t w[12], r[9], ch[5];
+    bool bad = false;
+    for (int k = 0; k < 12; k++) { w[k] = wit[k * n + i]; bad |= w[k] >= 17; }
+    for (int k = 0; k < 9; k++) { r[k] = rnd[k * n + i]; bad |= r[k] >= 17; }
+    for (int k = 0; k < 5; k++) { ch[k] = chal[k * n + i]; bad |= ch[k] >= 17; }
+    if (bad) { std::memset(w, 0, sizeof w); std::memset(r, 0, sizeof r); std::memset(ch, 0, sizeof ch); }
+    ProofRegs P;
+    uint32_t st = algo == 1 ? prove_one<ALGO_TABLE>(w, r, ch, hs.K, hs.T, P) : prove_one<ALGO_ARITH>(w, r, ch, hs.K, hs.T, P);
+    if (bad) st = PBH_ST_BAD_ENCODING;
+    for (int k = 0; k < 27; k++) proof[k * n + i] = 0;
+    status[i] = (uint8_t)st;
+    if (st == 0) {
+      for (int k = 0; k < 9; k++) {
+        proof[(2 * k) * n + i] = P.pt[k] & 0xFF; proof[(2 * k + 1) * n + i] = (P.pt[k] >> 8) & 0xFF;
+        if ((P.pt[k] >> 16) & 1) { if (k < 8) proof[18 * n + i] |= 1u << k; else proof[19 * n + i] |= 1; }
+      }
+      for (int k = 0; k < 7; k++) proof[(20 + k) * n + i] = (uint8_t)P.ev[k];
+    }
+  }
+  return 0;
+}
+
+int emul_verify_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t omega_pows, int algo, size_t n, const uint8_t* proof,
+                      const uint8_t* chal, const uint8_t* u, uint8_t* result, uint8_t* gt) {
+  HostSetup hs;
+  int rc = host_setup(*c, s, srs_n, omega_pows, hs, g_err);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    uint32_t px[9], py[9], ev[7], ch[5];
+    for (int k = 0; k < 9; k++) { px[k] = proof[(2 * k) * n + i]; py[k] = proof[(2 * k + 1) * n + i]; }
+    uint32_t infbits = proof[18 * n + i] | ((uint32_t)proof[19 * n + i] << 8);
+    for (int k = 0; k < 7; k++) ev[k] = proof[(20 + k) * n + i];
+    for (int k = 0; k < 5; k++) ch[k] = chal[k * n + i];
+    GT e1, e2;
+    uint32_t res = algo == 1 ? verify_one<ALGO_TABLE>(px, py, infbits, ev, ch, u[i], hs.K, hs.T, e1, e2)
+                             : verify_one<ALGO_ARITH>(px, py, infbits, ev, ch, u[i], hs.K, hs.T, e1, e2);
+    result[i] = (uint8_t)res;
+    if (gt) { gt[i] = e1.a; gt[n + i] = e1.b; gt[2 * n + i] = e2.a; gt[3 * n + i] = e2.b; }
+  }
+  return 0;
+}
+
+// G1 / pairing primitives of pbh_arith.cuh
+int emul_g1_add(const uint8_t p[3], const uint8_t q[3], uint8_t out[3]) {
+  HostSetup hs; pbh_circuit c; std::memset(&c, 0, sizeof c);
+  for (int i = 0; i < 4; i++) c.c_a_index[i] = c.c_b_index[i] = c.c_c_index[i] = 1;
+  if (host_setup(c, 2, 6, 4, hs, g_err)) return -1;
+  G1 a{p[0], p[1], (uint32_t)(p[2] != 0)}, b{q[0], q[1], (uint32_t)(q[2] != 0)};
+  bool bad;
+  G1 r = g1_add(a, b, hs.T.inv101, &bad);
+  out[0] = r.x; out[1] = r.y; out[2] = r.inf;
+  return bad ? 1 : 0;
+}
+// all 102 x 102 additions, all 102 x 101 scalar multiples, and pairings of all 102 points (plus flagged points
+// with coordinates) against q; outputs as flat arrays for the caller to compare with the oracle
+int emul_g1_smul(const uint8_t p[3], uint8_t k, uint8_t out[3]) {
+  static HostSetup hs; static bool init = false;
+  if (!init) { pbh_circuit c; std::memset(&c, 0, sizeof c); for (int i = 0; i < 4; i++) c.c_a_index[i] = c.c_b_index[i] = c.c_c_index[i] = 1;
+    if (host_setup(c, 2, 6, 4, hs, g_err)) return -1; init = true; }
+  G1 a{p[0], p[1], (uint32_t)(p[2] != 0)};
+  G1 r = g1_smul<7>(a, k, hs.T.inv101);
+  out[0] = r.x; out[1] = r.y; out[2] = r.inf;
+  return 0;
+}
+int emul_pairing(const uint8_t p[3], const uint8_t q[2], uint8_t out[2], uint8_t miller_out[2]) {
+  static HostSetup hs; static bool init = false;
+  if (!init) { pbh_circuit c; std::memset(&c, 0, sizeof c); for (int i = 0; i < 4; i++) c.c_a_index[i] = c.c_b_index[i] = c.c_c_index[i] = 1;
+    if (host_setup(c, 2, 6, 4, hs, g_err)) return -1; init = true; }
+  G1 a{p[0], p[1], (uint32_t)(p[2] != 0)};
+  GT f = miller_f17(a, q[0], q[1], hs.T.inv101);
+  GT e = gt_final_exp(f, hs.T.inv101);
+  out[0] = e.a; out[1] = e.b; miller_out[0] = f.a; miller_out[1] = f.b;
+  return 0;
+}
+int emul_gt_final_exp(const uint8_t f[2], uint8_t out[2]) {
+  static HostSetup hs; static bool init = false;
+  if (!init) { pbh_circuit c; std::memset(&c, 0, sizeof c); for (int i = 0; i < 4; i++) c.c_a_index[i] = c.c_b_index[i] = c.c_c_index[i] = 1;
+    if (host_setup(c, 2, 6, 4, hs, g_err)) return -1; init = true; }
+  GT x{f[0], f[1]};
+  GT e = gt_final_exp(x, hs.T.inv101);
+  out[0] = e.a; out[1] = e.b;
+  return 0;
+}
+
+}  // extern "C"

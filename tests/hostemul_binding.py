@@ -1,0 +1,85 @@
+"""ctypes binding of tests/hostemul/libhostemul.so (TEST INFRASTRUCTURE): the product's __host__ __device__
+per-item routines compiled with g++, so kernel logic can be checked against the oracle without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostemul")
+ROOT = os.path.dirname(os.path.dirname(HERE))
+u8p = C.POINTER(C.c_uint8)
+_E = None
+
+
+def load():
+    global _E
+    if _E is None:
+        so = os.path.join(HERE, "libhostemul.so")
+        srcs = [os.path.join(HERE, "hostemul.cpp")] + [os.path.join(ROOT, "plonk-by-fingers_b200", "csrc", f) for f in
+                                                       ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_verify.cuh", "pbh_setup.hpp")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, srcs[0]], check=True)
+        _E = C.CDLL(so)
+        _E.emul_last_error.restype = C.c_char_p
+        _E.emul_check_reductions.restype = C.c_uint64
+        _E.emul_tables_size.restype = C.c_size_t
+    return Emul(_E)
+
+
+def _p(a):
+    return a.ctypes.data_as(u8p)
+
+
+class Emul:
+    def __init__(self, lib):
+        self.lib = lib
+
+    def prove(self, circuit, wit, rand, chal, algo, s=2, srs_n=6, omega_pows=4):
+        wit, rand, chal = (np.ascontiguousarray(x, dtype=np.uint8) for x in (wit, rand, chal))
+        n = wit.shape[1]
+        proof = np.zeros((27, n), np.uint8); status = np.zeros(n, np.uint8)
+        rc = self.lib.emul_prove_batch(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), int(algo),
+                                       C.c_size_t(n), _p(wit), _p(rand), _p(chal), _p(proof), _p(status))
+        if rc:
+            raise RuntimeError((rc, self.lib.emul_last_error().decode()))
+        return proof, status
+
+    def verify(self, circuit, proof, chal, u, algo, s=2, srs_n=6, omega_pows=4):
+        proof, chal, u = (np.ascontiguousarray(x, dtype=np.uint8) for x in (proof, chal, u))
+        n = proof.shape[1]
+        res = np.zeros(n, np.uint8); gt = np.zeros((4, n), np.uint8)
+        rc = self.lib.emul_verify_batch(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), int(algo),
+                                        C.c_size_t(n), _p(proof), _p(chal), _p(u), _p(res), _p(gt))
+        if rc:
+            raise RuntimeError((rc, self.lib.emul_last_error().decode()))
+        return res, gt
+
+    def setup(self, circuit, s=2, srs_n=6, omega_pows=4):
+        g1s = np.zeros(3 * (srs_n + 1), np.uint8); g2 = np.zeros(4, np.uint8); consts = np.zeros(24, np.uint8)
+        rc = self.lib.emul_setup(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), _p(g1s), _p(g2), _p(consts),
+                                 None, C.c_size_t(0))
+        return rc, g1s.reshape(-1, 3), g2, consts.reshape(8, 3)
+
+    def g1_add(self, p, q):
+        o = (C.c_uint8 * 3)()
+        rc = self.lib.emul_g1_add((C.c_uint8 * 3)(*p), (C.c_uint8 * 3)(*q), o)
+        return rc, tuple(o)
+
+    def g1_smul(self, p, k):
+        o = (C.c_uint8 * 3)()
+        self.lib.emul_g1_smul((C.c_uint8 * 3)(*p), C.c_uint8(k), o)
+        return tuple(o)
+
+    def pairing(self, p, q):
+        o = (C.c_uint8 * 2)(); m = (C.c_uint8 * 2)()
+        self.lib.emul_pairing((C.c_uint8 * 3)(*p), (C.c_uint8 * 2)(*q), o, m)
+        return tuple(o), tuple(m)
+
+    def gt_final_exp(self, f):
+        o = (C.c_uint8 * 2)()
+        self.lib.emul_gt_final_exp((C.c_uint8 * 2)(*f), o)
+        return tuple(o)
+
+    def check_reductions(self):
+        return int(self.lib.emul_check_reductions())

@@ -172,8 +172,8 @@ def main():
         outs.append(dict(proof=torch.empty((27, n), dtype=torch.uint8, device=dev), status=torch.empty((n,), dtype=torch.uint8, device=dev),
                          result=torch.empty((n,), dtype=torch.uint8, device=dev), bitmap=None, digest=None))
     ctx.sync()
-    gathered_bits = torch.empty((world, (n + 7) // 8), dtype=torch.uint8, device=dev) if world > 1 else None
-    gathered_dig = torch.empty((world, 1), dtype=torch.int64, device=dev) if world > 1 else None
+    gathered_bits = torch.empty(world * ((n + 7) // 8), dtype=torch.uint8, device=dev) if world > 1 else None
+    gathered_dig = torch.empty(world, dtype=torch.int64, device=dev) if world > 1 else None
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step(k, ev=None):
@@ -192,7 +192,7 @@ def main():
             comm_stream.wait_event(done)
             with torch.cuda.stream(comm_stream):
                 dist.all_gather_into_tensor(gathered_bits, o["bitmap"])
-                dist.all_gather_into_tensor(gathered_dig, o["digest"])
+                dist.all_gather_into_tensor(gathered_dig, o["digest"].reshape(1))
 
     def barrier():
         if world > 1:
@@ -244,7 +244,7 @@ def main():
 
     # ---- end-to-end through the host-pointer C-ABI calls (pinned host buffers), rank 0's device at N = 1
     e2e = None
-    if world == 1:
+    if world == 1 and args.e2e_steps != 0:
         hw = [torch.empty(t.shape, dtype=torch.uint8).pin_memory() for t in ins[0][:4]]
         for h, t in zip(hw, ins[0][:4]):
             h.copy_(t)

@@ -153,6 +153,7 @@ extern "C" {
   switch (M) {                                                       \
     case 17: { using F = Fp<17>; __VA_ARGS__ } break;                \
     case 101: { using F = Fp<101>; __VA_ARGS__ } break;              \
+    case 257: { using F = Fp<257>; __VA_ARGS__ } break;              \
     case 337: { using F = Fp<337>; __VA_ARGS__ } break;              \
     case 104729: { using F = Fp<104729>; __VA_ARGS__ } break;        \
     case 15485863: { using F = Fp<15485863>; __VA_ARGS__ } break;    \

@@ -1,0 +1,81 @@
+"""The product's per-item routines (prove_one / verify_one / G1 / pairing of plonk-by-fingers_b200/csrc/*.cuh and the
+host setup), compiled for the host by tests/hostemul, against the oracle.  This is the CPU-side guard for the
+kernel logic; the same comparisons run on the GPU through the C ABI in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+
+def test_reduction_constants_exhaustive(hostemul):
+    """mod17 / mod101 / mod102 multiply-high reciprocals are exact over their whole documented ranges."""
+    assert hostemul.check_reductions() == 0
+
+
+@pytest.mark.parametrize("algo", (0, 1))
+@pytest.mark.parametrize("dist", (0, 1))
+def test_prove_verify_logic_matches_oracle(hostemul, oracle, algo, dist):
+    circ = oracle.pbh_test_circuit()
+    n = 25000
+    w, r, c, u, _ = oracle.generate_inputs(n, seed=4242 + dist, dist=dist, threads=8)
+    po, so = oracle.prove_batch(w, r, c, threads=8)
+    pe, se = hostemul.prove(circ, w, r, c, algo)
+    assert np.array_equal(se, so) and np.array_equal(pe, po)
+    vo, go = oracle.verify_batch(po, c, u, threads=8)
+    ve, ge = hostemul.verify(circ, po, c, u, algo)
+    assert np.array_equal(ve, vo) and np.array_equal(ge, go)
+
+
+@pytest.mark.parametrize("algo", (0, 1))
+def test_zero_blinder_corner_cases(hostemul, oracle, algo):
+    """Blinders and challenges drawn from {0, 1, 16}: short polynomials, the Q1 / Q5 / Q15 length logic."""
+    rng = np.random.default_rng(17)
+    n = 30000
+    w = oracle.generate_inputs(n, seed=5, dist=0, threads=8)[0]
+    r = rng.choice(np.array([0, 0, 0, 1, 16, 5], dtype=np.uint8), size=(9, n))
+    c = rng.choice(np.array([0, 1, 16, 3, 7], dtype=np.uint8), size=(5, n))
+    po, so = oracle.prove_batch(w, r, c, threads=8)
+    pe, se = hostemul.prove(oracle.pbh_test_circuit(), w, r, c, algo)
+    assert np.array_equal(se, so) and np.array_equal(pe, po)
+    assert (so == 3).sum() > 0 and (so == 4).sum() > 0      # the rare remainder class is exercised
+
+
+def test_setup_matches_oracle(hostemul, oracle):
+    circ = oracle.pbh_test_circuit()
+    for s in range(101):
+        for srs_n in (6, 9):
+            try:
+                og1s, og2, oc = oracle.setup(circuit=circ, s=s, srs_n=srs_n)
+                o_ok = True
+            except ArithmeticError:
+                o_ok = False
+            rc, g1s, g2, c = hostemul.setup(circ, s=s, srs_n=srs_n)
+            assert (rc == 0) == o_ok, (s, srs_n, rc)
+            if o_ok:
+                assert np.array_equal(g1s, og1s) and np.array_equal(g2, og2) and np.array_equal(c, oc)
+
+
+def test_group_law_exhaustive(hostemul, oracle):
+    """All 102 x 102 additions and a 102 x 101 scalar-multiple table of the kernels' g1_add / g1_smul."""
+    pts = [(x, y, 0) for x in range(101) for y in range(101) if (y * y - x * x * x - 3) % 101 == 0] + [(0, 0, 1)]
+    P = np.array(pts, dtype=np.uint8)
+    a = np.repeat(P, 102, axis=0); b = np.tile(P, (102, 1))
+    exp = oracle.g1_add_batch(np.ascontiguousarray(np.concatenate([a, b], axis=1).T))
+    for i in range(0, 102 * 102, 7):
+        rc, got = hostemul.g1_add(tuple(a[i]), tuple(b[i]))
+        assert rc == 0 and list(got) == exp[:, i].tolist()
+    for p in pts:
+        for k in (0, 1, 2, 3, 16, 17, 18, 33, 51, 100):
+            e = oracle.g1_mul(None if p[2] else p[:2], k)
+            e = (0, 0, 1) if e is None else (e[0], e[1], 0)
+            assert hostemul.g1_smul(p, k) == e
+
+
+def test_pairing_exhaustive(hostemul, oracle):
+    pts = [(x, y, 0) for x in range(101) for y in range(101) if (y * y - x * x * x - 3) % 101 == 0] + [(0, 0, 1), (1, 2, 1)]
+    for q in [(36, 31), (90, 82), (10, 16), (5, 77), (0, 0)]:
+        for p in pts:
+            e, m = hostemul.pairing(p, q)
+            po = None if (p[2] and p[0] == 0) else p
+            assert e == oracle.pairing(po, q) and m == oracle.miller(po, q), (p, q)
+    for a in range(101):
+        for b in range(0, 101, 3):
+            assert hostemul.gt_final_exp((a, b)) == oracle.gt_pow((a, b), 600)

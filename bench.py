@@ -277,8 +277,8 @@ def main():
     ach = prove_gbs if dominant == "prove_kernel" else verify_gbs
     int32 = {}
     try:
-        int32 = {"imad_lane_ops_per_s": ctx.measure_int32_peak(0), "alu_lane_ops_per_s": ctx.measure_int32_peak(1),
-                 "mixed_lane_ops_per_s": ctx.measure_int32_peak(2)}
+        names = ["imad", "lop3_iadd3", "half_imad_half_alu", "ffma", "hfma2_instr", "dp4a_instr", "imad_hi_iadd", "half_ffma_half_imad"]
+        int32 = {f"{nm}_thread_ops_per_s": ctx.measure_int32_peak(i) for i, nm in enumerate(names)}
     except Exception as e:  # pragma: no cover
         int32 = {"error": str(e)}
 

@@ -214,8 +214,10 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
                             uint8_t* u, uint8_t* attempt);
 
 /* ---- measurement helpers ------------------------------------------------------------------------ */
-/* Dependent-chain-free IMAD/IADD3 micro-benchmark: integer lane-operations per second the device
- * sustains (the INT32 roofline denominator).  which: 0 = IMAD, 1 = IADD3/LOP3, 2 = mixed */
+/* Pipe-rate micro-benchmark (independent register chains, no memory traffic): thread-level operations per second
+ * the device sustains for one instruction class; the INT32 / FMA roofline denominators of SURVEY.md §8d.
+ * which: 0 IMAD, 1 LOP3+IADD3, 2 half IMAD half ALU, 3 FFMA, 4 HFMA2 (counted once per instruction; each carries two
+ * fp16 lanes), 5 IDP.4A (dp4a; four byte MACs each), 6 IMAD.HI+IADD, 7 half FFMA half IMAD */
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second);
 
 #ifdef __cplusplus

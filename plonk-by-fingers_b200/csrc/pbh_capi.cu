@@ -528,7 +528,7 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
 
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second) {
   CTX_CHECK(ctx);
-  if (!lane_ops_per_second || which < 0 || which > 2) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
+  if (!lane_ops_per_second || which < 0 || which > 7) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   uint32_t* sink = nullptr;
   CUDA_TRY(ctx, cudaMalloc(&sink, 4));
@@ -538,9 +538,16 @@ int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second)
   const uint32_t iters = 4096;
   const int grid = ctx->sm_count * 8;
   auto launch = [&]() {
-    if (which == 0) int32_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink);
-    else if (which == 1) int32_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink);
-    else int32_peak_kernel<2><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink);
+    switch (which) {
+      case 0: int32_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 1: int32_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 2: int32_peak_kernel<2><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 3: int32_peak_kernel<3><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 4: int32_peak_kernel<4><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 5: int32_peak_kernel<5><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 6: int32_peak_kernel<6><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      default: int32_peak_kernel<7><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+    }
     ctx->launches++;
   };
   for (int w = 0; w < 3; w++) launch();
@@ -552,9 +559,10 @@ int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second)
     cudaEventSynchronize(e1);
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
-    // per inner repetition: 8 chains x (1 IMAD | 2 ALU ops | 4 IMAD + 8 ALU over the 8 chains)
-    double ops_per_thread = (double)iters * 8.0 * (which == 0 ? 8.0 : (which == 1 ? 16.0 : 12.0));
-    double ops = ops_per_thread * (double)grid * kBlock;
+    // per inner repetition over the 8 chains: 8 ops (IMAD / FFMA / HFMA2 / dp4a / mixed), 16 for LOP3+IADD3,
+    // 4 IMAD + 8 ALU for the mix, 16 for IMAD.HI + IADD
+    const double per_rep = (which == 1 || which == 6) ? 16.0 : (which == 2 ? 12.0 : 8.0);
+    double ops = (double)iters * 8.0 * per_rep * (double)grid * kBlock;
     if (ms > 0) best = std::max(best, ops / (ms * 1e-3));
   }
   cudaEventDestroy(e0);
@@ -564,4 +572,3 @@ int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second)
   *lane_ops_per_second = best;
   return PBH_OK;
 }
-

@@ -7,6 +7,7 @@
 // context's lookup tables (~2.7 KB) into shared memory once, then loop.  No tensor cores: nothing on this
 // path is a dense contraction.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/pbh_b200.h"
@@ -388,24 +389,68 @@ __global__ void __launch_bounds__(kBlock) generate_kernel(const Consts K, const 
   }
 }
 
-// ---- INT32 pipe peak: independent chains, no memory traffic -------------------------------
+// ---- pipe peaks: independent chains, no memory traffic ------------------------------------
+// WHICH: 0 IMAD, 1 LOP3+IADD3, 2 half IMAD half ALU, 3 FFMA, 4 HFMA2 (two fp16 lanes per op), 5 IDP.4A (dp4a),
+//        6 IMAD.HI, 7 half FFMA half IMAD
 template <int WHICH>
 __global__ void __launch_bounds__(kBlock) int32_peak_kernel(uint32_t iters, uint32_t seed, uint32_t* sink) {
   uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u, a4 = a0 * 11u + 4u, a5 = a0 * 13u + 5u,
            a6 = a0 * 17u + 6u, a7 = a0 * 19u + 7u;
   const uint32_t m = seed | 1u, c = seed ^ 0x9E3779B9u;
-  for (uint32_t it = 0; it < iters; it++) {
+  if (WHICH == 3 || WHICH == 7) {
+    float f0 = (float)(a0 & 255), f1 = (float)(a1 & 255), f2 = (float)(a2 & 255), f3 = (float)(a3 & 255), f4 = (float)(a4 & 255),
+          f5 = (float)(a5 & 255), f6 = (float)(a6 & 255), f7 = (float)(a7 & 255);
+    const float fm = 0.9999f + (float)(seed & 1u) * 1e-6f, fc = (float)(seed & 3u) * 0.25f;
+    for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
-    for (int rep = 0; rep < 8; rep++) {
-      if (WHICH == 0) {          // IMAD
-        a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
-        a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
-      } else if (WHICH == 1) {   // LOP3 / IADD3 (ALU pipe)
-        a0 = (a0 ^ m) + c; a1 = (a1 ^ m) + c; a2 = (a2 ^ m) + c; a3 = (a3 ^ m) + c;
-        a4 = (a4 ^ m) + c; a5 = (a5 ^ m) + c; a6 = (a6 ^ m) + c; a7 = (a7 ^ m) + c;
-      } else {                   // half IMAD, half ALU
-        a0 = a0 * m + c; a1 = (a1 ^ m) + c; a2 = a2 * m + c; a3 = (a3 ^ m) + c;
-        a4 = a4 * m + c; a5 = (a5 ^ m) + c; a6 = a6 * m + c; a7 = (a7 ^ m) + c;
+      for (int rep = 0; rep < 8; rep++) {
+        if (WHICH == 3) {
+          f0 = fmaf(f0, fm, fc); f1 = fmaf(f1, fm, fc); f2 = fmaf(f2, fm, fc); f3 = fmaf(f3, fm, fc);
+          f4 = fmaf(f4, fm, fc); f5 = fmaf(f5, fm, fc); f6 = fmaf(f6, fm, fc); f7 = fmaf(f7, fm, fc);
+        } else {
+          f0 = fmaf(f0, fm, fc); a1 = a1 * m + c; f2 = fmaf(f2, fm, fc); a3 = a3 * m + c;
+          f4 = fmaf(f4, fm, fc); a5 = a5 * m + c; f6 = fmaf(f6, fm, fc); a7 = a7 * m + c;
+        }
+      }
+    }
+    a0 = __float_as_uint(f0) ^ __float_as_uint(f2) ^ __float_as_uint(f4) ^ __float_as_uint(f6);
+    if (WHICH == 3) { a1 = __float_as_uint(f1); a3 = __float_as_uint(f3); a5 = __float_as_uint(f5); a7 = __float_as_uint(f7); }
+    a2 = a4 = a6 = 0;
+  } else if (WHICH == 4) {
+    __half2 h0 = __floats2half2_rn((float)(a0 & 7), 1.f), h1 = __floats2half2_rn((float)(a1 & 7), 2.f), h2 = __floats2half2_rn((float)(a2 & 7), 3.f),
+            h3 = __floats2half2_rn((float)(a3 & 7), 4.f), h4 = __floats2half2_rn((float)(a4 & 7), 5.f), h5 = __floats2half2_rn((float)(a5 & 7), 6.f),
+            h6 = __floats2half2_rn((float)(a6 & 7), 7.f), h7 = __floats2half2_rn((float)(a7 & 7), 8.f);
+    const __half2 hm = __floats2half2_rn(0.999f + (float)(seed & 1u) * 1e-3f, 0.998f), hc = __floats2half2_rn((float)(seed & 3u) * 0.25f, 0.5f);
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 8; rep++) {
+        h0 = __hfma2(h0, hm, hc); h1 = __hfma2(h1, hm, hc); h2 = __hfma2(h2, hm, hc); h3 = __hfma2(h3, hm, hc);
+        h4 = __hfma2(h4, hm, hc); h5 = __hfma2(h5, hm, hc); h6 = __hfma2(h6, hm, hc); h7 = __hfma2(h7, hm, hc);
+      }
+    }
+    __half2 s = __hadd2(__hadd2(__hadd2(h0, h1), __hadd2(h2, h3)), __hadd2(__hadd2(h4, h5), __hadd2(h6, h7)));
+    a0 = *reinterpret_cast<uint32_t*>(&s);
+    a1 = a2 = a3 = a4 = a5 = a6 = a7 = 0;
+  } else {
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 8; rep++) {
+        if (WHICH == 0) {          // IMAD
+          a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+          a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+        } else if (WHICH == 1) {   // LOP3 / IADD3 (ALU pipe)
+          a0 = (a0 ^ m) + c; a1 = (a1 ^ m) + c; a2 = (a2 ^ m) + c; a3 = (a3 ^ m) + c;
+          a4 = (a4 ^ m) + c; a5 = (a5 ^ m) + c; a6 = (a6 ^ m) + c; a7 = (a7 ^ m) + c;
+        } else if (WHICH == 2) {   // half IMAD, half ALU
+          a0 = a0 * m + c; a1 = (a1 ^ m) + c; a2 = a2 * m + c; a3 = (a3 ^ m) + c;
+          a4 = a4 * m + c; a5 = (a5 ^ m) + c; a6 = a6 * m + c; a7 = (a7 ^ m) + c;
+        } else if (WHICH == 5) {   // dp4a
+          a0 = __dp4a(a0, m, a0); a1 = __dp4a(a1, m, a1); a2 = __dp4a(a2, m, a2); a3 = __dp4a(a3, m, a3);
+          a4 = __dp4a(a4, m, a4); a5 = __dp4a(a5, m, a5); a6 = __dp4a(a6, m, a6); a7 = __dp4a(a7, m, a7);
+        } else {                   // IMAD.HI
+          a0 = __umulhi(a0, m) + c; a1 = __umulhi(a1, m) + c; a2 = __umulhi(a2, m) + c; a3 = __umulhi(a3, m) + c;
+          a4 = __umulhi(a4, m) + c; a5 = __umulhi(a5, m) + c; a6 = __umulhi(a6, m) + c; a7 = __umulhi(a7, m) + c;
+        }
       }
     }
   }

@@ -203,6 +203,25 @@ class Context:
         self._check(self.lib.pbh_ctx_get_verifier_constants(self.h, c.ctypes.data_as(u8p)), "pbh_ctx_get_verifier_constants")
         return c.reshape(8, 3)
 
+    # ---- stream ordering of the device-pointer API ----
+    # Kernels run on the context's own (non-blocking) stream.  Around every device-pointer call the context's stream
+    # first waits for the caller's current torch stream (inputs are ready) and the caller's stream then waits for the
+    # context's stream (outputs are ready), so the calls compose like ordinary torch ops.  Both waits are no-ops when
+    # the caller already runs under `with torch.cuda.stream(ctx.torch_stream())`, as bench.py does.
+    def _dev_begin(self):
+        import torch
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != self.stream_ptr:
+            if not hasattr(self, "_ext"):
+                self._ext = self.torch_stream()
+            self._ext.wait_stream(cur)
+            return cur
+        return None
+
+    def _dev_end(self, cur):
+        if cur is not None:
+            cur.wait_stream(self._ext)
+
     # ---- allocation helpers ----
     def _empty(self, like_dev, planes, n):
         if like_dev:
@@ -221,8 +240,10 @@ class Context:
         status = self._empty(W.dev, 1, n) if status is None else status
         P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status")
         fn = self.lib.pbh_prove_batch_dev if W.dev else self.lib.pbh_prove_batch
+        cur = self._dev_begin() if W.dev else None
         rc = fn(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch),
                 C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr))
+        self._dev_end(cur)
         self._check(rc, fn.__name__)
         return P.arr, S.arr.reshape(-1)
 
@@ -239,8 +260,10 @@ class Context:
             gt = self._empty(P.dev, 4, n) if gt is None else gt
             G = _Planes(gt, 4, n, "gt")
         fn = self.lib.pbh_verify_batch_dev if P.dev else self.lib.pbh_verify_batch
+        cur = self._dev_begin() if P.dev else None
         rc = fn(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch),
                 C.c_void_p(U.ptr), C.c_void_p(Rs.ptr), C.c_void_p(G.ptr if G else None), C.c_size_t(G.pitch if G else 0))
+        self._dev_end(cur)
         self._check(rc, fn.__name__)
         res = Rs.arr.reshape(-1)
         return (res, G.arr) if G else res
@@ -250,8 +273,10 @@ class Context:
         A = _Planes(arr, pin, name="in")
         out = self._empty(A.dev, pout, A.n)
         O = _Planes(out, pout, A.n, "out")
+        cur = self._dev_begin() if A.dev else None
         rc = fn(self.h, *pre, C.c_size_t(A.n), C.c_void_p(A.ptr), C.c_size_t(A.pitch), C.c_void_p(O.ptr), C.c_size_t(O.pitch),
                 int(A.dev))
+        self._dev_end(cur)
         self._check(rc, fn.__name__)
         return O.arr
 
@@ -267,9 +292,11 @@ class Context:
         B = _Planes(b, np.shape(b)[0] if not _is_torch(b) else b.shape[0], A.n, "b")
         la, lb = A.arr.shape[0], B.arr.shape[0]
         out = self._empty(A.dev, la + lb - 1, A.n); O = _Planes(out, la + lb - 1, A.n, "out")
+        cur = self._dev_begin() if A.dev else None
         rc = self.lib.pbh_poly_mul_batch(self.h, C.c_size_t(A.n), C.c_uint32(la), C.c_uint32(lb), C.c_void_p(A.ptr),
                                          C.c_size_t(A.pitch), C.c_void_p(B.ptr), C.c_size_t(B.pitch), C.c_void_p(O.ptr),
                                          C.c_size_t(O.pitch), int(A.dev))
+        self._dev_end(cur)
         self._check(rc, "pbh_poly_mul_batch")
         return O.arr
 
@@ -277,9 +304,11 @@ class Context:
         ln = a.shape[0]
         A = _Planes(a, ln, name="a"); B = _Planes(b, ln, A.n, "b")
         out = self._empty(A.dev, ln, A.n); O = _Planes(out, ln, A.n, "out")
+        cur = self._dev_begin() if A.dev else None
         rc = self.lib.pbh_poly_add_batch(self.h, C.c_size_t(A.n), C.c_uint32(ln), int(subtract), C.c_void_p(A.ptr),
                                          C.c_size_t(A.pitch), C.c_void_p(B.ptr), C.c_size_t(B.pitch), C.c_void_p(O.ptr),
                                          C.c_size_t(O.pitch), int(A.dev))
+        self._dev_end(cur)
         self._check(rc, "pbh_poly_add_batch")
         return O.arr
 
@@ -287,8 +316,10 @@ class Context:
         P = _Planes(p, 22, name="p")
         q = self._empty(P.dev, 18, P.n); r = self._empty(P.dev, 4, P.n)
         Q = _Planes(q, 18, P.n, "q"); R = _Planes(r, 4, P.n, "r")
+        cur = self._dev_begin() if P.dev else None
         rc = self.lib.pbh_poly_div_zh_batch(self.h, C.c_size_t(P.n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Q.ptr),
                                             C.c_size_t(Q.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch), int(P.dev))
+        self._dev_end(cur)
         self._check(rc, "pbh_poly_div_zh_batch")
         return Q.arr, R.arr
 
@@ -311,10 +342,12 @@ class Context:
         wit = torch.empty((12, n), dtype=torch.uint8, device=dev); rand = torch.empty((9, n), dtype=torch.uint8, device=dev)
         chal = torch.empty((5, n), dtype=torch.uint8, device=dev); u = torch.empty((n,), dtype=torch.uint8, device=dev)
         att = torch.empty((n,), dtype=torch.uint8, device=dev) if want_attempt else None
+        cur = self._dev_begin()
         rc = self.lib.pbh_generate_inputs_dev(self.h, C.c_size_t(n), C.c_uint64(first_index), C.c_uint64(seed), int(dist),
                                               C.c_void_p(wit.data_ptr()), C.c_size_t(n), C.c_void_p(rand.data_ptr()), C.c_size_t(n),
                                               C.c_void_p(chal.data_ptr()), C.c_size_t(n), C.c_void_p(u.data_ptr()),
                                               C.c_void_p(att.data_ptr() if want_attempt else None))
+        self._dev_end(cur)
         self._check(rc, "pbh_generate_inputs_dev")
         return (wit, rand, chal, u, att) if want_attempt else (wit, rand, chal, u)
 
@@ -322,17 +355,21 @@ class Context:
         import torch
         n = result.numel()
         out = torch.empty(((n + 7) // 8,), dtype=torch.uint8, device=result.device)
-        self._check(self.lib.pbh_pack_verdicts_dev(self.h, C.c_size_t(n), C.c_void_p(result.data_ptr()), C.c_void_p(out.data_ptr())),
-                    "pbh_pack_verdicts_dev")
+        cur = self._dev_begin()
+        rc = self.lib.pbh_pack_verdicts_dev(self.h, C.c_size_t(n), C.c_void_p(result.data_ptr()), C.c_void_p(out.data_ptr()))
+        self._dev_end(cur)
+        self._check(rc, "pbh_pack_verdicts_dev")
         return out
 
     def digest(self, data, first_index=0):
         """64-bit additive digest of a (planes, n) device batch; digests of disjoint shards sum to the whole batch's."""
         import torch
         D = _Planes(data, data.shape[0] if data.dim() > 1 else 1, name="data")
-        out = torch.zeros((1,), dtype=torch.int64, device=D.arr.device)
+        out = torch.empty((1,), dtype=torch.int64, device=D.arr.device)     # zeroed by the library on its own stream
+        cur = self._dev_begin()
         rc = self.lib.pbh_digest_dev(self.h, C.c_size_t(D.n), C.c_uint64(first_index), C.c_uint32(D.arr.shape[0]), C.c_void_p(D.ptr),
                                      C.c_size_t(D.pitch), C.c_void_p(out.data_ptr()))
+        self._dev_end(cur)
         self._check(rc, "pbh_digest_dev")
         return out
 

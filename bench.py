@@ -277,7 +277,7 @@ def main():
     ach = prove_gbs if dominant == "prove_kernel" else verify_gbs
     int32 = {}
     try:
-        names = ["imad", "lop3_iadd3", "half_imad_half_alu", "ffma", "hfma2_instr", "dp4a_instr", "imad_hi_iadd", "half_ffma_half_imad"]
+        names = ["imad", "lop3_iadd3", "half_imad_half_alu", "ffma", "hfma2_instr", "dp4a_instr", "imad_hi_iadd", "half_ffma_half_imad", "ffma_3reg", "imad_3reg"]
         int32 = {f"{nm}_thread_ops_per_s": ctx.measure_int32_peak(i) for i, nm in enumerate(names)}
     except Exception as e:  # pragma: no cover
         int32 = {"error": str(e)}

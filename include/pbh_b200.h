@@ -119,6 +119,10 @@ void pbh_ctx_destroy(pbh_ctx* ctx);
 const char* pbh_last_error(const pbh_ctx* ctx);   /* ctx may be NULL: last global (creation) error */
 int pbh_ctx_set_algo(pbh_ctx* ctx, int algo);     /* PBH_ALGO_* ; default PBH_ALGO_TABLE            */
 int pbh_ctx_get_algo(const pbh_ctx* ctx);
+/* Tuning switches (results never change).  PBH_OPT_PROVER_FP32: with PBH_ALGO_TABLE, run the prover's F_17
+ * arithmetic as exact small-integer FP32 on the FMA pipes (1, default) or as int32 IMAD arithmetic (0). */
+#define PBH_OPT_PROVER_FP32 1
+int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */
 /* CUDA stream handle (cudaStream_t) the `_dev` entry points launch on; for event timing. */
@@ -217,7 +221,8 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
 /* Pipe-rate micro-benchmark (independent register chains, no memory traffic): thread-level operations per second
  * the device sustains for one instruction class; the INT32 / FMA roofline denominators of SURVEY.md §8d.
  * which: 0 IMAD, 1 LOP3+IADD3, 2 half IMAD half ALU, 3 FFMA, 4 HFMA2 (counted once per instruction; each carries two
- * fp16 lanes), 5 IDP.4A (dp4a; four byte MACs each), 6 IMAD.HI+IADD, 7 half FFMA half IMAD */
+ * fp16 lanes), 5 IDP.4A (dp4a; four byte MACs each), 6 IMAD.HI+IADD, 7 half FFMA half IMAD,
+ * 8 FFMA with three register operands (polynomial MAC shape), 9 IMAD with three register operands */
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second);
 
 #ifdef __cplusplus

@@ -52,6 +52,7 @@ struct Tables {
   uint8_t inv17[32];     // inv17[a] = a^-1 mod 17, inv17[0] = 0
   uint8_t inv101[128];   // inv101[a] = a^-1 mod 101, inv101[0] = 0
   uint32_t pt17[32];     // [e]G for e < 17 as x | y<<8 | inf<<16     (G = (1,2), src/pbh/g1.rs:71-77)
+  float inv17c[32];      // centred inverse mod 17 as a float, indexed by the canonical residue (pbh_prove_f32.cuh)
   // Group-structure tables (PBH_ALGO_TABLE).  E(F_101): y^2 = x^3 + 3 is cyclic of order 102; a point's
   // index is its discrete log to a generator g102 chosen so that G = [6]g102; index 0 is the identity.
   uint8_t y_of_x[128];   // the root y <= 50 of x^3 + 3, 0xFF when x^3 + 3 is a non-residue

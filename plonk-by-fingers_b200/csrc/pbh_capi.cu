@@ -27,6 +27,7 @@ struct pbh_ctx {
   int device = 0;
   int sm_count = 148;
   int algo = PBH_ALGO_TABLE;
+  int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;
   Tables* d_tables = nullptr;
   uint8_t* d_wtab = nullptr;
@@ -153,6 +154,11 @@ int pbh_ctx_set_algo(pbh_ctx* ctx, int algo) {
   return PBH_OK;
 }
 int pbh_ctx_get_algo(const pbh_ctx* ctx) { return ctx ? ctx->algo : PBH_ERR_BAD_ARGUMENT; }
+int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
+  CTX_CHECK(ctx);
+  if (option == PBH_OPT_PROVER_FP32) { ctx->prover_fp32 = value != 0; return PBH_OK; }
+  return fail(ctx, PBH_ERR_BAD_ARGUMENT, "unknown option");
+}
 int pbh_ctx_device(const pbh_ctx* ctx) { return ctx ? ctx->device : PBH_ERR_BAD_ARGUMENT; }
 void* pbh_ctx_stream(pbh_ctx* ctx) { return ctx ? (void*)ctx->compute : nullptr; }
 uint64_t pbh_ctx_launch_count(const pbh_ctx* ctx) { return ctx ? ctx->launches : 0; }
@@ -190,7 +196,8 @@ int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
 static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
   if (A.n == 0) return PBH_OK;
   int grid = grid_for(ctx, A.n, 8);
-  if (ctx->algo == PBH_ALGO_TABLE) prove_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
+  if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32) prove_f32_kernel<<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A);
+  else if (ctx->algo == PBH_ALGO_TABLE) prove_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   else prove_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -528,7 +535,7 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
 
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second) {
   CTX_CHECK(ctx);
-  if (!lane_ops_per_second || which < 0 || which > 7) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
+  if (!lane_ops_per_second || which < 0 || which > 9) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   uint32_t* sink = nullptr;
   CUDA_TRY(ctx, cudaMalloc(&sink, 4));
@@ -546,7 +553,9 @@ int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second)
       case 4: int32_peak_kernel<4><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
       case 5: int32_peak_kernel<5><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
       case 6: int32_peak_kernel<6><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
-      default: int32_peak_kernel<7><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 7: int32_peak_kernel<7><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 8: mac3_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      default: mac3_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
     }
     ctx->launches++;
   };

@@ -12,6 +12,7 @@
 
 #include "../../include/pbh_b200.h"
 #include "pbh_verify.cuh"
+#include "pbh_prove_f32.cuh"
 
 namespace pbh {
 
@@ -75,6 +76,35 @@ __global__ void __launch_bounds__(kBlock) prove_kernel(const Consts K, const Tab
     }
     ProofRegs P;
     uint32_t status = prove_one<ALGO>(w, r, c, K, sT, P);
+    if (bad) status = PBH_ST_BAD_ENCODING;
+    store_proof(A, i, P, status);
+  }
+}
+
+// Plonk::prove with the F_17 arithmetic on the FP32 FMA pipes (pbh_prove_f32.cuh); PBH_ALGO_TABLE only
+__global__ void __launch_bounds__(kBlock) prove_f32_kernel(const Consts K, const ConstsF KF, const Tables* __restrict__ gT,
+                                                            const ProveArgs A) {
+  __shared__ Tables sT;
+  stage_tables(sT, gT);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w[12], r[9], c[5];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { w[k] = A.wit[(size_t)k * A.wit_pitch + i]; bad = bad || w[k] >= 17u; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) { r[k] = A.rnd[(size_t)k * A.rand_pitch + i]; bad = bad || r[k] >= 17u; }
+#pragma unroll
+    for (int k = 0; k < 5; k++) { c[k] = A.chal[(size_t)k * A.chal_pitch + i]; bad = bad || c[k] >= 17u; }
+    if (bad) {
+#pragma unroll
+      for (int k = 0; k < 12; k++) w[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) r[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 5; k++) c[k] = 0;
+    }
+    ProofRegs P;
+    uint32_t status = prove_item_f32(w, r, c, K, KF, sT, P);
     if (bad) status = PBH_ST_BAD_ENCODING;
     store_proof(A, i, P, status);
   }
@@ -456,6 +486,40 @@ __global__ void __launch_bounds__(kBlock) int32_peak_kernel(uint32_t iters, uint
   }
   uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
   if (r == 0x12345678u) sink[0] = r;   // keeps the chains alive
+}
+
+// three distinct register operands per instruction (no constant-bank or immediate operand), the shape of a
+// polynomial multiply-accumulate: WHICH 0 = FFMA, 1 = IMAD.  8 accumulators, 4 + 4 varying multiplicands.
+template <int WHICH>
+__global__ void __launch_bounds__(kBlock) mac3_peak_kernel(uint32_t iters, uint32_t seed, uint32_t* sink) {
+  if (WHICH == 0) {
+    float x0 = 1.0f + threadIdx.x * 1e-7f, x1 = x0 + 1e-6f, x2 = x0 + 2e-6f, x3 = x0 + 3e-6f;
+    float y0 = 1e-3f * (seed & 7), y1 = y0 + 1e-4f, y2 = y0 + 2e-4f, y3 = y0 + 3e-4f;
+    float c0 = 0, c1 = 1, c2 = 2, c3 = 3, c4 = 4, c5 = 5, c6 = 6, c7 = 7;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 8; rep++) {
+        c0 = fmaf(x0, y0, c0); c1 = fmaf(x0, y1, c1); c2 = fmaf(x1, y2, c2); c3 = fmaf(x1, y3, c3);
+        c4 = fmaf(x2, y0, c4); c5 = fmaf(x2, y1, c5); c6 = fmaf(x3, y2, c6); c7 = fmaf(x3, y3, c7);
+      }
+      x0 += c7 * 1e-30f; y0 += c0 * 1e-30f;   // keep the multiplicands loop-variant
+    }
+    float r = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+    if (r == 12345.678f) sink[0] = 1;
+  } else {
+    uint32_t x0 = seed + threadIdx.x, x1 = x0 * 3u, x2 = x0 * 5u, x3 = x0 * 7u, y0 = seed ^ 0x55u, y1 = y0 * 3u, y2 = y0 * 5u, y3 = y0 * 7u;
+    uint32_t c0 = 0, c1 = 1, c2 = 2, c3 = 3, c4 = 4, c5 = 5, c6 = 6, c7 = 7;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+      for (int rep = 0; rep < 8; rep++) {
+        c0 = x0 * y0 + c0; c1 = x0 * y1 + c1; c2 = x1 * y2 + c2; c3 = x1 * y3 + c3;
+        c4 = x2 * y0 + c4; c5 = x2 * y1 + c5; c6 = x3 * y2 + c6; c7 = x3 * y3 + c7;
+      }
+      x0 += c7 >> 31; y0 += c0 >> 31;
+    }
+    uint32_t r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    if (r == 0x12345678u) sink[0] = r;
+  }
 }
 
 }  // namespace pbh

@@ -113,34 +113,37 @@ struct ProofRegs {
   uint32_t ev[7];   // a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z
 };
 
+// constraints.satisfies(assigments), src/constraints.rs:198-230 (Q8: q_l multiplies b as well)
+PBH_HD bool unsatisfied(const uint32_t (&w)[12], const Consts& K) {
+  bool unsat = false;
+#pragma unroll
+  for (int n = 0; n < 4; n++) {
+    uint32_t r = K.q_l[n] * (w[n] + w[4 + n]) + K.q_o[n] * w[8 + n] + K.q_m[n] * mod17(w[n] * w[4 + n]) + K.q_c[n];
+    unsat = unsat || (mod17(r) != 0u);
+  }
+  // witness value k must equal witness value perm[k]; values are 5-bit fields of a 64-bit word so that the
+  // (uniform, runtime) permutation needs no local-memory indexing
+  unsigned long long packed = 0;
+#pragma unroll
+  for (int k = 0; k < 12; k++) packed |= (unsigned long long)w[k] << (5 * k);
+#pragma unroll
+  for (int k = 0; k < 12; k++) {
+    uint32_t other = (uint32_t)(packed >> (5u * K.perm[k])) & 31u;
+    unsat = unsat || (other != w[k]);
+  }
+  return unsat;
+}
+
 // w[12] = a[0..4) b[0..4) c[0..4); r[9] = b1..b9; ch[5] = alpha beta gamma z v.  All inputs < 17.
-// Returns the status byte.  `P` is fully defined only for status 0.
-template <int ALGO>
+// Returns the status byte.  `P` is fully defined only for status 0.  With UPTO_T the routine stops after the
+// quotient (sites :199 .. :376) — enough for items whose t(x) is known to be short (status 1-4 only).
+template <int ALGO, bool UPTO_T = false>
 PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
                           const Tables& T, ProofRegs& P) {
   const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], zc = ch[3], v = ch[4];
   const uint32_t n_pts = K.n_pts;
 
-  // ---- constraints.satisfies(assigments)                                   src/constraints.rs:198-230
-  bool unsat = false;
-#pragma unroll
-  for (int n = 0; n < 4; n++) {
-    // Q8: q_l multiplies b as well
-    uint32_t r = K.q_l[n] * (w[n] + w[4 + n]) + K.q_o[n] * w[8 + n] + K.q_m[n] * mod17(w[n] * w[4 + n]) + K.q_c[n];
-    unsat = unsat || (mod17(r) != 0u);
-  }
-  {
-    // witness value k must equal witness value perm[k]; values are 5-bit fields of a 64-bit word so that the
-    // (uniform, runtime) permutation needs no local-memory indexing
-    unsigned long long packed = 0;
-#pragma unroll
-    for (int k = 0; k < 12; k++) packed |= (unsigned long long)w[k] << (5 * k);
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-      uint32_t other = (uint32_t)(packed >> (5u * K.perm[k])) & 31u;
-      unsat = unsat || (other != w[k]);
-    }
-  }
+  const bool unsat = unsatisfied(w, K);
 
   // ---- wire polynomials                                                     src/plonk.rs:233-235, 248-252
   uint32_t fa[4], fb[4], fc[4];
@@ -268,6 +271,15 @@ PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], con
   for (int j = 0; j < 4; j++) rem_nz = rem_nz || (add17(num[j], t[j]) != 0u);  // src/plonk.rs:370
   bool t_short = (t[17] == 0u);                                                 // src/plonk.rs:376 (Q5)
 
+  if (UPTO_T) {
+    uint32_t st = t_short ? 4u : 0u;
+    if (rem_nz) st = 3;
+    if (oob_z) st = 5;
+    if (div0) st = 2;
+    if (oob_abc) st = 5;
+    if (unsat) st = 1;
+    return st;
+  }
   uint32_t tlo[6], tmid[6], thi[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) { tlo[i] = t[i]; tmid[i] = t[6 + i]; thi[i] = t[12 + i]; }

@@ -10,11 +10,13 @@
 
 #include "../../include/pbh_b200.h"
 #include "pbh_verify.cuh"
+#include "pbh_prove_f32.cuh"
 
 namespace pbh {
 
 struct HostSetup {
   Consts K;
+  ConstsF KF;   // the same constants as centred floats, for the FP32 prover
   Tables T;
   std::vector<G1> g1s;        // SRS.g1s
   uint32_t g2_1[2], g2_s[2];  // SRS.g2_1, SRS.g2_s
@@ -200,6 +202,17 @@ inline int host_setup(const pbh_circuit& c, uint32_t srs_secret, uint32_t srs_n,
     T.pair_1_a[i] = (uint8_t)e1.a; T.pair_1_b[i] = (uint8_t)e1.b;
     m = g1_add(m, gen, T.inv101);
   }
+  // ---- centred float copies for the FP32 prover (pbh_prove_f32.cuh)
+  auto cen = [](uint32_t x) { return x > 8u ? (float)x - 17.0f : (float)x; };
+  ConstsF& F = hs.KF;
+  for (int i = 0; i < 4; i++) {
+    F.q_l[i] = cen(K.q_l[i]); F.q_o[i] = cen(K.q_o[i]); F.q_m[i] = cen(K.q_m[i]); F.q_c[i] = cen(K.q_c[i]);
+    F.QL[i] = cen(K.QL[i]); F.QR[i] = cen(K.QR[i]); F.QO[i] = cen(K.QO[i]); F.QM[i] = cen(K.QM[i]); F.QC[i] = cen(K.QC[i]);
+    F.L1[i] = cen(K.L1[i]);
+    for (int wv = 0; wv < 3; wv++) { F.sig[wv][i] = cen(K.sig[wv][i]); F.S[wv][i] = cen(K.S[wv][i]); }
+  }
+  for (int i = 0; i < 10; i++) F.srs_dlog[i] = cen(K.srs_dlog[i]);
+  for (uint32_t a = 0; a < 17; a++) T.inv17c[a] = cen(T.inv17[a]);
   return PBH_OK;
 }
 

@@ -26,6 +26,7 @@ u16p = C.POINTER(C.c_uint16)
 ST_OK, ST_UNSATISFIED, ST_ACC_DIV0, ST_T_REMAINDER, ST_T_SLICE, ST_SRS_OOB, ST_BAD_ENCODING = 0, 1, 2, 3, 4, 5, 32
 VR_ACCEPT, VR_REJECT_PAIRING, VR_NOT_ON_CURVE, VR_NOT_IN_FIELD, VR_PANIC_ZH0, VR_BAD_ENCODING = 1, 0, 2, 4, 0x10, 0x20
 ALGO_ARITH, ALGO_TABLE = 0, 1
+OPT_PROVER_FP32 = 1
 DIST_UNIFORM, DIST_FULLPATH = 0, 1
 ERR = {0: "PBH_OK", -1: "PBH_ERR_BAD_ARGUMENT", -2: "PBH_ERR_SETUP_PANIC", -3: "PBH_ERR_CUDA", -4: "PBH_ERR_NO_DEVICE",
        -5: "PBH_ERR_UNSUPPORTED"}
@@ -38,7 +39,7 @@ PANIC_MESSAGES = {
     ST_BAD_ENCODING: "input byte outside the field (not representable in the reference)",
 }
 
-EXPORTS = """pbh_circuit_pbh_test pbh_ctx_create pbh_ctx_destroy pbh_last_error pbh_ctx_set_algo pbh_ctx_get_algo
+EXPORTS = """pbh_circuit_pbh_test pbh_ctx_create pbh_ctx_destroy pbh_last_error pbh_ctx_set_algo pbh_ctx_get_algo pbh_ctx_set_option
 pbh_ctx_device pbh_ctx_sync pbh_ctx_stream pbh_ctx_launch_count pbh_ctx_get_srs pbh_ctx_get_verifier_constants
 pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_ntt4_batch pbh_intt4_batch
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
@@ -173,6 +174,10 @@ class Context:
         code = {"arith": ALGO_ARITH, "table": ALGO_TABLE}.get(algo, algo)
         self._check(self.lib.pbh_ctx_set_algo(self.h, int(code)), "pbh_ctx_set_algo")
         self.algo = "table" if code == ALGO_TABLE else "arith"
+
+    def set_option(self, option, value):
+        """Tuning switches of include/pbh_b200.h (PBH_OPT_*); results never change."""
+        self._check(self.lib.pbh_ctx_set_option(self.h, int(option), int(value)), "pbh_ctx_set_option")
 
     def sync(self):
         self._check(self.lib.pbh_ctx_sync(self.h), "pbh_ctx_sync")

@@ -56,6 +56,9 @@ def gpu_ctx(product_lib):
     import pbh_b200
     assert _cuda_ok(), "gpu tests need a CUDA device"
     ctxs = {algo: pbh_b200.Context(device=0, algo=algo) for algo in ("table", "arith")}
+    # "table" runs the prover's arithmetic on the FP32 pipes (default); "table_int" is the same algorithm on int32 IMAD
+    ctxs["table_int"] = pbh_b200.Context(device=0, algo="table")
+    ctxs["table_int"].set_option(pbh_b200.OPT_PROVER_FP32, 0)
     yield ctxs
     for c in ctxs.values():
         c.close()

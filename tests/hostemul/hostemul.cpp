@@ -12,7 +12,62 @@ using namespace pbh;
 
 static std::string g_err;
 
+// ---- worst-case magnitude propagation through the FP32 prover core (pbh_prove_f32.cuh) ----------------------------
+// Bnd carries an upper bound of |value| for an integer-valued quantity.  Every arithmetic result must stay below 2^24
+// (exactly representable) and every reduction input at or below 2^23 (validity range of red17).
+namespace pbh {
+struct Bnd { double m; Bnd() : m(0) {} explicit Bnd(double x) : m(x) {} };
+static double g_max_exact = 0, g_max_red = 0;
+static bool g_violation = false;
+inline Bnd chk(double m) { if (m > g_max_exact) g_max_exact = m; if (m >= 16777216.0) g_violation = true; return Bnd(m); }
+inline Bnd f_const(float c, Bnd*) { return Bnd(c < 0 ? -c : c); }
+inline Bnd f_fma(Bnd a, Bnd b, Bnd c) { return chk(a.m * b.m + c.m); }
+inline Bnd f_mul(Bnd a, Bnd b) { return chk(a.m * b.m); }
+inline Bnd f_add(Bnd a, Bnd b) { return chk(a.m + b.m); }
+inline Bnd f_sub(Bnd a, Bnd b) { return chk(a.m + b.m); }
+inline Bnd f_red(Bnd x) { if (x.m > g_max_red) g_max_red = x.m; if (x.m > 8388608.0) g_violation = true; return Bnd(8); }
+inline bool f_is_zero(Bnd) { return false; }
+inline uint32_t f_canon(Bnd) { return 0; }
+}  // namespace pbh
+
 extern "C" {
+
+// Runs prove_core_f32 on magnitude bounds: inputs <= 16, every circuit / SRS constant at its centred maximum 8, SRS
+// discrete logs at 8, every n_pts from 1 to 10 (all out-of-bounds checks compiled in).  Returns 0 when no operation can
+// leave the exact range; max_exact / max_red receive the largest magnitudes seen.
+int emul_f32_bounds(double* max_exact, double* max_red) {
+  using namespace pbh;
+  g_max_exact = g_max_red = 0; g_violation = false;
+  ConstsF KF;
+  float* kf = reinterpret_cast<float*>(&KF);
+  for (size_t i = 0; i < sizeof(KF) / sizeof(float); i++) kf[i] = 8.0f;
+  float inv[32];
+  for (int i = 0; i < 32; i++) inv[i] = 8.0f;
+  for (uint32_t n_pts = 1; n_pts <= 10; n_pts++) {
+    Bnd w[12], r[9], c[5];
+    for (auto& x : w) x = Bnd(16);
+    for (auto& x : r) x = Bnd(16);
+    for (auto& x : c) x = Bnd(16);
+    ProofF pf;
+    prove_core_f32<Bnd>(w, r, c, KF, n_pts, inv, pf);
+  }
+  *max_exact = g_max_exact; *max_red = g_max_red;
+  return g_violation ? 1 : 0;
+}
+
+// red17 of pbh_prove_f32.cuh against x mod 17 for every integer |x| <= 2^23; returns the number of mismatches
+uint64_t emul_check_red17_f32() {
+  using namespace pbh;
+  uint64_t bad = 0;
+  for (int64_t x = -8388608; x <= 8388608; x++) {
+    float r = f_red(F32((float)x)).v;
+    int64_t m = ((x % 17) + 17) % 17;
+    int64_t c = m > 8 ? m - 17 : m;
+    bad += (r != (float)c);
+    bad += f_canon(F32(r)) != (uint32_t)m;
+  }
+  return bad;
+}
 
 const char* emul_last_error() { return g_err.c_str(); }
 
@@ -51,7 +106,8 @@ int emul_prove_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t om
     for (int k = 0; k < 5; k++) { ch[k] = chal[k * n + i]; bad |= ch[k] >= 17; }
     if (bad) { std::memset(w, 0, sizeof w); std::memset(r, 0, sizeof r); std::memset(ch, 0, sizeof ch); }
     ProofRegs P;
-    uint32_t st = algo == 1 ? prove_one<ALGO_TABLE>(w, r, ch, hs.K, hs.T, P) : prove_one<ALGO_ARITH>(w, r, ch, hs.K, hs.T, P);
+    uint32_t st = algo == 2 ? prove_item_f32(w, r, ch, hs.K, hs.KF, hs.T, P)
+                            : (algo == 1 ? prove_one<ALGO_TABLE>(w, r, ch, hs.K, hs.T, P) : prove_one<ALGO_ARITH>(w, r, ch, hs.K, hs.T, P));
     if (bad) st = PBH_ST_BAD_ENCODING;
     for (int k = 0; k < 27; k++) proof[k * n + i] = 0;
     status[i] = (uint8_t)st;

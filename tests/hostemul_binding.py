@@ -17,9 +17,9 @@ def load():
     if _E is None:
         so = os.path.join(HERE, "libhostemul.so")
         srcs = [os.path.join(HERE, "hostemul.cpp")] + [os.path.join(ROOT, "plonk-by-fingers_b200", "csrc", f) for f in
-                                                       ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_verify.cuh", "pbh_setup.hpp")]
+                                                       ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_prove_f32.cuh", "pbh_verify.cuh", "pbh_setup.hpp")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, srcs[0]], check=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-mfma", "-o", so, srcs[0]], check=True)
         _E = C.CDLL(so)
         _E.emul_last_error.restype = C.c_char_p
         _E.emul_check_reductions.restype = C.c_uint64
@@ -80,6 +80,15 @@ class Emul:
         o = (C.c_uint8 * 2)()
         self.lib.emul_gt_final_exp((C.c_uint8 * 2)(*f), o)
         return tuple(o)
+
+    def f32_bounds(self):
+        mx = C.c_double(); mr = C.c_double()
+        rc = self.lib.emul_f32_bounds(C.byref(mx), C.byref(mr))
+        return rc, mx.value, mr.value
+
+    def check_red17_f32(self):
+        self.lib.emul_check_red17_f32.restype = C.c_uint64
+        return int(self.lib.emul_check_red17_f32())
 
     def check_reductions(self):
         return int(self.lib.emul_check_reductions())

@@ -11,6 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ALGOS = ("table", "arith")
+CTXS = ("table", "table_int", "arith")   # gpu_ctx keys: table = FP32-pipe prover, table_int = int32 prover
 
 
 def _np(t):
@@ -81,7 +82,7 @@ def test_reference_panics_surface_as_exceptions(product_lib):
 # ---------------------------------------------------------------------------------------------
 # seeded batches, every status class, both distributions, both algorithms
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("algo", CTXS)
 @pytest.mark.parametrize("dist", (0, 1))
 def test_prove_verify_batches_match_oracle(gpu_ctx, oracle, algo, dist):
     ctx = gpu_ctx[algo]
@@ -132,7 +133,7 @@ def test_extra_end_to_end_tuples(gpu_ctx, oracle):
         xx, yy, zz = x * x % 17, y * y % 17, z * z % 17
         wit[:, i] = [x, y, z, xx, x, y, z, yy, xx, yy, zz, zz]
         rnd[:, i] = r; chal[:, i] = c; u[i] = uu
-    for algo in ALGOS:
+    for algo in CTXS:
         ctx = gpu_ctx[algo]
         proof, status = ctx.prove_batch(wit, rnd, chal)
         assert status.tolist() == [row[4] for row in rows]
@@ -203,12 +204,27 @@ def test_verify_adversarial_inputs(gpu_ctx, oracle, algo):
     assert set(np.unique(vo)) >= {0, 1, 2, 4, 0x10, 0x20}
 
 
+@pytest.mark.parametrize("algo", CTXS)
+def test_zero_blinder_corner_cases(gpu_ctx, oracle, algo):
+    """Blinders and challenges drawn from a few values with many zeros: short polynomials, the Q1 / Q5 / Q15 length
+    logic, and the hand-over between the FP32 fast path and the exact integer routine."""
+    rng = np.random.default_rng(17)
+    n = 60000
+    w = oracle.generate_inputs(n, seed=5, dist=0, threads=8)[0]
+    r = rng.choice(np.array([0, 0, 0, 1, 16, 5], dtype=np.uint8), size=(9, n))
+    c = rng.choice(np.array([0, 1, 16, 3, 7], dtype=np.uint8), size=(5, n))
+    po, so = oracle.prove_batch(w, r, c, threads=8)
+    p, s = gpu_ctx[algo].prove_batch(w, r, c)
+    assert np.array_equal(s, so) and np.array_equal(p, po)
+    assert (so == 3).sum() > 0 and (so == 4).sum() > 0 and (so == 0).sum() > 0
+
+
 def test_prove_bad_encoding(gpu_ctx, oracle):
     n = 512
     wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=3, dist=1)
     wo[5, 7] = 17; ro[0, 9] = 200; co[4, 11] = 255
     po, so = oracle.prove_batch(wo, ro, co)
-    for algo in ALGOS:
+    for algo in CTXS:
         p, s = gpu_ctx[algo].prove_batch(wo, ro, co)
         assert np.array_equal(s, so) and np.array_equal(p, po)
     assert so[7] == 32 and so[9] == 32 and so[11] == 32
@@ -249,8 +265,10 @@ def test_other_circuits_and_srs(product_lib, oracle):
             u = rng.integers(0, 17, size=n, dtype=np.uint8)
             po, so = oracle.prove_batch(wit, rnd, chal, circuit=oc, threads=8, **case)
             vo, go = oracle.verify_batch(po, chal, u, circuit=oc, threads=8, **case)
-            for algo in ALGOS:
-                with pbh_b200.Context(circuit=pc, device=0, algo=algo, **case) as ctx:
+            for algo in CTXS:
+                with pbh_b200.Context(circuit=pc, device=0, algo=algo.split("_")[0], **case) as ctx:
+                    if algo == "table_int":
+                        ctx.set_option(pbh_b200.OPT_PROVER_FP32, 0)
                     g1s, g2 = ctx.srs()
                     og1s, og2, oconst = oracle.setup(circuit=oc, **case)
                     assert np.array_equal(g1s, og1s) and np.array_equal(g2, og2)
@@ -476,6 +494,9 @@ def test_full_size_properties(gpu_ctx, oracle):
     w, r, c, u = t.generate_inputs(n, seed=0xB200, dist=1)
     pt, st = t.prove_batch(w, r, c)
     pa, sa = a.prove_batch(w, r, c)
+    pi, si = gpu_ctx["table_int"].prove_batch(w, r, c)
+    gpu_ctx["table_int"].sync()
+    assert torch.equal(pt, pi) and torch.equal(st, si)
     vt, gt_t = t.verify_batch(pt, c, u, want_gt=True)
     va, gt_a = a.verify_batch(pa, c, u, want_gt=True)
     t.sync(); a.sync()
@@ -501,7 +522,9 @@ def test_full_size_properties(gpu_ctx, oracle):
     wu, ru, cu, uu = t.generate_inputs(n, seed=1, dist=0)
     pu, su = t.prove_batch(wu, ru, cu)
     vu = t.verify_batch(pu, cu, uu)
-    t.sync()
+    pui, sui = gpu_ctx["table_int"].prove_batch(wu, ru, cu)
+    t.sync(); gpu_ctx["table_int"].sync()
+    assert torch.equal(pu, pui) and torch.equal(su, sui)      # FP32-pipe prover == int32 prover on 2^20 uniform items
     hist = torch.bincount(su.to(torch.int64), minlength=6).cpu().numpy() / n
     assert abs(hist[2] - 0.424) < 0.01 and abs(hist[4] - 0.149) < 0.01 and abs(hist[5] - 0.315) < 0.01 and hist[3] < 0.002
     ok = su == 0

@@ -10,9 +10,10 @@ def test_reduction_constants_exhaustive(hostemul):
     assert hostemul.check_reductions() == 0
 
 
-@pytest.mark.parametrize("algo", (0, 1))
+@pytest.mark.parametrize("algo", (0, 1, 2))
 @pytest.mark.parametrize("dist", (0, 1))
 def test_prove_verify_logic_matches_oracle(hostemul, oracle, algo, dist):
+    """algo 0 = ARITH, 1 = TABLE (int32 prover), 2 = TABLE with the FP32-pipe prover."""
     circ = oracle.pbh_test_circuit()
     n = 25000
     w, r, c, u, _ = oracle.generate_inputs(n, seed=4242 + dist, dist=dist, threads=8)
@@ -20,11 +21,20 @@ def test_prove_verify_logic_matches_oracle(hostemul, oracle, algo, dist):
     pe, se = hostemul.prove(circ, w, r, c, algo)
     assert np.array_equal(se, so) and np.array_equal(pe, po)
     vo, go = oracle.verify_batch(po, c, u, threads=8)
-    ve, ge = hostemul.verify(circ, po, c, u, algo)
+    ve, ge = hostemul.verify(circ, po, c, u, min(algo, 1))
     assert np.array_equal(ve, vo) and np.array_equal(ge, go)
 
 
-@pytest.mark.parametrize("algo", (0, 1))
+def test_f32_bounds(hostemul):
+    """Worst-case magnitude propagation through the FP32 prover core: every intermediate is an exactly representable
+    integer (< 2^24) and every reduction input is within red17's validated range (<= 2^23), for any circuit constants
+    and any SRS length; red17 itself is checked against x mod 17 for every integer |x| <= 2^23."""
+    rc, max_exact, max_red = hostemul.f32_bounds()
+    assert rc == 0 and max_exact < 2**24 and max_red <= 2**23, (rc, max_exact, max_red)
+    assert hostemul.check_red17_f32() == 0
+
+
+@pytest.mark.parametrize("algo", (0, 1, 2))
 def test_zero_blinder_corner_cases(hostemul, oracle, algo):
     """Blinders and challenges drawn from {0, 1, 16}: short polynomials, the Q1 / Q5 / Q15 length logic."""
     rng = np.random.default_rng(17)

@@ -122,6 +122,9 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 /* Tuning switches (results never change).  PBH_OPT_PROVER_FP32: with PBH_ALGO_TABLE, run the prover's F_17
  * arithmetic as exact small-integer FP32 on the FMA pipes (1, default) or as int32 IMAD arithmetic (0). */
 #define PBH_OPT_PROVER_FP32 1
+/* PBH_OPT_PROVER_LAUNCH_SHAPE: threads x min-resident-blocks of the FP32 prover: 0 = 256x2 (default), 1 = 256x1,
+ * 2 = 128x4, 3 = 128x5, 4 = 128x6 (register budget 128 / 255 / 128 / 96 / 80 per thread) */
+#define PBH_OPT_PROVER_LAUNCH_SHAPE 2
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */

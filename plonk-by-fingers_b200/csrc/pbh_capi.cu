@@ -27,6 +27,7 @@ struct pbh_ctx {
   int device = 0;
   int sm_count = 148;
   int algo = PBH_ALGO_TABLE;
+  int prover_variant = 0;
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;
   Tables* d_tables = nullptr;
@@ -157,6 +158,7 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx) { return ctx ? ctx->algo : PBH_ERR_BAD_
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
   CTX_CHECK(ctx);
   if (option == PBH_OPT_PROVER_FP32) { ctx->prover_fp32 = value != 0; return PBH_OK; }
+  if (option == PBH_OPT_PROVER_LAUNCH_SHAPE) { ctx->prover_variant = value; return PBH_OK; }
   return fail(ctx, PBH_ERR_BAD_ARGUMENT, "unknown option");
 }
 int pbh_ctx_device(const pbh_ctx* ctx) { return ctx ? ctx->device : PBH_ERR_BAD_ARGUMENT; }
@@ -196,8 +198,16 @@ int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
 static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
   if (A.n == 0) return PBH_OK;
   int grid = grid_for(ctx, A.n, 8);
-  if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32) prove_f32_kernel<<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A);
-  else if (ctx->algo == PBH_ALGO_TABLE) prove_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
+  if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32) {
+    // launch shape of the FP32 prover: threads per block / resident blocks per SM the register budget is capped for
+    switch (ctx->prover_variant) {
+      case 1: prove_f32_kernel<256, 1><<<grid_for(ctx, A.n, 8), 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      case 2: prove_f32_kernel<128, 4><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 16)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      case 3: prove_f32_kernel<128, 5><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 20)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      case 4: prove_f32_kernel<128, 6><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 24)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      default: prove_f32_kernel<256, 2><<<grid_for(ctx, A.n, 8), 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+    }
+  } else if (ctx->algo == PBH_ALGO_TABLE) prove_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   else prove_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());

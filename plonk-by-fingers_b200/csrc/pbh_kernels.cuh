@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(kBlock) prove_kernel(const Consts K, const Tab
 }
 
 // Plonk::prove with the F_17 arithmetic on the FP32 FMA pipes (pbh_prove_f32.cuh); PBH_ALGO_TABLE only
-__global__ void __launch_bounds__(kBlock) prove_f32_kernel(const Consts K, const ConstsF KF, const Tables* __restrict__ gT,
-                                                            const ProveArgs A) {
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) prove_f32_kernel(const Consts K, const ConstsF KF, const Tables* __restrict__ gT,
+                                                                         const ProveArgs A) {
   __shared__ Tables sT;
   stage_tables(sT, gT);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (size_t)gridDim.x * blockDim.x) {

@@ -117,7 +117,7 @@ PBH_HD uint32_t fcommit(const T (&c)[L], const ConstsF& KF, uint32_t n_pts, bool
   if (n_pts < (uint32_t)L) {                       // uniform, false for the usual 7-point SRS except for w_z
 #pragma unroll
     for (int j = 0; j < L; j++)
-      if ((uint32_t)j >= n_pts) oob = oob || !f_is_zero(reduced ? c[j] : f_red(c[j]));
+      if ((uint32_t)j >= n_pts) oob = oob | !f_is_zero(reduced ? c[j] : f_red(c[j]));
   }
   return f_canon(f_red(e));
 }
@@ -165,7 +165,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
     T d1 = f_red(f_fma(beta, f_const(KF.sig[0][i], tag), wa)), d2 = f_red(f_fma(beta, f_const(KF.sig[1][i], tag), wb)),
       d3 = f_red(f_fma(beta, f_const(KF.sig[2][i], tag), wc));
     T dsor = f_red(f_mul(f_mul(d1, d2), d3));
-    div0 = div0 || f_is_zero(dsor);                                          // src/plonk.rs:297 unwrap
+    div0 = div0 | f_is_zero(dsor);                                           // src/plonk.rs:297 unwrap
     T dinv = f_const(inv17c[f_canon(dsor)], tag);
     T dend = f_mul(f_mul(n1, n2), n3);                                       // |.| <= 512
     acc[i + 1] = f_red(f_mul(f_red(f_mul(acc[i], dinv)), f_red(dend)));
@@ -256,7 +256,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   for (int j = 17; j >= 0; j--) t[j] = (j + 4 < 18) ? f_add(num[j + 4], t[j + 4]) : num[j + 4];   // unreduced, |.| <= 40
   bool rem_nz = false;
 #pragma unroll
-  for (int j = 0; j < 4; j++) rem_nz = rem_nz || !f_is_zero(f_red(f_add(num[j], t[j])));           // src/plonk.rs:370
+  for (int j = 0; j < 4; j++) rem_nz = rem_nz | !f_is_zero(f_red(f_add(num[j], t[j])));           // src/plonk.rs:370
   bool t_short = f_is_zero(t[17]);                                                                   // src/plonk.rs:376 (Q5)
   T tlo[6], tmid[6], thi[6];
 #pragma unroll

@@ -204,9 +204,9 @@ int pbh_pairing_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch
 /* ---- shard summaries for the multi-GPU gather ---------------------------------- */
 /* Pack bit 0 of each result byte into a bitmap (item i -> bit i%8 of byte i/8), device pointers.  */
 int pbh_pack_verdicts_dev(pbh_ctx* ctx, size_t n, const uint8_t* result, uint8_t* bitmap);
-/* Order-independent-within-plane 64-bit digest of `planes` byte planes of n items starting at
- * global item index `first_index`: sum over items of mix64(global_index, plane, byte), so digests
- * of disjoint shards add up (mod 2^64) to the digest of the whole batch.  out: one uint64 (device). */
+/* 64-bit digest of `planes` byte planes of n items starting at global item index `first_index`: the sum over items
+ * (mod 2^64) of splitmix64(fnv(global_index, the item's bytes packed four planes per little-endian 32-bit word)), so
+ * digests of disjoint shards add up to the digest of the whole batch.  out: one uint64 (device). */
 int pbh_digest_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint32_t planes, const uint8_t* data, size_t pitch,
                    uint64_t* out);
 

@@ -611,13 +611,17 @@ int oracle_generate_inputs(const void* circuit, uint8_t s, uint32_t srs_n, uint8
   return 0;
 }
 
-static inline uint64_t mix64(uint64_t index, uint32_t plane, uint8_t byte) {
-  return splitmix64(index * 0x9E3779B97F4A7C15ull + ((uint64_t)plane << 8) + byte);
-}
 uint64_t oracle_digest(size_t n, uint64_t first_index, uint32_t planes, const uint8_t* data, size_t pitch) {
   uint64_t acc = 0;
-  for (uint32_t k = 0; k < planes; k++)
-    for (size_t i = 0; i < n; i++) acc += mix64(first_index + i, k, data[k * pitch + i]);
+  for (size_t i = 0; i < n; i++) {
+    uint64_t h = (first_index + i) * 0x9E3779B97F4A7C15ull + planes;
+    for (uint32_t k = 0; k < planes; k += 4) {
+      uint32_t wv = 0;
+      for (uint32_t b = 0; b < 4 && k + b < planes; b++) wv |= (uint32_t)data[(size_t)(k + b) * pitch + i] << (8 * b);
+      h = (h ^ wv) * 0x100000001B3ull;
+    }
+    acc += splitmix64(h);
+  }
   return acc;
 }
 int oracle_pack_verdicts(size_t n, const uint8_t* result, uint8_t* bitmap) {

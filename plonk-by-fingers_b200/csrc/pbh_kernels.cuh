@@ -356,13 +356,21 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
+// Digest of one item: FNV-1a-style 64-bit mixing over the item's bytes packed four planes per 32-bit word, seeded
+// with the global item index, finished with splitmix64.  The batch digest is the sum over items modulo 2^64, so
+// digests of disjoint shards add up to the digest of the whole batch.
 __global__ void __launch_bounds__(kBlock) digest_kernel(size_t n, uint64_t first_index, uint32_t planes,
                                                          const uint8_t* __restrict__ data, size_t pitch,
                                                          unsigned long long* __restrict__ out) {
   unsigned long long acc = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    for (uint32_t k = 0; k < planes; k++)
-      acc += splitmix64((first_index + i) * 0x9E3779B97F4A7C15ull + ((uint64_t)k << 8) + data[(size_t)k * pitch + i]);
+    uint64_t h = (first_index + i) * 0x9E3779B97F4A7C15ull + planes;
+    for (uint32_t k = 0; k < planes; k += 4) {
+      uint32_t wv = 0;
+      for (uint32_t b = 0; b < 4 && k + b < planes; b++) wv |= (uint32_t)data[(size_t)(k + b) * pitch + i] << (8 * b);
+      h = (h ^ wv) * 0x100000001B3ull;
+    }
+    acc += splitmix64(h);
   }
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);

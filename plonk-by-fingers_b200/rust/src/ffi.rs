@@ -1,0 +1,31 @@
+//! Raw bindings to include/pbh_b200.h (libpbh_b200.so).  SOURCE ONLY: never compiled in this repository.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct pbh_circuit {
+    pub q_l: [u8; 4], pub q_r: [u8; 4], pub q_o: [u8; 4], pub q_m: [u8; 4], pub q_c: [u8; 4],
+    pub c_a_wire: [u8; 4], pub c_a_index: [u8; 4],
+    pub c_b_wire: [u8; 4], pub c_b_index: [u8; 4],
+    pub c_c_wire: [u8; 4], pub c_c_index: [u8; 4],
+}
+#[repr(C)]
+pub struct pbh_ctx { _private: [u8; 0] }
+
+pub const PBH_OK: c_int = 0;
+pub const PBH_ERR_SETUP_PANIC: c_int = -2;
+
+#[link(name = "pbh_b200")]
+extern "C" {
+    pub fn pbh_ctx_create(circuit: *const pbh_circuit, srs_secret: u8, srs_n: u32, omega_pows: u8, device: c_int,
+                          out: *mut *mut pbh_ctx) -> c_int;
+    pub fn pbh_ctx_destroy(ctx: *mut pbh_ctx);
+    pub fn pbh_last_error(ctx: *const pbh_ctx) -> *const c_char;
+    pub fn pbh_ctx_get_srs(ctx: *const pbh_ctx, g1s_xy_inf: *mut u8, cap_points: usize, n_points: *mut u32, g2: *mut u8) -> c_int;
+    pub fn pbh_prove_batch(ctx: *mut pbh_ctx, n: usize, wit: *const u8, wit_pitch: usize, rand: *const u8, rand_pitch: usize,
+                           chal: *const u8, chal_pitch: usize, proof: *mut u8, proof_pitch: usize, status: *mut u8) -> c_int;
+    pub fn pbh_verify_batch(ctx: *mut pbh_ctx, n: usize, proof: *const u8, proof_pitch: usize, chal: *const u8, chal_pitch: usize,
+                            u: *const u8, result: *mut u8, gt: *mut u8, gt_pitch: usize) -> c_int;
+    pub fn pbh_ctx_stream(ctx: *mut pbh_ctx) -> *mut c_void;
+}

@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -162,37 +163,70 @@ def main():
     ctx = pbh_b200.Context(device=local, algo=args.algo)
     stream = ctx.torch_stream()
 
-    # ---- synthetic shard of this rank: item i of step-slot r has global index ((r * world) + rank) * n + i
+    # ---- synthetic shard of this rank: item i of ring slot r has global index ((r * world) + rank) * n + i
     ring = max(1, args.ring)
+    nb = (n + 7) // 8
+    assert nb % 8 == 0, "items per GPU must be a multiple of 64"
     ins, outs = [], []
     for r in range(ring):
         first = (r * world + rank) * n
         w, rd, c, u = ctx.generate_inputs(n, first_index=first, seed=SEED, dist=pbh_b200.DIST_FULLPATH)
         ins.append((w, rd, c, u, first))
+        summary = torch.zeros(nb + 8, dtype=torch.uint8, device=dev)       # verdict bitmap, then the 64-bit proof digest
         outs.append(dict(proof=torch.empty((27, n), dtype=torch.uint8, device=dev), status=torch.empty((n,), dtype=torch.uint8, device=dev),
-                         result=torch.empty((n,), dtype=torch.uint8, device=dev), bitmap=None, digest=None))
+                         result=torch.empty((n,), dtype=torch.uint8, device=dev), summary=summary, bitmap=summary[:nb],
+                         digest=summary[nb:].view(torch.int64),
+                         gathered=torch.empty(world * (nb + 8), dtype=torch.uint8, device=dev) if world > 1 else None,
+                         gather_done=None))
     ctx.sync()
-    gathered_bits = torch.empty(world * ((n + 7) // 8), dtype=torch.uint8, device=dev) if world > 1 else None
-    gathered_dig = torch.empty(world, dtype=torch.int64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    KERNELS_PER_STEP = 4   # prove, verify, pack_verdicts, digest (+ one 8-byte memset node)
 
-    def step(k, ev=None):
-        w, rd, c, u, first = ins[k % ring]
-        o = outs[k % ring]
-        if ev: ev[0].record(stream)
+    def kernels(slot):
+        w, rd, c, u, first = ins[slot]
+        o = outs[slot]
         ctx.prove_batch(w, rd, c, proof=o["proof"], status=o["status"])
-        if ev: ev[1].record(stream)
         ctx.verify_batch(o["proof"], c, u, result=o["result"])
-        if ev: ev[2].record(stream)
-        o["bitmap"] = ctx.pack_verdicts(o["result"])
-        o["digest"] = ctx.digest(o["proof"], first_index=first)
+        ctx.pack_verdicts(o["result"], out=o["bitmap"])
+        ctx.digest(o["proof"], first_index=first, out=o["digest"])
+
+    # one CUDA graph per ring slot: the step is four short kernels, so direct launches from Python are launch-bound
+    graphs, launch_mode = None, "direct"
+    if not args.no_graph:
+        try:
+            graphs = []
+            with torch.cuda.stream(stream):
+                for slot in range(ring):
+                    kernels(slot)                      # warm the allocator and the module before capture
+            torch.cuda.synchronize()
+            for slot in range(ring):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    kernels(slot)
+                graphs.append(g)
+            launch_mode = "cuda_graph"
+        except Exception as e:   # pragma: no cover - capture not supported
+            graphs, launch_mode = None, f"direct (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+
+    def step(k):
+        slot = k % ring
+        o = outs[slot]
+        if world > 1 and o["gather_done"] is not None:
+            stream.wait_event(o["gather_done"])        # the slot's previous all-gather has read its summary
+        if graphs is not None:
+            graphs[slot].replay()
+        else:
+            kernels(slot)
         if world > 1:
             done = torch.cuda.Event()
             done.record(stream)
             comm_stream.wait_event(done)
             with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(gathered_bits, o["bitmap"])
-                dist.all_gather_into_tensor(gathered_dig, o["digest"].reshape(1))
+                dist.all_gather_into_tensor(o["gathered"], o["summary"])     # the only collective: bitmaps + digests
+                o["gather_done"] = torch.cuda.Event()
+                o["gather_done"].record(comm_stream)
 
     def barrier():
         if world > 1:
@@ -207,28 +241,42 @@ def main():
     # ---- timed region: exactly K steps, device-timed, max over ranks
     sampler = ClockSampler(local)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    launches0 = ctx.launch_count
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     with torch.cuda.stream(stream):
         t_begin.record(stream)
         for k in range(args.steps):
-            step(k, evs[k])
+            step(k)
         if world > 1:
             stream.wait_stream(comm_stream)
         t_end.record(stream)
     barrier()
-    clocks = sampler.stop()
     ms_total = t_begin.elapsed_time(t_end)
-    launches = ctx.launch_count - launches0
+    launches = KERNELS_PER_STEP * args.steps
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    prove_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    verify_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     value = n * world * args.steps / (ms_total * 1e-3)
+
+    # ---- per-kernel durations for the roofline: each kernel alone, back to back over the ring, CUDA events on its stream
+    def time_kernel(fn, reps):
+        with torch.cuda.stream(stream):
+            for k in range(3):
+                fn(k % ring)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for k in range(reps):
+                fn(k % ring)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    reps = max(10, min(args.steps, 100))
+    prove_ms = time_kernel(lambda s_: ctx.prove_batch(ins[s_][0], ins[s_][1], ins[s_][2], proof=outs[s_]["proof"], status=outs[s_]["status"]), reps)
+    verify_ms = time_kernel(lambda s_: ctx.verify_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], result=outs[s_]["result"]), reps)
+    digest_ms = time_kernel(lambda s_: ctx.digest(outs[s_]["proof"], first_index=ins[s_][4], out=outs[s_]["digest"]), reps)
+    clocks = sampler.stop()
 
     # ---- sanity inside the bench: every timed item proved (status 0) and reached the pairing check
     o = outs[(args.steps - 1) % ring]
@@ -236,15 +284,9 @@ def main():
     accept = int((o["result"] == 1).sum().item())
     reached = int(((o["result"] == 1) | (o["result"] == 0)).sum().item())
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- end-to-end through the host-pointer C-ABI calls (pinned host buffers), rank 0's device at N = 1
+    # ---- end-to-end through the host-pointer C-ABI calls (pinned host buffers): every rank on its own device
     e2e = None
-    if world == 1 and args.e2e_steps != 0:
+    if args.e2e_steps != 0:
         hw = [torch.empty(t.shape, dtype=torch.uint8).pin_memory() for t in ins[0][:4]]
         for h, t in zip(hw, ins[0][:4]):
             h.copy_(t)
@@ -260,15 +302,26 @@ def main():
         for _ in range(3):
             e2e_step()
         ksteps = args.e2e_steps or max(5, min(args.steps, 50))
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(ksteps):
             e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        assert np.array_equal(h_status.numpy(), outs[0]["status"].cpu().numpy()) or ring > 1
-        e2e = {"value": n * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": n * (26 + 33), "d2h_bytes_per_step": n * (28 + 1),
-               "steps": ksteps, "ms_per_step": 1e3 * dt / ksteps, "host_memory": "pinned"}
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        assert np.array_equal(h_status.numpy(), outs[0]["status"].cpu().numpy())
+        e2e = {"value": n * world * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": n * (26 + 33) * world,
+               "d2h_bytes_per_step": n * (28 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt / ksteps, "host_memory": "pinned",
+               "timing": "host wall clock around synchronous C-ABI calls, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     peak, peak_src = measured_peaks()
     prove_gbs = 54.0 * n / (prove_ms * 1e-3) / 1e9
@@ -306,7 +359,9 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                      "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_item": 54 if dominant == "prove_kernel" else 34},
-        "kernels": {"prove_ms": prove_ms, "verify_ms": verify_ms, "proofs_per_s_per_gpu": n / (prove_ms * 1e-3),
+        "launch": launch_mode,
+        "kernels": {"how": "each kernel alone, back to back over the ring, CUDA events on the context's stream",
+                    "prove_ms": prove_ms, "verify_ms": verify_ms, "digest_ms": digest_ms, "proofs_per_s_per_gpu": n / (prove_ms * 1e-3),
                     "verifies_per_s_per_gpu": n / (verify_ms * 1e-3), "prove_GBps": prove_gbs, "verify_GBps": verify_gbs,
                     "prove_hbm_frac": prove_gbs / peak, "verify_hbm_frac": verify_gbs / peak},
         "int32_peak": int32,

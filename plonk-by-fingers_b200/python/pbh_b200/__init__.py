@@ -356,21 +356,24 @@ class Context:
         self._check(rc, "pbh_generate_inputs_dev")
         return (wit, rand, chal, u, att) if want_attempt else (wit, rand, chal, u)
 
-    def pack_verdicts(self, result):
+    def pack_verdicts(self, result, out=None):
         import torch
         n = result.numel()
-        out = torch.empty(((n + 7) // 8,), dtype=torch.uint8, device=result.device)
+        if out is None:
+            out = torch.empty(((n + 7) // 8,), dtype=torch.uint8, device=result.device)
         cur = self._dev_begin()
         rc = self.lib.pbh_pack_verdicts_dev(self.h, C.c_size_t(n), C.c_void_p(result.data_ptr()), C.c_void_p(out.data_ptr()))
         self._dev_end(cur)
         self._check(rc, "pbh_pack_verdicts_dev")
         return out
 
-    def digest(self, data, first_index=0):
-        """64-bit additive digest of a (planes, n) device batch; digests of disjoint shards sum to the whole batch's."""
+    def digest(self, data, first_index=0, out=None):
+        """64-bit additive digest of a (planes, n) device batch; digests of disjoint shards sum to the whole batch's.
+        `out`: optional int64 tensor of one element (8-byte aligned)."""
         import torch
         D = _Planes(data, data.shape[0] if data.dim() > 1 else 1, name="data")
-        out = torch.empty((1,), dtype=torch.int64, device=D.arr.device)     # zeroed by the library on its own stream
+        if out is None:
+            out = torch.empty((1,), dtype=torch.int64, device=D.arr.device)     # zeroed by the library on its own stream
         cur = self._dev_begin()
         rc = self.lib.pbh_digest_dev(self.h, C.c_size_t(D.n), C.c_uint64(first_index), C.c_uint32(D.arr.shape[0]), C.c_void_p(D.ptr),
                                      C.c_size_t(D.pitch), C.c_void_p(out.data_ptr()))

@@ -7,7 +7,7 @@ KREGEX=${2:-prove_kernel}
 shift 2 || true
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu --ring 2 --e2e-steps 0 $*"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu --no-graph --ring 2 --e2e-steps 0 $*"
 $CMD > $OUT/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/${TAG}_plain.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"

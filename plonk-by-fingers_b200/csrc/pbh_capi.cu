@@ -524,7 +524,9 @@ int pbh_digest_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint32_t planes
   CUDA_TRY(ctx, cudaMemsetAsync(out, 0, sizeof(uint64_t), ctx->compute));
   if (n == 0) return PBH_OK;
   if (!data || pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
-  digest_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, first_index, planes, data, pitch, (unsigned long long*)out);
+  const bool vec_ok = ((uintptr_t)data % 4 == 0) && (pitch % 4 == 0);
+  digest_kernel<<<grid_for(ctx, vec_ok ? (n + 3) / 4 : n, 8), kBlock, 0, ctx->compute>>>(n, first_index, planes, data, pitch,
+                                                                                      (unsigned long long*)out, vec_ok);
   SWEEP_FINISH(ctx);
   return PBH_OK;
 }

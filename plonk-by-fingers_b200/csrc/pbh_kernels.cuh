@@ -359,16 +359,40 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 // Digest of one item: FNV-1a-style 64-bit mixing over the item's bytes packed four planes per 32-bit word, seeded
 // with the global item index, finished with splitmix64.  The batch digest is the sum over items modulo 2^64, so
 // digests of disjoint shards add up to the digest of the whole batch.
+__device__ __forceinline__ uint64_t digest_item_begin(uint64_t index, uint32_t planes) { return index * 0x9E3779B97F4A7C15ull + planes; }
+__device__ __forceinline__ uint64_t digest_item_word(uint64_t h, uint32_t wv) { return (h ^ wv) * 0x100000001B3ull; }
+
+// vec_ok: data and pitch are 4-byte aligned, so a thread takes four consecutive items through one 32-bit word per
+// plane (128-byte warp transactions, four independent loads in flight) and transposes 4x4 bytes with PRMT.
 __global__ void __launch_bounds__(kBlock) digest_kernel(size_t n, uint64_t first_index, uint32_t planes,
                                                          const uint8_t* __restrict__ data, size_t pitch,
-                                                         unsigned long long* __restrict__ out) {
+                                                         unsigned long long* __restrict__ out, bool vec_ok) {
   unsigned long long acc = 0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    uint64_t h = (first_index + i) * 0x9E3779B97F4A7C15ull + planes;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t n4 = vec_ok ? n / 4 : 0;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    uint64_t h0 = digest_item_begin(first_index + 4 * q, planes), h1 = digest_item_begin(first_index + 4 * q + 1, planes),
+             h2 = digest_item_begin(first_index + 4 * q + 2, planes), h3 = digest_item_begin(first_index + 4 * q + 3, planes);
+    for (uint32_t k = 0; k < planes; k += 4) {
+      uint32_t w0 = reinterpret_cast<const uint32_t*>(data + (size_t)k * pitch)[q];
+      uint32_t w1 = k + 1 < planes ? reinterpret_cast<const uint32_t*>(data + (size_t)(k + 1) * pitch)[q] : 0u;
+      uint32_t w2 = k + 2 < planes ? reinterpret_cast<const uint32_t*>(data + (size_t)(k + 2) * pitch)[q] : 0u;
+      uint32_t w3 = k + 3 < planes ? reinterpret_cast<const uint32_t*>(data + (size_t)(k + 3) * pitch)[q] : 0u;
+      uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w0, w1, 0x7362);
+      uint32_t t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
+      h0 = digest_item_word(h0, __byte_perm(t0, t2, 0x5410));
+      h1 = digest_item_word(h1, __byte_perm(t0, t2, 0x7632));
+      h2 = digest_item_word(h2, __byte_perm(t1, t3, 0x5410));
+      h3 = digest_item_word(h3, __byte_perm(t1, t3, 0x7632));
+    }
+    acc += splitmix64(h0) + splitmix64(h1) + splitmix64(h2) + splitmix64(h3);
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t h = digest_item_begin(first_index + i, planes);
     for (uint32_t k = 0; k < planes; k += 4) {
       uint32_t wv = 0;
       for (uint32_t b = 0; b < 4 && k + b < planes; b++) wv |= (uint32_t)data[(size_t)(k + b) * pitch + i] << (8 * b);
-      h = (h ^ wv) * 0x100000001B3ull;
+      h = digest_item_word(h, wv);
     }
     acc += splitmix64(h);
   }

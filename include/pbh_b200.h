@@ -125,6 +125,9 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 /* PBH_OPT_PROVER_LAUNCH_SHAPE: threads x min-resident-blocks of the FP32 prover: 0 = 256x2 (default), 1 = 256x1,
  * 2 = 128x4, 3 = 128x5, 4 = 128x6 (register budget 128 / 255 / 128 / 96 / 80 per thread) */
 #define PBH_OPT_PROVER_LAUNCH_SHAPE 2
+/* PBH_OPT_TMA: stage 256-item tiles through shared memory with TMA bulk tensor copies (1, default; used when every
+ * base pointer and pitch is a multiple of 16 bytes) or use plain per-thread loads and stores (0). */
+#define PBH_OPT_TMA 3
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */

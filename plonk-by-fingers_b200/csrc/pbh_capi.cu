@@ -2,6 +2,7 @@
 //
 // There is no CPU fallback anywhere in this file: every entry point that computes launches a CUDA kernel on
 // the context's device, and context creation fails with PBH_ERR_NO_DEVICE when no device is usable.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -28,6 +29,7 @@ struct pbh_ctx {
   int sm_count = 148;
   int algo = PBH_ALGO_TABLE;
   int prover_variant = 0;
+  int use_tma = 1;                         // TMA-staged tiles when base/pitch alignment allows (PBH_OPT_TMA)
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;
   Tables* d_tables = nullptr;
@@ -159,6 +161,7 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
   CTX_CHECK(ctx);
   if (option == PBH_OPT_PROVER_FP32) { ctx->prover_fp32 = value != 0; return PBH_OK; }
   if (option == PBH_OPT_PROVER_LAUNCH_SHAPE) { ctx->prover_variant = value; return PBH_OK; }
+  if (option == PBH_OPT_TMA) { ctx->use_tma = value != 0; return PBH_OK; }
   return fail(ctx, PBH_ERR_BAD_ARGUMENT, "unknown option");
 }
 int pbh_ctx_device(const pbh_ctx* ctx) { return ctx ? ctx->device : PBH_ERR_BAD_ARGUMENT; }
@@ -194,9 +197,50 @@ int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
   return PBH_OK;
 }
 
+// ---- TMA tensor maps --------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that the library does not
+// link against libcuda directly.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// a (n items x planes) byte-plane batch as a 2-D u8 tensor with box (kTile, planes); false when TMA cannot address it
+static bool make_plane_map(CUtensorMap* map, const void* base, size_t n, size_t pitch, uint32_t planes) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || n == 0 || n >= ((size_t)1 << 31) || ((uintptr_t)base % 16) != 0 || (pitch % 16) != 0) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)n, planes};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch};
+  cuuint32_t box[2] = {(cuuint32_t)kTile, planes};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---- device-pointer entry points -----------------------------------------------------------------------
 static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
   if (A.n == 0) return PBH_OK;
+  if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32 && ctx->use_tma) {
+    ProveTmaMaps M;
+    if (make_plane_map(&M.wit, A.wit, A.n, A.wit_pitch, 12) && make_plane_map(&M.rnd, A.rnd, A.n, A.rand_pitch, 9) &&
+        make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) && make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27)) {
+      size_t tiles = (A.n + kTile - 1) / kTile;
+      int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2);   // persistent: two resident blocks per SM
+      prove_f32_tma_kernel<<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.status, A.n);
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaGetLastError());
+      return PBH_OK;
+    }
+    // base or pitch not 16-byte aligned: fall through to the plain-load kernel
+  }
   int grid = grid_for(ctx, A.n, 8);
   if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32) {
     // launch shape of the FP32 prover: threads per block / resident blocks per SM the register budget is capped for

@@ -13,6 +13,7 @@
 #include "../../include/pbh_b200.h"
 #include "pbh_verify.cuh"
 #include "pbh_prove_f32.cuh"
+#include "pbh_tma.cuh"
 
 namespace pbh {
 
@@ -109,6 +110,107 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) prove_f32_kernel(const Co
     if (bad) status = PBH_ST_BAD_ENCODING;
     store_proof(A, i, P, status);
   }
+}
+
+// ---- TMA-staged prover -------------------------------------------------------------------------------------------
+// Persistent blocks walk 256-item tiles.  One elected thread issues three TMA tile loads (witness, blinder and
+// challenge planes) for tile k+1 into the other shared-memory stage while the block computes tile k; completion is an
+// mbarrier transaction count.  Each thread then reads its 26 bytes with immediate-offset LDS (no per-plane address
+// arithmetic), the copy-constraint partner of a witness value is one LDS at a uniform offset, and the 27 proof planes
+// leave through one TMA tile store per tile (double-buffered; the hardware clips the ragged last tile).
+constexpr int kTile = 256;
+struct ProveTmaMaps {
+  CUtensorMap wit, rnd, chal, proof;   // 2-D u8 tensors (n items, planes), box = (kTile, planes)
+};
+struct ProveTmaSmem {
+  alignas(128) uint8_t in[2][26][kTile];    // planes 0..11 witness, 12..20 blinders, 21..25 challenges
+  alignas(128) uint8_t out[2][27][kTile];
+  alignas(8) uint64_t full[2];
+  Tables T;
+};
+
+__global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_constant__ ProveTmaMaps M, const Consts K, const ConstsF KF,
+                                                                  const Tables* __restrict__ gT, uint8_t* __restrict__ status_out,
+                                                                  size_t n) {
+  __shared__ ProveTmaSmem S;
+  const int tid = threadIdx.x;
+  stage_tables(S.T, gT);
+  if (tid == 0) {
+    tma::mbar_init(&S.full[0], 1);
+    tma::mbar_init(&S.full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  const size_t tiles = (n + kTile - 1) / kTile;
+  auto issue = [&](size_t tile, int stage) {
+    tma::mbar_arrive_expect_tx(&S.full[stage], 26 * kTile);
+    const int32_t c0 = (int32_t)(tile * kTile);
+    tma::load_2d(&S.in[stage][0][0], &M.wit, &S.full[stage], c0, 0);
+    tma::load_2d(&S.in[stage][12][0], &M.rnd, &S.full[stage], c0, 0);
+    tma::load_2d(&S.in[stage][21][0], &M.chal, &S.full[stage], c0, 0);
+  };
+  if (tid == 0 && blockIdx.x < tiles) issue(blockIdx.x, 0);
+  uint32_t phase0 = 0, phase1 = 0;
+  int stage = 0;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, stage ^= 1) {
+    const size_t next = tile + gridDim.x;
+    if (tid == 0 && next < tiles) issue(next, stage ^ 1);     // the other stage was released by the barrier below
+    if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
+
+    const uint8_t* in = &S.in[stage][0][tid];
+    uint32_t w[12], r[9], c[5];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { w[k] = in[k * kTile]; bad = bad | (w[k] >= 17u); }
+#pragma unroll
+    for (int k = 0; k < 9; k++) { r[k] = in[(12 + k) * kTile]; bad = bad | (r[k] >= 17u); }
+#pragma unroll
+    for (int k = 0; k < 5; k++) { c[k] = in[(21 + k) * kTile]; bad = bad | (c[k] >= 17u); }
+    // constraints.satisfies: gates from registers, copy-constraint partners straight from the staged tile
+    bool unsat = gates_unsatisfied(w, K);
+#pragma unroll
+    for (int k = 0; k < 12; k++) unsat = unsat | ((uint32_t)in[K.perm[k] * kTile] != w[k]);
+    if (bad) {
+#pragma unroll
+      for (int k = 0; k < 12; k++) w[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) r[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 5; k++) c[k] = 0;
+    }
+    ProofRegs P;
+    uint32_t status = prove_item_f32(w, r, c, K, KF, S.T, P, unsat ? 1 : 0);
+    if (bad) status = PBH_ST_BAD_ENCODING;
+
+    uint8_t* out = &S.out[stage][0][tid];
+    uint32_t inf_lo = 0, inf_hi = 0;
+    const bool ok = status == 0u;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      uint32_t pw = ok ? P.pt[k] : 0u;
+      out[(2 * k) * kTile] = (uint8_t)pw;
+      out[(2 * k + 1) * kTile] = (uint8_t)(pw >> 8);
+      uint32_t inf = (pw >> 16) & 1u;
+      if (k < 8) inf_lo |= inf << k; else inf_hi |= inf;
+    }
+    out[18 * kTile] = (uint8_t)inf_lo;
+    out[19 * kTile] = (uint8_t)inf_hi;
+#pragma unroll
+    for (int k = 0; k < 7; k++) out[(20 + k) * kTile] = (uint8_t)(ok ? P.ev[k] : 0u);
+    const size_t i = tile * kTile + tid;
+    if (i < n) status_out[i] = (uint8_t)status;
+
+    // the store issued one iteration ago (other out buffer) must have finished reading shared memory before anyone
+    // writes that buffer again in the next iteration; it has had a whole tile of compute to do so
+    if (tid == 0) tma::store_wait_read_all();
+    tma::fence_proxy_async();          // this thread's shared-memory writes -> visible to the TMA engine
+    __syncthreads();                   // also releases in[stage] for the prefetch of the iteration after next
+    if (tid == 0) {
+      tma::store_2d(&M.proof, &S.out[stage][0][0], (int32_t)(tile * kTile), 0);
+      tma::store_commit();
+    }
+  }
+  if (tid == 0) tma::store_wait_all();
 }
 
 struct VerifyArgs {

@@ -113,14 +113,20 @@ struct ProofRegs {
   uint32_t ev[7];   // a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z
 };
 
-// constraints.satisfies(assigments), src/constraints.rs:198-230 (Q8: q_l multiplies b as well)
-PBH_HD bool unsatisfied(const uint32_t (&w)[12], const Consts& K) {
+// gate part of constraints.satisfies, src/constraints.rs:200-210 (Q8: q_l multiplies b as well)
+PBH_HD bool gates_unsatisfied(const uint32_t (&w)[12], const Consts& K) {
   bool unsat = false;
 #pragma unroll
   for (int n = 0; n < 4; n++) {
     uint32_t r = K.q_l[n] * (w[n] + w[4 + n]) + K.q_o[n] * w[8 + n] + K.q_m[n] * mod17(w[n] * w[4 + n]) + K.q_c[n];
-    unsat = unsat || (mod17(r) != 0u);
+    unsat = unsat | (mod17(r) != 0u);
   }
+  return unsat;
+}
+
+// constraints.satisfies(assigments), src/constraints.rs:198-230
+PBH_HD bool unsatisfied(const uint32_t (&w)[12], const Consts& K) {
+  bool unsat = gates_unsatisfied(w, K);
   // witness value k must equal witness value perm[k]; values are 5-bit fields of a 64-bit word so that the
   // (uniform, runtime) permutation needs no local-memory indexing
   unsigned long long packed = 0;
@@ -137,13 +143,14 @@ PBH_HD bool unsatisfied(const uint32_t (&w)[12], const Consts& K) {
 // w[12] = a[0..4) b[0..4) c[0..4); r[9] = b1..b9; ch[5] = alpha beta gamma z v.  All inputs < 17.
 // Returns the status byte.  `P` is fully defined only for status 0.  With UPTO_T the routine stops after the
 // quotient (sites :199 .. :376) — enough for items whose t(x) is known to be short (status 1-4 only).
+// `unsat_known`: -1 = evaluate constraints.satisfies here; 0 / 1 = the caller already did (e.g. from shared memory).
 template <int ALGO, bool UPTO_T = false>
 PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
-                          const Tables& T, ProofRegs& P) {
+                          const Tables& T, ProofRegs& P, int unsat_known = -1) {
   const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], zc = ch[3], v = ch[4];
   const uint32_t n_pts = K.n_pts;
 
-  const bool unsat = unsatisfied(w, K);
+  const bool unsat = unsat_known < 0 ? unsatisfied(w, K) : (unsat_known != 0);
 
   // ---- wire polynomials                                                     src/plonk.rs:233-235, 248-252
   uint32_t fa[4], fb[4], fc[4];

@@ -9,8 +9,8 @@
 // 1.5*2^23 rounding constant, FADD, FFMA) and is valid for |x| <= 2^23 (the error of the fp32 reciprocal times |x|
 // stays below the 1/34 margin to the nearest rounding boundary).  Reductions are lazy: sums of products run
 // unreduced through whole polynomial products.  Every bound is machine-checked: the core below is templated on the
-// scalar type, and tests/hostemul instantiates it with a type that propagates worst-case magnitudes and fails if any
-// operation could leave the exact range (tests/test_hostemul_parity.py::test_f32_bounds).
+// scalar type, and the CPU test suite instantiates it with a type that propagates worst-case magnitudes and fails if
+// any operation could leave the exact range (test_f32_bounds).
 //
 // Scope of this fast path: it assumes alpha*b1*b3*b5*b7 != 0 (mod 17), i.e. t1+t2 has 22 coefficients, so the
 // reference's SubAssign quirk Q1 (src/poly.rs:192-203) cannot trigger.  Items that violate it can only end in
@@ -372,11 +372,12 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 // One proof through the fast path: FP32 core for the common case, exact integer routine for items whose quotient
 // is known to be short (alpha*b1*b3*b5*b7 = 0 mod 17: Q1/Q5 territory, status 1-4 only).  Inputs are canonical
 // bytes (< 17).  Output as packed points + canonical evaluations, like prove_one<ALGO_TABLE>.
+// `unsat_known`: -1 = evaluate constraints.satisfies here; 0 / 1 = already evaluated by the caller.
 PBH_HD uint32_t prove_item_f32(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
-                               const ConstsF& KF, const Tables& T, ProofRegs& P) {
+                               const ConstsF& KF, const Tables& T, ProofRegs& P, int unsat_known = -1) {
   const bool rare = ch[0] == 0u || rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
-  if (rare) return prove_one<ALGO_TABLE, true>(w, rnd, ch, K, T, P);
-  const bool unsat = unsatisfied(w, K);
+  if (rare) return prove_one<ALGO_TABLE, true>(w, rnd, ch, K, T, P, unsat_known);
+  const bool unsat = unsat_known < 0 ? unsatisfied(w, K) : (unsat_known != 0);
   F32* tag = nullptr;
   F32 wf[12], rf[9], cf[5];
 #pragma unroll

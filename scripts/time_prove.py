@@ -26,6 +26,10 @@ def prove(k):
 def verify(k):
     w, r, c, u = ins[k % ring]
     ctx.verify_batch(proof[k % ring], c, u, result=res)
+for tma_on in (1, 0):
+    ctx.set_option(pbh_b200.OPT_TMA, tma_on)
+    us = timeit(prove)
+    print(f"fp32 prover, TMA tiles={tma_on}:   {us:8.1f} us  {n/us/1e3:7.2f} G proofs/s  ok={int((status==0).sum())==n}")
 for shape in range(5):
     ctx.set_option(pbh_b200.OPT_PROVER_FP32, 1); ctx.set_option(2, shape)
     us = timeit(prove)

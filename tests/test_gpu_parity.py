@@ -11,7 +11,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ALGOS = ("table", "arith")
-CTXS = ("table", "table_int", "arith")   # gpu_ctx keys: table = FP32-pipe prover, table_int = int32 prover
+CTXS = ("table", "table_notma", "table_int", "arith")   # gpu_ctx keys: table = FP32-pipe prover with TMA tiles (default),
+# table_notma = same with plain loads/stores, table_int = int32 prover, arith = per-item curve arithmetic
 
 
 def _np(t):
@@ -453,6 +454,26 @@ def test_pitch_subranges_and_empty(gpu_ctx, oracle):
     p0, s0 = ctx.prove_batch(np.zeros((12, 0), np.uint8), np.zeros((9, 0), np.uint8), np.zeros((5, 0), np.uint8))
     assert p0.shape == (27, 0) and s0.shape == (0,)
     assert ctx.verify_batch(np.zeros((27, 0), np.uint8), np.zeros((5, 0), np.uint8), np.zeros((0,), np.uint8)).shape == (0,)
+
+
+@pytest.mark.parametrize("n", (1, 255, 256, 257, 30037, 65536 + 19))
+def test_tma_tiles_ragged_and_aligned(gpu_ctx, oracle, n):
+    """The TMA path needs 16-byte aligned bases and pitches; ragged item counts ride on an aligned pitch and the hardware
+    clips the last tile.  Same bytes as the plain-load path and the oracle, and nothing is written past item n."""
+    import torch
+    ctx = gpu_ctx["table"]
+    pitch = (n + 64 + 15) // 16 * 16
+    dev = torch.device("cuda", 0)
+    wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=n, dist=0)
+    po, so = oracle.prove_batch(wo, ro, co)
+    big = lambda planes: torch.full((planes, pitch), 0xAB, dtype=torch.uint8, device=dev)
+    W, R, Cc, P = big(12), big(9), big(5), big(27)
+    W[:, :n] = torch.from_numpy(wo).to(dev); R[:, :n] = torch.from_numpy(ro).to(dev); Cc[:, :n] = torch.from_numpy(co).to(dev)
+    S = torch.full((pitch,), 0xAB, dtype=torch.uint8, device=dev)
+    ctx.prove_batch(W[:, :n], R[:, :n], Cc[:, :n], proof=P[:, :n], status=S[:n])
+    ctx.sync()
+    assert np.array_equal(P[:, :n].cpu().numpy(), po) and np.array_equal(S[:n].cpu().numpy(), so)
+    assert bool((P[:, n:] == 0xAB).all()) and bool((S[n:] == 0xAB).all())
 
 
 def test_shard_summaries(gpu_ctx, oracle):

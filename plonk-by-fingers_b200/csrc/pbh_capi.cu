@@ -234,7 +234,7 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
         make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) && make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27)) {
       size_t tiles = (A.n + kTile - 1) / kTile;
       int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2);   // persistent: two resident blocks per SM
-      prove_f32_tma_kernel<<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.status, A.n);
+      prove_f32_tma_kernel<<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n);
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
       return PBH_OK;
@@ -259,6 +259,23 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
 }
 static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A) {
   if (A.n == 0) return PBH_OK;
+  if (ctx->use_tma) {
+    VerifyTmaMaps M;
+    if (make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27) && make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) &&
+        make_plane_map(&M.u, A.u, A.n, (A.n + 15) / 16 * 16, 1)) {
+      size_t tiles = (A.n + kTile - 1) / kTile;
+      if (ctx->algo == PBH_ALGO_TABLE) {
+        int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 4);
+        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A);
+      } else {
+        int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 3);
+        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A);
+      }
+      ctx->launches++;
+      CUDA_TRY(ctx, cudaGetLastError());
+      return PBH_OK;
+    }
+  }
   int grid = grid_for(ctx, A.n, 8);
   if (ctx->algo == PBH_ALGO_TABLE) verify_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   else verify_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);

@@ -130,8 +130,8 @@ struct ProveTmaSmem {
 };
 
 __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_constant__ ProveTmaMaps M, const Consts K, const ConstsF KF,
-                                                                  const Tables* __restrict__ gT, uint8_t* __restrict__ status_out,
-                                                                  size_t n) {
+                                                                  const Tables* __restrict__ gT, uint8_t* __restrict__ proof_out,
+                                                                  size_t proof_pitch, uint8_t* __restrict__ status_out, size_t n) {
   __shared__ ProveTmaSmem S;
   const int tid = threadIdx.x;
   stage_tables(S.T, gT);
@@ -200,12 +200,19 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     const size_t i = tile * kTile + tid;
     if (i < n) status_out[i] = (uint8_t)status;
 
+    // TMA clips the item dimension at 16-byte granularity (measured), so a partial last tile whose end is not 16-byte
+    // aligned is written with plain stores instead
+    const bool tma_store = (tile + 1) * kTile <= n || (n & 15) == 0;
+    if (!tma_store && i < n) {
+#pragma unroll
+      for (int k = 0; k < 27; k++) proof_out[(size_t)k * proof_pitch + i] = out[k * kTile];
+    }
     // the store issued one iteration ago (other out buffer) must have finished reading shared memory before anyone
     // writes that buffer again in the next iteration; it has had a whole tile of compute to do so
     if (tid == 0) tma::store_wait_read_all();
     tma::fence_proxy_async();          // this thread's shared-memory writes -> visible to the TMA engine
     __syncthreads();                   // also releases in[stage] for the prefetch of the iteration after next
-    if (tid == 0) {
+    if (tid == 0 && tma_store) {
       tma::store_2d(&M.proof, &S.out[stage][0][0], (int32_t)(tile * kTile), 0);
       tma::store_commit();
     }
@@ -247,6 +254,66 @@ __global__ void __launch_bounds__(kBlock) verify_kernel(const Consts K, const Ta
       A.gt[i] = (uint8_t)e1.a; A.gt[A.gt_pitch + i] = (uint8_t)e1.b;
       A.gt[2 * A.gt_pitch + i] = (uint8_t)e2.a; A.gt[3 * A.gt_pitch + i] = (uint8_t)e2.b;
     }
+  }
+}
+
+// ---- TMA-staged verifier: same tile pipeline as the prover; 33 input planes per item, one result byte out ---------------
+struct VerifyTmaMaps {
+  CUtensorMap proof, chal, u;
+};
+struct VerifyTmaSmem {
+  alignas(128) uint8_t in[2][34][kTile];    // planes 0..26 proof, 27..31 challenges, 32 u (33 unused: keeps stages 128-byte aligned)
+  alignas(8) uint64_t full[2];
+  Tables T;
+};
+template <int ALGO, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __grid_constant__ VerifyTmaMaps M, const Consts K,
+                                                                         const Tables* __restrict__ gT, const VerifyArgs A) {
+  __shared__ VerifyTmaSmem S;
+  const int tid = threadIdx.x;
+  stage_tables(S.T, gT);
+  if (tid == 0) {
+    tma::mbar_init(&S.full[0], 1);
+    tma::mbar_init(&S.full[1], 1);
+    tma::fence_mbar_init();
+  }
+  __syncthreads();
+  const size_t tiles = (A.n + kTile - 1) / kTile;
+  auto issue = [&](size_t tile, int stage) {
+    tma::mbar_arrive_expect_tx(&S.full[stage], 33 * kTile);
+    const int32_t c0 = (int32_t)(tile * kTile);
+    tma::load_2d(&S.in[stage][0][0], &M.proof, &S.full[stage], c0, 0);
+    tma::load_2d(&S.in[stage][27][0], &M.chal, &S.full[stage], c0, 0);
+    tma::load_2d(&S.in[stage][32][0], &M.u, &S.full[stage], c0, 0);
+  };
+  if (tid == 0 && blockIdx.x < tiles) issue(blockIdx.x, 0);
+  uint32_t phase0 = 0, phase1 = 0;
+  int stage = 0;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, stage ^= 1) {
+    const size_t next = tile + gridDim.x;
+    if (tid == 0 && next < tiles) issue(next, stage ^ 1);
+    if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
+    const uint8_t* in = &S.in[stage][0][tid];
+    uint32_t px[9], py[9], ev[7], ch[5];
+#pragma unroll
+    for (int k = 0; k < 9; k++) { px[k] = in[(2 * k) * kTile]; py[k] = in[(2 * k + 1) * kTile]; }
+    uint32_t infbits = (uint32_t)in[18 * kTile] | ((uint32_t)in[19 * kTile] << 8);
+#pragma unroll
+    for (int k = 0; k < 7; k++) ev[k] = in[(20 + k) * kTile];
+#pragma unroll
+    for (int k = 0; k < 5; k++) ch[k] = in[(27 + k) * kTile];
+    uint32_t u = in[32 * kTile];
+    GT e1, e2;
+    uint32_t res = verify_one<ALGO>(px, py, infbits, ev, ch, u, K, S.T, e1, e2);
+    const size_t i = tile * kTile + tid;
+    if (i < A.n) {
+      A.result[i] = (uint8_t)res;
+      if (A.gt) {
+        A.gt[i] = (uint8_t)e1.a; A.gt[A.gt_pitch + i] = (uint8_t)e1.b;
+        A.gt[2 * A.gt_pitch + i] = (uint8_t)e2.a; A.gt[3 * A.gt_pitch + i] = (uint8_t)e2.b;
+      }
+    }
+    __syncthreads();   // every thread has read in[stage]; it may be refilled by the prefetch of the iteration after next
   }
 }
 

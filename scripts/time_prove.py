@@ -30,10 +30,16 @@ for tma_on in (1, 0):
     ctx.set_option(pbh_b200.OPT_TMA, tma_on)
     us = timeit(prove)
     print(f"fp32 prover, TMA tiles={tma_on}:   {us:8.1f} us  {n/us/1e3:7.2f} G proofs/s  ok={int((status==0).sum())==n}")
-for shape in range(5):
+for shape in range(0):
     ctx.set_option(pbh_b200.OPT_PROVER_FP32, 1); ctx.set_option(2, shape)
     us = timeit(prove)
     print(f"fp32 prover launch shape {shape}: {us:8.1f} us  {n/us/1e3:7.2f} G proofs/s  ok={int((status==0).sum())==n}")
 ctx.set_option(pbh_b200.OPT_PROVER_FP32, 0)
 us = timeit(prove); print(f"int32 prover:               {us:8.1f} us  {n/us/1e3:7.2f} G proofs/s")
-us = timeit(verify); print(f"verify (table):             {us:8.1f} us  {n/us/1e3:7.2f} G verifies/s")
+for tma_on in (1, 0):
+    ctx.set_option(pbh_b200.OPT_TMA, tma_on)
+    us = timeit(verify); print(f"verify (table), TMA={tma_on}:     {us:8.1f} us  {n/us/1e3:7.2f} G verifies/s")
+ctx.set_option(pbh_b200.OPT_TMA, 1)
+ctx.set_algo("arith")
+us = timeit(verify); print(f"verify (arith), TMA=1:     {us:8.1f} us  {n/us/1e3:7.2f} G verifies/s")
+us = timeit(prove); print(f"prove (arith):             {us:8.1f} us  {n/us/1e3:7.2f} G proofs/s")

@@ -56,29 +56,25 @@ PBH_HD F32 f_from_u32(uint32_t b, F32*) {                          // exact for 
 #endif
 }
 
-// schoolbook products, unreduced
+// schoolbook products, unreduced, in outer-product order: consecutive FFMAs share the multiplicand a[i] (operand
+// reuse cache, fewer register-bank conflicts) and write different accumulators (independent chains)
 template <class T, int LA, int LB>
 PBH_HD void fpoly_mul(const T (&a)[LA], const T (&b)[LB], T (&out)[LA + LB - 1]) {
 #pragma unroll
-  for (int k = 0; k < LA + LB - 1; k++) {
-    bool first = true;
+  for (int i = 0; i < LA; i++) {
 #pragma unroll
-    for (int i = 0; i < LA; i++) {
-      if (k - i >= 0 && k - i < LB) {
-        out[k] = first ? f_mul(a[i], b[k - i]) : f_fma(a[i], b[k - i], out[k]);
-        first = false;
-      }
+    for (int j = 0; j < LB; j++) {
+      // out[i + j] is touched for the first time when i == 0 or j == LB - 1
+      out[i + j] = (i == 0 || j == LB - 1) ? f_mul(a[i], b[j]) : f_fma(a[i], b[j], out[i + j]);
     }
   }
 }
 template <class T, int LA, int LB, int LO>
 PBH_HD void fpoly_mac(const T (&a)[LA], const T (&b)[LB], T (&acc)[LO]) {
 #pragma unroll
-  for (int k = 0; k < LA + LB - 1; k++) {
+  for (int i = 0; i < LA; i++) {
 #pragma unroll
-    for (int i = 0; i < LA; i++) {
-      if (k - i >= 0 && k - i < LB) acc[k] = f_fma(a[i], b[k - i], acc[k]);
-    }
+    for (int j = 0; j < LB; j++) acc[i + j] = f_fma(a[i], b[j], acc[i + j]);
   }
 }
 
@@ -128,12 +124,10 @@ template <class T>
 PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (&ch_in)[5], const ConstsF& KF, uint32_t n_pts,
                                const float* inv17c, ProofF& P) {
   T* tag = nullptr;
-  // centre blinders and challenges: halves every bound below
-  T rnd[9], ch[5];
-#pragma unroll
-  for (int i = 0; i < 9; i++) rnd[i] = f_red(rnd_in[i]);
-#pragma unroll
-  for (int i = 0; i < 5; i++) ch[i] = f_red(ch_in[i]);
+  // blinders and challenges are used as they come (0..16); the bound check shows that centring them is not needed
+  // (worst-case magnitude 4.8 M, below red17's 2^23 range)
+  const T (&rnd)[9] = rnd_in;
+  const T (&ch)[5] = ch_in;
   const T alpha = ch[0], beta = ch[1], gamma = ch[2], zc = ch[3], v = ch[4];
 
   // ---- wire polynomials                                                     src/plonk.rs:233-235, 248-252
@@ -160,15 +154,15 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
     const float o1 = (i == 0) ? 1.f : (i == 1 ? 4.f : -1.f), o2 = (i == 0) ? 2.f : (i == 1 ? 8.f : -2.f),
                 o3 = (i == 0) ? 3.f : (i == 1 ? -5.f : -3.f);
     T wa = f_add(w[i], gamma), wb = f_add(w[4 + i], gamma), wc = f_add(w[8 + i], gamma);
-    T n1 = f_red(f_fma(beta, f_const(o1, tag), wa)), n2 = f_red(f_fma(beta, f_const(o2, tag), wb)),
-      n3 = f_red(f_fma(beta, f_const(o3, tag), wc));
-    T d1 = f_red(f_fma(beta, f_const(KF.sig[0][i], tag), wa)), d2 = f_red(f_fma(beta, f_const(KF.sig[1][i], tag), wb)),
-      d3 = f_red(f_fma(beta, f_const(KF.sig[2][i], tag), wc));
+    // factors stay unreduced (|.| <= 16 + 8 + 8*8 = 88): a product of three is below 2^20
+    T n1 = f_fma(beta, f_const(o1, tag), wa), n2 = f_fma(beta, f_const(o2, tag), wb), n3 = f_fma(beta, f_const(o3, tag), wc);
+    T d1 = f_fma(beta, f_const(KF.sig[0][i], tag), wa), d2 = f_fma(beta, f_const(KF.sig[1][i], tag), wb),
+      d3 = f_fma(beta, f_const(KF.sig[2][i], tag), wc);
     T dsor = f_red(f_mul(f_mul(d1, d2), d3));
     div0 = div0 | f_is_zero(dsor);                                           // src/plonk.rs:297 unwrap
     T dinv = f_const(inv17c[f_canon(dsor)], tag);
-    T dend = f_mul(f_mul(n1, n2), n3);                                       // |.| <= 512
-    acc[i + 1] = f_red(f_mul(f_red(f_mul(acc[i], dinv)), f_red(dend)));
+    T dend = f_red(f_mul(f_mul(n1, n2), n3));
+    acc[i + 1] = f_red(f_mul(f_mul(acc[i], dinv), dend));                    // |.| <= 8^3
   }
   T accx[4];
   fintt4(acc[0], acc[1], acc[2], acc[3], accx);
@@ -179,6 +173,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 
   // ---- quotient numerator: t1 + alpha (A'B'C' z - A''B''C'' z_omega) + alpha^2 (z - 1) L1     src/plonk.rs:339-369
   T num[22];
+  const T a2 = f_red(f_mul(alpha, alpha));
   {
     // t1 = a b q_m + a q_l + b q_r + c q_o + q_c
     T ab[11];
@@ -200,7 +195,6 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 #pragma unroll
     for (int i = 0; i < 4; i++) l1[i] = f_const(KF.L1[i], tag);
     fpoly_mul(zm, l1, t4);
-    T a2 = f_red(f_mul(alpha, alpha));
 #pragma unroll
     for (int i = 0; i < 22; i++) {
       T s = (i < 14) ? t1[i] : f_const(0.f, tag);
@@ -291,7 +285,6 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 
   // ---- linearisation polynomial r (unreduced, 10 coefficients)             src/plonk.rs:401-422 (Q2)
   T r[10];
-  T a2 = f_red(f_mul(alpha, alpha));
   {
     T bz = f_mul(beta, zc);
     T f1 = f_red(f_add(f_add(a_z, bz), gamma)), f2 = f_red(f_add(f_fma(bz, f_const(2.f, tag), b_z), gamma)),

@@ -21,8 +21,10 @@ std::mutex g_err_mutex;
 void set_global_error(const std::string& e) { std::lock_guard<std::mutex> l(g_err_mutex); g_last_error = e; }
 }  // namespace
 
-static constexpr size_t kChunk = (size_t)1 << 21;   // items per staged chunk of the host-pointer entry points
-static constexpr int kSlots = 2;                    // double buffering: copy of chunk k+1 overlaps compute of chunk k
+// Host-pointer entry points: the batch is cut into chunks that cycle through kSlots staging buffers, each with its own
+// stream, so the H2D copy of chunk k+2, the kernel of chunk k+1 and the D2H copy of chunk k overlap (PCIe is full duplex).
+static constexpr size_t kChunk = (size_t)1 << 18;   // items per staged chunk (14 MB of planes per slot)
+static constexpr int kSlots = 4;
 
 struct pbh_ctx {
   int device = 0;
@@ -35,8 +37,8 @@ struct pbh_ctx {
   Tables* d_tables = nullptr;
   uint8_t* d_wtab = nullptr;
   cudaStream_t compute = nullptr;          // `_dev` entry points
-  cudaStream_t slot_stream[kSlots] = {nullptr, nullptr};
-  uint8_t* slot_buf[kSlots] = {nullptr, nullptr};
+  cudaStream_t slot_stream[kSlots] = {};
+  uint8_t* slot_buf[kSlots] = {};
   size_t slot_bytes = 0;
   uint64_t launches = 0;
   std::string last_error;

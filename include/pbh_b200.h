@@ -128,6 +128,8 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 /* PBH_OPT_TMA: stage 256-item tiles through shared memory with TMA bulk tensor copies (1, default; used when every
  * base pointer and pitch is a multiple of 16 bytes) or use plain per-thread loads and stores (0). */
 #define PBH_OPT_TMA 3
+/* PBH_OPT_CHUNK_LOG2: log2 of the items per staged chunk of the host-pointer entry points (8..20, default 17). */
+#define PBH_OPT_CHUNK_LOG2 4
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */
@@ -161,6 +163,14 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
                      size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
 int pbh_verify_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
                          size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
+
+/* Extension (no counterpart in the reference): Plonk::prove followed by Plonk::verify of the fresh proofs with
+ * challenge `chal` and rand[0] = u, host pointers.  Same bytes as pbh_prove_batch + pbh_verify_batch, but a proof
+ * produced on the device does not cross PCIe twice.  Items whose status != PBH_ST_OK have a zeroed proof, for which
+ * verify answers PBH_VR_NOT_ON_CURVE. */
+int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand,
+                           size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, const uint8_t* u, uint8_t* proof,
+                           size_t proof_pitch, uint8_t* status, uint8_t* result);
 
 /* ---- sweep kernels (the per-kernel configs of BASELINE.json), HOST or DEVICE pointers --------- */
 /* `on_device` != 0: pointers are device pointers, kernels are only enqueued.                      */

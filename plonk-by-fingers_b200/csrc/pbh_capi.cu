@@ -23,7 +23,7 @@ void set_global_error(const std::string& e) { std::lock_guard<std::mutex> l(g_er
 
 // Host-pointer entry points: the batch is cut into chunks that cycle through kSlots staging buffers, each with its own
 // stream, so the H2D copy of chunk k+2, the kernel of chunk k+1 and the D2H copy of chunk k overlap (PCIe is full duplex).
-static constexpr size_t kChunk = (size_t)1 << 18;   // items per staged chunk (14 MB of planes per slot)
+static constexpr size_t kChunkMax = (size_t)1 << 20;   // upper bound of the staged chunk (staging buffers are sized for it lazily)
 static constexpr int kSlots = 4;
 
 struct pbh_ctx {
@@ -31,6 +31,7 @@ struct pbh_ctx {
   int sm_count = 148;
   int algo = PBH_ALGO_TABLE;
   int prover_variant = 0;
+  size_t chunk = (size_t)1 << 17;          // items per staged chunk of the host-pointer entry points (PBH_OPT_CHUNK_LOG2)
   int use_tma = 1;                         // TMA-staged tiles when base/pitch alignment allows (PBH_OPT_TMA)
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;
@@ -164,6 +165,11 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
   if (option == PBH_OPT_PROVER_FP32) { ctx->prover_fp32 = value != 0; return PBH_OK; }
   if (option == PBH_OPT_PROVER_LAUNCH_SHAPE) { ctx->prover_variant = value; return PBH_OK; }
   if (option == PBH_OPT_TMA) { ctx->use_tma = value != 0; return PBH_OK; }
+  if (option == PBH_OPT_CHUNK_LOG2) {
+    if (value < 8 || value > 20) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "chunk log2 must be in [8, 20]");
+    ctx->chunk = (size_t)1 << value;
+    return PBH_OK;
+  }
   return fail(ctx, PBH_ERR_BAD_ARGUMENT, "unknown option");
 }
 int pbh_ctx_device(const pbh_ctx* ctx) { return ctx ? ctx->device : PBH_ERR_BAD_ARGUMENT; }
@@ -310,7 +316,7 @@ int pbh_verify_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t pr
 
 // ---- host-pointer entry points: chunked, double-buffered H2D -> kernel -> D2H ----------------------------
 static int ensure_slots(pbh_ctx* ctx, size_t bytes_per_item) {
-  size_t need = bytes_per_item * kChunk;
+  size_t need = bytes_per_item * ctx->chunk;
   if (ctx->slot_bytes >= need) return PBH_OK;
   for (int s = 0; s < kSlots; s++) {
     if (ctx->slot_buf[s]) { CUDA_TRY(ctx, cudaFree(ctx->slot_buf[s])); ctx->slot_buf[s] = nullptr; }
@@ -328,23 +334,23 @@ int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch
   if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 26 + 28);
+  int rc = ensure_slots(ctx, 64);
   if (rc) return rc;
+  const size_t C = ctx->chunk;
   size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += kChunk, k++) {
-    size_t m = std::min(kChunk, n - lo);
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    size_t m = std::min(C, n - lo);
     int s = (int)(k % kSlots);
     cudaStream_t st = ctx->slot_stream[s];
     uint8_t* base = ctx->slot_buf[s];
-    uint8_t *d_wit = base, *d_rnd = base + 12 * kChunk, *d_chal = base + 21 * kChunk, *d_proof = base + 26 * kChunk,
-            *d_status = base + 53 * kChunk;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, kChunk, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, kChunk, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, kChunk, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
-    ProveArgs A{d_wit, kChunk, d_rnd, kChunk, d_chal, kChunk, d_proof, kChunk, d_status, m};
+    uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
+    ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
     rc = launch_prove(ctx, st, A);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, kChunk, m, 27, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
@@ -358,24 +364,63 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
   if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 26 + 28);   // one slot size for both directions: 33 + 1 + 4 <= 54
+  int rc = ensure_slots(ctx, 64);
   if (rc) return rc;
+  const size_t C = ctx->chunk;
   size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += kChunk, k++) {
-    size_t m = std::min(kChunk, n - lo);
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    size_t m = std::min(C, n - lo);
     int s = (int)(k % kSlots);
     cudaStream_t st = ctx->slot_stream[s];
     uint8_t* base = ctx->slot_buf[s];
-    uint8_t *d_proof = base, *d_chal = base + 27 * kChunk, *d_u = base + 32 * kChunk, *d_res = base + 33 * kChunk,
-            *d_gt = base + 34 * kChunk;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, kChunk, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, kChunk, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
+    uint8_t *d_proof = base, *d_chal = base + 27 * C, *d_u = base + 32 * C, *d_res = base + 33 * C, *d_gt = base + 34 * C;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
-    VerifyArgs A{d_proof, kChunk, d_chal, kChunk, d_u, d_res, gt ? d_gt : nullptr, kChunk, m};
+    VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, gt ? d_gt : nullptr, C, m};
     rc = launch_verify(ctx, st, A);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
-    if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, kChunk, m, 4, cudaMemcpyDeviceToHost, st));
+    if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, C, m, 4, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
+// prove then verify without the proof leaving the device in between: per chunk, H2D inputs -> prove kernel -> verify
+// kernel -> D2H proof + status + result
+int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
+                           const uint8_t* chal, size_t chal_pitch, const uint8_t* u, uint8_t* proof, size_t proof_pitch,
+                           uint8_t* status, uint8_t* result) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !chal || !u || !proof || !status || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_slots(ctx, 64);
+  if (rc) return rc;
+  const size_t C = ctx->chunk;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    size_t m = std::min(C, n - lo);
+    int s = (int)(k % kSlots);
+    cudaStream_t st = ctx->slot_stream[s];
+    uint8_t* base = ctx->slot_buf[s];
+    uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C,
+            *d_u = base + 54 * C, *d_res = base + 55 * C;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
+    ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
+    rc = launch_prove(ctx, st, A);
+    if (rc) return rc;
+    VerifyArgs V{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m};
+    rc = launch_verify(ctx, st, V);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
   return PBH_OK;

@@ -26,7 +26,7 @@ u16p = C.POINTER(C.c_uint16)
 ST_OK, ST_UNSATISFIED, ST_ACC_DIV0, ST_T_REMAINDER, ST_T_SLICE, ST_SRS_OOB, ST_BAD_ENCODING = 0, 1, 2, 3, 4, 5, 32
 VR_ACCEPT, VR_REJECT_PAIRING, VR_NOT_ON_CURVE, VR_NOT_IN_FIELD, VR_PANIC_ZH0, VR_BAD_ENCODING = 1, 0, 2, 4, 0x10, 0x20
 ALGO_ARITH, ALGO_TABLE = 0, 1
-OPT_PROVER_FP32, OPT_PROVER_LAUNCH_SHAPE, OPT_TMA = 1, 2, 3
+OPT_PROVER_FP32, OPT_PROVER_LAUNCH_SHAPE, OPT_TMA, OPT_CHUNK_LOG2 = 1, 2, 3, 4
 DIST_UNIFORM, DIST_FULLPATH = 0, 1
 ERR = {0: "PBH_OK", -1: "PBH_ERR_BAD_ARGUMENT", -2: "PBH_ERR_SETUP_PANIC", -3: "PBH_ERR_CUDA", -4: "PBH_ERR_NO_DEVICE",
        -5: "PBH_ERR_UNSUPPORTED"}
@@ -41,7 +41,7 @@ PANIC_MESSAGES = {
 
 EXPORTS = """pbh_circuit_pbh_test pbh_ctx_create pbh_ctx_destroy pbh_last_error pbh_ctx_set_algo pbh_ctx_get_algo pbh_ctx_set_option
 pbh_ctx_device pbh_ctx_sync pbh_ctx_stream pbh_ctx_launch_count pbh_ctx_get_srs pbh_ctx_get_verifier_constants
-pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_ntt4_batch pbh_intt4_batch
+pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_prove_verify_batch pbh_ntt4_batch pbh_intt4_batch
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
 pbh_measure_int32_peak""".split()
@@ -272,6 +272,22 @@ class Context:
         self._check(rc, fn.__name__)
         res = Rs.arr.reshape(-1)
         return (res, G.arr) if G else res
+
+    def prove_verify_batch(self, wit, rand, chal, u, proof=None, status=None, result=None):
+        """Host arrays only: prove, then verify the fresh proofs, with the proofs staying on the device in between."""
+        W = _Planes(wit, 12, name="wit"); n = W.n
+        R = _Planes(rand, 9, n, "rand"); Ch = _Planes(chal, 5, n, "chal"); U = _Planes(u, 1, n, "u")
+        if W.dev or R.dev or Ch.dev or U.dev:
+            raise PbhError("prove_verify_batch takes host arrays")
+        proof = np.empty((27, n), dtype=np.uint8) if proof is None else proof
+        status = np.empty((n,), dtype=np.uint8) if status is None else status
+        result = np.empty((n,), dtype=np.uint8) if result is None else result
+        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status"); Rs = _Planes(result, 1, n, "result")
+        rc = self.lib.pbh_prove_verify_batch(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr),
+                                             C.c_size_t(R.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(U.ptr),
+                                             C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr), C.c_void_p(Rs.ptr))
+        self._check(rc, "pbh_prove_verify_batch")
+        return P.arr, S.arr.reshape(-1), Rs.arr.reshape(-1)
 
     # ---- sweep kernels ----
     def _sweep(self, fn, arr, pin, pout, *pre):

@@ -476,6 +476,24 @@ def test_tma_tiles_ragged_and_aligned(gpu_ctx, oracle, n):
     assert bool((P[:, n:] == 0xAB).all()) and bool((S[n:] == 0xAB).all())
 
 
+@pytest.mark.parametrize("chunk_log2", (8, 12, 17))
+def test_host_pipeline_chunks_and_fused_call(product_lib, oracle, chunk_log2):
+    """Host-pointer entry points with several chunk sizes (many chunks cycling through the staging slots), and the fused
+    prove+verify extension: same bytes as the two separate calls and as the oracle."""
+    import pbh_b200
+    n = 70000 + 3
+    wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=chunk_log2, dist=0, threads=8)
+    po, so = oracle.prove_batch(wo, ro, co, threads=8)
+    vo = oracle.verify_batch(po, co, uo, threads=8, want_gt=False)
+    with pbh_b200.Context(device=0) as ctx:
+        ctx.set_option(pbh_b200.OPT_CHUNK_LOG2, chunk_log2)
+        p, s = ctx.prove_batch(wo, ro, co)
+        v = ctx.verify_batch(po, co, uo)
+        assert np.array_equal(p, po) and np.array_equal(s, so) and np.array_equal(v, vo)
+        p2, s2, v2 = ctx.prove_verify_batch(wo, ro, co, uo)
+        assert np.array_equal(p2, po) and np.array_equal(s2, so) and np.array_equal(v2, vo)
+
+
 def test_shard_summaries(gpu_ctx, oracle):
     """Verdict bitmaps and additive digests: identical whatever the shard count."""
     import torch

@@ -128,7 +128,7 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 /* PBH_OPT_TMA: stage 256-item tiles through shared memory with TMA bulk tensor copies (1, default; used when every
  * base pointer and pitch is a multiple of 16 bytes) or use plain per-thread loads and stores (0). */
 #define PBH_OPT_TMA 3
-/* PBH_OPT_CHUNK_LOG2: log2 of the items per staged chunk of the host-pointer entry points (8..20, default 17). */
+/* PBH_OPT_CHUNK_LOG2: log2 of the items per staged chunk of the host-pointer entry points (8..20, default 18: measured best on PCIe Gen5). */
 #define PBH_OPT_CHUNK_LOG2 4
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);

@@ -31,7 +31,7 @@ struct pbh_ctx {
   int sm_count = 148;
   int algo = PBH_ALGO_TABLE;
   int prover_variant = 0;
-  size_t chunk = (size_t)1 << 17;          // items per staged chunk of the host-pointer entry points (PBH_OPT_CHUNK_LOG2)
+  size_t chunk = (size_t)1 << 18;          // items per staged chunk of the host-pointer entry points (PBH_OPT_CHUNK_LOG2)
   int use_tma = 1;                         // TMA-staged tiles when base/pitch alignment allows (PBH_OPT_TMA)
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;

@@ -7,7 +7,7 @@
 
 A step is one pass of the hot path over one batch: prove 2^20 D_fullpath witnesses per GPU (configs[1] of
 BASELINE.json), verify the 2^20 proofs, pack the verdict bitmap and digest the proof bytes; with N > 1 every rank
-does that on its own shard and the bitmaps + digests are all-gathered over NCCL (the only collective, overlapped
+does that on its own shard (digest fused into the prover, bitmap into the verifier) and the bitmaps + digests are all-gathered over NCCL (the only collective, overlapped
 with the next step).  `value` counts proof+verify pairs per second over all ranks with inputs resident in HBM;
 `e2e` is the same work through the host-pointer C-ABI calls (pinned host buffers, H2D and D2H inside the timed
 region).  Inputs rotate through a ring of distinct batches larger than L2.
@@ -181,15 +181,13 @@ def main():
     ctx.sync()
     torch.cuda.synchronize()
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    KERNELS_PER_STEP = 4   # prove, verify, pack_verdicts, digest (+ one 8-byte memset node)
+    KERNELS_PER_STEP = 2   # prover (+ fused proof digest), verifier (+ fused verdict bitmap); plus one 8-byte memset node
 
     def kernels(slot):
         w, rd, c, u, first = ins[slot]
         o = outs[slot]
-        ctx.prove_batch(w, rd, c, proof=o["proof"], status=o["status"])
-        ctx.verify_batch(o["proof"], c, u, result=o["result"])
-        ctx.pack_verdicts(o["result"], out=o["bitmap"])
-        ctx.digest(o["proof"], first_index=first, out=o["digest"])
+        ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["digest"], first_index=first)
+        ctx.verify_bitmap_batch(o["proof"], c, u, o["result"], o["bitmap"])
 
     # one CUDA graph per ring slot: the step is four short kernels, so direct launches from Python are launch-bound
     graphs, launch_mode = None, "direct"
@@ -275,7 +273,10 @@ def main():
     reps = max(10, min(args.steps, 100))
     prove_ms = time_kernel(lambda s_: ctx.prove_batch(ins[s_][0], ins[s_][1], ins[s_][2], proof=outs[s_]["proof"], status=outs[s_]["status"]), reps)
     verify_ms = time_kernel(lambda s_: ctx.verify_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], result=outs[s_]["result"]), reps)
-    digest_ms = time_kernel(lambda s_: ctx.digest(outs[s_]["proof"], first_index=ins[s_][4], out=outs[s_]["digest"]), reps)
+    prove_digest_ms = time_kernel(lambda s_: ctx.prove_digest_batch(ins[s_][0], ins[s_][1], ins[s_][2], outs[s_]["proof"], outs[s_]["status"],
+                                                                    outs[s_]["digest"], first_index=ins[s_][4]), reps)
+    verify_bitmap_ms = time_kernel(lambda s_: ctx.verify_bitmap_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], outs[s_]["result"],
+                                                                      outs[s_]["bitmap"]), reps)
     clocks = sampler.stop()
 
     # ---- sanity inside the bench: every timed item proved (status 0) and reached the pairing check
@@ -376,7 +377,8 @@ def main():
                      "algorithmic_bytes_per_item": 54 if dominant == "prove_kernel" else 34},
         "launch": launch_mode,
         "kernels": {"how": "each kernel alone, back to back over the ring, CUDA events on the context's stream",
-                    "prove_ms": prove_ms, "verify_ms": verify_ms, "digest_ms": digest_ms, "proofs_per_s_per_gpu": n / (prove_ms * 1e-3),
+                    "prove_ms": prove_ms, "verify_ms": verify_ms, "prove_with_digest_ms": prove_digest_ms,
+                    "verify_with_bitmap_ms": verify_bitmap_ms, "proofs_per_s_per_gpu": n / (prove_ms * 1e-3),
                     "verifies_per_s_per_gpu": n / (verify_ms * 1e-3), "prove_GBps": prove_gbs, "verify_GBps": verify_gbs,
                     "prove_hbm_frac": prove_gbs / peak, "verify_hbm_frac": verify_gbs / peak},
         "int32_peak": int32,

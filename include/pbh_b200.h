@@ -217,11 +217,22 @@ int pbh_pairing_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch
 /* ---- shard summaries for the multi-GPU gather ---------------------------------- */
 /* Pack bit 0 of each result byte into a bitmap (item i -> bit i%8 of byte i/8), device pointers.  */
 int pbh_pack_verdicts_dev(pbh_ctx* ctx, size_t n, const uint8_t* result, uint8_t* bitmap);
-/* 64-bit digest of `planes` byte planes of n items starting at global item index `first_index`: the sum over items
- * (mod 2^64) of splitmix64(fnv(global_index, the item's bytes packed four planes per little-endian 32-bit word)), so
- * digests of disjoint shards add up to the digest of the whole batch.  out: one uint64 (device). */
+/* 64-bit digest of `planes` byte planes of n items starting at global item index `first_index`.  Per item: the bytes
+ * are packed four planes per little-endian 32-bit word and mixed into two 32-bit lanes seeded with the global index
+ * (murmur3-style multiply/rotate rounds, murmur3 finaliser); the batch digest is the sum of the 64-bit item values
+ * modulo 2^64, so digests of disjoint shards add up to the digest of the whole batch.  out: one uint64 (device). */
 int pbh_digest_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint32_t planes, const uint8_t* data, size_t pitch,
                    uint64_t* out);
+
+/* Fused variants for the multi-GPU summaries (device pointers).  Same results as the plain entry points followed by
+ * pbh_digest_dev(proof) / pbh_pack_verdicts_dev(result); the prover adds the digest of its 27 proof planes while the
+ * bytes are still in registers and the verifier packs the verdict bits with a warp ballot.
+ *   digest: one uint64, overwritten; bitmap: ceil(n/8) bytes, 4-byte aligned. */
+int pbh_prove_digest_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand,
+                               size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch,
+                               uint8_t* status, uint64_t first_index, uint64_t* digest);
+int pbh_verify_bitmap_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                                size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* bitmap);
 
 /* ---- synthetic inputs, device pointers ------------------------------------------ */
 #define PBH_DIST_UNIFORM 0   /* attempt k = 0 only: exercises every status class                    */

@@ -611,16 +611,20 @@ int oracle_generate_inputs(const void* circuit, uint8_t s, uint32_t srs_n, uint8
   return 0;
 }
 
+static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static inline uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
 uint64_t oracle_digest(size_t n, uint64_t first_index, uint32_t planes, const uint8_t* data, size_t pitch) {
   uint64_t acc = 0;
   for (size_t i = 0; i < n; i++) {
-    uint64_t h = (first_index + i) * 0x9E3779B97F4A7C15ull + planes;
+    uint64_t idx = first_index + i;
+    uint32_t a = (uint32_t)idx * 0x9E3779B1u + planes, b = (uint32_t)(idx >> 32) * 0x85EBCA77u + 0x27D4EB2Fu;
     for (uint32_t k = 0; k < planes; k += 4) {
       uint32_t wv = 0;
-      for (uint32_t b = 0; b < 4 && k + b < planes; b++) wv |= (uint32_t)data[(size_t)(k + b) * pitch + i] << (8 * b);
-      h = (h ^ wv) * 0x100000001B3ull;
+      for (uint32_t bb = 0; bb < 4 && k + bb < planes; bb++) wv |= (uint32_t)data[(size_t)(k + bb) * pitch + i] << (8 * bb);
+      a = rotl32((a ^ wv) * 0xCC9E2D51u, 15);
+      b = rotl32((b + wv) * 0x1B873593u, 13) ^ a;
     }
-    acc += splitmix64(h);
+    acc += ((uint64_t)fmix32(a ^ rotl32(b, 16)) << 32) | fmix32(b + a);
   }
   return acc;
 }

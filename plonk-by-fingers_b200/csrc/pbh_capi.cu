@@ -234,7 +234,18 @@ static bool make_plane_map(CUtensorMap* map, const void* base, size_t n, size_t 
 }
 
 // ---- device-pointer entry points -----------------------------------------------------------------------
-static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
+static int launch_digest(pbh_ctx* ctx, cudaStream_t st, size_t n, uint64_t first_index, uint32_t planes, const uint8_t* data,
+                         size_t pitch, uint64_t* out) {
+  const bool vec_ok = ((uintptr_t)data % 4 == 0) && (pitch % 4 == 0);
+  digest_kernel<<<grid_for(ctx, vec_ok ? (n + 3) / 4 : n, 8), kBlock, 0, st>>>(n, first_index, planes, data, pitch,
+                                                                             (unsigned long long*)out, vec_ok);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+
+// digest (nullable): device uint64, already zeroed on `st`; receives the digest of the 27 proof planes
+static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint64_t first_index = 0, uint64_t* digest = nullptr) {
   if (A.n == 0) return PBH_OK;
   if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32 && ctx->use_tma) {
     ProveTmaMaps M;
@@ -242,7 +253,8 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
         make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) && make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27)) {
       size_t tiles = (A.n + kTile - 1) / kTile;
       int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2);   // persistent: two resident blocks per SM
-      prove_f32_tma_kernel<<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n);
+      prove_f32_tma_kernel<<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n,
+                                                   first_index, (unsigned long long*)digest);
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
       return PBH_OK;
@@ -263,10 +275,14 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A) {
   else prove_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
+  if (digest) return launch_digest(ctx, st, A.n, first_index, 27, A.proof, A.proof_pitch, digest);   // not fused on this path
   return PBH_OK;
 }
-static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A) {
-  if (A.n == 0) return PBH_OK;
+static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) {
+  if (A_in.n == 0) return PBH_OK;
+  VerifyArgs A = A_in;
+  uint8_t* bitmap_later = nullptr;
+  if (A.bitmap && (((uintptr_t)A.bitmap % 4) != 0)) { bitmap_later = A.bitmap; A.bitmap = nullptr; }
   if (ctx->use_tma) {
     VerifyTmaMaps M;
     if (make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27) && make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) &&
@@ -281,14 +297,25 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A) {
       }
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
+      if (bitmap_later) {
+        pack_verdicts_kernel<<<grid_for(ctx, (A.n + 7) / 8, 8), kBlock, 0, st>>>(A.n, A.result, bitmap_later);
+        ctx->launches++;
+        CUDA_TRY(ctx, cudaGetLastError());
+      }
       return PBH_OK;
     }
   }
+  if (A.bitmap) { bitmap_later = A.bitmap; A.bitmap = nullptr; }   // the plain kernels do not pack
   int grid = grid_for(ctx, A.n, 8);
   if (ctx->algo == PBH_ALGO_TABLE) verify_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   else verify_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
+  if (bitmap_later) {
+    pack_verdicts_kernel<<<grid_for(ctx, (A.n + 7) / 8, 8), kBlock, 0, st>>>(A.n, A.result, bitmap_later);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+  }
   return PBH_OK;
 }
 
@@ -310,7 +337,32 @@ int pbh_verify_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t pr
   if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  VerifyArgs A{proof, proof_pitch, chal, chal_pitch, u, result, gt, gt_pitch, n};
+  VerifyArgs A{proof, proof_pitch, chal, chal_pitch, u, result, gt, gt_pitch, n, nullptr};
+  return launch_verify(ctx, ctx->compute, A);
+}
+
+int pbh_prove_digest_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
+                               const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status,
+                               uint64_t first_index, uint64_t* digest) {
+  CTX_CHECK(ctx);
+  if (!digest) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaMemsetAsync(digest, 0, sizeof(uint64_t), ctx->compute));
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  ProveArgs A{wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, proof, proof_pitch, status, n};
+  return launch_prove(ctx, ctx->compute, A, first_index, digest);
+}
+
+int pbh_verify_bitmap_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                                size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* bitmap) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proof || !chal || !u || !result || !bitmap) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (proof_pitch < n || chal_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  VerifyArgs A{proof, proof_pitch, chal, chal_pitch, u, result, nullptr, 0, n, bitmap};
   return launch_verify(ctx, ctx->compute, A);
 }
 
@@ -377,7 +429,7 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
-    VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, gt ? d_gt : nullptr, C, m};
+    VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, gt ? d_gt : nullptr, C, m, nullptr};
     rc = launch_verify(ctx, st, A);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
@@ -415,7 +467,7 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
     ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
     rc = launch_prove(ctx, st, A);
     if (rc) return rc;
-    VerifyArgs V{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m};
+    VerifyArgs V{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
     rc = launch_verify(ctx, st, V);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
@@ -632,11 +684,7 @@ int pbh_digest_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint32_t planes
   CUDA_TRY(ctx, cudaMemsetAsync(out, 0, sizeof(uint64_t), ctx->compute));
   if (n == 0) return PBH_OK;
   if (!data || pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
-  const bool vec_ok = ((uintptr_t)data % 4 == 0) && (pitch % 4 == 0);
-  digest_kernel<<<grid_for(ctx, vec_ok ? (n + 3) / 4 : n, 8), kBlock, 0, ctx->compute>>>(n, first_index, planes, data, pitch,
-                                                                                      (unsigned long long*)out, vec_ok);
-  SWEEP_FINISH(ctx);
-  return PBH_OK;
+  return launch_digest(ctx, ctx->compute, n, first_index, planes, data, pitch, out);
 }
 
 int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64_t seed, int dist, uint8_t* wit, size_t wit_pitch,

@@ -26,6 +26,30 @@ __device__ __forceinline__ void stage_tables(Tables& sT, const Tables* __restric
   __syncthreads();
 }
 
+// Digest of one item (include/pbh_b200.h): two 32-bit lanes, murmur3-style rounds over the item's bytes packed four
+// planes per word, murmur3 finaliser.  32-bit multiplies only: cheap on the integer pipes.
+struct DigestState { uint32_t a, b; };
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+__device__ __forceinline__ uint32_t fmix32(uint32_t h) { h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h; }
+__device__ __forceinline__ DigestState digest_item_begin(uint64_t index, uint32_t planes) {
+  DigestState d;
+  d.a = (uint32_t)index * 0x9E3779B1u + planes;
+  d.b = (uint32_t)(index >> 32) * 0x85EBCA77u + 0x27D4EB2Fu;
+  return d;
+}
+__device__ __forceinline__ void digest_item_word(DigestState& d, uint32_t wv) {
+  d.a = rotl32((d.a ^ wv) * 0xCC9E2D51u, 15);
+  d.b = rotl32((d.b + wv) * 0x1B873593u, 13) ^ d.a;
+}
+__device__ __forceinline__ unsigned long long digest_item_end(const DigestState& d) {
+  return ((unsigned long long)fmix32(d.a ^ rotl32(d.b, 16)) << 32) | fmix32(d.b + d.a);
+}
+// warp-reduce and add a per-thread partial sum into *out (one atomic per warp)
+__device__ __forceinline__ void digest_flush(unsigned long long acc, unsigned long long* out) {
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 struct ProveArgs {
   const uint8_t* wit; size_t wit_pitch;
   const uint8_t* rnd; size_t rand_pitch;
@@ -131,8 +155,10 @@ struct ProveTmaSmem {
 
 __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_constant__ ProveTmaMaps M, const Consts K, const ConstsF KF,
                                                                   const Tables* __restrict__ gT, uint8_t* __restrict__ proof_out,
-                                                                  size_t proof_pitch, uint8_t* __restrict__ status_out, size_t n) {
+                                                                  size_t proof_pitch, uint8_t* __restrict__ status_out, size_t n,
+                                                                  uint64_t first_index, unsigned long long* __restrict__ digest_out) {
   __shared__ ProveTmaSmem S;
+  unsigned long long digest_acc = 0;
   const int tid = threadIdx.x;
   stage_tables(S.T, gT);
   if (tid == 0) {
@@ -199,6 +225,23 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     for (int k = 0; k < 7; k++) out[(20 + k) * kTile] = (uint8_t)(ok ? P.ev[k] : 0u);
     const size_t i = tile * kTile + tid;
     if (i < n) status_out[i] = (uint8_t)status;
+    if (digest_out != nullptr && i < n) {
+      // digest of this item's 27 proof bytes (pbh_digest_dev's definition), from registers: planes 4k..4k+3 per word
+      uint32_t pp[9], ee[7];
+#pragma unroll
+      for (int k = 0; k < 9; k++) pp[k] = ok ? (P.pt[k] & 0xFFFFu) : 0u;
+#pragma unroll
+      for (int k = 0; k < 7; k++) ee[k] = ok ? P.ev[k] : 0u;
+      DigestState d = digest_item_begin(first_index + i, 27);
+      digest_item_word(d, pp[0] | (pp[1] << 16));
+      digest_item_word(d, pp[2] | (pp[3] << 16));
+      digest_item_word(d, pp[4] | (pp[5] << 16));
+      digest_item_word(d, pp[6] | (pp[7] << 16));
+      digest_item_word(d, pp[8] | (inf_lo << 16) | (inf_hi << 24));
+      digest_item_word(d, ee[0] | (ee[1] << 8) | (ee[2] << 16) | (ee[3] << 24));
+      digest_item_word(d, ee[4] | (ee[5] << 8) | (ee[6] << 16));
+      digest_acc += digest_item_end(d);
+    }
 
     // TMA clips the item dimension at 16-byte granularity (measured), so a partial last tile whose end is not 16-byte
     // aligned is written with plain stores instead
@@ -218,6 +261,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     }
   }
   if (tid == 0) tma::store_wait_all();
+  if (digest_out != nullptr) digest_flush(digest_acc, digest_out);   // one atomic per warp per launch
 }
 
 struct VerifyArgs {
@@ -227,6 +271,7 @@ struct VerifyArgs {
   uint8_t* result;
   uint8_t* gt; size_t gt_pitch;   // nullable
   size_t n;
+  uint8_t* bitmap;                // nullable, 4-byte aligned: verdict bit of item i -> bit i%8 of byte i/8 (TMA kernel only)
 };
 
 // Plonk::verify, src/plonk.rs:468-650
@@ -311,6 +356,18 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
       if (A.gt) {
         A.gt[i] = (uint8_t)e1.a; A.gt[A.gt_pitch + i] = (uint8_t)e1.b;
         A.gt[2 * A.gt_pitch + i] = (uint8_t)e2.a; A.gt[3 * A.gt_pitch + i] = (uint8_t)e2.b;
+      }
+    }
+    if (A.bitmap != nullptr) {
+      // 32 consecutive items per warp: the ballot word is four bitmap bytes (little endian)
+      const uint32_t bits = __ballot_sync(0xFFFFFFFFu, i < A.n && (res & 1u));
+      const size_t w0 = i - (tid & 31);             // first item of this warp
+      if ((tid & 31) == 0 && w0 < A.n) {
+        if (w0 + 32 <= A.n) {
+          *reinterpret_cast<uint32_t*>(A.bitmap + w0 / 8) = bits;
+        } else {
+          for (size_t b = 0; b < (A.n - w0 + 7) / 8; b++) A.bitmap[w0 / 8 + b] = (uint8_t)(bits >> (8 * b));
+        }
       }
     }
     __syncthreads();   // every thread has read in[stage]; it may be refilled by the prefetch of the iteration after next
@@ -528,9 +585,6 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 // Digest of one item: FNV-1a-style 64-bit mixing over the item's bytes packed four planes per 32-bit word, seeded
 // with the global item index, finished with splitmix64.  The batch digest is the sum over items modulo 2^64, so
 // digests of disjoint shards add up to the digest of the whole batch.
-__device__ __forceinline__ uint64_t digest_item_begin(uint64_t index, uint32_t planes) { return index * 0x9E3779B97F4A7C15ull + planes; }
-__device__ __forceinline__ uint64_t digest_item_word(uint64_t h, uint32_t wv) { return (h ^ wv) * 0x100000001B3ull; }
-
 // vec_ok: data and pitch are 4-byte aligned, so a thread takes four consecutive items through one 32-bit word per
 // plane (128-byte warp transactions, four independent loads in flight) and transposes 4x4 bytes with PRMT.
 __global__ void __launch_bounds__(kBlock) digest_kernel(size_t n, uint64_t first_index, uint32_t planes,
@@ -540,8 +594,8 @@ __global__ void __launch_bounds__(kBlock) digest_kernel(size_t n, uint64_t first
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t n4 = vec_ok ? n / 4 : 0;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
-    uint64_t h0 = digest_item_begin(first_index + 4 * q, planes), h1 = digest_item_begin(first_index + 4 * q + 1, planes),
-             h2 = digest_item_begin(first_index + 4 * q + 2, planes), h3 = digest_item_begin(first_index + 4 * q + 3, planes);
+    DigestState h0 = digest_item_begin(first_index + 4 * q, planes), h1 = digest_item_begin(first_index + 4 * q + 1, planes),
+                h2 = digest_item_begin(first_index + 4 * q + 2, planes), h3 = digest_item_begin(first_index + 4 * q + 3, planes);
     for (uint32_t k = 0; k < planes; k += 4) {
       uint32_t w0 = reinterpret_cast<const uint32_t*>(data + (size_t)k * pitch)[q];
       uint32_t w1 = k + 1 < planes ? reinterpret_cast<const uint32_t*>(data + (size_t)(k + 1) * pitch)[q] : 0u;
@@ -549,24 +603,23 @@ __global__ void __launch_bounds__(kBlock) digest_kernel(size_t n, uint64_t first
       uint32_t w3 = k + 3 < planes ? reinterpret_cast<const uint32_t*>(data + (size_t)(k + 3) * pitch)[q] : 0u;
       uint32_t t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w0, w1, 0x7362);
       uint32_t t2 = __byte_perm(w2, w3, 0x5140), t3 = __byte_perm(w2, w3, 0x7362);
-      h0 = digest_item_word(h0, __byte_perm(t0, t2, 0x5410));
-      h1 = digest_item_word(h1, __byte_perm(t0, t2, 0x7632));
-      h2 = digest_item_word(h2, __byte_perm(t1, t3, 0x5410));
-      h3 = digest_item_word(h3, __byte_perm(t1, t3, 0x7632));
+      digest_item_word(h0, __byte_perm(t0, t2, 0x5410));
+      digest_item_word(h1, __byte_perm(t0, t2, 0x7632));
+      digest_item_word(h2, __byte_perm(t1, t3, 0x5410));
+      digest_item_word(h3, __byte_perm(t1, t3, 0x7632));
     }
-    acc += splitmix64(h0) + splitmix64(h1) + splitmix64(h2) + splitmix64(h3);
+    acc += digest_item_end(h0) + digest_item_end(h1) + digest_item_end(h2) + digest_item_end(h3);
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint64_t h = digest_item_begin(first_index + i, planes);
+    DigestState h = digest_item_begin(first_index + i, planes);
     for (uint32_t k = 0; k < planes; k += 4) {
       uint32_t wv = 0;
       for (uint32_t b = 0; b < 4 && k + b < planes; b++) wv |= (uint32_t)data[(size_t)(k + b) * pitch + i] << (8 * b);
-      h = digest_item_word(h, wv);
+      digest_item_word(h, wv);
     }
-    acc += splitmix64(h);
+    acc += digest_item_end(h);
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xFFFFFFFFu, acc, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+  digest_flush(acc, out);
 }
 
 // ---- synthetic inputs; mirrors oracle_generate_inputs bit for bit -----------------------

@@ -41,7 +41,7 @@ PANIC_MESSAGES = {
 
 EXPORTS = """pbh_circuit_pbh_test pbh_ctx_create pbh_ctx_destroy pbh_last_error pbh_ctx_set_algo pbh_ctx_get_algo pbh_ctx_set_option
 pbh_ctx_device pbh_ctx_sync pbh_ctx_stream pbh_ctx_launch_count pbh_ctx_get_srs pbh_ctx_get_verifier_constants
-pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_prove_verify_batch pbh_ntt4_batch pbh_intt4_batch
+pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_prove_verify_batch pbh_prove_digest_batch_dev pbh_verify_bitmap_batch_dev pbh_ntt4_batch pbh_intt4_batch
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
 pbh_measure_int32_peak""".split()
@@ -272,6 +272,32 @@ class Context:
         self._check(rc, fn.__name__)
         res = Rs.arr.reshape(-1)
         return (res, G.arr) if G else res
+
+    def prove_digest_batch(self, wit, rand, chal, proof, status, digest, first_index=0):
+        """Device tensors: prove and add the additive digest of the 27 proof planes (== digest(proof, first_index)) in
+        the same kernel.  `digest`: int64 tensor of one element."""
+        W = _Planes(wit, 12, name="wit"); n = W.n
+        R = _Planes(rand, 9, n, "rand"); Ch = _Planes(chal, 5, n, "chal")
+        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status")
+        cur = self._dev_begin()
+        rc = self.lib.pbh_prove_digest_batch_dev(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr),
+                                                 C.c_size_t(R.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(P.ptr),
+                                                 C.c_size_t(P.pitch), C.c_void_p(S.ptr), C.c_uint64(first_index),
+                                                 C.c_void_p(digest.data_ptr()))
+        self._dev_end(cur)
+        self._check(rc, "pbh_prove_digest_batch_dev")
+        return P.arr, S.arr.reshape(-1), digest
+
+    def verify_bitmap_batch(self, proof, chal, u, result, bitmap):
+        """Device tensors: verify and pack the verdict bits (== pack_verdicts(result)) in the same kernel."""
+        P = _Planes(proof, 27, name="proof"); n = P.n
+        Ch = _Planes(chal, 5, n, "chal"); U = _Planes(u, 1, n, "u"); Rs = _Planes(result, 1, n, "result")
+        cur = self._dev_begin()
+        rc = self.lib.pbh_verify_bitmap_batch_dev(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Ch.ptr),
+                                                  C.c_size_t(Ch.pitch), C.c_void_p(U.ptr), C.c_void_p(Rs.ptr), C.c_void_p(bitmap.data_ptr()))
+        self._dev_end(cur)
+        self._check(rc, "pbh_verify_bitmap_batch_dev")
+        return Rs.arr.reshape(-1), bitmap
 
     def prove_verify_batch(self, wit, rand, chal, u, proof=None, status=None, result=None):
         """Host arrays only: prove, then verify the fresh proofs, with the proofs staying on the device in between."""

@@ -53,10 +53,14 @@ def gather_summaries(bitmap, digest, n_total, world, group=None):
 def gpu_compute(ctx, first_index, count, seed=0xB200, dist_kind=1):
     """One shard on this rank's GPU: generate -> prove -> verify -> pack verdicts -> digest proofs (all CUDA)."""
     w, r, c, u = ctx.generate_inputs(count, first_index=first_index, seed=seed, dist=dist_kind)
-    proof, status = ctx.prove_batch(w, r, c)
-    result = ctx.verify_batch(proof, c, u)
-    bitmap = ctx.pack_verdicts(result)
-    digest = ctx.digest(proof, first_index=first_index)
+    import torch
+    dev = w.device
+    proof = torch.empty((27, count), dtype=torch.uint8, device=dev); status = torch.empty((count,), dtype=torch.uint8, device=dev)
+    result = torch.empty((count,), dtype=torch.uint8, device=dev)
+    bitmap = torch.empty(((count + 7) // 8 + 3) // 4 * 4, dtype=torch.uint8, device=dev)[: (count + 7) // 8]
+    digest = torch.empty((1,), dtype=torch.int64, device=dev)
+    ctx.prove_digest_batch(w, r, c, proof, status, digest, first_index=first_index)   # digest fused into the prover
+    ctx.verify_bitmap_batch(proof, c, u, result, bitmap)                              # bitmap fused into the verifier
     ctx.sync()
     return bitmap, digest
 

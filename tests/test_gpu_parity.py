@@ -494,6 +494,37 @@ def test_host_pipeline_chunks_and_fused_call(product_lib, oracle, chunk_log2):
         assert np.array_equal(p2, po) and np.array_equal(s2, so) and np.array_equal(v2, vo)
 
 
+@pytest.mark.parametrize("algo", CTXS)
+@pytest.mark.parametrize("n", (5, 1000, 65536 + 77))
+def test_fused_digest_and_bitmap(gpu_ctx, oracle, algo, n):
+    """pbh_prove_digest_batch_dev / pbh_verify_bitmap_batch_dev == plain calls + pbh_digest_dev / pbh_pack_verdicts_dev == oracle,
+    on the TMA path (aligned pitch) and on the fallback paths."""
+    import torch
+    ctx = gpu_ctx[algo]
+    dev = torch.device("cuda", 0)
+    first = 12345678901
+    for pitch in (n, (n + 15) // 16 * 16):
+        wo, ro, co, uo, _ = oracle.generate_inputs(n, first_index=first, seed=9, dist=1 if n > 100 else 0)
+        po, so = oracle.prove_batch(wo, ro, co)
+        vo = oracle.verify_batch(po, co, uo, want_gt=False)
+        mk = lambda planes, src: (lambda t: (t[:, :n].copy_(torch.from_numpy(src).to(dev)), t[:, :n])[1])(
+            torch.zeros((planes, pitch), dtype=torch.uint8, device=dev))
+        w, r, c = mk(12, wo), mk(9, ro), mk(5, co)
+        u = torch.from_numpy(uo).to(dev)
+        proof = torch.zeros((27, pitch), dtype=torch.uint8, device=dev)[:, :n]
+        status = torch.zeros((n,), dtype=torch.uint8, device=dev); result = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        digest = torch.zeros((1,), dtype=torch.int64, device=dev)
+        bitmap = torch.full(((n + 7) // 8 + 8,), 0xEE, dtype=torch.uint8, device=dev)
+        ctx.prove_digest_batch(w, r, c, proof, status, digest, first_index=first)
+        ctx.verify_bitmap_batch(proof, c, u, result, bitmap[: (n + 7) // 8])
+        ctx.sync()
+        assert np.array_equal(proof.cpu().numpy(), po) and np.array_equal(status.cpu().numpy(), so)
+        assert np.array_equal(result.cpu().numpy(), vo)
+        assert (int(digest.item()) & (2**64 - 1)) == oracle.digest(po, first_index=first)
+        assert np.array_equal(bitmap[: (n + 7) // 8].cpu().numpy(), oracle.pack_verdicts(vo))
+        assert bool((bitmap[(n + 7) // 8:] == 0xEE).all())
+
+
 def test_shard_summaries(gpu_ctx, oracle):
     """Verdict bitmaps and additive digests: identical whatever the shard count."""
     import torch

@@ -494,6 +494,19 @@ def test_host_pipeline_chunks_and_fused_call(product_lib, oracle, chunk_log2):
         assert np.array_equal(p2, po) and np.array_equal(s2, so) and np.array_equal(v2, vo)
 
 
+_FUSED_CACHE = {}
+
+
+def _fused_case(n, first):
+    if n not in _FUSED_CACHE:
+        import oracle as O
+        wo, ro, co, uo, _ = O.generate_inputs(n, first_index=first, seed=9, dist=1 if n > 100 else 0, threads=8)
+        po, so = O.prove_batch(wo, ro, co, threads=8)
+        vo = O.verify_batch(po, co, uo, threads=8, want_gt=False)
+        _FUSED_CACHE[n] = (wo, ro, co, uo, po, so, vo)
+    return _FUSED_CACHE[n]
+
+
 @pytest.mark.parametrize("algo", CTXS)
 @pytest.mark.parametrize("n", (5, 1000, 65536 + 77))
 def test_fused_digest_and_bitmap(gpu_ctx, oracle, algo, n):
@@ -503,10 +516,8 @@ def test_fused_digest_and_bitmap(gpu_ctx, oracle, algo, n):
     ctx = gpu_ctx[algo]
     dev = torch.device("cuda", 0)
     first = 12345678901
+    wo, ro, co, uo, po, so, vo = _fused_case(n, first)
     for pitch in (n, (n + 15) // 16 * 16):
-        wo, ro, co, uo, _ = oracle.generate_inputs(n, first_index=first, seed=9, dist=1 if n > 100 else 0)
-        po, so = oracle.prove_batch(wo, ro, co)
-        vo = oracle.verify_batch(po, co, uo, want_gt=False)
         mk = lambda planes, src: (lambda t: (t[:, :n].copy_(torch.from_numpy(src).to(dev)), t[:, :n])[1])(
             torch.zeros((planes, pitch), dtype=torch.uint8, device=dev))
         w, r, c = mk(12, wo), mk(9, ro), mk(5, co)

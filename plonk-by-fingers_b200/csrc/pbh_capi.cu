@@ -37,6 +37,7 @@ struct pbh_ctx {
   HostSetup hs;
   Tables* d_tables = nullptr;
   uint8_t* d_wtab = nullptr;
+  unsigned int* d_tile_counters = nullptr;   // dynamic tile scheduler: [stream index][prove, verify]
   cudaStream_t compute = nullptr;          // `_dev` entry points
   cudaStream_t slot_stream[kSlots] = {};
   uint8_t* slot_buf[kSlots] = {};
@@ -126,6 +127,7 @@ int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_
     for (int y = 0; y < 17; y++)
       for (int z = 0; z < 17; z++)
         if ((x * x + y * y) % 17 == (z * z) % 17) { wtab[3 * nw] = x; wtab[3 * nw + 1] = y; wtab[3 * nw + 2] = z; nw++; }
+  if ((ce = cudaMalloc(&ctx->d_tile_counters, (1 + kSlots) * 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc(counters)", ce);
   if ((ce = cudaMalloc(&ctx->d_wtab, sizeof(wtab))) != cudaSuccess) return bail("cudaMalloc(wtab)", ce);
   if ((ce = cudaMemcpy(ctx->d_wtab, wtab, sizeof(wtab), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(wtab)", ce);
   *out = ctx;
@@ -142,6 +144,7 @@ void pbh_ctx_destroy(pbh_ctx* ctx) {
   if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_wtab) cudaFree(ctx->d_wtab);
+  if (ctx->d_tile_counters) cudaFree(ctx->d_tile_counters);
   delete ctx;
 }
 
@@ -205,6 +208,16 @@ int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
   return PBH_OK;
 }
 
+// the tile counter of the launch about to be enqueued on `st` (one pair per stream, so concurrent streams never share),
+// zeroed on that stream
+static unsigned int* fresh_tile_counter(pbh_ctx* ctx, cudaStream_t st, int which) {
+  int idx = 0;
+  for (int s = 0; s < kSlots; s++) if (st == ctx->slot_stream[s]) idx = 1 + s;
+  unsigned int* c = ctx->d_tile_counters + idx * 2 + which;
+  cudaMemsetAsync(c, 0, sizeof(unsigned int), st);
+  return c;
+}
+
 // ---- TMA tensor maps --------------------------------------------------------------------------------------------
 // cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime so that the library does not
 // link against libcuda directly.
@@ -254,7 +267,7 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint6
       size_t tiles = (A.n + kTile - 1) / kTile;
       int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2);   // persistent: two resident blocks per SM
       prove_f32_tma_kernel<<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n,
-                                                   first_index, (unsigned long long*)digest);
+                                                   first_index, (unsigned long long*)digest, fresh_tile_counter(ctx, st, 0));
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
       return PBH_OK;
@@ -290,10 +303,10 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
       size_t tiles = (A.n + kTile - 1) / kTile;
       if (ctx->algo == PBH_ALGO_TABLE) {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 4);
-        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A);
+        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A, fresh_tile_counter(ctx, st, 1));
       } else {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 3);
-        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A);
+        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A, fresh_tile_counter(ctx, st, 1));
       }
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());

@@ -150,13 +150,15 @@ struct ProveTmaSmem {
   alignas(128) uint8_t in[2][26][kTile];    // planes 0..11 witness, 12..20 blinders, 21..25 challenges
   alignas(128) uint8_t out[2][27][kTile];
   alignas(8) uint64_t full[2];
+  uint32_t tile_of_stage[2];                // dynamic tile scheduler: tile index staged in each buffer
   Tables T;
 };
 
 __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_constant__ ProveTmaMaps M, const Consts K, const ConstsF KF,
                                                                   const Tables* __restrict__ gT, uint8_t* __restrict__ proof_out,
                                                                   size_t proof_pitch, uint8_t* __restrict__ status_out, size_t n,
-                                                                  uint64_t first_index, unsigned long long* __restrict__ digest_out) {
+                                                                  uint64_t first_index, unsigned long long* __restrict__ digest_out,
+                                                                  unsigned int* __restrict__ tile_counter) {
   __shared__ ProveTmaSmem S;
   unsigned long long digest_acc = 0;
   const int tid = threadIdx.x;
@@ -175,12 +177,24 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     tma::load_2d(&S.in[stage][12][0], &M.rnd, &S.full[stage], c0, 0);
     tma::load_2d(&S.in[stage][21][0], &M.chal, &S.full[stage], c0, 0);
   };
-  if (tid == 0 && blockIdx.x < tiles) issue(blockIdx.x, 0);
+  // Tiles are handed out by an atomic counter (zeroed by the host before the launch), one iteration ahead of their use
+  // so that the TMA prefetch overlaps the current tile: blocks that start late, e.g. because a collective's CTAs hold an
+  // SM, simply take fewer tiles, and there is no wave-quantisation tail.
+  if (tid == 0) {
+    const uint32_t t0 = atomicAdd(tile_counter, 1u);
+    S.tile_of_stage[0] = t0;
+    if (t0 < tiles) issue(t0, 0);
+  }
+  __syncthreads();
   uint32_t phase0 = 0, phase1 = 0;
-  int stage = 0;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, stage ^= 1) {
-    const size_t next = tile + gridDim.x;
-    if (tid == 0 && next < tiles) issue(next, stage ^ 1);     // the other stage was released by the barrier below
+  for (int stage = 0;; stage ^= 1) {
+    const size_t tile = S.tile_of_stage[stage];
+    if (tile >= tiles) break;
+    if (tid == 0) {                                           // the other stage was released by the barrier below
+      const uint32_t nt = atomicAdd(tile_counter, 1u);
+      S.tile_of_stage[stage ^ 1] = nt;
+      if (nt < tiles) issue(nt, stage ^ 1);
+    }
     if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
 
     const uint8_t* in = &S.in[stage][0][tid];
@@ -309,11 +323,13 @@ struct VerifyTmaMaps {
 struct VerifyTmaSmem {
   alignas(128) uint8_t in[2][34][kTile];    // planes 0..26 proof, 27..31 challenges, 32 u (33 unused: keeps stages 128-byte aligned)
   alignas(8) uint64_t full[2];
+  uint32_t tile_of_stage[2];
   Tables T;
 };
 template <int ALGO, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __grid_constant__ VerifyTmaMaps M, const Consts K,
-                                                                         const Tables* __restrict__ gT, const VerifyArgs A) {
+                                                                         const Tables* __restrict__ gT, const VerifyArgs A,
+                                                                         unsigned int* __restrict__ tile_counter) {
   __shared__ VerifyTmaSmem S;
   const int tid = threadIdx.x;
   stage_tables(S.T, gT);
@@ -331,12 +347,21 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
     tma::load_2d(&S.in[stage][27][0], &M.chal, &S.full[stage], c0, 0);
     tma::load_2d(&S.in[stage][32][0], &M.u, &S.full[stage], c0, 0);
   };
-  if (tid == 0 && blockIdx.x < tiles) issue(blockIdx.x, 0);
+  if (tid == 0) {                                             // dynamic tile scheduler, see prove_f32_tma_kernel
+    const uint32_t t0 = atomicAdd(tile_counter, 1u);
+    S.tile_of_stage[0] = t0;
+    if (t0 < tiles) issue(t0, 0);
+  }
+  __syncthreads();
   uint32_t phase0 = 0, phase1 = 0;
-  int stage = 0;
-  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, stage ^= 1) {
-    const size_t next = tile + gridDim.x;
-    if (tid == 0 && next < tiles) issue(next, stage ^ 1);
+  for (int stage = 0;; stage ^= 1) {
+    const size_t tile = S.tile_of_stage[stage];
+    if (tile >= tiles) break;
+    if (tid == 0) {
+      const uint32_t nt = atomicAdd(tile_counter, 1u);
+      S.tile_of_stage[stage ^ 1] = nt;
+      if (nt < tiles) issue(nt, stage ^ 1);
+    }
     if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
     const uint8_t* in = &S.in[stage][0][tid];
     uint32_t px[9], py[9], ev[7], ch[5];

@@ -180,8 +180,11 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
   // Tiles are handed out by an atomic counter (zeroed by the host before the launch), one iteration ahead of their use
   // so that the TMA prefetch overlaps the current tile: blocks that start late, e.g. because a collective's CTAs hold an
   // SM, simply take fewer tiles, and there is no wave-quantisation tail.
+  // The index is fetched two iterations ahead (`pending`), so the atomic's round trip is never waited for.
+  uint32_t pending = 0;
   if (tid == 0) {
     const uint32_t t0 = atomicAdd(tile_counter, 1u);
+    pending = atomicAdd(tile_counter, 1u);
     S.tile_of_stage[0] = t0;
     if (t0 < tiles) issue(t0, 0);
   }
@@ -191,9 +194,12 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     const size_t tile = S.tile_of_stage[stage];
     if (tile >= tiles) break;
     if (tid == 0) {                                           // the other stage was released by the barrier below
-      const uint32_t nt = atomicAdd(tile_counter, 1u);
+      const uint32_t nt = pending;
       S.tile_of_stage[stage ^ 1] = nt;
-      if (nt < tiles) issue(nt, stage ^ 1);
+      if (nt < tiles) {
+        issue(nt, stage ^ 1);
+        pending = atomicAdd(tile_counter, 1u);                // consumed in the next iteration
+      }
     }
     if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
 
@@ -347,8 +353,10 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
     tma::load_2d(&S.in[stage][27][0], &M.chal, &S.full[stage], c0, 0);
     tma::load_2d(&S.in[stage][32][0], &M.u, &S.full[stage], c0, 0);
   };
+  uint32_t pending = 0;
   if (tid == 0) {                                             // dynamic tile scheduler, see prove_f32_tma_kernel
     const uint32_t t0 = atomicAdd(tile_counter, 1u);
+    pending = atomicAdd(tile_counter, 1u);
     S.tile_of_stage[0] = t0;
     if (t0 < tiles) issue(t0, 0);
   }
@@ -358,9 +366,12 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
     const size_t tile = S.tile_of_stage[stage];
     if (tile >= tiles) break;
     if (tid == 0) {
-      const uint32_t nt = atomicAdd(tile_counter, 1u);
+      const uint32_t nt = pending;
       S.tile_of_stage[stage ^ 1] = nt;
-      if (nt < tiles) issue(nt, stage ^ 1);
+      if (nt < tiles) {
+        issue(nt, stage ^ 1);
+        pending = atomicAdd(tile_counter, 1u);
+      }
     }
     if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
     const uint8_t* in = &S.in[stage][0][tid];

@@ -127,7 +127,8 @@ int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_
     for (int y = 0; y < 17; y++)
       for (int z = 0; z < 17; z++)
         if ((x * x + y * y) % 17 == (z * z) % 17) { wtab[3 * nw] = x; wtab[3 * nw + 1] = y; wtab[3 * nw + 2] = z; nw++; }
-  if ((ce = cudaMalloc(&ctx->d_tile_counters, (1 + kSlots) * 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc(counters)", ce);
+  if ((ce = cudaMalloc(&ctx->d_tile_counters, (1 + kSlots) * 4 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc(counters)", ce);
+  if ((ce = cudaMemset(ctx->d_tile_counters, 0, (1 + kSlots) * 4 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMemset(counters)", ce);
   if ((ce = cudaMalloc(&ctx->d_wtab, sizeof(wtab))) != cudaSuccess) return bail("cudaMalloc(wtab)", ce);
   if ((ce = cudaMemcpy(ctx->d_wtab, wtab, sizeof(wtab), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(wtab)", ce);
   *out = ctx;
@@ -213,9 +214,7 @@ int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
 static unsigned int* fresh_tile_counter(pbh_ctx* ctx, cudaStream_t st, int which) {
   int idx = 0;
   for (int s = 0; s < kSlots; s++) if (st == ctx->slot_stream[s]) idx = 1 + s;
-  unsigned int* c = ctx->d_tile_counters + idx * 2 + which;
-  cudaMemsetAsync(c, 0, sizeof(unsigned int), st);
-  return c;
+  return ctx->d_tile_counters + (idx * 2 + which) * 2;   // {next tile, blocks done}: self-resetting, zero between launches
 }
 
 // ---- TMA tensor maps --------------------------------------------------------------------------------------------

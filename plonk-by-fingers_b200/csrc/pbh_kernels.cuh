@@ -50,6 +50,19 @@ __device__ __forceinline__ void digest_flush(unsigned long long acc, unsigned lo
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
+// Dynamic tile scheduler state: c[0] = next tile, c[1] = blocks finished.  Both are zero between launches: the last
+// block to leave resets them, so no memset node is needed per launch (launches sharing a counter pair are stream-ordered).
+__device__ __forceinline__ void tile_scheduler_leave(unsigned int* c) {
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&c[1], 1u) == gridDim.x - 1) {
+      c[0] = 0u;
+      c[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
 struct ProveArgs {
   const uint8_t* wit; size_t wit_pitch;
   const uint8_t* rnd; size_t rand_pitch;
@@ -282,6 +295,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
   }
   if (tid == 0) tma::store_wait_all();
   if (digest_out != nullptr) digest_flush(digest_acc, digest_out);   // one atomic per warp per launch
+  tile_scheduler_leave(tile_counter);
 }
 
 struct VerifyArgs {
@@ -408,6 +422,7 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
     }
     __syncthreads();   // every thread has read in[stage]; it may be refilled by the prefetch of the iteration after next
   }
+  tile_scheduler_leave(tile_counter);
 }
 
 // ---- sweep kernels -------------------------------------------------------------------------------

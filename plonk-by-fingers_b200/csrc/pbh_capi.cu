@@ -302,10 +302,12 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
       size_t tiles = (A.n + kTile - 1) / kTile;
       if (ctx->algo == PBH_ALGO_TABLE) {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 4);
-        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A, fresh_tile_counter(ctx, st, 1));
+        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->prover_fp32 != 0, ctx->d_tables, A,
+                                                              fresh_tile_counter(ctx, st, 1));
       } else {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 3);
-        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->d_tables, A, fresh_tile_counter(ctx, st, 1));
+        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A,
+                                                              fresh_tile_counter(ctx, st, 1));
       }
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
@@ -319,8 +321,8 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
   }
   if (A.bitmap) { bitmap_later = A.bitmap; A.bitmap = nullptr; }   // the plain kernels do not pack
   int grid = grid_for(ctx, A.n, 8);
-  if (ctx->algo == PBH_ALGO_TABLE) verify_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
-  else verify_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
+  if (ctx->algo == PBH_ALGO_TABLE) verify_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->prover_fp32 != 0, ctx->d_tables, A);
+  else verify_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   if (bitmap_later) {

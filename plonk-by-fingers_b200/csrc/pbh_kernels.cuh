@@ -310,7 +310,8 @@ struct VerifyArgs {
 
 // Plonk::verify, src/plonk.rs:468-650
 template <int ALGO>
-__global__ void __launch_bounds__(kBlock) verify_kernel(const Consts K, const Tables* __restrict__ gT, const VerifyArgs A) {
+__global__ void __launch_bounds__(kBlock) verify_kernel(const Consts K, const ConstsF KF, const bool fp32, const Tables* __restrict__ gT,
+                                                         const VerifyArgs A) {
   __shared__ Tables sT;
   stage_tables(sT, gT);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (size_t)gridDim.x * blockDim.x) {
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(kBlock) verify_kernel(const Consts K, const Ta
     for (int k = 0; k < 5; k++) ch[k] = A.chal[(size_t)k * A.chal_pitch + i];
     uint32_t u = A.u[i];
     GT e1, e2;
-    uint32_t res = verify_one<ALGO>(px, py, infbits, ev, ch, u, K, sT, e1, e2);
+    uint32_t res = verify_one<ALGO>(px, py, infbits, ev, ch, u, K, sT, e1, e2, fp32 ? &KF : nullptr);
     A.result[i] = (uint8_t)res;
     if (A.gt) {
       A.gt[i] = (uint8_t)e1.a; A.gt[A.gt_pitch + i] = (uint8_t)e1.b;
@@ -348,6 +349,7 @@ struct VerifyTmaSmem {
 };
 template <int ALGO, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __grid_constant__ VerifyTmaMaps M, const Consts K,
+                                                                         const ConstsF KF, const bool fp32,
                                                                          const Tables* __restrict__ gT, const VerifyArgs A,
                                                                          unsigned int* __restrict__ tile_counter) {
   __shared__ VerifyTmaSmem S;
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
     for (int k = 0; k < 5; k++) ch[k] = in[(27 + k) * kTile];
     uint32_t u = in[32 * kTile];
     GT e1, e2;
-    uint32_t res = verify_one<ALGO>(px, py, infbits, ev, ch, u, K, S.T, e1, e2);
+    uint32_t res = verify_one<ALGO>(px, py, infbits, ev, ch, u, K, S.T, e1, e2, fp32 ? &KF : nullptr);
     const size_t i = tile * kTile + tid;
     if (i < A.n) {
       A.result[i] = (uint8_t)res;

@@ -48,6 +48,23 @@ PBH_HD uint32_t f_canon(F32 x) {
   return (uint32_t)(int)c;
 #endif
 }
+// rint(x / d) for an exact integer x (|x| < 2^21) that is never half-way between two multiples of d
+PBH_HD F32 f_rint_div(F32 x, float d, float inv_d, F32*) {
+  (void)d;
+  float t = fmaf(x.v, inv_d, 12582912.0f);
+  return F32(t - 12582912.0f);
+}
+// canonical residue 0..16 of a centred one, kept as a float
+PBH_HD F32 f_canon_f(F32 x, F32*) { return F32(x.v < 0.0f ? x.v + 17.0f : x.v); }
+// table index 0..101 of a centred residue mod 102
+PBH_HD uint32_t f_index102(F32 x) {
+  float c = x.v < 0.0f ? x.v + 102.0f : x.v;
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__float_as_int(c + 12582912.0f) & 0xFFu;
+#else
+  return (uint32_t)(int)c;
+#endif
+}
 PBH_HD F32 f_from_u32(uint32_t b, F32*) {                          // exact for b < 2^23
 #if defined(__CUDA_ARCH__)
   return F32(__int_as_float(0x4B000000 | (int)b) - 8388608.0f);
@@ -95,6 +112,7 @@ struct ConstsF {
   float QL[4], QR[4], QO[4], QM[4], QC[4];     // interpolated selectors
   float sig[3][4], S[3][4], L1[4];
   float srs_dlog[10];
+  float vdlog[8];                              // verifier: dlogs of the 8 constant commitments (pbh_verify.cuh)
 };
 
 struct ProofF {

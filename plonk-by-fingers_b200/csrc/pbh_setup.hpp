@@ -212,6 +212,7 @@ inline int host_setup(const pbh_circuit& c, uint32_t srs_secret, uint32_t srs_n,
     for (int wv = 0; wv < 3; wv++) { F.sig[wv][i] = cen(K.sig[wv][i]); F.S[wv][i] = cen(K.S[wv][i]); }
   }
   for (int i = 0; i < 10; i++) F.srs_dlog[i] = cen(K.srs_dlog[i]);
+  for (int i = 0; i < 8; i++) F.vdlog[i] = cen(K.vdlog[i]);
   for (uint32_t a = 0; a < 17; a++) T.inv17c[a] = cen(T.inv17[a]);
   return PBH_OK;
 }

@@ -14,7 +14,7 @@
 //          becomes arithmetic mod 102 and the two pairings against the fixed G2 points become 102-entry
 //          tables.  All tables fit in <= 32 shared-memory banks, so divergent lookups are conflict free.
 #pragma once
-#include "pbh_prove.cuh"
+#include "pbh_prove_f32.cuh"
 
 namespace pbh {
 
@@ -26,9 +26,13 @@ enum : uint32_t {
 // px, py: coordinates of a_s b_s c_s z_s t_lo_s t_mid_s t_hi_s w_z_s w_z_omega_s; infbits: bit k = point k's
 // `infinite` flag; ev: a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z; ch: alpha beta gamma z v; u = rand[0].
 // All raw bytes.  Returns the PBH_VR_* result byte; e1/e2 are defined when the pairing check was reached.
+// KF: non-null selects the FP32-pipe scalar path for PBH_ALGO_TABLE (verify_scalars_f32 below); null = int32 arithmetic.
+template <class TT> PBH_HD void verify_scalars_f32(const TT (&idx)[9], const TT (&ev)[7], const TT (&ch)[5], TT u, const ConstsF& VF,
+                                                   const float* inv17c, uint32_t& i1, uint32_t& i2, bool& zh0);
 template <int ALGO>
 PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9], uint32_t infbits, const uint32_t (&ev)[7],
-                           const uint32_t (&ch_in)[5], uint32_t u, const Consts& K, const Tables& T, GT& e1, GT& e2) {
+                           const uint32_t (&ch_in)[5], uint32_t u, const Consts& K, const Tables& T, GT& e1, GT& e2,
+                           const ConstsF* KF = nullptr) {
   e1.a = e1.b = e2.a = e2.b = 0;
   // ---- encoding (see include/pbh_b200.h).  Out-of-range bytes are replaced by 0 so that no table is indexed out
   // of bounds; the verdict of such an item is PBH_VR_BAD_ENCODING whatever is computed below.
@@ -68,6 +72,28 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
 #pragma unroll
   for (int k = 0; k < 7; k++) off_field = off_field || ev[k] >= 17u;
 
+  if (ALGO == ALGO_TABLE && KF != nullptr) {
+    F32* tag = nullptr;
+    F32 fidx[9], fev[7], fch[5];
+#pragma unroll
+    for (int k = 0; k < 9; k++) fidx[k] = f_from_u32(idx[k], tag);
+#pragma unroll
+    for (int k = 0; k < 7; k++) fev[k] = f_red(f_from_u32(ev[k], tag));      // also folds bytes >= 17 into range
+#pragma unroll
+    for (int k = 0; k < 5; k++) fch[k] = f_from_u32(ch[k], tag);
+    uint32_t i1, i2;
+    bool zh0f;
+    verify_scalars_f32<F32>(fidx, fev, fch, f_from_u32(u, tag), *KF, T.inv17c, i1, i2, zh0f);
+    e1.a = T.pair_s_a[i1]; e1.b = T.pair_s_b[i1];
+    e2.a = T.pair_1_a[i2]; e2.b = T.pair_1_b[i2];
+    uint32_t resf = (e1.a == e2.a && e1.b == e2.b) ? VR_ACCEPT : VR_REJECT_PAIRING;
+    if (zh0f) resf = VR_PANIC_ZH0;
+    if (off_field) resf = VR_NOT_IN_FIELD;
+    if (off_curve) resf = VR_NOT_ON_CURVE;
+    if (bad) resf = VR_BAD_ENCODING;
+    if (resf != VR_ACCEPT && resf != VR_REJECT_PAIRING) e1.a = e1.b = e2.a = e2.b = 0;
+    return resf;
+  }
   const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], z = ch[3], v = ch[4];
   // evaluations >= 17 are representable inputs (verdict false at Step 2); reduce them so that everything computed
   // below stays inside the table ranges
@@ -143,6 +169,64 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
   if (bad) res = VR_BAD_ENCODING;
   if (res != VR_ACCEPT && res != VR_REJECT_PAIRING) e1.a = e1.b = e2.a = e2.b = 0;
   return res;
+}
+
+// ---- PBH_ALGO_TABLE verifier with the F_17 scalar work on the FP32 pipes (see pbh_prove_f32.cuh for the rationale and
+// the exactness argument; bounds are machine-checked by the CPU test suite through the same template) ----------------
+// x mod 102 as an integer index 0..101 for an exact non-negative integer x < 2^20
+template <class T>
+PBH_HD T f_red102c(T x) {   // centred residue in [-51, 51]
+  T* tag = nullptr;
+  return f_fma(f_rint_div(x, 102.0f, 0.00980392156862745f, tag), f_const(-102.f, tag), x);
+}
+
+// idx[9]: discrete logs (0..101) of the nine proof points, flagged points already mapped to 0.  ev/ch/u: exact small
+// integers (evaluations already reduced mod 17 by the caller when >= 17).  Outputs the table indices of e_1_q1 and
+// e_2_q1 and whether Z_H(z) = 0.
+template <class T>
+PBH_HD void verify_scalars_f32(const T (&idx)[9], const T (&ev)[7], const T (&ch)[5], T u, const ConstsF& VF, const float* inv17c,
+                               uint32_t& i1, uint32_t& i2, bool& zh0) {
+  T* tag = nullptr;
+  const T alpha = ch[0], beta = ch[1], gamma = ch[2], z = ch[3], v = ch[4];
+  const T a_z = ev[0], b_z = ev[1], c_z = ev[2], s1_z = ev[3], s2_z = ev[4], r_z = ev[5], zw_z = ev[6];
+  // Steps 4-7                                                                 src/plonk.rs:553-579
+  T z2 = f_red(f_mul(z, z)), z3 = f_red(f_mul(z2, z)), z4 = f_red(f_mul(z2, z2));
+  T zh_z = f_red(f_sub(z4, f_const(1.f, tag)));
+  T l1_z = f_red(f_fma(f_const(VF.L1[3], tag), z3, f_fma(f_const(VF.L1[2], tag), z2, f_fma(f_const(VF.L1[1], tag), z, f_const(VF.L1[0], tag)))));
+  T a2 = f_red(f_mul(alpha, alpha));
+  T l1a2 = f_red(f_mul(l1_z, a2));
+  T perm_a = f_red(f_add(f_fma(beta, s1_z, gamma), a_z)), perm_b = f_red(f_add(f_fma(beta, s2_z, gamma), b_z));
+  T perm_ab = f_red(f_mul(perm_a, perm_b));
+  T perm = f_red(f_mul(f_mul(perm_ab, f_add(c_z, gamma)), zw_z));            // Q3: no alpha here
+  zh0 = f_is_zero(zh_z);                                                       // Q4
+  T t_z = f_red(f_mul(f_sub(f_sub(r_z, perm), l1a2), f_const(inv17c[f_canon(zh_z)], tag)));
+  // scalars of Steps 8-11                                                     src/plonk.rs:583-644
+  T v2 = f_red(f_mul(v, v)), v3 = f_red(f_mul(v2, v)), v4 = f_red(f_mul(v3, v)), v5 = f_red(f_mul(v4, v)), v6 = f_red(f_mul(v5, v));
+  T z6 = f_red(f_mul(z4, z2)), z12 = f_red(f_mul(z6, z6));
+  T bz = f_mul(beta, z);
+  T av = f_red(f_mul(a_z, v));
+  T s_qm = f_red(f_mul(av, b_z)), s_ql = av, s_qr = f_red(f_mul(b_z, v)), s_qo = f_red(f_mul(c_z, v)), s_qc = v;
+  T f1 = f_red(f_add(f_add(a_z, bz), gamma)), f2 = f_red(f_add(f_fma(bz, f_const(2.f, tag), b_z), gamma)),
+    f3 = f_red(f_add(f_fma(bz, f_const(3.f, tag), c_z), gamma));
+  T av_ = f_red(f_mul(alpha, v));
+  T s_zs = f_red(f_add(f_fma(f_red(f_mul(f_mul(f1, f2), f3)), av_, f_mul(l1a2, v)), u));
+  T s_s3 = f_red(f_mul(f_red(f_mul(perm_ab, av_)), f_red(f_mul(beta, zw_z))));
+  T s_e = f_red(f_fma(u, zw_z, f_fma(v6, s2_z, f_fma(v5, s1_z, f_fma(v4, c_z, f_fma(v3, b_z, f_fma(v2, a_z, f_fma(v, r_z, t_z))))))));
+  T s_wzw = f_red(f_mul(f_mul(u, z), f_const(4.f, tag)));
+  // fixed-base part in the exponent of G (mod 17): d_1 - d_3 + v^5 sigma_1 + v^6 sigma_2 - e
+  T efix = f_sub(f_fma(v6, f_const(VF.vdlog[6], tag), f_fma(v5, f_const(VF.vdlog[5], tag), f_fma(s_qc, f_const(VF.vdlog[4], tag),
+                 f_fma(s_qo, f_const(VF.vdlog[3], tag), f_fma(s_qr, f_const(VF.vdlog[2], tag), f_fma(s_ql, f_const(VF.vdlog[1], tag),
+                 f_mul(s_qm, f_const(VF.vdlog[0], tag)))))))), f_fma(s_s3, f_const(VF.vdlog[7], tag), s_e));
+  T efix_c = f_canon_f(f_red(efix), tag);
+  // group arithmetic in the exponent of g102 (mod 102); scalars must be the canonical integers 0..16 (gf of src/pbh/mod.rs:30-32)
+  T cu = u, cz = z, cw = f_canon_f(s_wzw, tag),   // u and z arrive canonical (0..16)
+    c6 = f_canon_f(z6, tag), c12 = f_canon_f(z12, tag),
+    czs = f_canon_f(s_zs, tag), c2 = f_canon_f(v2, tag), c3 = f_canon_f(v3, tag), c4 = f_canon_f(v4, tag);
+  T x1 = f_fma(cu, idx[8], idx[7]);
+  T x2 = f_fma(efix_c, f_const(6.f, tag), f_fma(c4, idx[2], f_fma(c3, idx[1], f_fma(c2, idx[0], f_fma(czs, idx[3], f_fma(c12, idx[6],
+         f_fma(c6, idx[5], f_add(f_fma(cw, idx[8], f_mul(cz, idx[7])), idx[4]))))))));
+  i1 = f_index102(f_red102c(x1));
+  i2 = f_index102(f_red102c(x2));
 }
 
 }  // namespace pbh

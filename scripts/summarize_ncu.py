@@ -49,5 +49,16 @@ with open(os.path.join(dst, f"{tag}_{kernel}_full.txt"), "w") as f:
         if w in hdr:
             i = hdr.index(w)
             f.write(f"{w:80s} {units[i]:16s} {' | '.join(v[i] for v in vals)}\n")
+# per-launch DRAM traffic of the profiled kernel, for bench.py's roofline.traffic
+import json
+def _bytes(name):
+    i = hdr.index(name); u = units[i]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+    return sum(float(v[i]) for v in vals) / len(vals) * scale
+tj = os.path.join(dst, "roofline_traffic.json")
+traffic = json.load(open(tj)) if os.path.exists(tj) else {}
+traffic[kernel] = {"tag": tag, "dram_read_bytes": _bytes("dram__bytes_read.sum"), "dram_write_bytes": _bytes("dram__bytes_write.sum"),
+                   "note": "ncu --set full, per launch, bench.py --steps 3 --ring 2 (2^20 items); writes of a 28 MB result mostly stay in the 126 MB L2 at capture time"}
+json.dump(traffic, open(tj, "w"), indent=1, sort_keys=True)
 print(open(os.path.join(dst, f"{tag}_launches.txt")).read())
 print(open(os.path.join(dst, f"{tag}_{kernel}_full.txt")).read())

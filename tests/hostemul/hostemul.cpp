@@ -28,6 +28,9 @@ inline Bnd f_sub(Bnd a, Bnd b) { return chk(a.m + b.m); }
 inline Bnd f_red(Bnd x) { if (x.m > g_max_red) g_max_red = x.m; if (x.m > 8388608.0) g_violation = true; return Bnd(8); }
 inline bool f_is_zero(Bnd) { return false; }
 inline uint32_t f_canon(Bnd) { return 0; }
+inline Bnd f_rint_div(Bnd x, float d, float, Bnd*) { if (x.m > g_max_red) g_max_red = x.m; if (x.m >= 2097152.0) g_violation = true; return chk(x.m / d + 1.0); }
+inline Bnd f_canon_f(Bnd, Bnd*) { return Bnd(16); }
+inline uint32_t f_index102(Bnd) { return 0; }
 }  // namespace pbh
 
 extern "C" {
@@ -50,6 +53,15 @@ int emul_f32_bounds(double* max_exact, double* max_red) {
     for (auto& x : c) x = Bnd(16);
     ProofF pf;
     prove_core_f32<Bnd>(w, r, c, KF, n_pts, inv, pf);
+  }
+  {
+    // the verifier's FP32 scalar path: discrete logs <= 101, evaluations reduced (<= 8), challenges and u <= 16
+    Bnd idx[9], ev[7], ch[5];
+    for (auto& x : idx) x = Bnd(101);
+    for (auto& x : ev) x = Bnd(8);
+    for (auto& x : ch) x = Bnd(16);
+    uint32_t i1, i2; bool zh0;
+    verify_scalars_f32<Bnd>(idx, ev, ch, Bnd(16), KF, inv, i1, i2, zh0);
   }
   *max_exact = g_max_exact; *max_red = g_max_red;
   return g_violation ? 1 : 0;
@@ -134,8 +146,9 @@ int emul_verify_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t o
     for (int k = 0; k < 7; k++) ev[k] = proof[(20 + k) * n + i];
     for (int k = 0; k < 5; k++) ch[k] = chal[k * n + i];
     GT e1, e2;
-    uint32_t res = algo == 1 ? verify_one<ALGO_TABLE>(px, py, infbits, ev, ch, u[i], hs.K, hs.T, e1, e2)
-                             : verify_one<ALGO_ARITH>(px, py, infbits, ev, ch, u[i], hs.K, hs.T, e1, e2);
+    uint32_t res = algo == 2 ? verify_one<ALGO_TABLE>(px, py, infbits, ev, ch, u[i], hs.K, hs.T, e1, e2, &hs.KF)
+                   : (algo == 1 ? verify_one<ALGO_TABLE>(px, py, infbits, ev, ch, u[i], hs.K, hs.T, e1, e2)
+                                : verify_one<ALGO_ARITH>(px, py, infbits, ev, ch, u[i], hs.K, hs.T, e1, e2));
     result[i] = (uint8_t)res;
     if (gt) { gt[i] = e1.a; gt[n + i] = e1.b; gt[2 * n + i] = e2.a; gt[3 * n + i] = e2.b; }
   }

@@ -21,7 +21,7 @@ def test_prove_verify_logic_matches_oracle(hostemul, oracle, algo, dist):
     pe, se = hostemul.prove(circ, w, r, c, algo)
     assert np.array_equal(se, so) and np.array_equal(pe, po)
     vo, go = oracle.verify_batch(po, c, u, threads=8)
-    ve, ge = hostemul.verify(circ, po, c, u, min(algo, 1))
+    ve, ge = hostemul.verify(circ, po, c, u, algo)     # algo 2: TABLE with the FP32-pipe scalar path
     assert np.array_equal(ve, vo) and np.array_equal(ge, go)
 
 

@@ -139,6 +139,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying CUDA graphs")
+    ap.add_argument("--no-cycle-graph", action="store_true", help="replay one graph per step instead of one per ring cycle")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -208,6 +209,42 @@ def main():
             graphs, launch_mode = None, f"direct (graph capture failed: {type(e).__name__})"
             torch.cuda.synchronize()
 
+    # One more graph holding a whole ring cycle (ring steps): kernels on the context's stream, each step's all-gather
+    # forked onto the side stream inside the graph so that it overlaps the next step's kernels; one replay per `ring`
+    # steps keeps the host (one Python process per GPU) out of the timed path.
+    cycle_graph = None
+    if graphs is not None and not args.no_cycle_graph:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for slot in range(ring):
+                    kernels(slot)
+                    if world > 1:
+                        ev_ = torch.cuda.Event()
+                        ev_.record(stream)
+                        comm_stream.wait_event(ev_)
+                        with torch.cuda.stream(comm_stream):
+                            dist.all_gather_into_tensor(outs[slot]["gathered"], outs[slot]["summary"])
+                if world > 1:
+                    stream.wait_stream(comm_stream)
+            cycle_graph = g
+            launch_mode = f"cuda_graph ({ring}-step cycle graph + per-step graphs for the remainder)"
+        except Exception as e:   # pragma: no cover
+            cycle_graph = None
+            launch_mode += f"; cycle graph unavailable: {type(e).__name__}"
+            torch.cuda.synchronize()
+
+    def run_steps(k0, count):
+        """Steps k0 .. k0+count-1 (k0 a multiple of ring): whole cycles through the cycle graph, the rest step by step."""
+        k = k0
+        if cycle_graph is not None:
+            while count - (k - k0) >= ring:
+                cycle_graph.replay()
+                k += ring
+        while k - k0 < count:
+            step(k)
+            k += 1
+
     def step(k):
         slot = k % ring
         o = outs[slot]
@@ -232,8 +269,9 @@ def main():
         torch.cuda.synchronize()
 
     with torch.cuda.stream(stream):
-        for k in range(max(3, args.warmup)):
-            step(k)
+        run_steps(0, max(3, args.warmup) + ring)     # warm-up covers both launch paths
+        if world > 1:
+            stream.wait_stream(comm_stream)
     barrier()
 
     # ---- timed region: exactly K steps, device-timed, max over ranks
@@ -243,8 +281,7 @@ def main():
     barrier()
     with torch.cuda.stream(stream):
         t_begin.record(stream)
-        for k in range(args.steps):
-            step(k)
+        run_steps(0, args.steps)
         if world > 1:
             stream.wait_stream(comm_stream)
         t_end.record(stream)

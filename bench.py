@@ -370,10 +370,18 @@ def main():
                "fused_call": {"value": n * world * ksteps / dtf, "unit": UNIT, "h2d_bytes_per_step": n * 27 * world,
                               "d2h_bytes_per_step": n * 29 * world, "api": "pbh_prove_verify_batch (extension)"}}
 
-    if rank != 0:
+    def finish():
+        """Multi-rank teardown: final barrier, then leave without destroy_process_group() — tearing the communicator down
+        while CUDA graphs that captured its collectives are alive was observed to hang."""
         if world > 1:
+            torch.cuda.synchronize()
             dist.barrier()
-            dist.destroy_process_group()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     peak, peak_src = measured_peaks()
@@ -432,9 +440,7 @@ def main():
         "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n},
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":

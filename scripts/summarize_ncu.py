@@ -57,7 +57,12 @@ def _bytes(name):
     return sum(float(v[i]) for v in vals) / len(vals) * scale
 tj = os.path.join(dst, "roofline_traffic.json")
 traffic = json.load(open(tj)) if os.path.exists(tj) else {}
+def _avg(name):
+    i = hdr.index(name)
+    return sum(float(v[i]) for v in vals) / len(vals)
 traffic[kernel] = {"tag": tag, "dram_read_bytes": _bytes("dram__bytes_read.sum"), "dram_write_bytes": _bytes("dram__bytes_write.sum"),
+                   "issue_active_pct": _avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                   "warp_instructions": _avg("smsp__inst_executed.sum"),
                    "note": "ncu --set full, per launch, bench.py --steps 3 --ring 2 (2^20 items); writes of a 28 MB result mostly stay in the 126 MB L2 at capture time"}
 json.dump(traffic, open(tj, "w"), indent=1, sort_keys=True)
 print(open(os.path.join(dst, f"{tag}_launches.txt")).read())

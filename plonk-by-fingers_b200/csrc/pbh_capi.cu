@@ -613,7 +613,9 @@ int pbh_poly_add_batch(pbh_ctx* ctx, size_t n, uint32_t len, int subtract, const
     d_out = stg.in<uint8_t>(nullptr, 0, n, len, ce); CUDA_TRY(ctx, ce);
     ap = bp = op = n;
   }
-  poly_add_kernel<<<grid_for(ctx, n, 16), kBlock, 0, ctx->compute>>>(n, len, subtract, d_a, ap, d_b, bp, d_out, op);
+  const bool vec_ok = ((uintptr_t)d_a % 4 == 0) && ((uintptr_t)d_b % 4 == 0) && ((uintptr_t)d_out % 4 == 0) && (ap % 4 == 0) && (bp % 4 == 0) &&
+                      (op % 4 == 0);
+  poly_add_kernel<<<grid_for(ctx, vec_ok ? (n + 3) / 4 : n, 16), kBlock, 0, ctx->compute>>>(n, len, subtract, d_a, ap, d_b, bp, d_out, op, vec_ok);
   SWEEP_FINISH(ctx);
   if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, len)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
   return PBH_OK;
@@ -630,7 +632,9 @@ int pbh_poly_div_zh_batch(pbh_ctx* ctx, size_t n, const uint8_t* p, size_t p_pit
     d_r = stg.in<uint8_t>(nullptr, 0, n, 4, ce); CUDA_TRY(ctx, ce);
     pp = qp = rp = n;
   }
-  poly_div_zh_kernel<<<grid_for(ctx, n, 16), kBlock, 0, ctx->compute>>>(n, d_p, pp, d_q, qp, d_r, rp);
+  const bool vec_ok = ((uintptr_t)d_p % 4 == 0) && ((uintptr_t)d_q % 4 == 0) && ((uintptr_t)d_r % 4 == 0) && (pp % 4 == 0) && (qp % 4 == 0) &&
+                      (rp % 4 == 0);
+  poly_div_zh_kernel<<<grid_for(ctx, vec_ok ? (n + 3) / 4 : n, 16), kBlock, 0, ctx->compute>>>(n, d_p, pp, d_q, qp, d_r, rp, vec_ok);
   SWEEP_FINISH(ctx);
   if (!on_device) {
     CUDA_TRY(ctx, stg.out(q, q_pitch, d_q, n, 18));

@@ -428,35 +428,58 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
 }
 
 // ---- sweep kernels -------------------------------------------------------------------------------
-// Each thread handles 4 consecutive items through one 32-bit word per plane where n allows it (HBM-bound
-// kernels: 128-byte warp transactions), with a byte-wise tail.
+// The HBM-bound sweeps (NTT-4 / iNTT-4, polynomial add, division by Z_H) work on four items at once: one 32-bit word
+// per plane holds the same coefficient of four consecutive items in its byte lanes, and all F_17 arithmetic is byte-lane
+// SWAR on the integer ALU pipe.  16 = -1 (mod 17), so a lane value x = 16a + b folds to b - a, the size-4 twiddles
+// are +-1 and +-4 (a 2-bit lane shift), and -c is 17 - c.  No multiplies, no cross-lane carries (bounds in comments).
+
+// every byte lane (0..255) -> its residue mod 17 (0..16)
+__device__ __forceinline__ uint32_t swar_mod17(uint32_t x) {
+  const uint32_t lo = x & 0x0F0F0F0Fu, hi = (x >> 4) & 0x0F0F0F0Fu;
+  const uint32_t t = lo + 0x11111111u - hi;                 // b - a + 17, lanes in [2, 32]
+  const uint32_t m = (t + 0x6F6F6F6Fu) & 0x80808080u;       // lane >= 17  <=>  lane + 111 >= 128
+  return t - ((m >> 7) + (m >> 3));                         // subtract 17 (= 1 + 16) from the flagged lanes
+}
+__device__ __forceinline__ uint32_t swar_neg17(uint32_t x) { return 0x11111111u - x; }   // lanes 0..16 -> 17 - lane (1..17)
+
+// forward: e_i = sum_j c_j 4^(ij); inverse: f_j = 13 sum_i 4^(-ij) v_i with 13 = 1/4 = -4   (src/fft.rs:66-106, src/plonk.rs:177-179)
+template <bool INVERSE>
+__device__ __forceinline__ void swar_ntt4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t (&o)[4]) {
+  w0 = swar_mod17(w0); w1 = swar_mod17(w1); w2 = swar_mod17(w2); w3 = swar_mod17(w3);   // any byte value is accepted
+  const uint32_t n1 = swar_neg17(w1), n2 = swar_neg17(w2), n3 = swar_neg17(w3);
+  const uint32_t s0 = w0 + w1 + w2 + w3;                            // lanes <= 64
+  const uint32_t sp = w0 + (w1 << 2) + n2 + (n3 << 2);              // c0 + 4c1 - c2 - 4c3, lanes <= 165
+  const uint32_t s2 = w0 + n1 + w2 + n3;                            // c0 - c1 + c2 - c3,   lanes <= 66
+  const uint32_t sm = w0 + (n1 << 2) + n2 + (w3 << 2);              // c0 - 4c1 - c2 + 4c3, lanes <= 165
+  if (!INVERSE) {
+    o[0] = swar_mod17(s0); o[1] = swar_mod17(sp); o[2] = swar_mod17(s2); o[3] = swar_mod17(sm);
+  } else {
+    // omega^-1 = -4 swaps the roles of sp and sm; then multiply by 13 = -4: 4 * (17 - residue) <= 68
+    o[0] = swar_mod17(swar_neg17(swar_mod17(s0)) << 2);
+    o[1] = swar_mod17(swar_neg17(swar_mod17(sm)) << 2);
+    o[2] = swar_mod17(swar_neg17(swar_mod17(s2)) << 2);
+    o[3] = swar_mod17(swar_neg17(swar_mod17(sp)) << 2);
+  }
+}
+
 template <bool INVERSE>
 __global__ void __launch_bounds__(kBlock) ntt4_kernel(size_t n, const uint8_t* __restrict__ in, size_t in_pitch,
                                                        uint8_t* __restrict__ out, size_t out_pitch, bool vec_ok) {
   const size_t n4 = vec_ok ? n / 4 : 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
-    uint32_t wv[4], ov[4] = {0, 0, 0, 0};
+    uint32_t wv[4], ov[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) wv[k] = reinterpret_cast<const uint32_t*>(in + (size_t)k * in_pitch)[q];
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      uint32_t e[4];
-      uint32_t v0 = (wv[0] >> (8 * b)) & 0xFF, v1 = (wv[1] >> (8 * b)) & 0xFF, v2 = (wv[2] >> (8 * b)) & 0xFF,
-               v3 = (wv[3] >> (8 * b)) & 0xFF;
-      if (INVERSE) intt4(v0, v1, v2, v3, e); else ntt4(v0, v1, v2, v3, e);
-#pragma unroll
-      for (int k = 0; k < 4; k++) ov[k] |= e[k] << (8 * b);
-    }
+    swar_ntt4<INVERSE>(wv[0], wv[1], wv[2], wv[3], ov);
 #pragma unroll
     for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = ov[k];
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint32_t e[4];
-    uint32_t v0 = in[i], v1 = in[in_pitch + i], v2 = in[2 * in_pitch + i], v3 = in[3 * in_pitch + i];
-    if (INVERSE) intt4(v0, v1, v2, v3, e); else ntt4(v0, v1, v2, v3, e);
+    uint32_t ov[4];
+    swar_ntt4<INVERSE>(in[i], in[in_pitch + i], in[2 * in_pitch + i], in[3 * in_pitch + i], ov);   // one live lane
 #pragma unroll
-    for (int k = 0; k < 4; k++) out[(size_t)k * out_pitch + i] = (uint8_t)e[k];
+    for (int k = 0; k < 4; k++) out[(size_t)k * out_pitch + i] = (uint8_t)ov[k];
   }
 }
 
@@ -524,31 +547,60 @@ __global__ void __launch_bounds__(kBlock) poly_mul_kernel(size_t n, uint32_t la,
   }
 }
 
+// coefficientwise a + b or a - b on `len` planes, four items per word                     src/poly.rs:165-203
 __global__ void __launch_bounds__(kBlock) poly_add_kernel(size_t n, uint32_t len, int subtract, const uint8_t* __restrict__ a,
                                                            size_t a_pitch, const uint8_t* __restrict__ b, size_t b_pitch,
-                                                           uint8_t* __restrict__ out, size_t out_pitch) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+                                                           uint8_t* __restrict__ out, size_t out_pitch, bool vec_ok) {
+  const size_t n4 = vec_ok ? n / 4 : 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
     for (uint32_t k = 0; k < len; k++) {
-      uint32_t x = a[(size_t)k * a_pitch + i], y = b[(size_t)k * b_pitch + i];
-      out[(size_t)k * out_pitch + i] = (uint8_t)mod17(subtract ? x + 17u * 16u - y : x + y);
+      uint32_t x = swar_mod17(reinterpret_cast<const uint32_t*>(a + (size_t)k * a_pitch)[q]);
+      uint32_t y = swar_mod17(reinterpret_cast<const uint32_t*>(b + (size_t)k * b_pitch)[q]);
+      reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = swar_mod17(x + (subtract ? swar_neg17(y) : y));
+    }
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (uint32_t k = 0; k < len; k++) {
+      uint32_t x = swar_mod17(a[(size_t)k * a_pitch + i]), y = swar_mod17(b[(size_t)k * b_pitch + i]);
+      out[(size_t)k * out_pitch + i] = (uint8_t)swar_mod17(x + (subtract ? swar_neg17(y) : y));
     }
   }
 }
 
-// (q, r) = p / (x^4 - 1): 22 planes -> 18 + 4 planes                         src/poly.rs:230-247, src/plonk.rs:369
+// (q, r) = p / (x^4 - 1): 22 planes -> 18 + 4 planes, four items per word          src/poly.rs:230-247, src/plonk.rs:369
+template <class W>
+__device__ __forceinline__ void swar_div_zh(const W (&num)[22], W (&t)[18], W (&r)[4]) {
+  // t[j] = num[j+4] + t[j+4]: at most 5 residues accumulate (lanes <= 80) before the fold
+#pragma unroll
+  for (int j = 17; j >= 0; j--) t[j] = (j + 4 < 18) ? swar_mod17(num[j + 4] + t[j + 4]) : num[j + 4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) r[j] = swar_mod17(num[j] + t[j]);
+}
 __global__ void __launch_bounds__(kBlock) poly_div_zh_kernel(size_t n, const uint8_t* __restrict__ p, size_t p_pitch,
                                                               uint8_t* __restrict__ q, size_t q_pitch, uint8_t* __restrict__ r,
-                                                              size_t r_pitch) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    uint32_t num[22], t[18];
+                                                              size_t r_pitch, bool vec_ok) {
+  const size_t n4 = vec_ok ? n / 4 : 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < n4; w += stride) {
+    uint32_t num[22], t[18], rem[4];
 #pragma unroll
-    for (int k = 0; k < 22; k++) num[k] = mod17(p[(size_t)k * p_pitch + i]);
+    for (int k = 0; k < 22; k++) num[k] = swar_mod17(reinterpret_cast<const uint32_t*>(p + (size_t)k * p_pitch)[w]);
+    swar_div_zh(num, t, rem);
 #pragma unroll
-    for (int j = 17; j >= 0; j--) t[j] = (j + 4 < 18) ? add17(num[j + 4], t[j + 4]) : num[j + 4];
+    for (int j = 0; j < 18; j++) reinterpret_cast<uint32_t*>(q + (size_t)j * q_pitch)[w] = t[j];
+#pragma unroll
+    for (int j = 0; j < 4; j++) reinterpret_cast<uint32_t*>(r + (size_t)j * r_pitch)[w] = rem[j];
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint32_t num[22], t[18], rem[4];
+#pragma unroll
+    for (int k = 0; k < 22; k++) num[k] = swar_mod17(p[(size_t)k * p_pitch + i]);
+    swar_div_zh(num, t, rem);
 #pragma unroll
     for (int j = 0; j < 18; j++) q[(size_t)j * q_pitch + i] = (uint8_t)t[j];
 #pragma unroll
-    for (int j = 0; j < 4; j++) r[(size_t)j * r_pitch + i] = (uint8_t)add17(num[j], t[j]);
+    for (int j = 0; j < 4; j++) r[(size_t)j * r_pitch + i] = (uint8_t)rem[j];
   }
 }
 

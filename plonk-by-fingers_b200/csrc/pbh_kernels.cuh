@@ -462,20 +462,42 @@ __device__ __forceinline__ void swar_ntt4(uint32_t w0, uint32_t w1, uint32_t w2,
   }
 }
 
+// vec: 0 = byte path, 4 = one 32-bit word per plane and thread (4 items), 16 = one 128-bit word (16 items; needs
+// 16-byte aligned bases and pitches).  Wider accesses keep more bytes in flight per thread: the kernel is
+// latency-limited, not ALU-limited.
 template <bool INVERSE>
 __global__ void __launch_bounds__(kBlock) ntt4_kernel(size_t n, const uint8_t* __restrict__ in, size_t in_pitch,
-                                                       uint8_t* __restrict__ out, size_t out_pitch, bool vec_ok) {
-  const size_t n4 = vec_ok ? n / 4 : 0;
+                                                       uint8_t* __restrict__ out, size_t out_pitch, int vec) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
-    uint32_t wv[4], ov[4];
+  size_t done = 0;
+  if (vec == 16) {
+    const size_t n16 = n / 16;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n16; q += stride) {
+      uint4 wv[4], ov[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) wv[k] = reinterpret_cast<const uint32_t*>(in + (size_t)k * in_pitch)[q];
-    swar_ntt4<INVERSE>(wv[0], wv[1], wv[2], wv[3], ov);
+      for (int k = 0; k < 4; k++) wv[k] = reinterpret_cast<const uint4*>(in + (size_t)k * in_pitch)[q];
+      uint32_t o[4];
+      swar_ntt4<INVERSE>(wv[0].x, wv[1].x, wv[2].x, wv[3].x, o); ov[0].x = o[0]; ov[1].x = o[1]; ov[2].x = o[2]; ov[3].x = o[3];
+      swar_ntt4<INVERSE>(wv[0].y, wv[1].y, wv[2].y, wv[3].y, o); ov[0].y = o[0]; ov[1].y = o[1]; ov[2].y = o[2]; ov[3].y = o[3];
+      swar_ntt4<INVERSE>(wv[0].z, wv[1].z, wv[2].z, wv[3].z, o); ov[0].z = o[0]; ov[1].z = o[1]; ov[2].z = o[2]; ov[3].z = o[3];
+      swar_ntt4<INVERSE>(wv[0].w, wv[1].w, wv[2].w, wv[3].w, o); ov[0].w = o[0]; ov[1].w = o[1]; ov[2].w = o[2]; ov[3].w = o[3];
 #pragma unroll
-    for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = ov[k];
+      for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(out + (size_t)k * out_pitch)[q] = ov[k];
+    }
+    done = n16 * 16;
+  } else if (vec == 4) {
+    const size_t n4 = n / 4;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+      uint32_t wv[4], ov[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) wv[k] = reinterpret_cast<const uint32_t*>(in + (size_t)k * in_pitch)[q];
+      swar_ntt4<INVERSE>(wv[0], wv[1], wv[2], wv[3], ov);
+#pragma unroll
+      for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = ov[k];
+    }
+    done = n4 * 4;
   }
-  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  for (size_t i = done + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint32_t ov[4];
     swar_ntt4<INVERSE>(in[i], in[in_pitch + i], in[2 * in_pitch + i], in[3 * in_pitch + i], ov);   // one live lane
 #pragma unroll
@@ -554,10 +576,21 @@ __global__ void __launch_bounds__(kBlock) poly_add_kernel(size_t n, uint32_t len
   const size_t n4 = vec_ok ? n / 4 : 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
-    for (uint32_t k = 0; k < len; k++) {
-      uint32_t x = swar_mod17(reinterpret_cast<const uint32_t*>(a + (size_t)k * a_pitch)[q]);
-      uint32_t y = swar_mod17(reinterpret_cast<const uint32_t*>(b + (size_t)k * b_pitch)[q]);
-      reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = swar_mod17(x + (subtract ? swar_neg17(y) : y));
+    for (uint32_t k0 = 0; k0 < len; k0 += 8) {      // eight planes' loads are issued before any is consumed
+      uint32_t x[8], y[8];
+#pragma unroll
+      for (uint32_t j = 0; j < 8; j++) {
+        const bool live = k0 + j < len;
+        x[j] = live ? reinterpret_cast<const uint32_t*>(a + (size_t)(k0 + j) * a_pitch)[q] : 0u;
+        y[j] = live ? reinterpret_cast<const uint32_t*>(b + (size_t)(k0 + j) * b_pitch)[q] : 0u;
+      }
+#pragma unroll
+      for (uint32_t j = 0; j < 8; j++) {
+        if (k0 + j < len) {
+          const uint32_t yy = swar_mod17(y[j]);
+          reinterpret_cast<uint32_t*>(out + (size_t)(k0 + j) * out_pitch)[q] = swar_mod17(swar_mod17(x[j]) + (subtract ? swar_neg17(yy) : yy));
+        }
+      }
     }
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {

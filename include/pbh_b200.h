@@ -249,7 +249,8 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
  * the device sustains for one instruction class; the INT32 / FMA roofline denominators of SURVEY.md §8d.
  * which: 0 IMAD, 1 LOP3+IADD3, 2 half IMAD half ALU, 3 FFMA, 4 HFMA2 (counted once per instruction; each carries two
  * fp16 lanes), 5 IDP.4A (dp4a; four byte MACs each), 6 IMAD.HI+IADD, 7 half FFMA half IMAD,
- * 8 FFMA with three register operands (polynomial MAC shape), 9 IMAD with three register operands */
+ * 8 FFMA with three register operands (polynomial MAC shape), 9 IMAD with three register operands,
+ * 10 FFMA2 (packed fp32x2, counted per instruction) with three register-pair operands, 11 FFMA2 with a broadcast-pair multiplicand */
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second);
 
 #ifdef __cplusplus

@@ -722,7 +722,7 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
 
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second) {
   CTX_CHECK(ctx);
-  if (!lane_ops_per_second || which < 0 || which > 9) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
+  if (!lane_ops_per_second || which < 0 || which > 11) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   uint32_t* sink = nullptr;
   CUDA_TRY(ctx, cudaMalloc(&sink, 4));
@@ -742,7 +742,9 @@ int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second)
       case 6: int32_peak_kernel<6><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
       case 7: int32_peak_kernel<7><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
       case 8: mac3_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
-      default: mac3_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 9: mac3_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 10: ffma2_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      default: ffma2_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
     }
     ctx->launches++;
   };

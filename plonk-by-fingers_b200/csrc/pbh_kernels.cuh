@@ -915,4 +915,39 @@ __global__ void __launch_bounds__(kBlock) mac3_peak_kernel(uint32_t iters, uint3
   }
 }
 
+// packed fp32x2 FMA (FFMA2, new on sm_100): three distinct 64-bit register-pair operands per instruction, the shape a
+// pair-packed polynomial MAC would have.  WHICH 0: all-pair operands; 1: one operand is a broadcast pair (a, a) built
+// from a scalar (the multiplicand of a row of an outer-product MAC).
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+template <int WHICH>
+__global__ void __launch_bounds__(kBlock) ffma2_peak_kernel(uint32_t iters, uint32_t seed, uint32_t* sink) {
+  float s0 = 1.0f + threadIdx.x * 1e-7f, s1 = s0 + 1e-6f, s2 = s0 + 2e-6f, s3 = s0 + 3e-6f;
+  unsigned long long x0 = pack2(s0, s1), x1 = pack2(s1, s2), x2 = pack2(s2, s3), x3 = pack2(s3, s0);
+  float t0 = 1e-3f * (seed & 7);
+  unsigned long long y0 = pack2(t0, t0 + 1e-4f), y1 = pack2(t0 + 2e-4f, t0 + 3e-4f), y2 = pack2(t0 + 4e-4f, t0 + 5e-4f), y3 = pack2(t0 + 6e-4f, t0 + 7e-4f);
+  unsigned long long c0 = pack2(0, 1), c1 = pack2(2, 3), c2 = pack2(4, 5), c3 = pack2(6, 7), c4 = pack2(8, 9), c5 = pack2(10, 11), c6 = pack2(12, 13),
+                     c7 = pack2(14, 15);
+  for (uint32_t it = 0; it < iters; it++) {
+    if (WHICH == 1) { x0 = pack2(s0, s0); x1 = pack2(s1, s1); x2 = pack2(s2, s2); x3 = pack2(s3, s3); }
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+      c0 = ffma2(x0, y0, c0); c1 = ffma2(x0, y1, c1); c2 = ffma2(x1, y2, c2); c3 = ffma2(x1, y3, c3);
+      c4 = ffma2(x2, y0, c4); c5 = ffma2(x2, y1, c5); c6 = ffma2(x3, y2, c6); c7 = ffma2(x3, y3, c7);
+    }
+    s0 += __uint_as_float((uint32_t)c7) * 1e-30f; y0 = ffma2(c0, pack2(1e-30f, 1e-30f), y0);
+    if (WHICH == 0) x0 = ffma2(c7, pack2(1e-30f, 1e-30f), x0);
+  }
+  unsigned long long r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  if (r == 0x123456789ull) sink[0] = 1;
+}
+
 }  // namespace pbh

@@ -75,8 +75,12 @@ PBH_HD F32 f_from_u32(uint32_t b, F32*) {                          // exact for 
 
 // schoolbook products, unreduced, in outer-product order: consecutive FFMAs share the multiplicand a[i] (operand
 // reuse cache, fewer register-bank conflicts) and write different accumulators (independent chains)
+#ifndef PBH_MAC_ORDER
+#define PBH_MAC_ORDER 0
+#endif
 template <class T, int LA, int LB>
 PBH_HD void fpoly_mul(const T (&a)[LA], const T (&b)[LB], T (&out)[LA + LB - 1]) {
+#if PBH_MAC_ORDER == 0
 #pragma unroll
   for (int i = 0; i < LA; i++) {
 #pragma unroll
@@ -85,6 +89,25 @@ PBH_HD void fpoly_mul(const T (&a)[LA], const T (&b)[LB], T (&out)[LA + LB - 1])
       out[i + j] = (i == 0 || j == LB - 1) ? f_mul(a[i], b[j]) : f_fma(a[i], b[j], out[i + j]);
     }
   }
+#elif PBH_MAC_ORDER == 1
+#pragma unroll
+  for (int k = 0; k < LA + LB - 1; k++) {
+    bool first = true;
+#pragma unroll
+    for (int i = 0; i < LA; i++) {
+      if (k - i >= 0 && k - i < LB) { out[k] = first ? f_mul(a[i], b[k - i]) : f_fma(a[i], b[k - i], out[k]); first = false; }
+    }
+  }
+#else
+  // column order: fixed b[j], varying a[i]
+#pragma unroll
+  for (int j = 0; j < LB; j++) {
+#pragma unroll
+    for (int i = 0; i < LA; i++) {
+      out[i + j] = (j == 0 || i == LA - 1) ? f_mul(a[i], b[j]) : f_fma(a[i], b[j], out[i + j]);
+    }
+  }
+#endif
 }
 template <class T, int LA, int LB, int LO>
 PBH_HD void fpoly_mac(const T (&a)[LA], const T (&b)[LB], T (&acc)[LO]) {

@@ -611,3 +611,69 @@ def test_full_size_properties(gpu_ctx, oracle):
     ok = su == 0
     acc = float(((vu == 1) & ok).sum()) / n
     assert abs(acc - 0.032) < 0.005
+
+
+def test_config2_verifier_16m(gpu_ctx, oracle):
+    """BASELINE.json configs[2]: 16 M proofs through the verifier.  Size-independent properties: the two verifier
+    algorithms (group tables vs per-item curve arithmetic + Miller loop) agree byte for byte, accept <=> e1 == e2,
+    tampered evaluations never raise the acceptance count, an oracle-checked strided sample."""
+    import torch
+    n = 1 << 24
+    t, a = gpu_ctx["table"], gpu_ctx["arith"]
+    w, r, c, u = t.generate_inputs(n, seed=0xB200, dist=1)
+    proof, status = t.prove_batch(w, r, c)
+    vt, gt_t = t.verify_batch(proof, c, u, want_gt=True)
+    va, gt_a = a.verify_batch(proof, c, u, want_gt=True)
+    t.sync(); a.sync()
+    assert int((status != 0).sum()) == 0
+    assert torch.equal(vt, va) and torch.equal(gt_t, gt_a)
+    assert torch.equal((gt_t[0] == gt_t[2]) & (gt_t[1] == gt_t[3]), vt == 1)
+    accepted = int((vt == 1).sum())
+    assert 0.55 < accepted / n < 0.75                     # ~63 % of full-path items verify (SURVEY.md §2.4: 3.2 / 5.1)
+    bad = proof.clone(); bad[20] = (bad[20] + 1) % 17      # a_z tampered everywhere
+    vb = t.verify_batch(bad, c, u)
+    t.sync()
+    assert int(((vb != 0) & (vb != 1)).sum()) == 0 and int((vb == 1).sum()) < accepted
+    idx = torch.arange(0, n, 40009, device=w.device)
+    po, so = oracle.prove_batch(*(x[..., idx].cpu().numpy() for x in (w, r, c)), threads=8)
+    vo, go = oracle.verify_batch(po, c[:, idx].cpu().numpy(), u[idx].cpu().numpy(), threads=8)
+    assert np.array_equal(proof[:, idx].cpu().numpy(), po) and np.array_equal(vt[idx].cpu().numpy(), vo)
+    assert np.array_equal(gt_t[:, idx].cpu().numpy(), go)
+
+
+def test_config4_256m_end_to_end_sharding(gpu_ctx, oracle):
+    """BASELINE.json configs[4] at full size on one GPU: 2^28 witnesses proved and verified as 1 shard and as 8 shards
+    (the ranks of an 8-GPU run, executed one after the other here): identical verdict bitmaps, digests add up."""
+    import torch
+    from pbh_b200 import sharding
+    ctx = gpu_ctx["table"]
+    n = 1 << 28
+    dev = torch.device("cuda", 0)
+
+    def run(first, count):
+        w, r, c, u = ctx.generate_inputs(count, first_index=first, seed=0xB200, dist=1)
+        proof = torch.empty((27, count), dtype=torch.uint8, device=dev); status = torch.empty((count,), dtype=torch.uint8, device=dev)
+        result = torch.empty((count,), dtype=torch.uint8, device=dev); bitmap = torch.empty((count // 8,), dtype=torch.uint8, device=dev)
+        digest = torch.empty((1,), dtype=torch.int64, device=dev)
+        ctx.prove_digest_batch(w, r, c, proof, status, digest, first_index=first)
+        ctx.verify_bitmap_batch(proof, c, u, result, bitmap)
+        ctx.sync()
+        ok = int((status != 0).sum()) == 0
+        sample = (proof[:, ::(1 << 20) + 7].cpu().numpy(), w[:, ::(1 << 20) + 7].cpu().numpy(), r[:, ::(1 << 20) + 7].cpu().numpy(),
+                  c[:, ::(1 << 20) + 7].cpu().numpy())
+        return bitmap, int(digest.item()) & (2**64 - 1), ok, sample
+
+    whole_bitmap, whole_digest, ok, sample = run(0, n)
+    assert ok
+    po, so = oracle.prove_batch(sample[1], sample[2], sample[3], threads=8)
+    assert np.array_equal(sample[0], po)                    # an oracle-checked strided sample of the 2^28 proofs
+    whole_bitmap = whole_bitmap.cpu()
+    total = 0
+    parts = []
+    for rank in range(8):
+        lo, hi = sharding.shard_range(n, rank, 8)
+        b, d, ok, _ = run(lo, hi - lo)
+        assert ok
+        parts.append(b.cpu()); total = (total + d) % 2**64
+    assert total == whole_digest
+    assert torch.equal(torch.cat(parts), whole_bitmap)

@@ -106,7 +106,12 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
     threads = max(1, O.hardware_threads())
-    sample = 20000 * threads if args.cpu_sample is None else args.cpu_sample
+    if args.cpu_sample is None:
+        # bounded sample: size the step so that the whole --steps K run stays near one minute of wall clock
+        rate, _ = cpu_leg(2000 * threads, threads)
+        sample = int(max(1000 * threads, min(20000 * threads, rate * 60.0 / max(1, args.steps))))
+    else:
+        sample = args.cpu_sample
     for _ in range(args.warmup):
         cpu_leg(max(1000, sample // 10), threads)
     t_total = 0.0

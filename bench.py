@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-arith", action="store_true", help="skip timing the PBH_ALGO_ARITH kernels")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--no-cycle-graph", action="store_true", help="replay one graph per step instead of one per ring cycle")
     args = ap.parse_args()
@@ -320,6 +321,16 @@ def main():
     verify_bitmap_ms = time_kernel(lambda s_: ctx.verify_bitmap_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], outs[s_]["result"],
                                                                       outs[s_]["bitmap"]), reps)
     clocks = sampler.stop()
+    # the same kernels with per-item curve arithmetic (PBH_ALGO_ARITH: fixed-base MSM commitments, Straus MSM, Miller loops,
+    # final exponentiations): reported beside the default group-table algorithm, both bit-exact
+    arith = None
+    if args.algo == "table" and not args.no_arith:
+        ctx.set_algo("arith")
+        ap_ms = time_kernel(lambda s_: ctx.prove_batch(ins[s_][0], ins[s_][1], ins[s_][2], proof=outs[s_]["proof"], status=outs[s_]["status"]), 20)
+        av_ms = time_kernel(lambda s_: ctx.verify_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], result=outs[s_]["result"]), 20)
+        ctx.set_algo("table")
+        arith = {"prove_ms": ap_ms, "verify_ms": av_ms, "proofs_per_s_per_gpu": n / (ap_ms * 1e-3), "verifies_per_s_per_gpu": n / (av_ms * 1e-3),
+                 "prove_plus_verify_per_s_per_gpu": n / ((ap_ms + av_ms) * 1e-3)}
 
     # ---- sanity inside the bench: every timed item proved (status 0) and reached the pairing check
     o = outs[(args.steps - 1) % ring]
@@ -445,6 +456,7 @@ def main():
                     "verify_with_bitmap_ms": verify_bitmap_ms, "proofs_per_s_per_gpu": n / (prove_ms * 1e-3),
                     "verifies_per_s_per_gpu": n / (verify_ms * 1e-3), "prove_GBps": prove_gbs, "verify_GBps": verify_gbs,
                     "prove_hbm_frac": prove_gbs / peak, "verify_hbm_frac": verify_gbs / peak},
+        "arith_algo_kernels": arith,
         "int32_peak": int32,
         "cpu_baseline": cpu,
         "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n},

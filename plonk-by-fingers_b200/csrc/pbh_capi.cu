@@ -259,14 +259,18 @@ static int launch_digest(pbh_ctx* ctx, cudaStream_t st, size_t n, uint64_t first
 // digest (nullable): device uint64, already zeroed on `st`; receives the digest of the 27 proof planes
 static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint64_t first_index = 0, uint64_t* digest = nullptr) {
   if (A.n == 0) return PBH_OK;
-  if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32 && ctx->use_tma) {
+  if (ctx->prover_fp32 && ctx->use_tma) {
     ProveTmaMaps M;
     if (make_plane_map(&M.wit, A.wit, A.n, A.wit_pitch, 12) && make_plane_map(&M.rnd, A.rnd, A.n, A.rand_pitch, 9) &&
         make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) && make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27)) {
       size_t tiles = (A.n + kTile - 1) / kTile;
       int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2);   // persistent: two resident blocks per SM
-      prove_f32_tma_kernel<<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n,
-                                                   first_index, (unsigned long long*)digest, fresh_tile_counter(ctx, st, 0));
+      if (ctx->algo == PBH_ALGO_TABLE)
+        prove_f32_tma_kernel<ALGO_TABLE><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status,
+                                                                 A.n, first_index, (unsigned long long*)digest, fresh_tile_counter(ctx, st, 0));
+      else
+        prove_f32_tma_kernel<ALGO_ARITH><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status,
+                                                                 A.n, first_index, (unsigned long long*)digest, fresh_tile_counter(ctx, st, 0));
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
       return PBH_OK;
@@ -274,14 +278,16 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint6
     // base or pitch not 16-byte aligned: fall through to the plain-load kernel
   }
   int grid = grid_for(ctx, A.n, 8);
-  if (ctx->algo == PBH_ALGO_TABLE && ctx->prover_fp32) {
+  if (ctx->prover_fp32 && ctx->algo == PBH_ALGO_ARITH) {
+    prove_f32_kernel<ALGO_ARITH, 256, 2><<<grid_for(ctx, A.n, 8), 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A);
+  } else if (ctx->prover_fp32) {
     // launch shape of the FP32 prover: threads per block / resident blocks per SM the register budget is capped for
     switch (ctx->prover_variant) {
-      case 1: prove_f32_kernel<256, 1><<<grid_for(ctx, A.n, 8), 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
-      case 2: prove_f32_kernel<128, 4><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 16)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
-      case 3: prove_f32_kernel<128, 5><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 20)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
-      case 4: prove_f32_kernel<128, 6><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 24)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
-      default: prove_f32_kernel<256, 2><<<grid_for(ctx, A.n, 8), 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      case 1: prove_f32_kernel<ALGO_TABLE, 256, 1><<<grid_for(ctx, A.n, 8), 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      case 2: prove_f32_kernel<ALGO_TABLE, 128, 4><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 16)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      case 3: prove_f32_kernel<ALGO_TABLE, 128, 5><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 20)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      case 4: prove_f32_kernel<ALGO_TABLE, 128, 6><<<(int)std::max<size_t>(1, std::min((A.n + 127) / 128, (size_t)ctx->sm_count * 24)), 128, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
+      default: prove_f32_kernel<ALGO_TABLE, 256, 2><<<grid_for(ctx, A.n, 8), 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->d_tables, A); break;
     }
   } else if (ctx->algo == PBH_ALGO_TABLE) prove_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   else prove_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);

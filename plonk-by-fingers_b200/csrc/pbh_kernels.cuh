@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kBlock) prove_kernel(const Consts K, const Tab
 }
 
 // Plonk::prove with the F_17 arithmetic on the FP32 FMA pipes (pbh_prove_f32.cuh); PBH_ALGO_TABLE only
-template <int THREADS, int MIN_BLOCKS>
+template <int ALGO, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) prove_f32_kernel(const Consts K, const ConstsF KF, const Tables* __restrict__ gT,
                                                                          const ProveArgs A) {
   __shared__ Tables sT;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) prove_f32_kernel(const Co
       for (int k = 0; k < 5; k++) c[k] = 0;
     }
     ProofRegs P;
-    uint32_t status = prove_item_f32(w, r, c, K, KF, sT, P);
+    uint32_t status = prove_item_f32<ALGO>(w, r, c, K, KF, sT, P);
     if (bad) status = PBH_ST_BAD_ENCODING;
     store_proof(A, i, P, status);
   }
@@ -167,6 +167,7 @@ struct ProveTmaSmem {
   Tables T;
 };
 
+template <int ALGO>
 __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_constant__ ProveTmaMaps M, const Consts K, const ConstsF KF,
                                                                   const Tables* __restrict__ gT, uint8_t* __restrict__ proof_out,
                                                                   size_t proof_pitch, uint8_t* __restrict__ status_out, size_t n,
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
       for (int k = 0; k < 5; k++) c[k] = 0;
     }
     ProofRegs P;
-    uint32_t status = prove_item_f32(w, r, c, K, KF, S.T, P, unsat ? 1 : 0);
+    uint32_t status = prove_item_f32<ALGO>(w, r, c, K, KF, S.T, P, unsat ? 1 : 0);
     if (bad) status = PBH_ST_BAD_ENCODING;
 
     uint8_t* out = &S.out[stage][0][tid];

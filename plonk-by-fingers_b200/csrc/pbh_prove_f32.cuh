@@ -139,31 +139,43 @@ struct ConstsF {
 };
 
 struct ProofF {
-  uint32_t e[9];     // discrete logs (base G, 0..16) of a_s b_s c_s z_s t_lo_s t_mid_s t_hi_s w_z_s w_z_omega_s
+  uint32_t e[9];     // a_s b_s c_s z_s t_lo_s t_mid_s t_hi_s w_z_s w_z_omega_s: discrete logs base G (TABLE) or packed points (ARITH)
   uint32_t ev[7];    // canonical evaluations
 };
 
-// dot product with the SRS discrete logs -> exponent of G (SRS::eval_at_s in the exponent, see commit<> of
-// pbh_prove.cuh); `oob` is set when a coefficient at or beyond n_pts is non-zero (src/plonk.rs:56)
-template <class T, int L>
-PBH_HD uint32_t fcommit(const T (&c)[L], const ConstsF& KF, uint32_t n_pts, bool reduced, bool& oob) {
+// SRS::eval_at_s of a coefficient array (src/plonk.rs:51-58); `oob` is set when a coefficient at or beyond n_pts is
+// non-zero (the reference then indexes g1s out of bounds, src/plonk.rs:56).
+//   ALGO_TABLE: dot product with the SRS discrete logs -> exponent of G (see commit<> of pbh_prove.cuh); returns 0..16.
+//   ALGO_ARITH: per-term fixed-base multiples [c_i]g1s[i] added with the affine group law; returns the packed point.
+template <int ALGO, class T, int L>
+PBH_HD uint32_t fcommit(const T (&c)[L], const ConstsF& KF, const Tables& Tb, uint32_t n_pts, bool reduced, bool& oob) {
   T* tag = nullptr;
-  T e = f_mul(c[0], f_const(KF.srs_dlog[0], tag));
-#pragma unroll
-  for (int i = 1; i < L; i++) e = f_fma(c[i], f_const(KF.srs_dlog[i], tag), e);
   if (n_pts < (uint32_t)L) {                       // uniform, false for the usual 7-point SRS except for w_z
 #pragma unroll
     for (int j = 0; j < L; j++)
       if ((uint32_t)j >= n_pts) oob = oob | !f_is_zero(reduced ? c[j] : f_red(c[j]));
   }
-  return f_canon(f_red(e));
+  if (ALGO == ALGO_TABLE) {
+    T e = f_mul(c[0], f_const(KF.srs_dlog[0], tag));
+#pragma unroll
+    for (int i = 1; i < L; i++) e = f_fma(c[i], f_const(KF.srs_dlog[i], tag), e);
+    return f_canon(f_red(e));
+  } else {
+    G1 acc = g1_identity();
+#pragma unroll
+    for (int i = 0; i < L; i++) {
+      const uint32_t ci = f_canon(reduced ? c[i] : f_red(c[i]));
+      acc = g1_add(acc, g1_unpack(Tb.srs_mult[i][ci]), Tb.inv101);
+    }
+    return g1_pack(acc);
+  }
 }
 
 // w[12], rnd[9], ch[5]: inputs as exact small integers (0..16).  inv17c: centred inverses as floats, indexed by the
 // canonical residue.  Returns the status byte among {0, 2, 3, 4, 5} (satisfiability, status 1, is the caller's).
-template <class T>
-PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (&ch_in)[5], const ConstsF& KF, uint32_t n_pts,
-                               const float* inv17c, ProofF& P) {
+template <int ALGO, class T>
+PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (&ch_in)[5], const ConstsF& KF, const Tables& Tb,
+                               uint32_t n_pts, const float* inv17c, ProofF& P) {
   T* tag = nullptr;
   // blinders and challenges are used as they come (0..16); the bound check shows that centring them is not needed
   // (worst-case magnitude 4.8 M, below red17's 2^23 range)
@@ -181,9 +193,9 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   b[0] = f_sub(fb[0], rnd[3]); b[1] = f_sub(fb[1], rnd[2]); b[2] = fb[2]; b[3] = fb[3]; b[4] = rnd[3]; b[5] = rnd[2];
   c[0] = f_sub(fc[0], rnd[5]); c[1] = f_sub(fc[1], rnd[4]); c[2] = fc[2]; c[3] = fc[3]; c[4] = rnd[5]; c[5] = rnd[4];
   bool oob_abc = false, oob_z = false, oob_t = false, oob_w = false;
-  P.e[0] = fcommit(a, KF, n_pts, false, oob_abc);                             // src/plonk.rs:255-257
-  P.e[1] = fcommit(b, KF, n_pts, false, oob_abc);
-  P.e[2] = fcommit(c, KF, n_pts, false, oob_abc);
+  P.e[0] = fcommit<ALGO>(a, KF, Tb, n_pts, false, oob_abc);                             // src/plonk.rs:255-257
+  P.e[1] = fcommit<ALGO>(b, KF, Tb, n_pts, false, oob_abc);
+  P.e[2] = fcommit<ALGO>(c, KF, Tb, n_pts, false, oob_abc);
 
   // ---- accumulator                                                          src/plonk.rs:278-299
   T acc[4];
@@ -210,7 +222,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   T z[7];
   z[0] = f_sub(accx[0], rnd[8]); z[1] = f_sub(accx[1], rnd[7]); z[2] = f_sub(accx[2], rnd[6]); z[3] = accx[3];
   z[4] = rnd[8]; z[5] = rnd[7]; z[6] = rnd[6];
-  P.e[3] = fcommit(z, KF, n_pts, false, oob_z);                               // src/plonk.rs:313
+  P.e[3] = fcommit<ALGO>(z, KF, Tb, n_pts, false, oob_z);                               // src/plonk.rs:313
 
   // ---- quotient numerator: t1 + alpha (A'B'C' z - A''B''C'' z_omega) + alpha^2 (z - 1) L1     src/plonk.rs:339-369
   T num[22];
@@ -296,9 +308,9 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   T tlo[6], tmid[6], thi[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) { tlo[i] = t[i]; tmid[i] = t[6 + i]; thi[i] = t[12 + i]; }
-  P.e[6] = fcommit(thi, KF, n_pts, false, oob_t);                             // src/plonk.rs:383-385
-  P.e[5] = fcommit(tmid, KF, n_pts, false, oob_t);
-  P.e[4] = fcommit(tlo, KF, n_pts, false, oob_t);
+  P.e[6] = fcommit<ALGO>(thi, KF, Tb, n_pts, false, oob_t);                             // src/plonk.rs:383-385
+  P.e[5] = fcommit<ALGO>(tmid, KF, Tb, n_pts, false, oob_t);
+  P.e[4] = fcommit<ALGO>(tlo, KF, Tb, n_pts, false, oob_t);
 
   // ---- evaluations at z                                                     src/plonk.rs:393-399
   T zp[10];
@@ -386,8 +398,8 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 #pragma unroll
     for (int k = 4; k >= 0; k--) wzw[k] = f_red(f_fma(zo, wzw[k + 1], z[k + 1]));
   }
-  P.e[7] = fcommit(wz, KF, n_pts, true, oob_w);                               // src/plonk.rs:445-446 -> :56 (Q2)
-  P.e[8] = fcommit(wzw, KF, n_pts, true, oob_w);
+  P.e[7] = fcommit<ALGO>(wz, KF, Tb, n_pts, true, oob_w);                               // src/plonk.rs:445-446 -> :56 (Q2)
+  P.e[8] = fcommit<ALGO>(wzw, KF, Tb, n_pts, true, oob_w);
 
   P.ev[0] = f_canon(a_z); P.ev[1] = f_canon(b_z); P.ev[2] = f_canon(c_z); P.ev[3] = f_canon(s1_z); P.ev[4] = f_canon(s2_z);
   P.ev[5] = f_canon(r_z); P.ev[6] = f_canon(zw_z);
@@ -407,10 +419,11 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 // is known to be short (alpha*b1*b3*b5*b7 = 0 mod 17: Q1/Q5 territory, status 1-4 only).  Inputs are canonical
 // bytes (< 17).  Output as packed points + canonical evaluations, like prove_one<ALGO_TABLE>.
 // `unsat_known`: -1 = evaluate constraints.satisfies here; 0 / 1 = already evaluated by the caller.
+template <int ALGO>
 PBH_HD uint32_t prove_item_f32(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
                                const ConstsF& KF, const Tables& T, ProofRegs& P, int unsat_known = -1) {
   const bool rare = ch[0] == 0u || rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
-  if (rare) return prove_one<ALGO_TABLE, true>(w, rnd, ch, K, T, P, unsat_known);
+  if (rare) return prove_one<ALGO_TABLE, true>(w, rnd, ch, K, T, P, unsat_known);   // status only: the algorithm is irrelevant
   const bool unsat = unsat_known < 0 ? unsatisfied(w, K) : (unsat_known != 0);
   F32* tag = nullptr;
   F32 wf[12], rf[9], cf[5];
@@ -421,9 +434,9 @@ PBH_HD uint32_t prove_item_f32(const uint32_t (&w)[12], const uint32_t (&rnd)[9]
 #pragma unroll
   for (int i = 0; i < 5; i++) cf[i] = f_from_u32(ch[i], tag);
   ProofF pf;
-  uint32_t status = prove_core_f32<F32>(wf, rf, cf, KF, K.n_pts, T.inv17c, pf);
+  uint32_t status = prove_core_f32<ALGO, F32>(wf, rf, cf, KF, T, K.n_pts, T.inv17c, pf);
 #pragma unroll
-  for (int k = 0; k < 9; k++) P.pt[k] = T.pt17[pf.e[k]];
+  for (int k = 0; k < 9; k++) P.pt[k] = (ALGO == ALGO_TABLE) ? T.pt17[pf.e[k]] : pf.e[k];
 #pragma unroll
   for (int k = 0; k < 7; k++) P.ev[k] = pf.ev[k];
   // program order of the reference: the satisfiability assert comes first; an SRS too short for a, b, c (only

@@ -59,6 +59,9 @@ def gpu_ctx(product_lib):
     # "table" runs the prover's arithmetic on the FP32 pipes (default); "table_int" is the same algorithm on int32 IMAD
     ctxs["table_int"] = pbh_b200.Context(device=0, algo="table")
     ctxs["table_int"].set_option(pbh_b200.OPT_PROVER_FP32, 0)
+    # per-item curve arithmetic with the int32 prover (the default "arith" context uses the FP32 core for the F_17 work)
+    ctxs["arith_int"] = pbh_b200.Context(device=0, algo="arith")
+    ctxs["arith_int"].set_option(pbh_b200.OPT_PROVER_FP32, 0)
     # FP32 prover with plain per-thread loads/stores instead of TMA-staged tiles
     ctxs["table_notma"] = pbh_b200.Context(device=0, algo="table")
     ctxs["table_notma"].set_option(pbh_b200.OPT_TMA, 0)

@@ -52,7 +52,9 @@ int emul_f32_bounds(double* max_exact, double* max_red) {
     for (auto& x : r) x = Bnd(16);
     for (auto& x : c) x = Bnd(16);
     ProofF pf;
-    prove_core_f32<Bnd>(w, r, c, KF, n_pts, inv, pf);
+    Tables tb; std::memset(&tb, 0, sizeof tb);
+    prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, KF, tb, n_pts, inv, pf);
+    prove_core_f32<ALGO_ARITH, Bnd>(w, r, c, KF, tb, n_pts, inv, pf);
   }
   {
     // the verifier's FP32 scalar path: discrete logs <= 101, evaluations reduced (<= 8), challenges and u <= 16
@@ -118,7 +120,8 @@ int emul_prove_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t om
     for (int k = 0; k < 5; k++) { ch[k] = chal[k * n + i]; bad |= ch[k] >= 17; }
     if (bad) { std::memset(w, 0, sizeof w); std::memset(r, 0, sizeof r); std::memset(ch, 0, sizeof ch); }
     ProofRegs P;
-    uint32_t st = algo == 2 ? prove_item_f32(w, r, ch, hs.K, hs.KF, hs.T, P)
+    uint32_t st = algo == 3 ? prove_item_f32<ALGO_ARITH>(w, r, ch, hs.K, hs.KF, hs.T, P)
+                : algo == 2 ? prove_item_f32<ALGO_TABLE>(w, r, ch, hs.K, hs.KF, hs.T, P)
                             : (algo == 1 ? prove_one<ALGO_TABLE>(w, r, ch, hs.K, hs.T, P) : prove_one<ALGO_ARITH>(w, r, ch, hs.K, hs.T, P));
     if (bad) st = PBH_ST_BAD_ENCODING;
     for (int k = 0; k < 27; k++) proof[k * n + i] = 0;

@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ALGOS = ("table", "arith")
-CTXS = ("table", "table_notma", "table_int", "arith")   # gpu_ctx keys: table = FP32-pipe prover with TMA tiles (default),
+CTXS = ("table", "table_notma", "table_int", "arith", "arith_int")   # gpu_ctx keys: table = FP32-pipe prover with TMA tiles (default),
 # table_notma = same with plain loads/stores, table_int = int32 prover, arith = per-item curve arithmetic
 
 
@@ -268,8 +268,10 @@ def test_other_circuits_and_srs(product_lib, oracle):
             vo, go = oracle.verify_batch(po, chal, u, circuit=oc, threads=8, **case)
             for algo in CTXS:
                 with pbh_b200.Context(circuit=pc, device=0, algo=algo.split("_")[0], **case) as ctx:
-                    if algo == "table_int":
+                    if algo.endswith("_int"):
                         ctx.set_option(pbh_b200.OPT_PROVER_FP32, 0)
+                    if algo.endswith("_notma"):
+                        ctx.set_option(pbh_b200.OPT_TMA, 0)
                     g1s, g2 = ctx.srs()
                     og1s, og2, oconst = oracle.setup(circuit=oc, **case)
                     assert np.array_equal(g1s, og1s) and np.array_equal(g2, og2)

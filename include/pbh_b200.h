@@ -172,6 +172,37 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
                            size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, const uint8_t* u, uint8_t* proof,
                            size_t proof_pitch, uint8_t* status, uint8_t* result);
 
+/* ---- record (array-of-structs) wire format — SURVEY.md §8(f) row 3 ---------------------------------------------
+ * The reference has no serialisation (Proof only derives Debug, PartialEq: src/plonk.rs:61).  These 32-byte records let a
+ * host exchange `Vec<Proof>` / per-item inputs with the library without per-field copies; the library transposes between
+ * records and byte planes on the device. */
+typedef struct pbh_witness_record {  /* one prove / verify input: Assigments + rand + Challange (src/plonk.rs:191-197, 468-474) */
+  uint8_t wit[12];      /* a[0..4) b[0..4) c[0..4) */
+  uint8_t rand[9];      /* b1..b9 */
+  uint8_t chal[5];      /* alpha beta gamma z v */
+  uint8_t u;            /* verifier rand[0] */
+  uint8_t reserved[5];  /* ignored on input */
+} pbh_witness_record;
+typedef struct pbh_proof_record {    /* one Proof (src/plonk.rs:61-95) + its status */
+  uint8_t xy[18];       /* x, y of a_s b_s c_s z_s t_lo_s t_mid_s t_hi_s w_z_s w_z_omega_s */
+  uint8_t inf_lo, inf_hi; /* `infinite` flags: bit k of inf_lo for points 0..7, bit 0 of inf_hi for point 8 */
+  uint8_t evals[7];     /* a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z */
+  uint8_t status;       /* PBH_ST_* (written by prove, ignored by verify) */
+  uint8_t reserved[4];  /* written as zero */
+} pbh_proof_record;
+/* Plonk::prove over n records (host pointers): out[i] = proof and status of in[i]. */
+int pbh_prove_records(pbh_ctx* ctx, size_t n, const pbh_witness_record* in, pbh_proof_record* out);
+/* Plonk::verify over n records (host pointers): proofs[i] checked with params[i].chal and params[i].u; result n bytes of PBH_VR_*. */
+int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, const pbh_witness_record* params, uint8_t* result);
+/* Device-side transposes between records and byte planes (device pointers).  Null plane pointers are skipped.
+ * witness records <-> wit (12 planes), rand (9), chal (5), u (1); proof records <-> proof (27 planes), status (1). */
+int pbh_witness_records_to_planes_dev(pbh_ctx* ctx, size_t n, const pbh_witness_record* rec, uint8_t* wit, size_t wit_pitch,
+                                      uint8_t* rand, size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u);
+int pbh_proof_records_to_planes_dev(pbh_ctx* ctx, size_t n, const pbh_proof_record* rec, uint8_t* proof, size_t proof_pitch,
+                                    uint8_t* status);
+int pbh_proof_planes_to_records_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status,
+                                    pbh_proof_record* rec);
+
 /* ---- sweep kernels (the per-kernel configs of BASELINE.json), HOST or DEVICE pointers --------- */
 /* `on_device` != 0: pointers are device pointers, kernels are only enqueued.                      */
 

@@ -406,7 +406,7 @@ int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch
   if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 64);
+  int rc = ensure_slots(ctx, 128);
   if (rc) return rc;
   const size_t C = ctx->chunk;
   size_t k = 0;
@@ -436,7 +436,7 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
   if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 64);
+  int rc = ensure_slots(ctx, 128);
   if (rc) return rc;
   const size_t C = ctx->chunk;
   size_t k = 0;
@@ -469,7 +469,7 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
   if (!wit || !rnd || !chal || !u || !proof || !status || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 64);
+  int rc = ensure_slots(ctx, 128);
   if (rc) return rc;
   const size_t C = ctx->chunk;
   size_t k = 0;
@@ -492,6 +492,109 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
+// ---- record wire format ------------------------------------------------------------------------------------------
+static_assert(sizeof(pbh_witness_record) == 32 && sizeof(pbh_proof_record) == 32, "records are 32 bytes");
+
+int pbh_witness_records_to_planes_dev(pbh_ctx* ctx, size_t n, const pbh_witness_record* rec, uint8_t* wit, size_t wit_pitch, uint8_t* rnd,
+                                      size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!rec || ((uintptr_t)rec % 16) != 0) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "records must be 16-byte aligned");
+  if ((wit && wit_pitch < n) || (rnd && rand_pitch < n) || (chal && chal_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  witness_records_to_planes_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, rec, wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, u);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+int pbh_proof_records_to_planes_dev(pbh_ctx* ctx, size_t n, const pbh_proof_record* rec, uint8_t* proof, size_t proof_pitch, uint8_t* status) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!rec || ((uintptr_t)rec % 16) != 0) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "records must be 16-byte aligned");
+  if (proof && proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  proof_records_to_planes_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, rec, proof, proof_pitch, status);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+int pbh_proof_planes_to_records_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status,
+                                    pbh_proof_record* rec) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!rec || !proof || ((uintptr_t)rec % 16) != 0) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer or records not 16-byte aligned");
+  if (proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  proof_planes_to_records_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, proof, proof_pitch, status, rec);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+
+// host records: per chunk, H2D records -> transpose -> plane kernels -> transpose -> D2H records, over the staging slots
+int pbh_prove_records(pbh_ctx* ctx, size_t n, const pbh_witness_record* in, pbh_proof_record* out) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!in || !out) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_slots(ctx, 128);
+  if (rc) return rc;
+  const size_t C = ctx->chunk;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    size_t m = std::min(C, n - lo);
+    int s = (int)(k % kSlots);
+    cudaStream_t st = ctx->slot_stream[s];
+    uint8_t* base = ctx->slot_buf[s];
+    uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C;
+    pbh_witness_record* d_in = reinterpret_cast<pbh_witness_record*>(base + 64 * C);
+    pbh_proof_record* d_out = reinterpret_cast<pbh_proof_record*>(base + 96 * C);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in + lo, m * sizeof(pbh_witness_record), cudaMemcpyHostToDevice, st));
+    witness_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_in, d_wit, C, d_rnd, C, d_chal, C, nullptr);
+    ctx->launches++;
+    ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
+    rc = launch_prove(ctx, st, A);
+    if (rc) return rc;
+    proof_planes_to_records_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_proof, C, d_status, d_out);
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out + lo, d_out, m * sizeof(pbh_proof_record), cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
+int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, const pbh_witness_record* params, uint8_t* result) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proofs || !params || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_slots(ctx, 128);
+  if (rc) return rc;
+  const size_t C = ctx->chunk;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    size_t m = std::min(C, n - lo);
+    int s = (int)(k % kSlots);
+    cudaStream_t st = ctx->slot_stream[s];
+    uint8_t* base = ctx->slot_buf[s];
+    uint8_t *d_proof = base, *d_chal = base + 27 * C, *d_u = base + 32 * C, *d_res = base + 33 * C;
+    pbh_witness_record* d_par = reinterpret_cast<pbh_witness_record*>(base + 64 * C);
+    pbh_proof_record* d_prf = reinterpret_cast<pbh_proof_record*>(base + 96 * C);
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_prf, proofs + lo, m * sizeof(pbh_proof_record), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_par, params + lo, m * sizeof(pbh_witness_record), cudaMemcpyHostToDevice, st));
+    proof_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_prf, d_proof, C, nullptr);
+    witness_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_par, nullptr, 0, nullptr, 0, d_chal, C, d_u);
+    ctx->launches += 2;
+    VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
+    rc = launch_verify(ctx, st, A);
+    if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));

@@ -699,6 +699,66 @@ __global__ void __launch_bounds__(kBlock) pairing_kernel(const Tables* __restric
   }
 }
 
+// ---- record <-> plane transposes (include/pbh_b200.h "record wire format") ------------------------------------------
+// One thread per 32-byte record: two 128-bit accesses on the record side (a warp touches 1 KB contiguously), byte-wide
+// coalesced accesses on the plane side.
+__device__ __forceinline__ void load_record(const void* rec, size_t i, uint32_t (&wv)[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(rec) + 2 * i;
+  uint4 lo = p[0], hi = p[1];
+  wv[0] = lo.x; wv[1] = lo.y; wv[2] = lo.z; wv[3] = lo.w; wv[4] = hi.x; wv[5] = hi.y; wv[6] = hi.z; wv[7] = hi.w;
+}
+__device__ __forceinline__ uint32_t record_byte(const uint32_t (&wv)[8], int k) { return (wv[k >> 2] >> (8 * (k & 3))) & 0xFFu; }
+
+__global__ void __launch_bounds__(kBlock) witness_records_to_planes_kernel(size_t n, const pbh_witness_record* __restrict__ rec,
+                                                                            uint8_t* __restrict__ wit, size_t wit_pitch,
+                                                                            uint8_t* __restrict__ rnd, size_t rand_pitch,
+                                                                            uint8_t* __restrict__ chal, size_t chal_pitch,
+                                                                            uint8_t* __restrict__ u) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t wv[8];
+    load_record(rec, i, wv);
+    if (wit) {
+#pragma unroll
+      for (int k = 0; k < 12; k++) wit[(size_t)k * wit_pitch + i] = (uint8_t)record_byte(wv, k);
+    }
+    if (rnd) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) rnd[(size_t)k * rand_pitch + i] = (uint8_t)record_byte(wv, 12 + k);
+    }
+    if (chal) {
+#pragma unroll
+      for (int k = 0; k < 5; k++) chal[(size_t)k * chal_pitch + i] = (uint8_t)record_byte(wv, 21 + k);
+    }
+    if (u) u[i] = (uint8_t)record_byte(wv, 26);
+  }
+}
+__global__ void __launch_bounds__(kBlock) proof_records_to_planes_kernel(size_t n, const pbh_proof_record* __restrict__ rec,
+                                                                          uint8_t* __restrict__ proof, size_t proof_pitch,
+                                                                          uint8_t* __restrict__ status) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t wv[8];
+    load_record(rec, i, wv);
+    if (proof) {
+#pragma unroll
+      for (int k = 0; k < 27; k++) proof[(size_t)k * proof_pitch + i] = (uint8_t)record_byte(wv, k);
+    }
+    if (status) status[i] = (uint8_t)record_byte(wv, 27);
+  }
+}
+__global__ void __launch_bounds__(kBlock) proof_planes_to_records_kernel(size_t n, const uint8_t* __restrict__ proof, size_t proof_pitch,
+                                                                          const uint8_t* __restrict__ status,
+                                                                          pbh_proof_record* __restrict__ rec) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t wv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 27; k++) wv[k >> 2] |= (uint32_t)proof[(size_t)k * proof_pitch + i] << (8 * (k & 3));
+    if (status) wv[6] |= (uint32_t)status[i] << 24;
+    uint4* p = reinterpret_cast<uint4*>(rec) + 2 * i;
+    p[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    p[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+  }
+}
+
 // ---- shard summaries ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) pack_verdicts_kernel(size_t n, const uint8_t* __restrict__ result,
                                                                 uint8_t* __restrict__ bitmap) {

@@ -41,10 +41,45 @@ PANIC_MESSAGES = {
 
 EXPORTS = """pbh_circuit_pbh_test pbh_ctx_create pbh_ctx_destroy pbh_last_error pbh_ctx_set_algo pbh_ctx_get_algo pbh_ctx_set_option
 pbh_ctx_device pbh_ctx_sync pbh_ctx_stream pbh_ctx_launch_count pbh_ctx_get_srs pbh_ctx_get_verifier_constants
-pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_prove_verify_batch pbh_prove_digest_batch_dev pbh_verify_bitmap_batch_dev pbh_ntt4_batch pbh_intt4_batch
+pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_prove_verify_batch pbh_prove_records pbh_verify_records pbh_witness_records_to_planes_dev
+pbh_proof_records_to_planes_dev pbh_proof_planes_to_records_dev pbh_prove_digest_batch_dev pbh_verify_bitmap_batch_dev pbh_ntt4_batch pbh_intt4_batch
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
 pbh_measure_int32_peak""".split()
+
+
+# 32-byte records of include/pbh_b200.h
+WITNESS_RECORD = np.dtype([("wit", np.uint8, (12,)), ("rand", np.uint8, (9,)), ("chal", np.uint8, (5,)), ("u", np.uint8), ("reserved", np.uint8, (5,))])
+PROOF_RECORD = np.dtype([("xy", np.uint8, (18,)), ("inf_lo", np.uint8), ("inf_hi", np.uint8), ("evals", np.uint8, (7,)), ("status", np.uint8),
+                         ("reserved", np.uint8, (4,))])
+
+
+def witness_records(wit, rand, chal, u=None):
+    """Byte planes (12,n) (9,n) (5,n) [(n,)] -> array of WITNESS_RECORD."""
+    n = np.shape(wit)[1]
+    rec = np.zeros(n, dtype=WITNESS_RECORD)
+    rec["wit"] = np.asarray(wit).T; rec["rand"] = np.asarray(rand).T; rec["chal"] = np.asarray(chal).T
+    if u is not None:
+        rec["u"] = np.asarray(u)
+    return rec
+
+
+def proof_records(proof, status=None):
+    """Byte planes (27,n) [(n,)] -> array of PROOF_RECORD."""
+    proof = np.asarray(proof)
+    rec = np.zeros(proof.shape[1], dtype=PROOF_RECORD)
+    rec["xy"] = proof[:18].T; rec["inf_lo"] = proof[18]; rec["inf_hi"] = proof[19]; rec["evals"] = proof[20:27].T
+    if status is not None:
+        rec["status"] = np.asarray(status)
+    return rec
+
+
+def proof_planes(rec):
+    """Array of PROOF_RECORD -> ((27,n) planes, (n,) status)."""
+    n = rec.shape[0]
+    proof = np.zeros((27, n), dtype=np.uint8)
+    proof[:18] = rec["xy"].T; proof[18] = rec["inf_lo"]; proof[19] = rec["inf_hi"]; proof[20:27] = rec["evals"].T
+    return proof, rec["status"].copy()
 
 
 class PbhError(RuntimeError):
@@ -314,6 +349,25 @@ class Context:
                                              C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr), C.c_void_p(Rs.ptr))
         self._check(rc, "pbh_prove_verify_batch")
         return P.arr, S.arr.reshape(-1), Rs.arr.reshape(-1)
+
+    # ---- record (array-of-structs) wire format ----
+    def prove_records(self, records):
+        """records: numpy array of WITNESS_RECORD (host) -> numpy array of PROOF_RECORD."""
+        rec = np.ascontiguousarray(records, dtype=WITNESS_RECORD)
+        out = np.zeros(rec.shape[0], dtype=PROOF_RECORD)
+        rc = self.lib.pbh_prove_records(self.h, C.c_size_t(rec.shape[0]), C.c_void_p(rec.ctypes.data), C.c_void_p(out.ctypes.data))
+        self._check(rc, "pbh_prove_records")
+        return out
+
+    def verify_records(self, proofs, params):
+        prf = np.ascontiguousarray(proofs, dtype=PROOF_RECORD); par = np.ascontiguousarray(params, dtype=WITNESS_RECORD)
+        if prf.shape[0] != par.shape[0]:
+            raise PbhError("proofs and params must have the same length")
+        res = np.zeros(prf.shape[0], dtype=np.uint8)
+        rc = self.lib.pbh_verify_records(self.h, C.c_size_t(prf.shape[0]), C.c_void_p(prf.ctypes.data), C.c_void_p(par.ctypes.data),
+                                         C.c_void_p(res.ctypes.data))
+        self._check(rc, "pbh_verify_records")
+        return res
 
     # ---- sweep kernels ----
     def _sweep(self, fn, arr, pin, pout, *pre):

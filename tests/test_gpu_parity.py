@@ -679,3 +679,23 @@ def test_config4_256m_end_to_end_sharding(gpu_ctx, oracle):
         parts.append(b.cpu()); total = (total + d) % 2**64
     assert total == whole_digest
     assert torch.equal(torch.cat(parts), whole_bitmap)
+
+
+@pytest.mark.parametrize("algo", ("table", "arith"))
+def test_record_wire_format(gpu_ctx, oracle, algo):
+    """32-byte array-of-structs records in, records out — same bytes as the plane API and the oracle."""
+    import pbh_b200
+    ctx = gpu_ctx[algo]
+    n = 300000 + 11                      # more than one staged chunk
+    wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=41, dist=0, threads=8)
+    po, so = oracle.prove_batch(wo, ro, co, threads=8)
+    vo = oracle.verify_batch(po, co, uo, threads=8, want_gt=False)
+    assert pbh_b200.WITNESS_RECORD.itemsize == 32 and pbh_b200.PROOF_RECORD.itemsize == 32
+    wrec = pbh_b200.witness_records(wo, ro, co, uo)
+    wrec["reserved"] = 0xAA              # ignored on input
+    prec = ctx.prove_records(wrec)
+    p, s = pbh_b200.proof_planes(prec)
+    assert np.array_equal(p, po) and np.array_equal(s, so) and not prec["reserved"].any()
+    res = ctx.verify_records(pbh_b200.proof_records(po, so), wrec)
+    assert np.array_equal(res, vo)
+    assert ctx.prove_records(wrec[:0]).shape == (0,)

@@ -130,6 +130,9 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 #define PBH_OPT_TMA 3
 /* PBH_OPT_CHUNK_LOG2: log2 of the items per staged chunk of the host-pointer entry points (8..20, default 18: measured best on PCIe Gen5). */
 #define PBH_OPT_CHUNK_LOG2 4
+/* PBH_OPT_SPECIALISE: when the context is the reference's own test circuit with SRS::create(2, 6), run the prover
+ * instantiation whose circuit and SRS constants are compile-time (1, default) or the generic kernel (0). */
+#define PBH_OPT_SPECIALISE 5
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */

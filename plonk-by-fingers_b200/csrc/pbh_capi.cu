@@ -32,6 +32,8 @@ struct pbh_ctx {
   int algo = PBH_ALGO_TABLE;
   int prover_variant = 0;
   size_t chunk = (size_t)1 << 18;          // items per staged chunk of the host-pointer entry points (PBH_OPT_CHUNK_LOG2)
+  bool pbh_circuit = false;                // the context's constants equal the compile-time PbhCK (pbh_prove_f32.cuh)
+  int specialise = 1;                      // PBH_OPT_SPECIALISE
   int use_tma = 1;                         // TMA-staged tiles when base/pitch alignment allows (PBH_OPT_TMA)
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;
@@ -96,6 +98,7 @@ int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_
   std::string err;
   int rc = host_setup(*circuit, srs_secret, srs_n, omega_pows, ctx->hs, err);
   if (rc != PBH_OK) { set_global_error(err); delete ctx; return rc; }
+  ctx->pbh_circuit = consts_match_pbh(ctx->hs.KF, ctx->hs.K.n_pts);
 
   int count = 0;
   cudaError_t ce = cudaGetDeviceCount(&count);
@@ -169,6 +172,7 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
   if (option == PBH_OPT_PROVER_FP32) { ctx->prover_fp32 = value != 0; return PBH_OK; }
   if (option == PBH_OPT_PROVER_LAUNCH_SHAPE) { ctx->prover_variant = value; return PBH_OK; }
   if (option == PBH_OPT_TMA) { ctx->use_tma = value != 0; return PBH_OK; }
+  if (option == PBH_OPT_SPECIALISE) { ctx->specialise = value != 0; return PBH_OK; }
   if (option == PBH_OPT_CHUNK_LOG2) {
     if (value < 8 || value > 20) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "chunk log2 must be in [8, 20]");
     ctx->chunk = (size_t)1 << value;
@@ -265,12 +269,18 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint6
         make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) && make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27)) {
       size_t tiles = (A.n + kTile - 1) / kTile;
       int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2);   // persistent: two resident blocks per SM
-      if (ctx->algo == PBH_ALGO_TABLE)
-        prove_f32_tma_kernel<ALGO_TABLE><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status,
-                                                                 A.n, first_index, (unsigned long long*)digest, fresh_tile_counter(ctx, st, 0));
+      unsigned int* tc = fresh_tile_counter(ctx, st, 0);
+      unsigned long long* dg = (unsigned long long*)digest;
+      // the compile-time instantiation for the reference's own circuit + SRS(2, 6) when the context's constants match it
+      const bool special = ctx->pbh_circuit && ctx->specialise;
+      if (ctx->algo == PBH_ALGO_TABLE && special)
+        prove_f32_tma_kernel<ALGO_TABLE, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
+      else if (ctx->algo == PBH_ALGO_TABLE)
+        prove_f32_tma_kernel<ALGO_TABLE, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
+      else if (special)
+        prove_f32_tma_kernel<ALGO_ARITH, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
       else
-        prove_f32_tma_kernel<ALGO_ARITH><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status,
-                                                                 A.n, first_index, (unsigned long long*)digest, fresh_tile_counter(ctx, st, 0));
+        prove_f32_tma_kernel<ALGO_ARITH, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
       return PBH_OK;

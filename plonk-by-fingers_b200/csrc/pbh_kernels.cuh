@@ -167,7 +167,7 @@ struct ProveTmaSmem {
   Tables T;
 };
 
-template <int ALGO>
+template <int ALGO, bool PBH_CIRCUIT>
 __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_constant__ ProveTmaMaps M, const Consts K, const ConstsF KF,
                                                                   const Tables* __restrict__ gT, uint8_t* __restrict__ proof_out,
                                                                   size_t proof_pitch, uint8_t* __restrict__ status_out, size_t n,
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
       for (int k = 0; k < 5; k++) c[k] = 0;
     }
     ProofRegs P;
-    uint32_t status = prove_item_f32<ALGO>(w, r, c, K, KF, S.T, P, unsat ? 1 : 0);
+    uint32_t status = prove_item_f32<ALGO, PBH_CIRCUIT>(w, r, c, K, KF, S.T, P, unsat ? 1 : 0);
     if (bad) status = PBH_ST_BAD_ENCODING;
 
     uint8_t* out = &S.out[stage][0][tid];

@@ -138,6 +138,58 @@ struct ConstsF {
   float vdlog[8];                              // verifier: dlogs of the 8 constant commitments (pbh_verify.cuh)
 };
 
+// Where the core reads circuit / SRS constants from.  RuntimeCK: the context's ConstsF (any 4-gate circuit, any SRS).
+// PbhCK: the reference's own circuit (src/pbh/mod.rs:56-67) with SRS::create(2, 6) as compile-time constants, so zero
+// coefficients vanish, +-1 become additions and the SRS-bounds checks fold away; used only when the context's constants
+// are exactly these (checked at context creation).
+struct RuntimeCK {
+  const ConstsF& F;
+  uint32_t npts;
+  PBH_HD float QL(int i) const { return F.QL[i]; }
+  PBH_HD float QR(int i) const { return F.QR[i]; }
+  PBH_HD float QO(int i) const { return F.QO[i]; }
+  PBH_HD float QM(int i) const { return F.QM[i]; }
+  PBH_HD float QC(int i) const { return F.QC[i]; }
+  PBH_HD float sig(int w, int i) const { return F.sig[w][i]; }
+  PBH_HD float S(int w, int i) const { return F.S[w][i]; }
+  PBH_HD float L1(int i) const { return F.L1[i]; }
+  PBH_HD float srs_dlog(int i) const { return F.srs_dlog[i]; }
+  PBH_HD uint32_t n_pts() const { return npts; }
+};
+struct PbhCK {
+  PBH_HD constexpr float QL(int i) const { return i == 0 ? -4.f : (i == 1 ? 1.f : (i == 2 ? 4.f : -1.f)); }
+  PBH_HD constexpr float QR(int i) const { return QL(i); }
+  PBH_HD constexpr float QO(int i) const { return i == 0 ? -1.f : 0.f; }
+  PBH_HD constexpr float QM(int i) const { return i == 0 ? 5.f : (i == 1 ? -1.f : (i == 2 ? -4.f : 1.f)); }
+  PBH_HD constexpr float QC(int) const { return 0.f; }
+  PBH_HD constexpr float sig(int w, int i) const {
+    return w == 0 ? (i == 0 ? 2.f : (i == 1 ? 8.f : (i == 2 ? -2.f : 3.f)))
+         : w == 1 ? (i == 0 ? 1.f : (i == 1 ? 4.f : (i == 2 ? -1.f : -5.f)))
+                  : (i == 0 ? -4.f : (i == 1 ? -8.f : (i == 2 ? 5.f : -3.f)));
+  }
+  PBH_HD constexpr float S(int w, int i) const {
+    return w == 0 ? (i == 0 ? 7.f : (i == 1 ? -4.f : (i == 2 ? -7.f : 6.f)))
+         : w == 1 ? (i == 0 ? 4.f : (i == 1 ? 0.f : (i == 2 ? -4.f : 1.f)))
+                  : (i == 0 ? 6.f : (i == 1 ? 7.f : (i == 2 ? 3.f : -3.f)));
+  }
+  PBH_HD constexpr float L1(int) const { return -4.f; }
+  PBH_HD constexpr float srs_dlog(int i) const {
+    return i == 0 ? 1.f : (i == 1 ? 2.f : (i == 2 ? 4.f : (i == 3 ? 8.f : (i == 4 ? -1.f : (i == 5 ? -2.f : (i == 6 ? -4.f : 0.f))))));
+  }
+  PBH_HD constexpr uint32_t n_pts() const { return 7u; }
+};
+// true when a context's float constants are exactly PbhCK's
+inline bool consts_match_pbh(const ConstsF& F, uint32_t n_pts) {
+  PbhCK c;
+  bool ok = n_pts == 7;
+  for (int i = 0; i < 4; i++) {
+    ok = ok && F.QL[i] == c.QL(i) && F.QR[i] == c.QR(i) && F.QO[i] == c.QO(i) && F.QM[i] == c.QM(i) && F.QC[i] == c.QC(i) && F.L1[i] == c.L1(i);
+    for (int w = 0; w < 3; w++) ok = ok && F.sig[w][i] == c.sig(w, i) && F.S[w][i] == c.S(w, i);
+  }
+  for (int i = 0; i < 10; i++) ok = ok && F.srs_dlog[i] == c.srs_dlog(i);
+  return ok;
+}
+
 struct ProofF {
   uint32_t e[9];     // a_s b_s c_s z_s t_lo_s t_mid_s t_hi_s w_z_s w_z_omega_s: discrete logs base G (TABLE) or packed points (ARITH)
   uint32_t ev[7];    // canonical evaluations
@@ -147,18 +199,19 @@ struct ProofF {
 // non-zero (the reference then indexes g1s out of bounds, src/plonk.rs:56).
 //   ALGO_TABLE: dot product with the SRS discrete logs -> exponent of G (see commit<> of pbh_prove.cuh); returns 0..16.
 //   ALGO_ARITH: per-term fixed-base multiples [c_i]g1s[i] added with the affine group law; returns the packed point.
-template <int ALGO, class T, int L>
-PBH_HD uint32_t fcommit(const T (&c)[L], const ConstsF& KF, const Tables& Tb, uint32_t n_pts, bool reduced, bool& oob) {
+template <int ALGO, class T, class CK, int L>
+PBH_HD uint32_t fcommit(const T (&c)[L], const CK& ck, const Tables& Tb, bool reduced, bool& oob) {
   T* tag = nullptr;
+  const uint32_t n_pts = ck.n_pts();
   if (n_pts < (uint32_t)L) {                       // uniform, false for the usual 7-point SRS except for w_z
 #pragma unroll
     for (int j = 0; j < L; j++)
       if ((uint32_t)j >= n_pts) oob = oob | !f_is_zero(reduced ? c[j] : f_red(c[j]));
   }
   if (ALGO == ALGO_TABLE) {
-    T e = f_mul(c[0], f_const(KF.srs_dlog[0], tag));
+    T e = f_mul(c[0], f_const(ck.srs_dlog(0), tag));
 #pragma unroll
-    for (int i = 1; i < L; i++) e = f_fma(c[i], f_const(KF.srs_dlog[i], tag), e);
+    for (int i = 1; i < L; i++) e = f_fma(c[i], f_const(ck.srs_dlog(i), tag), e);
     return f_canon(f_red(e));
   } else {
     G1 acc = g1_identity();
@@ -173,9 +226,9 @@ PBH_HD uint32_t fcommit(const T (&c)[L], const ConstsF& KF, const Tables& Tb, ui
 
 // w[12], rnd[9], ch[5]: inputs as exact small integers (0..16).  inv17c: centred inverses as floats, indexed by the
 // canonical residue.  Returns the status byte among {0, 2, 3, 4, 5} (satisfiability, status 1, is the caller's).
-template <int ALGO, class T>
-PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (&ch_in)[5], const ConstsF& KF, const Tables& Tb,
-                               uint32_t n_pts, const float* inv17c, ProofF& P) {
+template <int ALGO, class T, class CK>
+PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (&ch_in)[5], const CK& ck, const Tables& Tb,
+                               const float* inv17c, ProofF& P) {
   T* tag = nullptr;
   // blinders and challenges are used as they come (0..16); the bound check shows that centring them is not needed
   // (worst-case magnitude 4.8 M, below red17's 2^23 range)
@@ -193,9 +246,9 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   b[0] = f_sub(fb[0], rnd[3]); b[1] = f_sub(fb[1], rnd[2]); b[2] = fb[2]; b[3] = fb[3]; b[4] = rnd[3]; b[5] = rnd[2];
   c[0] = f_sub(fc[0], rnd[5]); c[1] = f_sub(fc[1], rnd[4]); c[2] = fc[2]; c[3] = fc[3]; c[4] = rnd[5]; c[5] = rnd[4];
   bool oob_abc = false, oob_z = false, oob_t = false, oob_w = false;
-  P.e[0] = fcommit<ALGO>(a, KF, Tb, n_pts, false, oob_abc);                             // src/plonk.rs:255-257
-  P.e[1] = fcommit<ALGO>(b, KF, Tb, n_pts, false, oob_abc);
-  P.e[2] = fcommit<ALGO>(c, KF, Tb, n_pts, false, oob_abc);
+  P.e[0] = fcommit<ALGO, T>(a, ck, Tb, false, oob_abc);                             // src/plonk.rs:255-257
+  P.e[1] = fcommit<ALGO, T>(b, ck, Tb, false, oob_abc);
+  P.e[2] = fcommit<ALGO, T>(c, ck, Tb, false, oob_abc);
 
   // ---- accumulator                                                          src/plonk.rs:278-299
   T acc[4];
@@ -209,8 +262,8 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
     T wa = f_add(w[i], gamma), wb = f_add(w[4 + i], gamma), wc = f_add(w[8 + i], gamma);
     // factors stay unreduced (|.| <= 16 + 8 + 8*8 = 88): a product of three is below 2^20
     T n1 = f_fma(beta, f_const(o1, tag), wa), n2 = f_fma(beta, f_const(o2, tag), wb), n3 = f_fma(beta, f_const(o3, tag), wc);
-    T d1 = f_fma(beta, f_const(KF.sig[0][i], tag), wa), d2 = f_fma(beta, f_const(KF.sig[1][i], tag), wb),
-      d3 = f_fma(beta, f_const(KF.sig[2][i], tag), wc);
+    T d1 = f_fma(beta, f_const(ck.sig(0, i), tag), wa), d2 = f_fma(beta, f_const(ck.sig(1, i), tag), wb),
+      d3 = f_fma(beta, f_const(ck.sig(2, i), tag), wc);
     T dsor = f_red(f_mul(f_mul(d1, d2), d3));
     div0 = div0 | f_is_zero(dsor);                                           // src/plonk.rs:297 unwrap
     T dinv = f_const(inv17c[f_canon(dsor)], tag);
@@ -222,7 +275,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   T z[7];
   z[0] = f_sub(accx[0], rnd[8]); z[1] = f_sub(accx[1], rnd[7]); z[2] = f_sub(accx[2], rnd[6]); z[3] = accx[3];
   z[4] = rnd[8]; z[5] = rnd[7]; z[6] = rnd[6];
-  P.e[3] = fcommit<ALGO>(z, KF, Tb, n_pts, false, oob_z);                               // src/plonk.rs:313
+  P.e[3] = fcommit<ALGO, T>(z, ck, Tb, false, oob_z);                               // src/plonk.rs:313
 
   // ---- quotient numerator: t1 + alpha (A'B'C' z - A''B''C'' z_omega) + alpha^2 (z - 1) L1     src/plonk.rs:339-369
   T num[22];
@@ -233,20 +286,20 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
     fpoly_mul(a, b, ab);
     T qm[4], ql[4], qr[4], qo[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { qm[i] = f_const(KF.QM[i], tag); ql[i] = f_const(KF.QL[i], tag); qr[i] = f_const(KF.QR[i], tag); qo[i] = f_const(KF.QO[i], tag); }
+    for (int i = 0; i < 4; i++) { qm[i] = f_const(ck.QM(i), tag); ql[i] = f_const(ck.QL(i), tag); qr[i] = f_const(ck.QR(i), tag); qo[i] = f_const(ck.QO(i), tag); }
     T t1[14];
     fpoly_mul(ab, qm, t1);
     fpoly_mac(a, ql, t1);
     fpoly_mac(b, qr, t1);
     fpoly_mac(c, qo, t1);
 #pragma unroll
-    for (int i = 0; i < 4; i++) t1[i] = f_add(t1[i], f_const(KF.QC[i], tag));
+    for (int i = 0; i < 4; i++) t1[i] = f_add(t1[i], f_const(ck.QC(i), tag));
     // alpha^2 (z - 1) L1
     T zm[7], l1[4], t4[10];
 #pragma unroll
     for (int i = 0; i < 7; i++) zm[i] = (i == 0) ? f_sub(z[0], f_const(1.f, tag)) : z[i];
 #pragma unroll
-    for (int i = 0; i < 4; i++) l1[i] = f_const(KF.L1[i], tag);
+    for (int i = 0; i < 4; i++) l1[i] = f_const(ck.L1(i), tag);
     fpoly_mul(zm, l1, t4);
 #pragma unroll
     for (int i = 0; i < 22; i++) {
@@ -279,9 +332,9 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
     T A[6], B[6], C[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      A[i] = (i < 4) ? f_fma(beta, f_const(KF.S[0][i], tag), a[i]) : a[i];
-      B[i] = (i < 4) ? f_fma(beta, f_const(KF.S[1][i], tag), b[i]) : b[i];
-      C[i] = (i < 4) ? f_fma(beta, f_const(KF.S[2][i], tag), c[i]) : c[i];
+      A[i] = (i < 4) ? f_fma(beta, f_const(ck.S(0, i), tag), a[i]) : a[i];
+      B[i] = (i < 4) ? f_fma(beta, f_const(ck.S(1, i), tag), b[i]) : b[i];
+      C[i] = (i < 4) ? f_fma(beta, f_const(ck.S(2, i), tag), c[i]) : c[i];
     }
     A[0] = f_add(A[0], gamma); B[0] = f_add(B[0], gamma); C[0] = f_add(C[0], gamma);
 #pragma unroll
@@ -308,9 +361,9 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   T tlo[6], tmid[6], thi[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) { tlo[i] = t[i]; tmid[i] = t[6 + i]; thi[i] = t[12 + i]; }
-  P.e[6] = fcommit<ALGO>(thi, KF, Tb, n_pts, false, oob_t);                             // src/plonk.rs:383-385
-  P.e[5] = fcommit<ALGO>(tmid, KF, Tb, n_pts, false, oob_t);
-  P.e[4] = fcommit<ALGO>(tlo, KF, Tb, n_pts, false, oob_t);
+  P.e[6] = fcommit<ALGO, T>(thi, ck, Tb, false, oob_t);                             // src/plonk.rs:383-385
+  P.e[5] = fcommit<ALGO, T>(tmid, ck, Tb, false, oob_t);
+  P.e[4] = fcommit<ALGO, T>(tlo, ck, Tb, false, oob_t);
 
   // ---- evaluations at z                                                     src/plonk.rs:393-399
   T zp[10];
@@ -325,11 +378,11 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   }
 #pragma unroll
   for (int i = 1; i < 7; i++) zw_z = f_fma(zw[i], zp[i], zw_z);
-  T s1_z = f_const(KF.S[0][0], tag), s2_z = f_const(KF.S[1][0], tag), l1_z = f_const(KF.L1[0], tag);
+  T s1_z = f_const(ck.S(0, 0), tag), s2_z = f_const(ck.S(1, 0), tag), l1_z = f_const(ck.L1(0), tag);
 #pragma unroll
   for (int i = 1; i < 4; i++) {
-    s1_z = f_fma(f_const(KF.S[0][i], tag), zp[i], s1_z); s2_z = f_fma(f_const(KF.S[1][i], tag), zp[i], s2_z);
-    l1_z = f_fma(f_const(KF.L1[i], tag), zp[i], l1_z);
+    s1_z = f_fma(f_const(ck.S(0, i), tag), zp[i], s1_z); s2_z = f_fma(f_const(ck.S(1, i), tag), zp[i], s2_z);
+    l1_z = f_fma(f_const(ck.L1(i), tag), zp[i], l1_z);
   }
   a_z = f_red(a_z); b_z = f_red(b_z); c_z = f_red(c_z); s1_z = f_red(s1_z); s2_z = f_red(s2_z); zw_z = f_red(zw_z); l1_z = f_red(l1_z);
   const T z6 = zp[6];
@@ -348,7 +401,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
     T k3s = f_red(f_mul(f_red(f_mul(f_mul(g1v, g2v), alpha)), f_red(f_mul(beta, zw_z))));
     T s3[4], zs3[10];
 #pragma unroll
-    for (int i = 0; i < 4; i++) s3[i] = f_const(KF.S[2][i], tag);
+    for (int i = 0; i < 4; i++) s3[i] = f_const(ck.S(2, i), tag);
     fpoly_mul(z, s3, zs3);
     T ab_z = f_red(f_mul(a_z, b_z));
 #pragma unroll
@@ -356,9 +409,9 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
       T s = f_mul(k3s, zs3[i]);
       if (i < 7) s = f_fma(kz, z[i], s);
       if (i < 4) {
-        s = f_fma(ab_z, f_const(KF.QM[i], tag), s); s = f_fma(a_z, f_const(KF.QL[i], tag), s);
-        s = f_fma(b_z, f_const(KF.QR[i], tag), s); s = f_fma(c_z, f_const(KF.QO[i], tag), s);
-        s = f_add(s, f_const(KF.QC[i], tag));
+        s = f_fma(ab_z, f_const(ck.QM(i), tag), s); s = f_fma(a_z, f_const(ck.QL(i), tag), s);
+        s = f_fma(b_z, f_const(ck.QR(i), tag), s); s = f_fma(c_z, f_const(ck.QO(i), tag), s);
+        s = f_add(s, f_const(ck.QC(i), tag));
       }
       r[i] = s;
     }
@@ -378,7 +431,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
       s = f_add(s, tlo[i]); s = f_fma(z6, tmid[i], s); s = f_fma(z12, thi[i], s);
       s = f_fma(v2, a[i], s); s = f_fma(v3, b[i], s); s = f_fma(v4, c[i], s);
     }
-    if (i < 4) { s = f_fma(v5, f_const(KF.S[0][i], tag), s); s = f_fma(v6, f_const(KF.S[1][i], tag), s); }
+    if (i < 4) { s = f_fma(v5, f_const(ck.S(0, i), tag), s); s = f_fma(v6, f_const(ck.S(1, i), tag), s); }
     wn[i] = s;
   }
   {
@@ -398,8 +451,8 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 #pragma unroll
     for (int k = 4; k >= 0; k--) wzw[k] = f_red(f_fma(zo, wzw[k + 1], z[k + 1]));
   }
-  P.e[7] = fcommit<ALGO>(wz, KF, Tb, n_pts, true, oob_w);                               // src/plonk.rs:445-446 -> :56 (Q2)
-  P.e[8] = fcommit<ALGO>(wzw, KF, Tb, n_pts, true, oob_w);
+  P.e[7] = fcommit<ALGO, T>(wz, ck, Tb, true, oob_w);                               // src/plonk.rs:445-446 -> :56 (Q2)
+  P.e[8] = fcommit<ALGO, T>(wzw, ck, Tb, true, oob_w);
 
   P.ev[0] = f_canon(a_z); P.ev[1] = f_canon(b_z); P.ev[2] = f_canon(c_z); P.ev[3] = f_canon(s1_z); P.ev[4] = f_canon(s2_z);
   P.ev[5] = f_canon(r_z); P.ev[6] = f_canon(zw_z);
@@ -419,7 +472,8 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 // is known to be short (alpha*b1*b3*b5*b7 = 0 mod 17: Q1/Q5 territory, status 1-4 only).  Inputs are canonical
 // bytes (< 17).  Output as packed points + canonical evaluations, like prove_one<ALGO_TABLE>.
 // `unsat_known`: -1 = evaluate constraints.satisfies here; 0 / 1 = already evaluated by the caller.
-template <int ALGO>
+// PBH_CIRCUIT = true: the context's constants equal PbhCK's (checked by the host), use the compile-time instantiation.
+template <int ALGO, bool PBH_CIRCUIT = false>
 PBH_HD uint32_t prove_item_f32(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
                                const ConstsF& KF, const Tables& T, ProofRegs& P, int unsat_known = -1) {
   const bool rare = ch[0] == 0u || rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
@@ -434,7 +488,12 @@ PBH_HD uint32_t prove_item_f32(const uint32_t (&w)[12], const uint32_t (&rnd)[9]
 #pragma unroll
   for (int i = 0; i < 5; i++) cf[i] = f_from_u32(ch[i], tag);
   ProofF pf;
-  uint32_t status = prove_core_f32<ALGO, F32>(wf, rf, cf, KF, T, K.n_pts, T.inv17c, pf);
+  uint32_t status;
+  if (PBH_CIRCUIT) {
+    status = prove_core_f32<ALGO, F32>(wf, rf, cf, PbhCK(), T, T.inv17c, pf);
+  } else {
+    status = prove_core_f32<ALGO, F32>(wf, rf, cf, RuntimeCK{KF, K.n_pts}, T, T.inv17c, pf);
+  }
 #pragma unroll
   for (int k = 0; k < 9; k++) P.pt[k] = (ALGO == ALGO_TABLE) ? T.pt17[pf.e[k]] : pf.e[k];
 #pragma unroll

@@ -26,6 +26,11 @@ def prove(k):
 def verify(k):
     w, r, c, u = ins[k % ring]
     ctx.verify_batch(proof[k % ring], c, u, result=res)
+for spec in (1, 0):
+    ctx.set_option(pbh_b200.OPT_SPECIALISE, spec)
+    us = timeit(prove)
+    print(f"fp32 prover, compile-time circuit constants={spec}: {us:8.1f} us  {n/us/1e3:7.2f} G proofs/s")
+ctx.set_option(pbh_b200.OPT_SPECIALISE, 1)
 for tma_on in (1, 0):
     ctx.set_option(pbh_b200.OPT_TMA, tma_on)
     us = timeit(prove)

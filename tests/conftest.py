@@ -62,6 +62,9 @@ def gpu_ctx(product_lib):
     # per-item curve arithmetic with the int32 prover (the default "arith" context uses the FP32 core for the F_17 work)
     ctxs["arith_int"] = pbh_b200.Context(device=0, algo="arith")
     ctxs["arith_int"].set_option(pbh_b200.OPT_PROVER_FP32, 0)
+    # FP32 prover, generic instantiation (run-time circuit constants) even though the circuit is the reference's own
+    ctxs["table_generic"] = pbh_b200.Context(device=0, algo="table")
+    ctxs["table_generic"].set_option(pbh_b200.OPT_SPECIALISE, 0)
     # FP32 prover with plain per-thread loads/stores instead of TMA-staged tiles
     ctxs["table_notma"] = pbh_b200.Context(device=0, algo="table")
     ctxs["table_notma"].set_option(pbh_b200.OPT_TMA, 0)

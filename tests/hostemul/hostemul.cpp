@@ -53,8 +53,9 @@ int emul_f32_bounds(double* max_exact, double* max_red) {
     for (auto& x : c) x = Bnd(16);
     ProofF pf;
     Tables tb; std::memset(&tb, 0, sizeof tb);
-    prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, KF, tb, n_pts, inv, pf);
-    prove_core_f32<ALGO_ARITH, Bnd>(w, r, c, KF, tb, n_pts, inv, pf);
+    prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, RuntimeCK{KF, n_pts}, tb, inv, pf);
+    prove_core_f32<ALGO_ARITH, Bnd>(w, r, c, RuntimeCK{KF, n_pts}, tb, inv, pf);
+    prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, PbhCK(), tb, inv, pf);
   }
   {
     // the verifier's FP32 scalar path: discrete logs <= 101, evaluations reduced (<= 8), challenges and u <= 16
@@ -120,7 +121,9 @@ int emul_prove_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t om
     for (int k = 0; k < 5; k++) { ch[k] = chal[k * n + i]; bad |= ch[k] >= 17; }
     if (bad) { std::memset(w, 0, sizeof w); std::memset(r, 0, sizeof r); std::memset(ch, 0, sizeof ch); }
     ProofRegs P;
-    uint32_t st = algo == 3 ? prove_item_f32<ALGO_ARITH>(w, r, ch, hs.K, hs.KF, hs.T, P)
+    const bool special = consts_match_pbh(hs.KF, hs.K.n_pts);
+    uint32_t st = algo == 4 ? (special ? prove_item_f32<ALGO_TABLE, true>(w, r, ch, hs.K, hs.KF, hs.T, P) : 0xFFu)
+                : algo == 3 ? prove_item_f32<ALGO_ARITH>(w, r, ch, hs.K, hs.KF, hs.T, P)
                 : algo == 2 ? prove_item_f32<ALGO_TABLE>(w, r, ch, hs.K, hs.KF, hs.T, P)
                             : (algo == 1 ? prove_one<ALGO_TABLE>(w, r, ch, hs.K, hs.T, P) : prove_one<ALGO_ARITH>(w, r, ch, hs.K, hs.T, P));
     if (bad) st = PBH_ST_BAD_ENCODING;

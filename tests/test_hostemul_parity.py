@@ -10,10 +10,11 @@ def test_reduction_constants_exhaustive(hostemul):
     assert hostemul.check_reductions() == 0
 
 
-@pytest.mark.parametrize("algo", (0, 1, 2, 3))
+@pytest.mark.parametrize("algo", (0, 1, 2, 3, 4))
 @pytest.mark.parametrize("dist", (0, 1))
 def test_prove_verify_logic_matches_oracle(hostemul, oracle, algo, dist):
-    """algo 0 = ARITH (int32), 1 = TABLE (int32), 2 = TABLE on the FP32 pipes, 3 = ARITH commitments on the FP32 core."""
+    """algo 0 = ARITH (int32), 1 = TABLE (int32), 2 = TABLE on the FP32 pipes, 3 = ARITH commitments on the FP32 core,
+    4 = TABLE on the FP32 pipes with the compile-time constants of the reference's own circuit."""
     circ = oracle.pbh_test_circuit()
     n = 25000
     w, r, c, u, _ = oracle.generate_inputs(n, seed=4242 + dist, dist=dist, threads=8)
@@ -34,7 +35,7 @@ def test_f32_bounds(hostemul):
     assert hostemul.check_red17_f32() == 0
 
 
-@pytest.mark.parametrize("algo", (0, 1, 2, 3))
+@pytest.mark.parametrize("algo", (0, 1, 2, 3, 4))
 def test_zero_blinder_corner_cases(hostemul, oracle, algo):
     """Blinders and challenges drawn from {0, 1, 16}: short polynomials, the Q1 / Q5 / Q15 length logic."""
     rng = np.random.default_rng(17)

@@ -700,3 +700,32 @@ def test_record_wire_format(gpu_ctx, oracle, algo):
     res = ctx.verify_records(pbh_b200.proof_records(po, so), wrec)
     assert np.array_equal(res, vo)
     assert ctx.prove_records(wrec[:0]).shape == (0,)
+
+
+@pytest.mark.parametrize("algo", ("table", "arith"))
+def test_fuzz_arbitrary_bytes(gpu_ctx, oracle, algo):
+    """Every input byte may take any of the 256 values (2 % of bytes are replaced by uniform random bytes): the status /
+    result classes, the zeroed outputs and every other byte still match the oracle; nothing is read or written out of
+    bounds (the verdict of a malformed item is decided before any table is indexed)."""
+    ctx = gpu_ctx[algo]
+    rng = np.random.default_rng(123)
+    n = 120000
+    wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=55, dist=1, threads=8)
+    po, _ = oracle.prove_batch(wo, ro, co, threads=8)
+
+    def corrupt(a):
+        a = a.copy()
+        mask = rng.random(a.shape) < 0.02
+        a[mask] = rng.integers(0, 256, size=int(mask.sum()), dtype=np.uint8)
+        return a
+
+    w2, r2, c2 = corrupt(wo), corrupt(ro), corrupt(co)
+    pe, se = oracle.prove_batch(w2, r2, c2, threads=8)
+    p, s = ctx.prove_batch(w2, r2, c2)
+    assert np.array_equal(s, se) and np.array_equal(p, pe)
+    assert (se == 32).sum() > 0 and (se == 0).sum() > 0
+    p3, c3, u3 = corrupt(po), corrupt(co), corrupt(uo)
+    ve, ge = oracle.verify_batch(p3, c3, u3, threads=8)
+    v, g = ctx.verify_batch(p3, c3, u3, want_gt=True)
+    assert np.array_equal(v, ve) and np.array_equal(g, ge)
+    assert set(np.unique(ve)) >= {0, 1, 2, 4, 0x20}

@@ -90,3 +90,28 @@ def test_pairing_exhaustive(hostemul, oracle):
     for a in range(101):
         for b in range(0, 101, 3):
             assert hostemul.gt_final_exp((a, b)) == oracle.gt_pow((a, b), 600)
+
+
+@pytest.mark.parametrize("algo", (1, 2, 3))
+def test_fuzz_arbitrary_bytes(hostemul, oracle, algo):
+    """Any byte value in any input plane: same classes and bytes as the oracle (CPU guard of the GPU fuzz test)."""
+    rng = np.random.default_rng(321)
+    n = 40000
+    circ = oracle.pbh_test_circuit()
+    wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=56, dist=1, threads=8)
+    po, _ = oracle.prove_batch(wo, ro, co, threads=8)
+
+    def corrupt(a):
+        a = a.copy()
+        mask = rng.random(a.shape) < 0.02
+        a[mask] = rng.integers(0, 256, size=int(mask.sum()), dtype=np.uint8)
+        return a
+
+    w2, r2, c2 = corrupt(wo), corrupt(ro), corrupt(co)
+    pe, se = oracle.prove_batch(w2, r2, c2, threads=8)
+    p, s = hostemul.prove(circ, w2, r2, c2, algo)
+    assert np.array_equal(s, se) and np.array_equal(p, pe)
+    p3, c3, u3 = corrupt(po), corrupt(co), corrupt(uo)
+    ve, ge = oracle.verify_batch(p3, c3, u3, threads=8)
+    v, g = hostemul.verify(circ, p3, c3, u3, algo)
+    assert np.array_equal(v, ve) and np.array_equal(g, ge)

@@ -7,8 +7,8 @@
 
 A step is one pass of the hot path over one batch: prove 2^20 D_fullpath witnesses per GPU (configs[1] of
 BASELINE.json), verify the 2^20 proofs, pack the verdict bitmap and digest the proof bytes; with N > 1 every rank
-does that on its own shard (digest fused into the prover, bitmap into the verifier) and the bitmaps + digests are all-gathered over NCCL (the only collective, overlapped
-with the next step).  `value` counts proof+verify pairs per second over all ranks with inputs resident in HBM;
+does that on its own shard (digest fused into the prover, bitmap into the verifier) and the bitmaps + digests are
+all-gathered over NCCL (the only collective: one per ring cycle, overlapped with the next cycle's kernels).  `value` counts proof+verify pairs per second over all ranks with inputs resident in HBM;
 `e2e` is the same work through the host-pointer C-ABI calls (pinned host buffers, H2D and D2H inside the timed
 region).  Inputs rotate through a ring of distinct batches larger than L2.
 """
@@ -175,26 +175,34 @@ def main():
     nb = (n + 7) // 8
     assert nb % 8 == 0, "items per GPU must be a multiple of 64"
     ins, outs = [], []
+    # Summaries (verdict bitmap, then the 64-bit proof digest) of a whole ring cycle are contiguous so that ONE all-gather
+    # can carry them; two sets, so that cycle c+1's kernels write set (c+1)%2 while set c%2 is still being gathered.
+    row = nb + 8
+    summary_all = [torch.zeros(ring * row, dtype=torch.uint8, device=dev) for _ in range(2)]
+    gathered_all = [torch.empty(world * ring * row, dtype=torch.uint8, device=dev) if world > 1 else None for _ in range(2)]
+    cycle_done = [None, None]
     for r in range(ring):
         first = (r * world + rank) * n
         w, rd, c, u = ctx.generate_inputs(n, first_index=first, seed=SEED, dist=pbh_b200.DIST_FULLPATH)
         ins.append((w, rd, c, u, first))
-        summary = torch.zeros(nb + 8, dtype=torch.uint8, device=dev)       # verdict bitmap, then the 64-bit proof digest
+        views = []
+        for b in range(2):
+            summary = summary_all[b][r * row:(r + 1) * row]
+            views.append(dict(summary=summary, bitmap=summary[:nb], digest=summary[nb:].view(torch.int64)))
         outs.append(dict(proof=torch.empty((27, n), dtype=torch.uint8, device=dev), status=torch.empty((n,), dtype=torch.uint8, device=dev),
-                         result=torch.empty((n,), dtype=torch.uint8, device=dev), summary=summary, bitmap=summary[:nb],
-                         digest=summary[nb:].view(torch.int64),
-                         gathered=torch.empty(world * (nb + 8), dtype=torch.uint8, device=dev) if world > 1 else None,
+                         result=torch.empty((n,), dtype=torch.uint8, device=dev), sets=views, **views[0],
+                         gathered=torch.empty(world * row, dtype=torch.uint8, device=dev) if world > 1 else None,
                          gather_done=None))
     ctx.sync()
     torch.cuda.synchronize()
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     KERNELS_PER_STEP = 2   # prover (+ fused proof digest), verifier (+ fused verdict bitmap); plus one 8-byte memset node
 
-    def kernels(slot):
+    def kernels(slot, b=0):
         w, rd, c, u, first = ins[slot]
         o = outs[slot]
-        ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["digest"], first_index=first)
-        ctx.verify_bitmap_batch(o["proof"], c, u, o["result"], o["bitmap"])
+        ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
+        ctx.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
 
     # one CUDA graph per ring slot: the step is four short kernels, so direct launches from Python are launch-bound
     graphs, launch_mode = None, "direct"
@@ -215,38 +223,49 @@ def main():
             graphs, launch_mode = None, f"direct (graph capture failed: {type(e).__name__})"
             torch.cuda.synchronize()
 
-    # One more graph holding a whole ring cycle (ring steps): kernels on the context's stream, each step's all-gather
-    # forked onto the side stream inside the graph so that it overlaps the next step's kernels; one replay per `ring`
-    # steps keeps the host (one Python process per GPU) out of the timed path.
-    cycle_graph = None
+    # Two more graphs, each holding the kernels of a whole ring cycle (ring steps) and writing summary set 0 / 1; one
+    # replay per `ring` steps keeps the host (one Python process per GPU) out of the timed path.  The cycle's summaries
+    # travel in ONE all-gather, enqueued on the side stream behind the cycle, so that it overlaps the next cycle's
+    # kernels: the same bytes as one all-gather per step, one `ring`-th of the collectives.
+    cycle_graphs = None
     if graphs is not None and not args.no_cycle_graph:
         try:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=stream):
-                for slot in range(ring):
-                    kernels(slot)
-                    if world > 1:
-                        ev_ = torch.cuda.Event()
-                        ev_.record(stream)
-                        comm_stream.wait_event(ev_)
-                        with torch.cuda.stream(comm_stream):
-                            dist.all_gather_into_tensor(outs[slot]["gathered"], outs[slot]["summary"])
-                if world > 1:
-                    stream.wait_stream(comm_stream)
-            cycle_graph = g
-            launch_mode = f"cuda_graph ({ring}-step cycle graph + per-step graphs for the remainder)"
+            cycle_graphs = []
+            for b in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    for slot in range(ring):
+                        kernels(slot, b)
+                cycle_graphs.append(g)
+            launch_mode = f"cuda_graph ({ring}-step cycle graphs, one all-gather per cycle; per-step graphs for the remainder)"
         except Exception as e:   # pragma: no cover
-            cycle_graph = None
+            cycle_graphs = None
             launch_mode += f"; cycle graph unavailable: {type(e).__name__}"
             torch.cuda.synchronize()
 
+    cycles_run = [0]
+
     def run_steps(k0, count):
-        """Steps k0 .. k0+count-1 (k0 a multiple of ring): whole cycles through the cycle graph, the rest step by step."""
+        """Steps k0 .. k0+count-1 (k0 a multiple of ring): whole cycles through the cycle graphs, the rest step by step."""
         k = k0
-        if cycle_graph is not None:
+        if cycle_graphs is not None:
             while count - (k - k0) >= ring:
-                cycle_graph.replay()
+                b = cycles_run[0] % 2
+                cycles_run[0] += 1
+                if cycle_done[b] is not None:
+                    stream.wait_event(cycle_done[b])   # the previous all-gather of this set has read it
+                cycle_graphs[b].replay()
+                if world > 1:
+                    ev_ = torch.cuda.Event()
+                    ev_.record(stream)
+                    comm_stream.wait_event(ev_)
+                    with torch.cuda.stream(comm_stream):
+                        dist.all_gather_into_tensor(gathered_all[b], summary_all[b])   # the only collective
+                        cycle_done[b] = torch.cuda.Event()
+                        cycle_done[b].record(comm_stream)
                 k += ring
+            if k - k0 < count and cycle_done[0] is not None:
+                stream.wait_event(cycle_done[0])       # the remainder steps write set 0
         while k - k0 < count:
             step(k)
             k += 1
@@ -337,6 +356,15 @@ def main():
     ok_status = int((o["status"] != 0).sum().item()) == 0
     accept = int((o["result"] == 1).sum().item())
     reached = int(((o["result"] == 1) | (o["result"] == 0)).sum().item())
+    # the gathered summaries of the last whole cycle: this rank's slice is its own summary, and every rank's digests are there
+    gather_ok = None
+    if world > 1 and cycle_graphs is not None and cycles_run[0] > 0:
+        torch.cuda.synchronize()
+        b = (cycles_run[0] - 1) % 2
+        g_ = gathered_all[b].view(world, ring, row)
+        digests = g_[:, :, nb:].contiguous().view(torch.int64)
+        gather_ok = bool(torch.equal(g_[rank].reshape(-1), summary_all[b])) and int((digests == 0).sum().item()) == 0 \
+            and int(torch.unique(digests).numel()) == world * ring
 
     # ---- end-to-end through the host-pointer C-ABI calls (pinned host buffers): every rank on its own device
     e2e = None
@@ -459,7 +487,7 @@ def main():
         "arith_algo_kernels": arith,
         "int32_peak": int32,
         "cpu_baseline": cpu,
-        "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n},
+        "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n, "gathered_summaries_ok": gather_ok},
     }
     print(json.dumps(line))
     finish()

@@ -409,7 +409,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dtf = float(t.item())
         e2e = {"value": n * world * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": n * (26 + 33) * world,
-               "d2h_bytes_per_step": n * (28 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt / ksteps, "host_memory": "pinned",
+               "d2h_bytes_per_step": n * (28 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt / ksteps, "host_memory": "pinned (the kernels run in place on it: PBH_OPT_HOST_DIRECT)",
                "timing": "host wall clock around synchronous C-ABI calls (pbh_prove_batch then pbh_verify_batch), max over ranks",
                "fused_call": {"value": n * world * ksteps / dtf, "unit": UNIT, "h2d_bytes_per_step": n * 27 * world,
                               "d2h_bytes_per_step": n * 29 * world, "api": "pbh_prove_verify_batch (extension)"}}

@@ -133,6 +133,11 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 /* PBH_OPT_SPECIALISE: when the context is the reference's own test circuit with SRS::create(2, 6), run the prover
  * instantiation whose circuit and SRS constants are compile-time (1, default) or the generic kernel (0). */
 #define PBH_OPT_SPECIALISE 5
+/* PBH_OPT_HOST_DIRECT: when EVERY buffer of pbh_prove_batch / pbh_verify_batch is page-locked and mapped
+ * (cudaHostAlloc, cudaHostRegister), run the kernel in place on the caller's memory - its tile loads and stores cross
+ * PCIe directly - instead of staging chunks through device buffers (1, default; 0 = always stage).  Pageable buffers
+ * always take the staged path. */
+#define PBH_OPT_HOST_DIRECT 6
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */

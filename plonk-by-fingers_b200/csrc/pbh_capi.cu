@@ -35,6 +35,7 @@ struct pbh_ctx {
   bool pbh_circuit = false;                // the context's constants equal the compile-time PbhCK (pbh_prove_f32.cuh)
   int specialise = 1;                      // PBH_OPT_SPECIALISE
   int use_tma = 1;                         // TMA-staged tiles when base/pitch alignment allows (PBH_OPT_TMA)
+  int host_direct = 1;                     // PBH_OPT_HOST_DIRECT: run the kernels in place on page-locked, mapped host buffers
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;
   Tables* d_tables = nullptr;
@@ -173,6 +174,7 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
   if (option == PBH_OPT_PROVER_LAUNCH_SHAPE) { ctx->prover_variant = value; return PBH_OK; }
   if (option == PBH_OPT_TMA) { ctx->use_tma = value != 0; return PBH_OK; }
   if (option == PBH_OPT_SPECIALISE) { ctx->specialise = value != 0; return PBH_OK; }
+  if (option == PBH_OPT_HOST_DIRECT) { ctx->host_direct = value != 0; return PBH_OK; }
   if (option == PBH_OPT_CHUNK_LOG2) {
     if (value < 8 || value > 20) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "chunk log2 must be in [8, 20]");
     ctx->chunk = (size_t)1 << value;
@@ -409,6 +411,24 @@ static int ensure_slots(pbh_ctx* ctx, size_t bytes_per_item) {
   return PBH_OK;
 }
 
+// The device-side alias of a host range when the whole range is page-locked and mapped (cudaHostAlloc /
+// cudaHostRegister under unified addressing), else nullptr.  When every buffer of a host-pointer call has one, the tile
+// kernel runs in place on the caller's memory: its TMA loads and stores cross PCIe tile by tile, so upload, compute and
+// download overlap at 256-item granularity with no staging copy, no pipeline fill/drain and one launch.  Measured on
+// PCIe Gen5 x16 (scripts/time_zero_copy.py): prove 0.83 ms per 2^20 items against 0.97 ms for the best staged chunking
+// (the copy engine pays about a microsecond per row of a pitched copy, which bounds how small a staged chunk can be).
+static uint8_t* mapped_host_alias(pbh_ctx* ctx, const uint8_t* p, size_t span) {
+  if (!ctx->host_direct || !p || span == 0) return nullptr;
+  cudaPointerAttributes lo{}, hi{};
+  if (cudaPointerGetAttributes(&lo, p) != cudaSuccess || cudaPointerGetAttributes(&hi, p + span - 1) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (lo.type != cudaMemoryTypeHost || hi.type != cudaMemoryTypeHost || !lo.devicePointer || !hi.devicePointer) return nullptr;
+  if ((const uint8_t*)hi.devicePointer - (const uint8_t*)lo.devicePointer != (ptrdiff_t)(span - 1)) return nullptr;
+  return (uint8_t*)lo.devicePointer;
+}
+
 int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
                     const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status) {
   CTX_CHECK(ctx);
@@ -416,7 +436,20 @@ int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch
   if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 128);
+  int rc;
+  {
+    const uint8_t *a_wit = mapped_host_alias(ctx, wit, 11 * wit_pitch + n), *a_rnd = mapped_host_alias(ctx, rnd, 8 * rand_pitch + n),
+                  *a_chal = mapped_host_alias(ctx, chal, 4 * chal_pitch + n);
+    uint8_t *a_proof = mapped_host_alias(ctx, proof, 26 * proof_pitch + n), *a_status = mapped_host_alias(ctx, status, n);
+    if (a_wit && a_rnd && a_chal && a_proof && a_status) {
+      ProveArgs A{a_wit, wit_pitch, a_rnd, rand_pitch, a_chal, chal_pitch, a_proof, proof_pitch, a_status, n};
+      rc = launch_prove(ctx, ctx->slot_stream[0], A);
+      if (rc) return rc;
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
+      return PBH_OK;
+    }
+  }
+  rc = ensure_slots(ctx, 128);
   if (rc) return rc;
   const size_t C = ctx->chunk;
   size_t k = 0;
@@ -446,7 +479,20 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
   if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 128);
+  int rc;
+  {
+    const uint8_t *a_proof = mapped_host_alias(ctx, proof, 26 * proof_pitch + n), *a_chal = mapped_host_alias(ctx, chal, 4 * chal_pitch + n),
+                  *a_u = mapped_host_alias(ctx, u, n);
+    uint8_t *a_res = mapped_host_alias(ctx, result, n), *a_gt = gt ? mapped_host_alias(ctx, gt, 3 * gt_pitch + n) : nullptr;
+    if (a_proof && a_chal && a_u && a_res && (!gt || a_gt)) {
+      VerifyArgs A{a_proof, proof_pitch, a_chal, chal_pitch, a_u, a_res, a_gt, gt_pitch, n, nullptr};
+      rc = launch_verify(ctx, ctx->slot_stream[0], A);
+      if (rc) return rc;
+      CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[0]));
+      return PBH_OK;
+    }
+  }
+  rc = ensure_slots(ctx, 128);
   if (rc) return rc;
   const size_t C = ctx->chunk;
   size_t k = 0;

@@ -497,6 +497,40 @@ def test_host_pipeline_chunks_and_fused_call(product_lib, oracle, chunk_log2):
         assert np.array_equal(p2, po) and np.array_equal(s2, so) and np.array_equal(v2, vo)
 
 
+@pytest.mark.parametrize("n,pitch", ((1, 16), (255, 256), (4099, 4099), (70003, 70016), (70003, 70004)))
+def test_pinned_host_buffers_run_in_place(product_lib, oracle, n, pitch):
+    """Page-locked, mapped host buffers: the kernels run in place on them (PBH_OPT_HOST_DIRECT), TMA tiles when base and
+    pitch are 16-byte aligned, plain loads/stores otherwise.  Same bytes as the staged path and as the oracle; bytes
+    beyond the n items of each plane are never written; the verifier's GT output takes the same path."""
+    import torch
+    import pbh_b200
+    wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=pitch, dist=0, threads=8)
+    po, so = oracle.prove_batch(wo, ro, co, threads=8)
+    vo, go = oracle.verify_batch(po, co, uo, threads=8, want_gt=True)
+
+    def pinned(planes, src=None):
+        t = torch.full((planes, pitch), 0xAB, dtype=torch.uint8).pin_memory()
+        if src is not None:
+            t[:, :n] = torch.from_numpy(np.atleast_2d(src))
+        return t
+
+    W, R, Cc, U = pinned(12, wo), pinned(9, ro), pinned(5, co), pinned(1, uo)
+    with pbh_b200.Context(device=0) as ctx:
+        launches = {}
+        for direct in (1, 0):
+            ctx.set_option(pbh_b200.OPT_HOST_DIRECT, direct)
+            P, S, V, G = pinned(27), pinned(1), pinned(1), pinned(4)
+            l0 = ctx.launch_count
+            ctx.prove_batch(W.numpy()[:, :n], R.numpy()[:, :n], Cc.numpy()[:, :n], proof=P.numpy()[:, :n], status=S.numpy()[0, :n])
+            ctx.verify_batch(P.numpy()[:, :n], Cc.numpy()[:, :n], U.numpy()[0, :n], result=V.numpy()[0, :n], gt=G.numpy()[:, :n])
+            launches[direct] = ctx.launch_count - l0
+            assert np.array_equal(P.numpy()[:, :n], po) and np.array_equal(S.numpy()[0, :n], so)
+            assert np.array_equal(V.numpy()[0, :n], vo) and np.array_equal(G.numpy()[:, :n], go)
+            for t in (P, S, V, G):
+                assert bool((t[:, n:] == 0xAB).all())
+        assert launches[1] == 2      # one prover launch, one verifier launch: no chunking on the in-place path
+
+
 _FUSED_CACHE = {}
 
 

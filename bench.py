@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-arith", action="store_true", help="skip timing the PBH_ALGO_ARITH kernels")
+    ap.add_argument("--no-fs", action="store_true", help="skip timing the Fiat-Shamir kernels")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--no-cycle-graph", action="store_true", help="replay one graph per step instead of one per ring cycle")
     args = ap.parse_args()
@@ -366,6 +367,23 @@ def main():
         gather_ok = bool(torch.equal(g_[rank].reshape(-1), summary_all[b])) and int((digests == 0).sum().item()) == 0 \
             and int(torch.unique(digests).numel()) == world * ring
 
+    # ---- Fiat-Shamir variants: same witnesses and blinders, challenges derived on the device
+    # from the SHA-256 transcript; reported beside the headline, not part of it.  With transcript-derived (uniform)
+    # challenges most proofs end in one of the reference's panics; `proofs_produced` says how many did not.
+    fs = None
+    if args.algo == "table" and not args.no_fs:
+        f_proof = torch.empty((27, n), dtype=torch.uint8, device=dev)
+        f_status = torch.empty((n,), dtype=torch.uint8, device=dev)
+        f_result = torch.empty((n,), dtype=torch.uint8, device=dev)
+        f_chal = torch.empty((6, n), dtype=torch.uint8, device=dev)
+        fp_ms = time_kernel(lambda s_: ctx.prove_fs_batch(ins[s_][0], ins[s_][1], proof=f_proof, status=f_status, chal=f_chal), 10)
+        produced = int((f_status == 0).sum().item())
+        fv_ms = time_kernel(lambda s_: ctx.verify_fs_batch(f_proof, result=f_result, chal=f_chal), 10)
+        fs = {"prove_fs_ms": fp_ms, "verify_fs_ms": fv_ms, "proofs_per_s_per_gpu": n / (fp_ms * 1e-3), "verifies_per_s_per_gpu": n / (fv_ms * 1e-3),
+              "proofs_produced": produced, "accepted": int((f_result == 1).sum().item()), "items": n,
+              "hash": "SHA-256, 5 compressions per proof and per verification"}
+        del f_proof, f_status, f_result, f_chal
+
     # ---- end-to-end through the host-pointer C-ABI calls (pinned host buffers): every rank on its own device
     e2e = None
     if args.e2e_steps != 0:
@@ -485,6 +503,7 @@ def main():
                     "verifies_per_s_per_gpu": n / (verify_ms * 1e-3), "prove_GBps": prove_gbs, "verify_GBps": verify_gbs,
                     "prove_hbm_frac": prove_gbs / peak, "verify_hbm_frac": verify_gbs / peak},
         "arith_algo_kernels": arith,
+        "fiat_shamir_kernels": fs,
         "int32_peak": int32,
         "cpu_baseline": cpu,
         "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n, "gathered_summaries_ok": gather_ok},

@@ -180,6 +180,40 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
                            size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, const uint8_t* u, uint8_t* proof,
                            size_t proof_pitch, uint8_t* status, uint8_t* result);
 
+/* ---- Fiat-Shamir transcript — SURVEY.md §8(f) row 1 -------------------------------------------------------------
+ * The reference leaves the five challenges and the verifier's rand[0] to the caller (src/plonk.rs:195, 201-206, 472-473,
+ * 519).  These entry points derive them on the device, so a batch needs no host-made challenges.  Everything else is
+ * Plonk::prove / Plonk::verify unchanged: a Fiat-Shamir proof is exactly the proof pbh_prove_batch returns when it is
+ * handed the derived challenges, with the same status byte, and pbh_verify_fs_batch answers what pbh_verify_batch
+ * answers for the derived challenges and u.
+ *
+ * Transcript.  A state is 32 bytes; state_{k+1} = SHA-256(state_k || message_k) (FIPS 180-4; every message is at most
+ * 12 bytes, so each step is a single compression).  A G1 point is absorbed as the four bytes (x, y, infinite as 0/1, 0),
+ * an evaluation as its byte.  A challenge is a big-endian 64-bit slice of the new state reduced mod 17.
+ *   state_0 = SHA-256("plonk-by-fingers/fiat-shamir/v1" || omega_pows || the 44 bytes of pbh_circuit in declaration
+ *             order || number of SRS points || the SRS points (4 bytes each) || g2_1.a g2_1.b g2_s.a g2_s.b)
+ *   state_1 = H(state_0 || a_s b_s c_s)                 beta  = bytes 0..7 of state_1 mod 17, gamma = bytes 8..15 mod 17
+ *   state_2 = H(state_1 || z_s)                         alpha = bytes 0..7 of state_2 mod 17
+ *   state_3 = H(state_2 || t_lo_s t_mid_s t_hi_s)       z     = bytes 0..7 of state_3 mod 17
+ *   state_4 = H(state_3 || a_z b_z c_z s_sigma_1_z s_sigma_2_z r_z z_omega_z)          v = bytes 0..7 of state_4 mod 17
+ *   state_5 = H(state_4 || w_z_s w_z_omega_s)           u     = bytes 0..7 of state_5 mod 17
+ * The prover asks for each challenge where the reference first uses it (beta, gamma: src/plonk.rs:283; alpha: :343;
+ * z: :393; v: :430), so a proof that panics early never needs the later ones.  The reference's quirks are kept: most
+ * uniformly drawn challenges end in one of its panics, reported in the status byte as usual.
+ * chal_out (nullable): 6 planes alpha beta gamma z v u; zero for items whose status != PBH_ST_OK (prove) or whose
+ * result is PBH_VR_BAD_ENCODING (verify). */
+#define PBH_FS_CHAL_PLANES 6
+int pbh_ctx_get_fs_seed(const pbh_ctx* ctx, uint8_t state_0[32]);
+int pbh_prove_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand, size_t rand_pitch,
+                       uint8_t* proof, size_t proof_pitch, uint8_t* status, uint8_t* chal_out, size_t chal_pitch);
+int pbh_prove_fs_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand, size_t rand_pitch,
+                           uint8_t* proof, size_t proof_pitch, uint8_t* status, uint8_t* chal_out, size_t chal_pitch);
+/* proof 27 planes in; result n bytes of PBH_VR_*; gt (nullable) as in pbh_verify_batch */
+int pbh_verify_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, uint8_t* result, uint8_t* chal_out,
+                        size_t chal_pitch, uint8_t* gt, size_t gt_pitch);
+int pbh_verify_fs_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, uint8_t* result, uint8_t* chal_out,
+                            size_t chal_pitch, uint8_t* gt, size_t gt_pitch);
+
 /* ---- record (array-of-structs) wire format — SURVEY.md §8(f) row 3 ---------------------------------------------
  * The reference has no serialisation (Proof only derives Debug, PartialEq: src/plonk.rs:61).  These 32-byte records let a
  * host exchange `Vec<Proof>` / per-item inputs with the library without per-field copies; the library transposes between
@@ -289,7 +323,8 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
  * which: 0 IMAD, 1 LOP3+IADD3, 2 half IMAD half ALU, 3 FFMA, 4 HFMA2 (counted once per instruction; each carries two
  * fp16 lanes), 5 IDP.4A (dp4a; four byte MACs each), 6 IMAD.HI+IADD, 7 half FFMA half IMAD,
  * 8 FFMA with three register operands (polynomial MAC shape), 9 IMAD with three register operands,
- * 10 FFMA2 (packed fp32x2, counted per instruction) with three register-pair operands, 11 FFMA2 with a broadcast-pair multiplicand */
+ * 10 FFMA2 (packed fp32x2, counted per instruction) with three register-pair operands, 11 FFMA2 with a broadcast-pair multiplicand,
+ * 12 SHF (funnel shift), 13 IMAD.WIDE.U32, 14 LOP3 alone, 15 IADD3 alone, 16 PRMT (the SHA-256 transcript's instruction classes) */
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second);
 
 #ifdef __cplusplus

@@ -238,6 +238,52 @@ def prove_batch(wit, rand, chal, circuit=None, s=2, srs_n=6, omega_pows=4, threa
     return proof, status
 
 
+# ---- Fiat-Shamir variants (include/pbh_b200.h, "Fiat-Shamir transcript") --------------------------------
+def sha256(data):
+    data = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = np.zeros(32, dtype=np.uint8)
+    lib().oracle_sha256(_p(data) if data.size else None, C.c_size_t(data.size), _p(out))
+    return out.tobytes()
+
+
+def fs_seed(circuit=None, s=2, srs_n=6, omega_pows=4):
+    circuit = circuit or pbh_test_circuit()
+    out = np.zeros(32, dtype=np.uint8)
+    if lib().oracle_fs_seed(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), _p(out)):
+        raise ArithmeticError("setup would panic in the reference")
+    return out.tobytes()
+
+
+def prove_fs_batch(wit, rand, circuit=None, s=2, srs_n=6, omega_pows=4, threads=1, partial=False):
+    """-> proof (27,n), status (n,), chal (6,n) = alpha beta gamma z v u derived from the transcript."""
+    circuit = circuit or pbh_test_circuit()
+    wit = np.ascontiguousarray(wit, dtype=np.uint8); rand = np.ascontiguousarray(rand, dtype=np.uint8)
+    n = wit.shape[1]
+    assert wit.shape == (12, n) and rand.shape == (9, n)
+    proof = np.zeros((27, n), dtype=np.uint8); status = np.zeros(n, dtype=np.uint8); chal = np.zeros((6, n), dtype=np.uint8)
+    rc = lib().oracle_prove_fs_batch(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), C.c_size_t(n),
+                                     _p(wit), C.c_size_t(n), _p(rand), C.c_size_t(n), _p(proof), C.c_size_t(n), _p(status),
+                                     _p(chal), C.c_size_t(n), int(bool(partial)), int(threads))
+    if rc:
+        raise ArithmeticError("setup would panic in the reference")
+    return proof, status, chal
+
+
+def verify_fs_batch(proof, circuit=None, s=2, srs_n=6, omega_pows=4, threads=1, want_gt=False):
+    """-> result (n,), chal (6,n) [, gt (4,n)]"""
+    circuit = circuit or pbh_test_circuit()
+    proof = np.ascontiguousarray(proof, dtype=np.uint8)
+    n = proof.shape[1]
+    assert proof.shape == (27, n)
+    result = np.zeros(n, dtype=np.uint8); chal = np.zeros((6, n), dtype=np.uint8); gt = np.zeros((4, n), dtype=np.uint8)
+    rc = lib().oracle_verify_fs_batch(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), C.c_size_t(n),
+                                      _p(proof), C.c_size_t(n), _p(result), _p(chal), C.c_size_t(n),
+                                      _p(gt) if want_gt else None, C.c_size_t(n), int(threads))
+    if rc:
+        raise ArithmeticError("setup would panic in the reference")
+    return (result, chal, gt) if want_gt else (result, chal)
+
+
 def verify_batch(proof, chal, u, circuit=None, s=2, srs_n=6, omega_pows=4, threads=1, want_gt=True):
     circuit = circuit or pbh_test_circuit()
     proof = np.ascontiguousarray(proof, dtype=np.uint8); chal = np.ascontiguousarray(chal, dtype=np.uint8)

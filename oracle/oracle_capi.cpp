@@ -98,6 +98,45 @@ int prove_one(const Setup& st, const uint8_t w[12], const uint8_t r[9], const ui
   }
 }
 
+// Fiat-Shamir seed of a context (include/pbh_b200.h, "Fiat-Shamir transcript"): SHA-256 over a domain tag, omega_pows,
+// the circuit description and the SRS
+void fs_seed(const Setup& st, const circuit_desc& d, uint8_t omega_pows, uint8_t out[32]) {
+  std::vector<uint8_t> m;
+  const char* tag = "plonk-by-fingers/fiat-shamir/v1";
+  for (const char* c = tag; *c; c++) m.push_back((uint8_t)*c);
+  m.push_back(omega_pows);
+  const uint8_t* sel[5] = {d.q_l, d.q_r, d.q_o, d.q_m, d.q_c};
+  for (int k = 0; k < 5; k++) for (int i = 0; i < 4; i++) m.push_back((uint8_t)(sel[k][i] % 17));
+  const uint8_t* cc[6] = {d.c_a_wire, d.c_a_index, d.c_b_wire, d.c_b_index, d.c_c_wire, d.c_c_index};
+  for (int k = 0; k < 6; k++) for (int i = 0; i < 4; i++) m.push_back(cc[k][i]);
+  const SRS& srs = st.plonk->srs;
+  m.push_back((uint8_t)srs.g1s.size());
+  for (const G1P& p : srs.g1s) FsTranscript::put_point(m, p);
+  m.push_back((uint8_t)srs.g2_1.a.v); m.push_back((uint8_t)srs.g2_1.b.v);
+  m.push_back((uint8_t)srs.g2_s.a.v); m.push_back((uint8_t)srs.g2_s.b.v);
+  Sha256::hash(m, out);
+}
+
+// one proof with transcript-derived challenges; `derived` = alpha beta gamma z v u (those derived before a panic, 0 after)
+int prove_one_fs(const Setup& st, const uint8_t seed[32], const uint8_t w[12], const uint8_t r[9], Proof& pr, uint8_t derived[6]) {
+  for (int k = 0; k < 6; k++) derived[k] = 0;
+  for (int k = 0; k < 12; k++) if (w[k] >= 17) return 32;
+  for (int k = 0; k < 9; k++) if (r[k] >= 17) return 32;
+  Assigments as;
+  for (int k = 0; k < 4; k++) { as.a.push_back(f17(w[k])); as.b.push_back(f17(w[4 + k])); as.c.push_back(f17(w[8 + k])); }
+  F17 rand[9];
+  for (int k = 0; k < 9; k++) rand[k] = f17(r[k]);
+  FsTranscript tr(seed);
+  int status = 0;
+  try {
+    pr = st.plonk->prove_cs(st.constraints, as, tr, rand);
+  } catch (const Panic& p) {
+    status = p.site;
+  }
+  for (int k = 0; k < 6; k++) derived[k] = tr.derived[k];
+  return status;
+}
+
 void store_proof(const Proof& pr, uint8_t* proof, size_t pitch, size_t i) {
   const G1P* pts[9] = {&pr.a_s, &pr.b_s, &pr.c_s, &pr.z_s, &pr.t_lo_s, &pr.t_mid_s, &pr.t_hi_s, &pr.w_z_s, &pr.w_z_omega_s};
   for (int k = 0; k < 9; k++) put_point(proof, pitch, i, k, *pts[k]);
@@ -403,6 +442,83 @@ int oracle_prove_batch(const void* circuit, uint8_t s, uint32_t srs_n, uint8_t o
     }
   });
   return 0;
+}
+
+// ---- Fiat-Shamir variants: challenges derived from the transcript instead of passed in ----
+int oracle_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
+  Sha256 h; h.update(data, len); h.finish(out);
+  return 0;
+}
+int oracle_fs_seed(const void* circuit, uint8_t s, uint32_t srs_n, uint8_t omega_pows, uint8_t out[32]) {
+  auto st = make_setup((const circuit_desc*)circuit, s, srs_n, omega_pows);
+  if (!st) return -2;
+  fs_seed(*st, *(const circuit_desc*)circuit, omega_pows, out);
+  return 0;
+}
+// chal_out (nullable): 6 planes alpha beta gamma z v u.  partial = 0: zero for items whose status != 0 (the product's
+// contract); partial = 1: the challenges derived before the panic are kept (test aid).
+int oracle_prove_fs_batch(const void* circuit, uint8_t s, uint32_t srs_n, uint8_t omega_pows, size_t n, const uint8_t* wit,
+                          size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch, uint8_t* proof, size_t proof_pitch,
+                          uint8_t* status, uint8_t* chal_out, size_t chal_pitch, int partial, int threads) {
+  auto st = make_setup((const circuit_desc*)circuit, s, srs_n, omega_pows);
+  if (!st) return -2;
+  uint8_t seed[32];
+  fs_seed(*st, *(const circuit_desc*)circuit, omega_pows, seed);
+  parallel_for(n, threads, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+      uint8_t w[12], r[9], d[6];
+      for (int k = 0; k < 12; k++) w[k] = wit[k * wit_pitch + i];
+      for (int k = 0; k < 9; k++) r[k] = rnd[k * rand_pitch + i];
+      for (int k = 0; k < 27; k++) proof[k * proof_pitch + i] = 0;
+      Proof pr;
+      int stt = prove_one_fs(*st, seed, w, r, pr, d);
+      status[i] = (uint8_t)stt;
+      if (stt == 0) store_proof(pr, proof, proof_pitch, i);
+      if (chal_out) for (int k = 0; k < 6; k++) chal_out[k * chal_pitch + i] = (stt == 0 || partial) ? d[k] : 0;
+    }
+  });
+  return 0;
+}
+
+int oracle_verify_batch(const void* circuit, uint8_t s, uint32_t srs_n, uint8_t omega_pows, size_t n,
+                        const uint8_t* proof, size_t proof_pitch, const uint8_t* chal, size_t chal_pitch,
+                        const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch, int threads);
+
+// The verifier replays the transcript over the proof bytes (each point as x, y, infinite, 0; evaluations as they are)
+// and then runs Plonk::verify with the derived Challange and rand[0] = u.  Items with a coordinate byte >= 101 or a
+// stray flag bit answer 0x20 and get zero challenges.
+int oracle_verify_fs_batch(const void* circuit, uint8_t s, uint32_t srs_n, uint8_t omega_pows, size_t n, const uint8_t* proof,
+                           size_t proof_pitch, uint8_t* result, uint8_t* chal_out, size_t chal_pitch, uint8_t* gt,
+                           size_t gt_pitch, int threads) {
+  auto st = make_setup((const circuit_desc*)circuit, s, srs_n, omega_pows);
+  if (!st) return -2;
+  uint8_t seed[32];
+  fs_seed(*st, *(const circuit_desc*)circuit, omega_pows, seed);
+  std::vector<uint8_t> chal(6 * n, 0);
+  parallel_for(n, threads, [&](size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+      bool bad = false;
+      for (int k = 0; k < 18; k++) bad |= proof[k * proof_pitch + i] >= 101;
+      bad |= (proof[19 * proof_pitch + i] & 0xFE) != 0;
+      if (bad) continue;
+      G1P pt[9];
+      for (int k = 0; k < 9; k++) pt[k] = get_point(proof, proof_pitch, i, k);
+      F17 ev[7];
+      for (int k = 0; k < 7; k++) ev[k].v = proof[(20 + k) * proof_pitch + i];
+      FsTranscript tr(seed);
+      F17 beta, gamma;
+      tr.beta_gamma(pt[0], pt[1], pt[2], beta, gamma);
+      tr.alpha(pt[3]);
+      tr.zeta(pt[4], pt[5], pt[6]);
+      tr.v(ev);
+      tr.u(pt[7], pt[8]);
+      for (int k = 0; k < 6; k++) chal[k * n + i] = tr.derived[k];
+    }
+  });
+  int rc = oracle_verify_batch(circuit, s, srs_n, omega_pows, n, proof, proof_pitch, chal.data(), n, chal.data() + 5 * n, result, gt,
+                               gt_pitch, threads);
+  if (chal_out) for (int k = 0; k < 6; k++) for (size_t i = 0; i < n; i++) chal_out[k * chal_pitch + i] = chal[k * n + i];
+  return rc;
 }
 
 int oracle_verify_batch(const void* circuit, uint8_t s, uint32_t srs_n, uint8_t omega_pows, size_t n,

@@ -667,6 +667,145 @@ struct Proof {                                                                  
 
 struct Challange { F17 alpha, beta, gamma, z, v; };                               // :97-108
 
+// challenge source of Plonk::prove_cs that returns the caller's Challange: the reference's behaviour
+struct FixedChallenges {
+  Challange ch;
+  void beta_gamma(const G1P&, const G1P&, const G1P&, F17& beta, F17& gamma) { beta = ch.beta; gamma = ch.gamma; }
+  F17 alpha(const G1P&) { return ch.alpha; }
+  F17 zeta(const G1P&, const G1P&, const G1P&) { return ch.z; }
+  F17 v(const F17 (&)[7]) { return ch.v; }
+  void u(const G1P&, const G1P&) {}
+};
+
+// ---- Fiat-Shamir transcript (no counterpart in the reference, which leaves the challenges to
+// the caller: src/plonk.rs:201-206).  Specified in include/pbh_b200.h ("Fiat-Shamir transcript"); restated here
+// independently of the product's implementation and pinned against hashlib in tests/test_fiat_shamir.py. ----
+struct Sha256 {                                                                   // FIPS 180-4
+  uint32_t h[8];
+  uint8_t buf[64];
+  uint64_t len = 0;
+  Sha256() {
+    static const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    for (int i = 0; i < 8; i++) h[i] = iv[i];
+  }
+  static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+  static const uint32_t* round_constants() {
+    // first 32 bits of the fractional parts of the cube roots of the first 64 primes, computed rather than tabulated
+    static uint32_t k[64];
+    static bool done = false;
+    if (!done) {
+      int count = 0;
+      for (uint32_t p = 2; count < 64; p++) {
+        bool prime = true;
+        for (uint32_t d = 2; d * d <= p; d++) if (p % d == 0) { prime = false; break; }
+        if (!prime) continue;
+        // floor(frac(cbrt(p)) * 2^32) by integer bisection on y^3 <= p * 2^96, y = cbrt(p) * 2^32
+        unsigned __int128 target = (unsigned __int128)p << 96;
+        uint64_t lo = 0, hi = (uint64_t)8 << 32;
+        while (hi - lo > 1) {
+          uint64_t mid = lo + (hi - lo) / 2;
+          // mid^3 may overflow 128 bits only if mid >= 2^42.67; mid < 2^35 here
+          unsigned __int128 cube = (unsigned __int128)mid * mid * mid;
+          if (cube <= target) lo = mid; else hi = mid;
+        }
+        k[count++] = (uint32_t)lo;
+      }
+      done = true;
+    }
+    return k;
+  }
+  void block(const uint8_t* p) {
+    const uint32_t* K = round_constants();
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++) w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+      uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+      uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+      w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; i++) {
+      uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25), ch = (e & f) ^ (~e & g);
+      uint32_t t1 = hh + S1 + ch + K[i] + w[i];
+      uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22), maj = (a & b) ^ (a & c) ^ (b & c);
+      uint32_t t2 = S0 + maj;
+      hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+  }
+  void update(const uint8_t* p, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+      buf[len % 64] = p[i];
+      len++;
+      if (len % 64 == 0) block(buf);
+    }
+  }
+  void finish(uint8_t out[32]) {
+    uint64_t bits = len * 8;
+    uint8_t pad = 0x80;
+    update(&pad, 1);
+    pad = 0;
+    while (len % 64 != 56) update(&pad, 1);
+    uint8_t lb[8];
+    for (int i = 0; i < 8; i++) lb[i] = (uint8_t)(bits >> (56 - 8 * i));
+    update(lb, 8);
+    for (int i = 0; i < 8; i++) { out[4 * i] = (uint8_t)(h[i] >> 24); out[4 * i + 1] = (uint8_t)(h[i] >> 16); out[4 * i + 2] = (uint8_t)(h[i] >> 8); out[4 * i + 3] = (uint8_t)h[i]; }
+  }
+  static void hash(const std::vector<uint8_t>& m, uint8_t out[32]) { Sha256 s; s.update(m.data(), m.size()); s.finish(out); }
+};
+
+// state_{k+1} = SHA-256(state_k || message_k); a challenge is a big-endian 64-bit slice of the new state, mod 17
+struct FsTranscript {
+  uint8_t state[32];
+  uint8_t derived[6] = {0, 0, 0, 0, 0, 0};   // alpha beta gamma z v u, in the Challange order followed by u
+  int n_derived = 0;                          // how many absorb steps ran (for tests: challenges after a panic stay 0)
+  explicit FsTranscript(const uint8_t seed[32]) { for (int i = 0; i < 32; i++) state[i] = seed[i]; }
+  static void put_point(std::vector<uint8_t>& m, const G1P& p) {
+    m.push_back((uint8_t)p.x.v); m.push_back((uint8_t)p.y.v); m.push_back(p.infinite ? 1 : 0); m.push_back(0);
+  }
+  void absorb(const std::vector<uint8_t>& msg) {
+    std::vector<uint8_t> m(state, state + 32);
+    m.insert(m.end(), msg.begin(), msg.end());
+    Sha256::hash(m, state);
+    n_derived++;
+  }
+  uint8_t squeeze(int k) const {               // k-th 8-byte slice of the state as a big-endian integer, mod 17
+    uint64_t x = 0;
+    for (int i = 0; i < 8; i++) x = (x << 8) | state[8 * k + i];
+    return (uint8_t)(x % 17);
+  }
+  void beta_gamma(const G1P& a, const G1P& b, const G1P& c, F17& beta, F17& gamma) {
+    std::vector<uint8_t> m; put_point(m, a); put_point(m, b); put_point(m, c);
+    absorb(m);
+    derived[1] = squeeze(0); derived[2] = squeeze(1);
+    beta = f17(derived[1]); gamma = f17(derived[2]);
+  }
+  F17 alpha(const G1P& z) {
+    std::vector<uint8_t> m; put_point(m, z);
+    absorb(m);
+    derived[0] = squeeze(0);
+    return f17(derived[0]);
+  }
+  F17 zeta(const G1P& lo, const G1P& mid, const G1P& hi) {
+    std::vector<uint8_t> m; put_point(m, lo); put_point(m, mid); put_point(m, hi);
+    absorb(m);
+    derived[3] = squeeze(0);
+    return f17(derived[3]);
+  }
+  F17 v(const F17 (&ev)[7]) {
+    std::vector<uint8_t> m;
+    for (int i = 0; i < 7; i++) m.push_back((uint8_t)ev[i].v);
+    absorb(m);
+    derived[4] = squeeze(0);
+    return f17(derived[4]);
+  }
+  void u(const G1P& wz, const G1P& wzw) {
+    std::vector<uint8_t> m; put_point(m, wz); put_point(m, wzw);
+    absorb(m);
+    derived[5] = squeeze(0);
+  }
+};
+
 // optional trace of prover intermediates, for cross-checking SURVEY.md §9
 struct ProveTrace {
   std::vector<F17> sigma_1, sigma_2, sigma_3, acc;
@@ -718,9 +857,19 @@ struct Plonk {                                                                  
   // src/plonk.rs:191-466
   Proof prove(const Constrains& constraints, const Assigments& assigments, const Challange& ch,
               const F17 (&rand)[9], ProveTrace* tr = nullptr) const {
+    FixedChallenges cs{ch};
+    return prove_cs(constraints, assigments, cs, rand, tr);
+  }
+
+  // The same function with the five challenges asked from `cs` at the point where the reference first needs each of
+  // them (the reference receives them as an argument, src/plonk.rs:195, 201-206): beta and gamma after the round-1
+  // commitments, alpha after [z], z after the quotient commitments, v after the evaluations.  FixedChallenges hands
+  // back the caller's Challange, which makes this the reference's prove; FsTranscript (below) derives them.
+  template <class CS>
+  Proof prove_cs(const Constrains& constraints, const Assigments& assigments, CS& cs, const F17 (&rand)[9],
+                 ProveTrace* tr = nullptr) const {
     using P = Poly<F17>;
     if (!constraints.satisfies(assigments)) throw Panic{SITE_UNSATISFIED, "constraints not satisfied"};  // :199
-    const F17 alpha = ch.alpha, beta = ch.beta, gamma = ch.gamma, z = ch.z, v = ch.v;
     const F17 omega = OMEGA(), k1 = K1(), k2 = K2();
     const uint64_t n = constraints.c_a.size();
 
@@ -748,6 +897,8 @@ struct Plonk {                                                                  
     G1P a_s = srs.eval_at_s(a_x);
     G1P b_s = srs.eval_at_s(b_x);
     G1P c_s = srs.eval_at_s(c_x);
+    F17 beta, gamma;
+    cs.beta_gamma(a_s, b_s, c_s, beta, gamma);
 
     // round 2                                                                    // :267-313
     F17 b7 = rand[6], b8 = rand[7], b9 = rand[8];
@@ -766,6 +917,7 @@ struct Plonk {                                                                  
     if (!(acc_x.eval(omega.pow(n)) == F17::one())) throw Panic{SITE_ACC_ASSERT, "acc(w^n) != 1"};   // :307 (Q7)
     P z_x = P({b9, b8, b7}) * z_h_x + acc_x;
     G1P z_s = srs.eval_at_s(z_x);
+    const F17 alpha = cs.alpha(z_s);
 
     // round 3                                                                    // :328-385
     std::vector<F17> lagrange_vector(h.size(), F17::zero());
@@ -805,6 +957,7 @@ struct Plonk {                                                                  
     G1P t_hi_s = srs.eval_at_s(t_hi_x);
     G1P t_mid_s = srs.eval_at_s(t_mid_x);
     G1P t_lo_s = srs.eval_at_s(t_lo_x);
+    const F17 z = cs.zeta(t_lo_s, t_mid_s, t_hi_s);
 
     // round 4                                                                    // :393-422
     F17 a_z = a_x.eval(z), b_z = b_x.eval(z), c_z = c_x.eval(z);
@@ -824,6 +977,8 @@ struct Plonk {                                                                  
     P r_4_x = z_x * l_1_x.eval(z) * alpha.pow(2);
     P r_x = r_1_x + r_2_x + r_3_x + r_4_x;
     F17 r_z = r_x.eval(z);
+    const F17 evals[7] = {a_z, b_z, c_z, s_sigma_1_z, s_sigma_2_z, r_z, z_omega_z};
+    const F17 v = cs.v(evals);
 
     // round 5                                                                    // :430-446
     P w_num = (t_lo_x + t_mid_x * z.pow(n + 2) + t_hi_x * z.pow(2 * n + 4) - t_z) + (r_x - r_z) * v +
@@ -850,6 +1005,7 @@ struct Plonk {                                                                  
     pr.t_hi_s = t_hi_s; pr.w_z_s = w_z_s; pr.w_z_omega_s = w_z_omega_s;
     pr.a_z = a_z; pr.b_z = b_z; pr.c_z = c_z; pr.s_sigma_1_z = s_sigma_1_z; pr.s_sigma_2_z = s_sigma_2_z;
     pr.r_z = r_z; pr.z_omega_z = z_omega_z;
+    cs.u(w_z_s, w_z_omega_s);
     return pr;
   }
 

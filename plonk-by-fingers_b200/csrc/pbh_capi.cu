@@ -554,6 +554,124 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
   return PBH_OK;
 }
 
+// ---- Fiat-Shamir entry points -----------------------------------------------------------------
+static FsSeed fs_seed_of(const pbh_ctx* ctx) {
+  FsSeed s;
+  for (int i = 0; i < 8; i++) s.w[i] = ctx->hs.fs_seed[i];
+  return s;
+}
+int pbh_ctx_get_fs_seed(const pbh_ctx* ctx, uint8_t seed[32]) {
+  if (!ctx || !seed) return PBH_ERR_BAD_ARGUMENT;
+  for (int i = 0; i < 8; i++)
+    for (int b = 0; b < 4; b++) seed[4 * i + b] = (uint8_t)(ctx->hs.fs_seed[i] >> (24 - 8 * b));
+  return PBH_OK;
+}
+static int launch_prove_fs(pbh_ctx* ctx, cudaStream_t st, const ProveFsArgs& F) {
+  if (F.base.n == 0) return PBH_OK;
+  const int grid = grid_for(ctx, F.base.n, 2);
+  const FsSeed seed = fs_seed_of(ctx);
+  const bool special = ctx->pbh_circuit && ctx->specialise;
+  if (ctx->algo == PBH_ALGO_TABLE) {
+    if (!ctx->prover_fp32) prove_fs_kernel<ALGO_TABLE, false, false><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, seed, ctx->d_tables, F);
+    else if (special) prove_fs_kernel<ALGO_TABLE, true, true><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, seed, ctx->d_tables, F);
+    else prove_fs_kernel<ALGO_TABLE, true, false><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, seed, ctx->d_tables, F);
+  } else {
+    if (!ctx->prover_fp32) prove_fs_kernel<ALGO_ARITH, false, false><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, seed, ctx->d_tables, F);
+    else prove_fs_kernel<ALGO_ARITH, true, false><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, seed, ctx->d_tables, F);
+  }
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+static int launch_verify_fs(pbh_ctx* ctx, cudaStream_t st, const VerifyFsArgs& F) {
+  if (F.base.n == 0) return PBH_OK;
+  const int grid = grid_for(ctx, F.base.n, 2);
+  const FsSeed seed = fs_seed_of(ctx);
+  if (ctx->algo == PBH_ALGO_TABLE) verify_fs_kernel<ALGO_TABLE><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->prover_fp32 != 0, seed, ctx->d_tables, F);
+  else verify_fs_kernel<ALGO_ARITH><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, false, seed, ctx->d_tables, F);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+
+int pbh_prove_fs_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
+                           uint8_t* proof, size_t proof_pitch, uint8_t* status, uint8_t* chal_out, size_t chal_pitch) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || proof_pitch < n || (chal_out && chal_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  ProveFsArgs F{{wit, wit_pitch, rnd, rand_pitch, nullptr, 0, proof, proof_pitch, status, n}, chal_out, chal_pitch};
+  return launch_prove_fs(ctx, ctx->compute, F);
+}
+int pbh_verify_fs_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, uint8_t* result, uint8_t* chal_out,
+                            size_t chal_pitch, uint8_t* gt, size_t gt_pitch) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proof || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (proof_pitch < n || (chal_out && chal_pitch < n) || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  VerifyFsArgs F{{proof, proof_pitch, nullptr, 0, nullptr, result, gt, gt_pitch, n, nullptr}, chal_out, chal_pitch};
+  return launch_verify_fs(ctx, ctx->compute, F);
+}
+int pbh_prove_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
+                       uint8_t* proof, size_t proof_pitch, uint8_t* status, uint8_t* chal_out, size_t chal_pitch) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || proof_pitch < n || (chal_out && chal_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_slots(ctx, 128);
+  if (rc) return rc;
+  const size_t C = ctx->chunk;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    size_t m = std::min(C, n - lo);
+    int s = (int)(k % kSlots);
+    cudaStream_t st = ctx->slot_stream[s];
+    uint8_t* base = ctx->slot_buf[s];
+    uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_proof = base + 21 * C, *d_status = base + 48 * C, *d_chal = base + 49 * C;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
+    ProveFsArgs F{{d_wit, C, d_rnd, C, nullptr, 0, d_proof, C, d_status, m}, chal_out ? d_chal : nullptr, C};
+    rc = launch_prove_fs(ctx, st, F);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
+    if (chal_out) CUDA_TRY(ctx, cudaMemcpy2DAsync(chal_out + lo, chal_pitch, d_chal, C, m, 6, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+int pbh_verify_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, uint8_t* result, uint8_t* chal_out,
+                        size_t chal_pitch, uint8_t* gt, size_t gt_pitch) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proof || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (proof_pitch < n || (chal_out && chal_pitch < n) || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = ensure_slots(ctx, 128);
+  if (rc) return rc;
+  const size_t C = ctx->chunk;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    size_t m = std::min(C, n - lo);
+    int s = (int)(k % kSlots);
+    cudaStream_t st = ctx->slot_stream[s];
+    uint8_t* base = ctx->slot_buf[s];
+    uint8_t *d_proof = base, *d_res = base + 27 * C, *d_chal = base + 28 * C, *d_gt = base + 34 * C;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
+    VerifyFsArgs F{{d_proof, C, nullptr, 0, nullptr, d_res, gt ? d_gt : nullptr, C, m, nullptr}, chal_out ? d_chal : nullptr, C};
+    rc = launch_verify_fs(ctx, st, F);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
+    if (chal_out) CUDA_TRY(ctx, cudaMemcpy2DAsync(chal_out + lo, chal_pitch, d_chal, C, m, 6, cudaMemcpyDeviceToHost, st));
+    if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, C, m, 4, cudaMemcpyDeviceToHost, st));
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
 // ---- record wire format ------------------------------------------------------------------------------------------
 static_assert(sizeof(pbh_witness_record) == 32 && sizeof(pbh_proof_record) == 32, "records are 32 bytes");
 
@@ -887,7 +1005,7 @@ int pbh_generate_inputs_dev(pbh_ctx* ctx, size_t n, uint64_t first_index, uint64
 
 int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second) {
   CTX_CHECK(ctx);
-  if (!lane_ops_per_second || which < 0 || which > 11) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
+  if (!lane_ops_per_second || which < 0 || which > 16) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad argument");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   uint32_t* sink = nullptr;
   CUDA_TRY(ctx, cudaMalloc(&sink, 4));
@@ -909,7 +1027,12 @@ int pbh_measure_int32_peak(pbh_ctx* ctx, int which, double* lane_ops_per_second)
       case 8: mac3_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
       case 9: mac3_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
       case 10: ffma2_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
-      default: ffma2_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 11: ffma2_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 12: shift_peak_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 13: shift_peak_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 14: shift_peak_kernel<2><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      case 15: shift_peak_kernel<3><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
+      default: shift_peak_kernel<4><<<grid, kBlock, 0, ctx->compute>>>(iters, 12345u, sink); break;
     }
     ctx->launches++;
   };

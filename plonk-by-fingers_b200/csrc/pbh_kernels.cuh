@@ -149,6 +149,44 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) prove_f32_kernel(const Co
   }
 }
 
+// ---- Fiat-Shamir prover: no challenge planes in; five SHA-256 compressions per proof make the
+// kernel ALU-bound (integer pipes), so it keeps plain per-thread loads and stores.
+struct FsSeed { uint32_t w[8]; };
+struct ProveFsArgs {
+  ProveArgs base;                        // chal unused
+  uint8_t* chal_out; size_t chal_pitch;  // nullable: 6 planes alpha beta gamma z v u (zero when status != 0)
+};
+template <int ALGO, bool FP32, bool PBH_CIRCUIT>
+__global__ void __launch_bounds__(256, 2) prove_fs_kernel(const Consts K, const ConstsF KF, const FsSeed seed, const Tables* __restrict__ gT,
+                                                           const ProveFsArgs F) {
+  __shared__ Tables sT;
+  stage_tables(sT, gT);
+  const ProveArgs& A = F.base;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w[12], r[9];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { w[k] = A.wit[(size_t)k * A.wit_pitch + i]; bad = bad || w[k] >= 17u; }
+#pragma unroll
+    for (int k = 0; k < 9; k++) { r[k] = A.rnd[(size_t)k * A.rand_pitch + i]; bad = bad || r[k] >= 17u; }
+    if (bad) {
+#pragma unroll
+      for (int k = 0; k < 12; k++) w[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 9; k++) r[k] = 0;
+    }
+    ProofRegs P;
+    uint32_t derived[6];
+    uint32_t status = prove_item_fs<ALGO, FP32, PBH_CIRCUIT>(w, r, seed.w, K, KF, sT, P, derived, F.chal_out != nullptr);
+    if (bad) status = PBH_ST_BAD_ENCODING;
+    store_proof(A, i, P, status);
+    if (F.chal_out) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) F.chal_out[(size_t)k * F.chal_pitch + i] = (uint8_t)(status == 0u ? derived[k] : 0u);
+    }
+  }
+}
+
 // ---- TMA-staged prover -------------------------------------------------------------------------------------------
 // Persistent blocks walk 256-item tiles.  One elected thread issues three TMA tile loads (witness, blinder and
 // challenge planes) for tile k+1 into the other shared-memory stage while the block computes tile k; completion is an
@@ -334,6 +372,42 @@ __global__ void __launch_bounds__(kBlock) verify_kernel(const Consts K, const Co
     if (A.gt) {
       A.gt[i] = (uint8_t)e1.a; A.gt[A.gt_pitch + i] = (uint8_t)e1.b;
       A.gt[2 * A.gt_pitch + i] = (uint8_t)e2.a; A.gt[3 * A.gt_pitch + i] = (uint8_t)e2.b;
+    }
+  }
+}
+
+// Fiat-Shamir verifier: the Challange and rand[0] are replayed from the proof bytes (verify_one_fs)
+struct VerifyFsArgs {
+  VerifyArgs base;                       // chal, u, bitmap unused
+  uint8_t* chal_out; size_t chal_pitch;  // nullable: 6 planes alpha beta gamma z v u (zero for PBH_VR_BAD_ENCODING)
+};
+template <int ALGO>
+__global__ void __launch_bounds__(256, 2) verify_fs_kernel(const Consts K, const ConstsF KF, const bool fp32, const FsSeed seed,
+                                                            const Tables* __restrict__ gT, const VerifyFsArgs F) {
+  __shared__ Tables sT;
+  stage_tables(sT, gT);
+  const VerifyArgs& A = F.base;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t px[9], py[9], ev[7];
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      px[k] = A.proof[(size_t)(2 * k) * A.proof_pitch + i];
+      py[k] = A.proof[(size_t)(2 * k + 1) * A.proof_pitch + i];
+    }
+    uint32_t infbits = (uint32_t)A.proof[(size_t)18 * A.proof_pitch + i] | ((uint32_t)A.proof[(size_t)19 * A.proof_pitch + i] << 8);
+#pragma unroll
+    for (int k = 0; k < 7; k++) ev[k] = A.proof[(size_t)(20 + k) * A.proof_pitch + i];
+    GT e1, e2;
+    uint32_t derived[6];
+    uint32_t res = verify_one_fs<ALGO>(px, py, infbits, ev, seed.w, K, sT, e1, e2, fp32 ? &KF : nullptr, derived);
+    A.result[i] = (uint8_t)res;
+    if (A.gt) {
+      A.gt[i] = (uint8_t)e1.a; A.gt[A.gt_pitch + i] = (uint8_t)e1.b;
+      A.gt[2 * A.gt_pitch + i] = (uint8_t)e2.a; A.gt[3 * A.gt_pitch + i] = (uint8_t)e2.b;
+    }
+    if (F.chal_out) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) F.chal_out[(size_t)k * F.chal_pitch + i] = (uint8_t)derived[k];
     }
   }
 }
@@ -940,6 +1014,43 @@ __global__ void __launch_bounds__(kBlock) int32_peak_kernel(uint32_t iters, uint
   }
   uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
   if (r == 0x12345678u) sink[0] = r;   // keeps the chains alive
+}
+
+// shift / logic instruction classes of the SHA-256 transcript kernels, one instruction per chain step.
+// WHICH: 0 SHF (funnel shift of two registers), 1 IMAD.WIDE.U32 (64-bit product-accumulate: both halves of a rotation),
+//        2 LOP3 (three-register xor), 3 IADD3 (three-register add), 4 PRMT (byte permute)
+template <int WHICH>
+__global__ void __launch_bounds__(kBlock) shift_peak_kernel(uint32_t iters, uint32_t seed, uint32_t* sink) {
+  uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u + 1u, a2 = a0 * 5u + 2u, a3 = a0 * 7u + 3u, a4 = a0 * 11u + 4u, a5 = a0 * 13u + 5u,
+           a6 = a0 * 17u + 6u, a7 = a0 * 19u + 7u;
+  const uint32_t m = seed | 0x10001u;
+  unsigned long long p0 = a0, p1 = a1, p2 = a2, p3 = a3, p4 = a4, p5 = a5, p6 = a6, p7 = a7;
+  for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+      if (WHICH == 0) {
+        a0 = __funnelshift_r(a0, a1, 7); a1 = __funnelshift_r(a1, a2, 7); a2 = __funnelshift_r(a2, a3, 7); a3 = __funnelshift_r(a3, a4, 7);
+        a4 = __funnelshift_r(a4, a5, 7); a5 = __funnelshift_r(a5, a6, 7); a6 = __funnelshift_r(a6, a7, 7); a7 = __funnelshift_r(a7, a0, 7);
+      } else if (WHICH == 1) {
+        p0 = (unsigned long long)(uint32_t)p0 * m + p0; p1 = (unsigned long long)(uint32_t)p1 * m + p1;
+        p2 = (unsigned long long)(uint32_t)p2 * m + p2; p3 = (unsigned long long)(uint32_t)p3 * m + p3;
+        p4 = (unsigned long long)(uint32_t)p4 * m + p4; p5 = (unsigned long long)(uint32_t)p5 * m + p5;
+        p6 = (unsigned long long)(uint32_t)p6 * m + p6; p7 = (unsigned long long)(uint32_t)p7 * m + p7;
+      } else if (WHICH == 2) {
+        a0 = a0 ^ a1 ^ a2; a1 = a1 ^ a2 ^ a3; a2 = a2 ^ a3 ^ a4; a3 = a3 ^ a4 ^ a5;
+        a4 = a4 ^ a5 ^ a6; a5 = a5 ^ a6 ^ a7; a6 = a6 ^ a7 ^ a0; a7 = a7 ^ a0 ^ a1;
+      } else if (WHICH == 3) {
+        a0 = a0 + a1 + a2; a1 = a1 + a2 + a3; a2 = a2 + a3 + a4; a3 = a3 + a4 + a5;
+        a4 = a4 + a5 + a6; a5 = a5 + a6 + a7; a6 = a6 + a7 + a0; a7 = a7 + a0 + a1;
+      } else {
+        a0 = __byte_perm(a0, a1, 0x6543); a1 = __byte_perm(a1, a2, 0x6543); a2 = __byte_perm(a2, a3, 0x6543); a3 = __byte_perm(a3, a4, 0x6543);
+        a4 = __byte_perm(a4, a5, 0x6543); a5 = __byte_perm(a5, a6, 0x6543); a6 = __byte_perm(a6, a7, 0x6543); a7 = __byte_perm(a7, a0, 0x6543);
+      }
+    }
+  }
+  uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+  unsigned long long q = p0 ^ p1 ^ p2 ^ p3 ^ p4 ^ p5 ^ p6 ^ p7;
+  if ((r ^ (uint32_t)q ^ (uint32_t)(q >> 32)) == 0x12345678u) sink[0] = r;
 }
 
 // three distinct register operands per instruction (no constant-bank or immediate operand), the shape of a

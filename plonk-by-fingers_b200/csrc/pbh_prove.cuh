@@ -12,6 +12,7 @@
 // The reference's panics become the status byte of include/pbh_b200.h, first failing site in program order.
 #pragma once
 #include "pbh_arith.cuh"
+#include "pbh_fs.cuh"
 
 namespace pbh {
 
@@ -144,10 +145,10 @@ PBH_HD bool unsatisfied(const uint32_t (&w)[12], const Consts& K) {
 // Returns the status byte.  `P` is fully defined only for status 0.  With UPTO_T the routine stops after the
 // quotient (sites :199 .. :376) — enough for items whose t(x) is known to be short (status 1-4 only).
 // `unsat_known`: -1 = evaluate constraints.satisfies here; 0 / 1 = the caller already did (e.g. from shared memory).
-template <int ALGO, bool UPTO_T = false>
-PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
-                          const Tables& T, ProofRegs& P, int unsat_known = -1) {
-  const uint32_t alpha = ch[0], beta = ch[1], gamma = ch[2], zc = ch[3], v = ch[4];
+// The challenges come from `cs` (pbh_fs.cuh) at the point where the reference first uses each.
+template <int ALGO, bool UPTO_T, class CS>
+PBH_HD uint32_t prove_one_cs(const uint32_t (&w)[12], const uint32_t (&rnd)[9], CS& cs, const Consts& K, const Tables& T,
+                             ProofRegs& P, int unsat_known = -1) {
   const uint32_t n_pts = K.n_pts;
 
   const bool unsat = unsat_known < 0 ? unsatisfied(w, K) : (unsat_known != 0);
@@ -167,6 +168,8 @@ PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], con
   P.pt[0] = commit<ALGO>(a, K, T);                                           // src/plonk.rs:255-257
   P.pt[1] = commit<ALGO>(b, K, T);
   P.pt[2] = commit<ALGO>(c, K, T);
+  uint32_t beta, gamma;
+  cs.beta_gamma(P.pt[0], P.pt[1], P.pt[2], beta, gamma);
 
   // ---- accumulator                                                          src/plonk.rs:278-299
   const uint32_t bg = gamma;
@@ -191,6 +194,7 @@ PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], con
   z[4] = rnd[8]; z[5] = rnd[7]; z[6] = rnd[6];
   bool oob_z = longer_than(z, n_pts);
   P.pt[3] = commit<ALGO>(z, K, T);                                           // src/plonk.rs:313
+  const uint32_t alpha = cs.alpha(P.pt[3]);
 
   // ---- quotient numerator                                                   src/plonk.rs:339-369
   uint32_t t12[22];   // t1 + t2
@@ -294,6 +298,7 @@ PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], con
   P.pt[4] = commit<ALGO>(tlo, K, T);                                         // src/plonk.rs:383-385
   P.pt[5] = commit<ALGO>(tmid, K, T);
   P.pt[6] = commit<ALGO>(thi, K, T);
+  const uint32_t zc = cs.zeta(P.pt[4], P.pt[5], P.pt[6]);
 
   // ---- evaluations at z                                                     src/plonk.rs:393-399
   uint32_t zp[10];   // powers of the challenge z
@@ -347,6 +352,8 @@ PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], con
 #pragma unroll
   for (int i = 0; i < 10; i++) r_z += r[i] * zp[i];
   r_z = mod17(r_z);
+  P.ev[0] = a_z; P.ev[1] = b_z; P.ev[2] = c_z; P.ev[3] = s1_z; P.ev[4] = s2_z; P.ev[5] = r_z; P.ev[6] = zw_z;
+  const uint32_t v = cs.v(P.ev);
 
   // ---- opening polynomials                                                  src/plonk.rs:430-446
   uint32_t v2 = mul17(v, v), v3 = mul17(v2, v), v4 = mul17(v3, v), v5 = mul17(v4, v), v6 = mul17(v5, v);
@@ -381,8 +388,7 @@ PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], con
   // table slots at or beyond n_pts are only reachable together with oob_w
   P.pt[7] = commit<ALGO>(wz, K, T);
   P.pt[8] = commit<ALGO>(wzw, K, T);
-
-  P.ev[0] = a_z; P.ev[1] = b_z; P.ev[2] = c_z; P.ev[3] = s1_z; P.ev[4] = s2_z; P.ev[5] = r_z; P.ev[6] = zw_z;
+  cs.u(P.pt[7], P.pt[8]);
 
   // first failing site in program order
   uint32_t status = 0;
@@ -395,6 +401,14 @@ PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], con
   if (oob_abc) status = 5;
   if (unsat) status = 1;
   return status;
+}
+
+// the reference's interface: the caller supplies the Challange
+template <int ALGO, bool UPTO_T = false>
+PBH_HD uint32_t prove_one(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
+                          const Tables& T, ProofRegs& P, int unsat_known = -1) {
+  FixedChal<uint32_t> cs(ch);
+  return prove_one_cs<ALGO, UPTO_T>(w, rnd, cs, K, T, P, unsat_known);
 }
 
 }  // namespace pbh

@@ -226,15 +226,16 @@ PBH_HD uint32_t fcommit(const T (&c)[L], const CK& ck, const Tables& Tb, bool re
 
 // w[12], rnd[9], ch[5]: inputs as exact small integers (0..16).  inv17c: centred inverses as floats, indexed by the
 // canonical residue.  Returns the status byte among {0, 2, 3, 4, 5} (satisfiability, status 1, is the caller's).
-template <int ALGO, class T, class CK>
-PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (&ch_in)[5], const CK& ck, const Tables& Tb,
-                               const float* inv17c, ProofF& P) {
+// The challenges come from `cs` (pbh_fs.cuh) as values 0..16 at the point where the reference first uses each.
+template <int ALGO, class T, class CK, class CS>
+PBH_HD uint32_t prove_core_f32_cs(const T (&w)[12], const T (&rnd_in)[9], CS& cs, const CK& ck, const Tables& Tb,
+                                  const float* inv17c, ProofF& P) {
   T* tag = nullptr;
   // blinders and challenges are used as they come (0..16); the bound check shows that centring them is not needed
   // (worst-case magnitude 4.8 M, below red17's 2^23 range)
   const T (&rnd)[9] = rnd_in;
-  const T (&ch)[5] = ch_in;
-  const T alpha = ch[0], beta = ch[1], gamma = ch[2], zc = ch[3], v = ch[4];
+  // packed point of a commitment, for the challenge sources that hash it
+  auto point_of = [&](uint32_t e) -> uint32_t { return CS::kNeedsPoints ? ((ALGO == ALGO_TABLE) ? Tb.pt17[e] : e) : 0u; };
 
   // ---- wire polynomials                                                     src/plonk.rs:233-235, 248-252
   T fa[4], fb[4], fc[4];
@@ -249,6 +250,8 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   P.e[0] = fcommit<ALGO, T>(a, ck, Tb, false, oob_abc);                             // src/plonk.rs:255-257
   P.e[1] = fcommit<ALGO, T>(b, ck, Tb, false, oob_abc);
   P.e[2] = fcommit<ALGO, T>(c, ck, Tb, false, oob_abc);
+  T beta, gamma;
+  cs.beta_gamma(point_of(P.e[0]), point_of(P.e[1]), point_of(P.e[2]), beta, gamma);
 
   // ---- accumulator                                                          src/plonk.rs:278-299
   T acc[4];
@@ -276,6 +279,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   z[0] = f_sub(accx[0], rnd[8]); z[1] = f_sub(accx[1], rnd[7]); z[2] = f_sub(accx[2], rnd[6]); z[3] = accx[3];
   z[4] = rnd[8]; z[5] = rnd[7]; z[6] = rnd[6];
   P.e[3] = fcommit<ALGO, T>(z, ck, Tb, false, oob_z);                               // src/plonk.rs:313
+  const T alpha = cs.alpha(point_of(P.e[3]));
 
   // ---- quotient numerator: t1 + alpha (A'B'C' z - A''B''C'' z_omega) + alpha^2 (z - 1) L1     src/plonk.rs:339-369
   T num[22];
@@ -364,6 +368,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   P.e[6] = fcommit<ALGO, T>(thi, ck, Tb, false, oob_t);                             // src/plonk.rs:383-385
   P.e[5] = fcommit<ALGO, T>(tmid, ck, Tb, false, oob_t);
   P.e[4] = fcommit<ALGO, T>(tlo, ck, Tb, false, oob_t);
+  const T zc = cs.zeta(point_of(P.e[4]), point_of(P.e[5]), point_of(P.e[6]));
 
   // ---- evaluations at z                                                     src/plonk.rs:393-399
   T zp[10];
@@ -420,6 +425,9 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
 #pragma unroll
   for (int i = 1; i < 10; i++) r_z = f_fma(r[i], zp[i], r_z);
   r_z = f_red(r_z);
+  P.ev[0] = f_canon(a_z); P.ev[1] = f_canon(b_z); P.ev[2] = f_canon(c_z); P.ev[3] = f_canon(s1_z); P.ev[4] = f_canon(s2_z);
+  P.ev[5] = f_canon(r_z); P.ev[6] = f_canon(zw_z);
+  const T v = cs.v(P.ev);
 
   // ---- opening polynomials                                                  src/plonk.rs:430-446
   T v2 = f_red(f_mul(v, v)), v3 = f_red(f_mul(v2, v)), v4 = f_red(f_mul(v3, v)), v5 = f_red(f_mul(v4, v)), v6 = f_red(f_mul(v5, v));
@@ -453,9 +461,7 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   }
   P.e[7] = fcommit<ALGO, T>(wz, ck, Tb, true, oob_w);                               // src/plonk.rs:445-446 -> :56 (Q2)
   P.e[8] = fcommit<ALGO, T>(wzw, ck, Tb, true, oob_w);
-
-  P.ev[0] = f_canon(a_z); P.ev[1] = f_canon(b_z); P.ev[2] = f_canon(c_z); P.ev[3] = f_canon(s1_z); P.ev[4] = f_canon(s2_z);
-  P.ev[5] = f_canon(r_z); P.ev[6] = f_canon(zw_z);
+  cs.u(point_of(P.e[7]), point_of(P.e[8]));
 
   uint32_t status = 0;
   if (oob_w) status = 5;
@@ -466,6 +472,14 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   if (div0) status = 2;
   if (oob_abc) status = 5;
   return status;
+}
+
+// the reference's interface: the caller supplies the Challange
+template <int ALGO, class T, class CK>
+PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (&ch_in)[5], const CK& ck, const Tables& Tb,
+                               const float* inv17c, ProofF& P) {
+  FixedChal<T> cs(ch_in);
+  return prove_core_f32_cs<ALGO, T>(w, rnd_in, cs, ck, Tb, inv17c, P);
 }
 
 // One proof through the fast path: FP32 core for the common case, exact integer routine for items whose quotient
@@ -500,6 +514,48 @@ PBH_HD uint32_t prove_item_f32(const uint32_t (&w)[12], const uint32_t (&rnd)[9]
   for (int k = 0; k < 7; k++) P.ev[k] = pf.ev[k];
   // program order of the reference: the satisfiability assert comes first; an SRS too short for a, b, c (only
   // with fewer than 6 SRS points) precedes the accumulator
+  if (unsat) status = 1;
+  return status;
+}
+
+// ---- Fiat-Shamir prover item: the challenges come from the SHA-256 transcript seeded with the
+// context's `seed`.  `derived` receives alpha beta gamma z v u (those derived before a failing site; the caller zeroes
+// them with the proof when status != 0).  FP32 = false runs the int32 routine for every item.
+struct ConvF32 { PBH_HD F32 operator()(uint32_t x) const { return f_from_u32(x, (F32*)nullptr); } };
+
+template <int ALGO, bool FP32, bool PBH_CIRCUIT>
+PBH_HD uint32_t prove_item_fs(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&seed)[8], const Consts& K,
+                              const ConstsF& KF, const Tables& T, ProofRegs& P, uint32_t (&derived)[6], bool want_u = true) {
+  // a zero among b1, b3, b5, b7 makes the quotient short whatever the challenges are (status 1-4 only), and only then
+  // can the reference's SubAssign quirk (Q1) fire: those items take the exact-length integer routine
+  const bool rare = rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
+  if (!FP32 || rare) {
+    FsChal<uint32_t, ConvU32> cs(seed, want_u);
+    uint32_t status;
+    if (FP32) status = prove_one_cs<ALGO_TABLE, true>(w, rnd, cs, K, T, P, -1);
+    else status = prove_one_cs<ALGO, false>(w, rnd, cs, K, T, P, -1);
+#pragma unroll
+    for (int k = 0; k < 6; k++) derived[k] = cs.derived[k];
+    return status;
+  }
+  const bool unsat = unsatisfied(w, K);
+  F32* tag = nullptr;
+  F32 wf[12], rf[9];
+#pragma unroll
+  for (int i = 0; i < 12; i++) wf[i] = f_from_u32(w[i], tag);
+#pragma unroll
+  for (int i = 0; i < 9; i++) rf[i] = f_from_u32(rnd[i], tag);
+  FsChal<F32, ConvF32> cs(seed, want_u);
+  ProofF pf;
+  uint32_t status;
+  if (PBH_CIRCUIT) status = prove_core_f32_cs<ALGO, F32>(wf, rf, cs, PbhCK(), T, T.inv17c, pf);
+  else status = prove_core_f32_cs<ALGO, F32>(wf, rf, cs, RuntimeCK{KF, K.n_pts}, T, T.inv17c, pf);
+#pragma unroll
+  for (int k = 0; k < 9; k++) P.pt[k] = (ALGO == ALGO_TABLE) ? T.pt17[pf.e[k]] : pf.e[k];
+#pragma unroll
+  for (int k = 0; k < 7; k++) P.ev[k] = pf.ev[k];
+#pragma unroll
+  for (int k = 0; k < 6; k++) derived[k] = cs.derived[k];
   if (unsat) status = 1;
   return status;
 }

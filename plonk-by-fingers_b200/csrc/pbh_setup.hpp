@@ -22,6 +22,7 @@ struct HostSetup {
   uint32_t g2_1[2], g2_s[2];  // SRS.g2_1, SRS.g2_s
   G1 vconst[8];               // q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s
   uint32_t g102_idx_of_G;     // == 6
+  uint32_t fs_seed[8];        // initial state of the Fiat-Shamir transcript (include/pbh_b200.h), SHA-256 words
 };
 
 // "G2" of src/pbh/g2.rs:58-101: (a, b*u), u^2 = -2, no identity; returns false where the reference panics (Q12)
@@ -214,6 +215,19 @@ inline int host_setup(const pbh_circuit& c, uint32_t srs_secret, uint32_t srs_n,
   for (int i = 0; i < 10; i++) F.srs_dlog[i] = cen(K.srs_dlog[i]);
   for (int i = 0; i < 8; i++) F.vdlog[i] = cen(K.vdlog[i]);
   for (uint32_t a = 0; a < 17; a++) T.inv17c[a] = cen(T.inv17[a]);
+
+  // ---- Fiat-Shamir seed: SHA-256(tag || omega_pows || circuit || SRS), see include/pbh_b200.h
+  {
+    std::vector<uint8_t> m;
+    for (const char* t = "plonk-by-fingers/fiat-shamir/v1"; *t; t++) m.push_back((uint8_t)*t);
+    m.push_back((uint8_t)omega_pows);
+    const uint8_t* fields[11] = {c.q_l, c.q_r, c.q_o, c.q_m, c.q_c, c.c_a_wire, c.c_a_index, c.c_b_wire, c.c_b_index, c.c_c_wire, c.c_c_index};
+    for (int f = 0; f < 11; f++) for (int i = 0; i < 4; i++) m.push_back(fields[f][i]);
+    m.push_back((uint8_t)hs.g1s.size());
+    for (const G1& pnt : hs.g1s) { m.push_back((uint8_t)pnt.x); m.push_back((uint8_t)pnt.y); m.push_back((uint8_t)pnt.inf); m.push_back(0); }
+    m.push_back((uint8_t)hs.g2_1[0]); m.push_back((uint8_t)hs.g2_1[1]); m.push_back((uint8_t)hs.g2_s[0]); m.push_back((uint8_t)hs.g2_s[1]);
+    sha256_host(m.data(), m.size(), hs.fs_seed);
+  }
   return PBH_OK;
 }
 

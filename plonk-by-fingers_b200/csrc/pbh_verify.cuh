@@ -229,4 +229,28 @@ PBH_HD void verify_scalars_f32(const T (&idx)[9], const T (&ev)[7], const T (&ch
   i2 = f_index102(f_red102c(x2));
 }
 
+// ---- Fiat-Shamir verifier: replay the transcript over the proof bytes as they are (each point
+// as x, y, infinite, 0; the evaluation bytes unreduced), then Plonk::verify with the derived Challange and rand[0] = u.
+// `derived` = alpha beta gamma z v u.
+template <int ALGO>
+PBH_HD uint32_t verify_one_fs(const uint32_t (&px)[9], const uint32_t (&py)[9], uint32_t infbits, const uint32_t (&ev)[7],
+                              const uint32_t (&seed)[8], const Consts& K, const Tables& T, GT& e1, GT& e2, const ConstsF* KF,
+                              uint32_t (&derived)[6]) {
+  uint32_t pk[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) pk[k] = (px[k] & 0xFFu) | ((py[k] & 0xFFu) << 8) | (((infbits >> k) & 1u) << 16);
+  FsChal<uint32_t, ConvU32> cs(seed);
+  uint32_t beta, gamma;
+  cs.beta_gamma(pk[0], pk[1], pk[2], beta, gamma);
+  cs.alpha(pk[3]);
+  cs.zeta(pk[4], pk[5], pk[6]);
+  cs.v(ev);
+  cs.u(pk[7], pk[8]);
+  const uint32_t ch[5] = {cs.derived[0], cs.derived[1], cs.derived[2], cs.derived[3], cs.derived[4]};
+  const uint32_t res = verify_one<ALGO>(px, py, infbits, ev, ch, cs.derived[5], K, T, e1, e2, KF);
+#pragma unroll
+  for (int k = 0; k < 6; k++) derived[k] = (res == VR_BAD_ENCODING) ? 0u : cs.derived[k];
+  return res;
+}
+
 }  // namespace pbh

@@ -45,7 +45,7 @@ pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_pr
 pbh_proof_records_to_planes_dev pbh_proof_planes_to_records_dev pbh_prove_digest_batch_dev pbh_verify_bitmap_batch_dev pbh_ntt4_batch pbh_intt4_batch
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
-pbh_measure_int32_peak""".split()
+pbh_measure_int32_peak pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -349,6 +349,57 @@ class Context:
                                              C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr), C.c_void_p(Rs.ptr))
         self._check(rc, "pbh_prove_verify_batch")
         return P.arr, S.arr.reshape(-1), Rs.arr.reshape(-1)
+
+    # ---- Fiat-Shamir transcript (include/pbh_b200.h): the challenges and u are derived on the device ----
+    def fs_seed(self):
+        out = (C.c_uint8 * 32)()
+        self._check(self.lib.pbh_ctx_get_fs_seed(self.h, out), "pbh_ctx_get_fs_seed")
+        return bytes(out)
+
+    def prove_fs_batch(self, wit, rand, proof=None, status=None, chal=None, want_chal=True):
+        """wit (12,n), rand (9,n) -> proof (27,n), status (n,) [, chal (6,n) = alpha beta gamma z v u]."""
+        W = _Planes(wit, 12, name="wit"); n = W.n
+        R = _Planes(rand, 9, n, "rand")
+        if W.dev != R.dev:
+            raise PbhError("all batches must live on the same side (host or device)")
+        proof = self._empty(W.dev, 27, n) if proof is None else proof
+        status = self._empty(W.dev, 1, n) if status is None else status
+        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status")
+        Ch = None
+        if want_chal or chal is not None:
+            chal = self._empty(W.dev, 6, n) if chal is None else chal
+            Ch = _Planes(chal, 6, n, "chal")
+        fn = self.lib.pbh_prove_fs_batch_dev if W.dev else self.lib.pbh_prove_fs_batch
+        cur = self._dev_begin() if W.dev else None
+        rc = fn(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch),
+                C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr), C.c_void_p(Ch.ptr if Ch else None),
+                C.c_size_t(Ch.pitch if Ch else 0))
+        self._dev_end(cur)
+        self._check(rc, fn.__name__)
+        return (P.arr, S.arr.reshape(-1), Ch.arr) if Ch else (P.arr, S.arr.reshape(-1))
+
+    def verify_fs_batch(self, proof, result=None, chal=None, want_chal=True, gt=None, want_gt=False):
+        """proof (27,n) -> result (n,) [, chal (6,n)] [, gt (4,n)]."""
+        P = _Planes(proof, 27, name="proof"); n = P.n
+        result = self._empty(P.dev, 1, n) if result is None else result
+        Rs = _Planes(result, 1, n, "result")
+        Ch = G = None
+        if want_chal or chal is not None:
+            chal = self._empty(P.dev, 6, n) if chal is None else chal
+            Ch = _Planes(chal, 6, n, "chal")
+        if want_gt or gt is not None:
+            gt = self._empty(P.dev, 4, n) if gt is None else gt
+            G = _Planes(gt, 4, n, "gt")
+        fn = self.lib.pbh_verify_fs_batch_dev if P.dev else self.lib.pbh_verify_fs_batch
+        cur = self._dev_begin() if P.dev else None
+        rc = fn(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Rs.ptr), C.c_void_p(Ch.ptr if Ch else None),
+                C.c_size_t(Ch.pitch if Ch else 0), C.c_void_p(G.ptr if G else None), C.c_size_t(G.pitch if G else 0))
+        self._dev_end(cur)
+        self._check(rc, fn.__name__)
+        out = [Rs.arr.reshape(-1)]
+        if Ch: out.append(Ch.arr)
+        if G: out.append(G.arr)
+        return out[0] if len(out) == 1 else tuple(out)
 
     # ---- record (array-of-structs) wire format ----
     def prove_records(self, records):

@@ -161,6 +161,83 @@ int emul_verify_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t o
   return 0;
 }
 
+// ---- Fiat-Shamir item routines (pbh_fs.cuh, pbh_sha256.cuh) ----
+int emul_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
+  uint32_t h[8];
+  sha256_host(data, len, h);
+  for (int i = 0; i < 8; i++) for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(h[i] >> (24 - 8 * b));
+  return 0;
+}
+// state <- SHA-256(state || msg) through the single-compression device routine; len <= 23
+int emul_sha256_absorb(uint8_t state[32], const uint8_t* msg, int len) {
+  uint32_t st[8], m[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 8; i++) st[i] = ((uint32_t)state[4 * i] << 24) | ((uint32_t)state[4 * i + 1] << 16) | ((uint32_t)state[4 * i + 2] << 8) | state[4 * i + 3];
+  for (int i = 0; i < len; i++) m[i / 4] |= (uint32_t)msg[i] << (24 - 8 * (i % 4));
+  sha256_absorb(st, m, len);
+  for (int i = 0; i < 8; i++) for (int b = 0; b < 4; b++) state[4 * i + b] = (uint8_t)(st[i] >> (24 - 8 * b));
+  return 0;
+}
+int emul_fs_seed(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t omega_pows, uint8_t out[32]) {
+  HostSetup hs;
+  int rc = host_setup(*c, s, srs_n, omega_pows, hs, g_err);
+  if (rc) return rc;
+  for (int i = 0; i < 8; i++) for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(hs.fs_seed[i] >> (24 - 8 * b));
+  return 0;
+}
+// algo: 0 ARITH int, 1 TABLE int, 2 TABLE f32, 3 ARITH f32, 4 TABLE f32 specialised
+int emul_prove_fs_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t omega_pows, int algo, size_t n, const uint8_t* wit,
+                        const uint8_t* rnd, uint8_t* proof, uint8_t* status, uint8_t* chal_out) {
+  HostSetup hs;
+  int rc = host_setup(*c, s, srs_n, omega_pows, hs, g_err);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    uint32_t w[12], r[9], d[6];
+    bool bad = false;
+    for (int k = 0; k < 12; k++) { w[k] = wit[k * n + i]; bad |= w[k] >= 17; }
+    for (int k = 0; k < 9; k++) { r[k] = rnd[k * n + i]; bad |= r[k] >= 17; }
+    if (bad) { std::memset(w, 0, sizeof w); std::memset(r, 0, sizeof r); }
+    ProofRegs P;
+    const bool special = consts_match_pbh(hs.KF, hs.K.n_pts);
+    uint32_t st = algo == 4 ? (special ? prove_item_fs<ALGO_TABLE, true, true>(w, r, hs.fs_seed, hs.K, hs.KF, hs.T, P, d) : 0xFFu)
+                : algo == 3 ? prove_item_fs<ALGO_ARITH, true, false>(w, r, hs.fs_seed, hs.K, hs.KF, hs.T, P, d)
+                : algo == 2 ? prove_item_fs<ALGO_TABLE, true, false>(w, r, hs.fs_seed, hs.K, hs.KF, hs.T, P, d)
+                : algo == 1 ? prove_item_fs<ALGO_TABLE, false, false>(w, r, hs.fs_seed, hs.K, hs.KF, hs.T, P, d)
+                            : prove_item_fs<ALGO_ARITH, false, false>(w, r, hs.fs_seed, hs.K, hs.KF, hs.T, P, d);
+    if (bad) st = PBH_ST_BAD_ENCODING;
+    for (int k = 0; k < 27; k++) proof[k * n + i] = 0;
+    status[i] = (uint8_t)st;
+    for (int k = 0; k < 6; k++) chal_out[k * n + i] = st == 0 ? (uint8_t)d[k] : 0;
+    if (st == 0) {
+      for (int k = 0; k < 9; k++) {
+        proof[(2 * k) * n + i] = P.pt[k] & 0xFF; proof[(2 * k + 1) * n + i] = (P.pt[k] >> 8) & 0xFF;
+        if ((P.pt[k] >> 16) & 1) { if (k < 8) proof[18 * n + i] |= 1u << k; else proof[19 * n + i] |= 1; }
+      }
+      for (int k = 0; k < 7; k++) proof[(20 + k) * n + i] = (uint8_t)P.ev[k];
+    }
+  }
+  return 0;
+}
+int emul_verify_fs_batch(const pbh_circuit* c, uint8_t s, uint32_t srs_n, uint8_t omega_pows, int algo, size_t n, const uint8_t* proof,
+                         uint8_t* result, uint8_t* chal_out, uint8_t* gt) {
+  HostSetup hs;
+  int rc = host_setup(*c, s, srs_n, omega_pows, hs, g_err);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; i++) {
+    uint32_t px[9], py[9], ev[7], d[6];
+    for (int k = 0; k < 9; k++) { px[k] = proof[(2 * k) * n + i]; py[k] = proof[(2 * k + 1) * n + i]; }
+    uint32_t infbits = proof[18 * n + i] | ((uint32_t)proof[19 * n + i] << 8);
+    for (int k = 0; k < 7; k++) ev[k] = proof[(20 + k) * n + i];
+    GT e1, e2;
+    uint32_t res = algo == 2 ? verify_one_fs<ALGO_TABLE>(px, py, infbits, ev, hs.fs_seed, hs.K, hs.T, e1, e2, &hs.KF, d)
+                   : (algo == 1 ? verify_one_fs<ALGO_TABLE>(px, py, infbits, ev, hs.fs_seed, hs.K, hs.T, e1, e2, nullptr, d)
+                                : verify_one_fs<ALGO_ARITH>(px, py, infbits, ev, hs.fs_seed, hs.K, hs.T, e1, e2, nullptr, d));
+    result[i] = (uint8_t)res;
+    for (int k = 0; k < 6; k++) chal_out[k * n + i] = (uint8_t)d[k];
+    if (gt) { gt[i] = e1.a; gt[n + i] = e1.b; gt[2 * n + i] = e2.a; gt[3 * n + i] = e2.b; }
+  }
+  return 0;
+}
+
 // G1 / pairing primitives of pbh_arith.cuh
 int emul_g1_add(const uint8_t p[3], const uint8_t q[3], uint8_t out[3]) {
   HostSetup hs; pbh_circuit c; std::memset(&c, 0, sizeof c);

@@ -17,7 +17,7 @@ def load():
     if _E is None:
         so = os.path.join(HERE, "libhostemul.so")
         srcs = [os.path.join(HERE, "hostemul.cpp")] + [os.path.join(ROOT, "plonk-by-fingers_b200", "csrc", f) for f in
-                                                       ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_prove_f32.cuh", "pbh_verify.cuh", "pbh_setup.hpp")]
+                                                       ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_prove_f32.cuh", "pbh_verify.cuh", "pbh_setup.hpp", "pbh_sha256.cuh", "pbh_fs.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-mfma", "-o", so, srcs[0]], check=True)
         _E = C.CDLL(so)
@@ -54,6 +54,46 @@ class Emul:
         if rc:
             raise RuntimeError((rc, self.lib.emul_last_error().decode()))
         return res, gt
+
+    # ---- Fiat-Shamir routines ----
+    def sha256(self, data):
+        data = np.frombuffer(bytes(data), dtype=np.uint8)
+        out = np.zeros(32, np.uint8)
+        self.lib.emul_sha256(_p(data) if data.size else None, C.c_size_t(data.size), _p(out))
+        return out.tobytes()
+
+    def sha256_absorb(self, state, msg):
+        st = np.frombuffer(bytes(state), dtype=np.uint8).copy()
+        m = np.frombuffer(bytes(msg), dtype=np.uint8)
+        self.lib.emul_sha256_absorb(_p(st), _p(m) if m.size else None, int(m.size))
+        return st.tobytes()
+
+    def fs_seed(self, circuit, s=2, srs_n=6, omega_pows=4):
+        out = np.zeros(32, np.uint8)
+        rc = self.lib.emul_fs_seed(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), _p(out))
+        if rc:
+            raise RuntimeError((rc, self.lib.emul_last_error().decode()))
+        return out.tobytes()
+
+    def prove_fs(self, circuit, wit, rand, algo, s=2, srs_n=6, omega_pows=4):
+        wit, rand = (np.ascontiguousarray(x, dtype=np.uint8) for x in (wit, rand))
+        n = wit.shape[1]
+        proof = np.zeros((27, n), np.uint8); status = np.zeros(n, np.uint8); chal = np.zeros((6, n), np.uint8)
+        rc = self.lib.emul_prove_fs_batch(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), int(algo),
+                                          C.c_size_t(n), _p(wit), _p(rand), _p(proof), _p(status), _p(chal))
+        if rc:
+            raise RuntimeError((rc, self.lib.emul_last_error().decode()))
+        return proof, status, chal
+
+    def verify_fs(self, circuit, proof, algo, s=2, srs_n=6, omega_pows=4):
+        proof = np.ascontiguousarray(proof, dtype=np.uint8)
+        n = proof.shape[1]
+        res = np.zeros(n, np.uint8); chal = np.zeros((6, n), np.uint8); gt = np.zeros((4, n), np.uint8)
+        rc = self.lib.emul_verify_fs_batch(C.byref(circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), int(algo),
+                                           C.c_size_t(n), _p(proof), _p(res), _p(chal), _p(gt))
+        if rc:
+            raise RuntimeError((rc, self.lib.emul_last_error().decode()))
+        return res, chal, gt
 
     def setup(self, circuit, s=2, srs_n=6, omega_pows=4):
         g1s = np.zeros(3 * (srs_n + 1), np.uint8); g2 = np.zeros(4, np.uint8); consts = np.zeros(24, np.uint8)

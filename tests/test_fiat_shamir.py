@@ -1,0 +1,225 @@
+"""Fiat-Shamir transcript (specified in include/pbh_b200.h).
+
+The reference takes its challenges from the caller (src/plonk.rs:195, 201-206), so there is no reference vector for the
+transcript itself.  It is pinned three ways instead:
+  * both SHA-256 implementations (the oracle's and the product's, the latter compiled for the host) against hashlib;
+  * the oracle's transcript replayed here in Python with hashlib from the proof bytes alone;
+  * "a Fiat-Shamir proof is the reference's proof for the derived challenges": the oracle's pinned prove/verify,
+    handed the derived challenges, must return the same bytes and status.
+The product's per-item routines (compiled for the host by tests/hostemul) and, with -m gpu, the CUDA kernels through the
+C ABI are then compared with the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+MESSAGES = (b"", b"abc", b"a" * 55, b"a" * 56, b"a" * 63, b"a" * 64, b"a" * 65, bytes(range(256)) * 3,
+            b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq")
+
+
+def _enc_point(p, i, k):
+    inf = (p[18, i] >> k) & 1 if k < 8 else p[19, i] & 1
+    return bytes([int(p[2 * k, i]), int(p[2 * k + 1, i]), int(inf), 0])
+
+
+def _squeeze(state, k):
+    return int.from_bytes(state[8 * k:8 * k + 8], "big") % 17
+
+
+def replay(seed, p, i):
+    """alpha beta gamma z v u of proof column i, per the transcript of include/pbh_b200.h, with hashlib."""
+    st = hashlib.sha256(seed + _enc_point(p, i, 0) + _enc_point(p, i, 1) + _enc_point(p, i, 2)).digest()
+    beta, gamma = _squeeze(st, 0), _squeeze(st, 1)
+    st = hashlib.sha256(st + _enc_point(p, i, 3)).digest()
+    alpha = _squeeze(st, 0)
+    st = hashlib.sha256(st + _enc_point(p, i, 4) + _enc_point(p, i, 5) + _enc_point(p, i, 6)).digest()
+    z = _squeeze(st, 0)
+    st = hashlib.sha256(st + bytes(int(x) for x in p[20:27, i])).digest()
+    v = _squeeze(st, 0)
+    st = hashlib.sha256(st + _enc_point(p, i, 7) + _enc_point(p, i, 8)).digest()
+    return [alpha, beta, gamma, z, v, _squeeze(st, 0)]
+
+
+def expected_seed(circuit, g1s, g2, omega_pows=4):
+    m = b"plonk-by-fingers/fiat-shamir/v1" + bytes([omega_pows]) + bytes(circuit)
+    m += bytes([len(g1s)]) + b"".join(bytes([int(x), int(y), int(f), 0]) for x, y, f in g1s) + bytes(int(b) for b in g2)
+    return hashlib.sha256(m).digest()
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU
+def test_sha256_implementations_match_hashlib(oracle, hostemul):
+    assert hashlib.sha256(b"abc").hexdigest() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"   # FIPS 180-4 B.1
+    for m in MESSAGES:
+        assert oracle.sha256(m) == hashlib.sha256(m).digest()
+        assert hostemul.sha256(m) == hashlib.sha256(m).digest()
+    rng = np.random.default_rng(1)
+    for length in range(0, 24):      # the single-compression routine the kernels use: state || up to 23 bytes
+        for _ in range(20):
+            st, msg = rng.bytes(32), rng.bytes(length)
+            assert hostemul.sha256_absorb(st, msg) == hashlib.sha256(st + msg).digest()
+
+
+@pytest.mark.parametrize("s,srs_n", ((2, 6), (3, 6), (2, 9), (5, 4)))
+def test_seed_binds_circuit_and_srs(oracle, hostemul, s, srs_n):
+    circ = oracle.pbh_test_circuit()
+    g1s, g2, _ = oracle.setup(circuit=circ, s=s, srs_n=srs_n)
+    want = expected_seed(circ, g1s, g2)
+    assert oracle.fs_seed(circuit=circ, s=s, srs_n=srs_n) == want
+    assert hostemul.fs_seed(circ, s=s, srs_n=srs_n) == want
+    other = oracle.pbh_test_circuit()
+    other.q_c[0] = 1
+    assert oracle.fs_seed(circuit=other, s=s, srs_n=srs_n) != want
+
+
+def test_oracle_transcript_replayed_with_hashlib(oracle):
+    """The challenges the oracle derives are the ones the specification gives for the proof bytes, and the proof is the
+    reference's proof (pinned non-Fiat-Shamir path) for those challenges; so is the status of every failing item."""
+    n = 20000
+    w, r, _, _, _ = oracle.generate_inputs(n, seed=31, dist=0, threads=8)
+    p, s, ch = oracle.prove_fs_batch(w, r, threads=8, partial=True)
+    seed = oracle.fs_seed()
+    ok = np.nonzero(s == 0)[0]
+    assert len(ok) > 1000 and set(np.unique(s)) >= {0, 2, 4, 5}
+    for i in ok[:3000]:
+        assert replay(seed, p, i) == ch[:, i].tolist()
+    p2, s2 = oracle.prove_batch(w, r, ch[:5], threads=8)
+    assert np.array_equal(s2, s) and np.array_equal(p2, p)
+    # the product's contract zeroes the challenges of failing items
+    _, s3, ch3 = oracle.prove_fs_batch(w, r, threads=8)
+    assert np.array_equal(s3, s) and not ch3[:, s != 0].any() and np.array_equal(ch3[:, ok], ch[:, ok])
+    # verifier: same challenges from the proof bytes alone, same answer as the pinned verify with them
+    res, chv = oracle.verify_fs_batch(p, threads=8)
+    assert np.array_equal(chv[:, ok], ch[:, ok])
+    direct = oracle.verify_batch(p, chv[:5], chv[5], threads=8, want_gt=False)
+    assert np.array_equal(res, direct)
+    assert (res[ok] == 1).sum() > 100 and (res[ok] == 0x10).sum() > 100      # accepted proofs, and z in H (Q4)
+
+
+@pytest.mark.parametrize("algo", (0, 1, 2, 3, 4))
+def test_product_routines_match_oracle(hostemul, oracle, algo):
+    """prove_item_fs / verify_one_fs of the kernels, compiled for the host: bit-exact with the oracle, including the
+    items whose transcript-derived alpha is 0 and the zero-blinder items that take the integer routine."""
+    circ = oracle.pbh_test_circuit()
+    n = 25000
+    w, r, _, _, _ = oracle.generate_inputs(n, seed=900 + algo, dist=0, threads=8)
+    r[:, :4000] = np.random.default_rng(algo).choice(np.array([0, 0, 1, 16, 5], dtype=np.uint8), size=(9, 4000))
+    po, so, co = oracle.prove_fs_batch(w, r, threads=8)
+    pe, se, ce = hostemul.prove_fs(circ, w, r, algo)
+    assert np.array_equal(se, so) and np.array_equal(pe, po) and np.array_equal(ce, co)
+    assert ((so == 0) & (co[0] == 0)).sum() == 0 and (so == 3).sum() + (so == 4).sum() > 0
+    if algo <= 2:
+        ro, cvo, go = oracle.verify_fs_batch(po, threads=8, want_gt=True)
+        re, cve, ge = hostemul.verify_fs(circ, po, algo)
+        assert np.array_equal(re, ro) and np.array_equal(cve, cvo) and np.array_equal(ge, go)
+
+
+def test_other_circuit_and_srs(hostemul, oracle):
+    """Run-time constants: a different SRS secret and length, and a circuit with other selector values."""
+    circ = oracle.pbh_test_circuit()
+    circ.q_c[3] = 2
+    n = 6000
+    w, r, _, _, _ = oracle.generate_inputs(n, seed=5, dist=0, threads=8)
+    for s, srs_n in ((3, 6), (2, 9)):
+        po, so, co = oracle.prove_fs_batch(w, r, circuit=circ, s=s, srs_n=srs_n, threads=8)
+        for algo in (1, 2, 3):
+            pe, se, ce = hostemul.prove_fs(circ, w, r, algo, s=s, srs_n=srs_n)
+            assert np.array_equal(se, so) and np.array_equal(pe, po) and np.array_equal(ce, co)
+
+
+def test_tampered_and_malformed_proofs(hostemul, oracle):
+    """Any change to an accepted proof changes the derived challenges (so it is judged under different ones); bad
+    encodings answer 0x20 with zero challenges; evaluation bytes >= 17 are hashed as they are and fail in_field."""
+    circ = oracle.pbh_test_circuit()
+    n = 12000
+    w, r, _, _, _ = oracle.generate_inputs(n, seed=77, dist=0, threads=8)
+    p, s, ch = oracle.prove_fs_batch(w, r, threads=8)
+    res, _ = oracle.verify_fs_batch(p, threads=8)
+    acc = np.nonzero((s == 0) & (res == 1))[0][:300]
+    assert len(acc) >= 100
+    rng = np.random.default_rng(3)
+    q = p[:, acc].copy()
+    for j in range(q.shape[1]):
+        k = int(rng.integers(0, 27))
+        q[k, j] = (int(q[k, j]) + int(rng.integers(1, 17))) % (17 if k >= 20 else (2 if k == 19 else 101))
+    q[20, :20] = 200                     # not in the field
+    q[0, 20:40] = 101                    # bad encoding
+    ro, co = oracle.verify_fs_batch(q, threads=8)
+    for algo in (0, 1, 2):
+        re, ce, _ = hostemul.verify_fs(circ, q, algo)
+        assert np.array_equal(re, ro) and np.array_equal(ce, co)
+    changed = (q != p[:, acc]).any(axis=0)
+    assert (ro[changed] == 1).sum() <= 0.05 * changed.sum()      # the toy field leaves collisions; most tampering fails
+    assert (ro[20:40] == 0x20).all() and not co[:, 20:40].any() and (ro[:20] & 0x06).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+CTXS = ("table", "arith", "table_int", "arith_int", "table_generic")
+
+
+@pytest.mark.gpu
+def test_gpu_seed(gpu_ctx, oracle):
+    assert gpu_ctx["table"].fs_seed() == oracle.fs_seed()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("algo", CTXS)
+@pytest.mark.parametrize("n", (1, 255, 70003))
+def test_gpu_fs_matches_oracle(gpu_ctx, oracle, algo, n):
+    """pbh_prove_fs_batch / pbh_verify_fs_batch, device and host pointers, against the oracle."""
+    import torch
+    ctx = gpu_ctx[algo]
+    w, r, _, _, _ = oracle.generate_inputs(n, seed=n + 1, dist=0, threads=8)
+    if n > 1000:
+        r[:, :3000] = np.random.default_rng(n).choice(np.array([0, 0, 1, 16, 5], dtype=np.uint8), size=(9, 3000))
+    po, so, co = oracle.prove_fs_batch(w, r, threads=8)
+    ro, cvo, go = oracle.verify_fs_batch(po, threads=8, want_gt=True)
+    dev = torch.device("cuda", 0)
+    p, s, c = ctx.prove_fs_batch(torch.from_numpy(w).to(dev), torch.from_numpy(r).to(dev))
+    res, cv, g = ctx.verify_fs_batch(p, want_gt=True)
+    ctx.sync()
+    assert np.array_equal(s.cpu().numpy(), so) and np.array_equal(p.cpu().numpy(), po) and np.array_equal(c.cpu().numpy(), co)
+    assert np.array_equal(res.cpu().numpy(), ro) and np.array_equal(cv.cpu().numpy(), cvo) and np.array_equal(g.cpu().numpy(), go)
+    # host pointers (staged chunks), without the optional challenge planes
+    ph, sh = ctx.prove_fs_batch(w, r, want_chal=False)
+    rh = ctx.verify_fs_batch(ph, want_chal=False)
+    assert np.array_equal(sh, so) and np.array_equal(ph, po) and np.array_equal(rh, ro)
+
+
+@pytest.mark.gpu
+def test_gpu_fs_equals_plain_path_with_derived_challenges(gpu_ctx, oracle):
+    """On the device: a Fiat-Shamir proof is what the TMA prover returns for the derived challenges, and the
+    Fiat-Shamir verdict is the plain verifier's verdict for them."""
+    import torch
+    ctx = gpu_ctx["table"]
+    n = 1 << 18
+    w, r, _, _ = ctx.generate_inputs(n, seed=5, dist=0)
+    p, s, c = ctx.prove_fs_batch(w, r)
+    ok = s == 0
+    assert int(ok.sum()) > n // 20
+    # failing items have zero challenges: compare where the transcript completed
+    p2, s2 = ctx.prove_batch(w[:, ok], r[:, ok], c[:5][:, ok].contiguous())
+    ctx.sync()
+    assert bool((s2 == 0).all()) and bool(torch.equal(p2, p[:, ok]))
+    res, cv = ctx.verify_fs_batch(p)
+    res2 = ctx.verify_batch(p[:, ok].contiguous(), cv[:5][:, ok].contiguous(), cv[5][ok].contiguous())
+    ctx.sync()
+    assert bool(torch.equal(cv[:, ok], c[:, ok])) and bool(torch.equal(res[ok], res2))
+    assert int((res[ok] == 1).sum()) > 0
+
+
+@pytest.mark.gpu
+def test_gpu_fs_pitch_and_guard_bytes(gpu_ctx, oracle):
+    import torch
+    ctx = gpu_ctx["table"]
+    dev = torch.device("cuda", 0)
+    n, pitch = 1000, 1024 + 8
+    w, r, _, _, _ = oracle.generate_inputs(n, seed=8, dist=0, threads=4)
+    po, so, co = oracle.prove_fs_batch(w, r, threads=4)
+    big = lambda planes: torch.full((planes, pitch), 0xAB, dtype=torch.uint8, device=dev)
+    W, R, P, S, Cc = big(12), big(9), big(27), big(1), big(6)
+    W[:, :n] = torch.from_numpy(w).to(dev); R[:, :n] = torch.from_numpy(r).to(dev)
+    ctx.prove_fs_batch(W[:, :n], R[:, :n], proof=P[:, :n], status=S[0, :n], chal=Cc[:, :n])
+    ctx.sync()
+    assert np.array_equal(P[:, :n].cpu().numpy(), po) and np.array_equal(S[0, :n].cpu().numpy(), so) and np.array_equal(Cc[:, :n].cpu().numpy(), co)
+    for t in (P, S, Cc):
+        assert bool((t[:, n:] == 0xAB).all())

@@ -57,3 +57,9 @@ pts = rnd(4, 101); pts[2] = 0
 report("g1_smul", 7, timeit(lambda: ctx.g1_smul_batch(pts)), "src/pbh/g1.rs:146-168 (7-bit scalars)")
 pq = rnd(5, 101); pq[2] = 0
 report("pairing", 7, timeit(lambda: ctx.pairing_batch(pq)), "src/pbh/pairing.rs:12-47 (Miller loop + final exponentiation)")
+p8 = rnd(8, 17)
+report("poly_scale_7", 15, timeit(lambda: ctx.poly_scale_batch(p8)), "7 coefficient planes + scalar in, 7 out; src/poly.rs:220-228")
+report("poly_eval_7", 9, timeit(lambda: ctx.poly_eval_batch(p8)), "7 + point in, 1 out; src/poly.rs:71-79")
+report("poly_div_linear_7", 15, timeit(lambda: ctx.poly_div_linear_batch(p8)), "7 + c in, 6 + 1 out; src/poly.rs:230-247, src/plonk.rs:437-442")
+p11 = rnd(11, 17)
+report("poly_div_linear_10", 21, timeit(lambda: ctx.poly_div_linear_batch(p11)), "the w_z quotient shape of src/plonk.rs:437")

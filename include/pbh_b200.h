@@ -261,6 +261,22 @@ int pbh_intt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* evals, size_t in_pitc
 int pbh_ntt_generic_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t omega, uint32_t size, int inverse,
                           const uint16_t* in, size_t in_pitch_elems, uint16_t* out, size_t out_pitch_elems,
                           int on_device);
+/* mul_ntt (src/fft.rs:109-132) with CooleyTurkey over F_modulus: a (la uint16 planes) and b (lb planes) are zero-extended
+ * to la + lb values (a power of two in [2, 64], omega a primitive root of that order), transformed, multiplied
+ * pointwise and transformed back; la + lb planes out (the top one is 0).  Reproduces src/fft.rs:171-183. */
+int pbh_mul_ntt_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t omega, uint32_t la, uint32_t lb, const uint16_t* a,
+                      size_t a_pitch_elems, const uint16_t* b, size_t b_pitch_elems, uint16_t* out, size_t out_pitch_elems,
+                      int on_device);
+/* The next three take `len` coefficient planes over F_17 (zero padded, len <= 64) followed by ONE operand plane.
+ * Poly * scalar (src/poly.rs:220-228; the scalar plane): len planes out. */
+int pbh_poly_scale_batch(pbh_ctx* ctx, size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
+                         int on_device);
+/* Poly::eval at the point plane (src/poly.rs:71-79): n bytes out. */
+int pbh_poly_eval_batch(pbh_ctx* ctx, size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, int on_device);
+/* Poly / (x - c), c the operand plane (src/poly.rs:230-247 with the linear divisors of src/plonk.rs:437-442): len planes out,
+ * the len - 1 quotient coefficients then the remainder (= p(c)). */
+int pbh_poly_div_linear_batch(pbh_ctx* ctx, size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out,
+                              size_t out_pitch, int on_device);
 /* schoolbook product over F_17 (src/poly.rs:205-218): la, lb coefficient planes (zero padded) in,
  * la+lb-1 planes out (la, lb <= 16). */
 int pbh_poly_mul_batch(pbh_ctx* ctx, size_t n, uint32_t la, uint32_t lb, const uint8_t* a, size_t a_pitch,

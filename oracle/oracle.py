@@ -325,12 +325,12 @@ def generate_inputs(n, first_index=0, seed=0xB200, dist=1, circuit=None, s=2, sr
     return wit, rand, chal, u, attempt
 
 
-def _planes(fn, nin, nout, arr, *pre):
+def _planes(fn, nin, nout, arr, *pre, skip_n=False):
     arr = np.ascontiguousarray(arr, dtype=np.uint8)
     n = arr.shape[1]
     assert arr.shape[0] == nin
     out = np.zeros((nout, n), dtype=np.uint8)
-    rc = fn(*pre, C.c_size_t(n), _p(arr), C.c_size_t(n), _p(out), C.c_size_t(n))
+    rc = fn(*pre, *(() if skip_n else (C.c_size_t(n),)), _p(arr), C.c_size_t(n), _p(out), C.c_size_t(n))
     assert rc == 0
     return out
 
@@ -370,6 +370,41 @@ def poly_div_zh_batch(p):
     rc = lib().oracle_poly_div_zh_batch(C.c_size_t(n), _p(p), C.c_size_t(n), _p(q), C.c_size_t(n), _p(r), C.c_size_t(n))
     assert rc == 0
     return q, r
+
+
+def poly_scale_batch(arr):
+    """arr: len coefficient planes + 1 scalar plane -> len planes (src/poly.rs:220-228)."""
+    return _planes(lib().oracle_poly_scale_batch, arr.shape[0], arr.shape[0] - 1, arr, C.c_size_t(arr.shape[1]), C.c_uint32(arr.shape[0] - 1), skip_n=True)
+
+
+def poly_eval_batch(arr):
+    """arr: len coefficient planes + 1 plane of points -> (n,) evaluations (src/poly.rs:71-79)."""
+    arr = np.ascontiguousarray(arr, dtype=np.uint8)
+    n = arr.shape[1]
+    out = np.zeros(n, dtype=np.uint8)
+    rc = lib().oracle_poly_eval_batch(C.c_size_t(n), C.c_uint32(arr.shape[0] - 1), _p(arr), C.c_size_t(n), _p(out))
+    assert rc == 0
+    return out
+
+
+def poly_div_linear_batch(arr):
+    """arr: len coefficient planes + 1 plane c -> len planes: quotient of p / (x - c) (len-1 planes), then the remainder."""
+    return _planes(lib().oracle_poly_div_linear_batch, arr.shape[0], arr.shape[0] - 1, arr, C.c_size_t(arr.shape[1]), C.c_uint32(arr.shape[0] - 1), skip_n=True)
+
+
+def mul_ntt_batch(a, b, modulus, omega):
+    """mul_ntt (src/fft.rs:109-132) over CooleyTurkey: a (la, n), b (lb, n) uint16 -> (la + lb, n)."""
+    a = np.ascontiguousarray(a, dtype=np.uint16); b = np.ascontiguousarray(b, dtype=np.uint16)
+    la, n = a.shape; lb = b.shape[0]
+    out = np.zeros((la + lb, n), dtype=np.uint16)
+    u16p = C.POINTER(C.c_uint16)
+    rc = lib().oracle_mul_ntt_batch(C.c_size_t(n), C.c_uint64(modulus), C.c_uint64(omega), C.c_uint32(la + lb), C.c_uint32(la), C.c_uint32(lb),
+                                    a.ctypes.data_as(u16p), C.c_size_t(n), b.ctypes.data_as(u16p), C.c_size_t(n),
+                                    out.ctypes.data_as(u16p), C.c_size_t(n))
+    if rc == 1:
+        raise ArithmeticError("reference would panic")
+    assert rc == 0
+    return out
 
 
 def digest(data, first_index=0):

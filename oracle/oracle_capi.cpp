@@ -649,6 +649,58 @@ int oracle_poly_div_zh_batch(size_t n, const uint8_t* p, size_t p_pitch, uint8_t
   }
   return 0;
 }
+// in: len coefficient planes then one scalar plane
+int oracle_poly_scale_batch(size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch) {
+  for (size_t i = 0; i < n; i++) {
+    std::vector<F17> v;
+    for (uint32_t k = 0; k < len; k++) v.push_back(f17(in[k * in_pitch + i]));
+    Poly<F17> p = Poly<F17>(v) * f17(in[len * in_pitch + i]);                       // src/poly.rs:220-228 (Q15)
+    for (uint32_t k = 0; k < len; k++) out[k * out_pitch + i] = k < p.c.size() ? (uint8_t)p.c[k].v : 0;
+  }
+  return 0;
+}
+// in: len coefficient planes then the point x; out: one plane
+int oracle_poly_eval_batch(size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out) {
+  for (size_t i = 0; i < n; i++) {
+    std::vector<F17> v;
+    for (uint32_t k = 0; k < len; k++) v.push_back(f17(in[k * in_pitch + i]));
+    out[i] = (uint8_t)Poly<F17>(v).eval(f17(in[len * in_pitch + i])).v;             // src/poly.rs:71-79
+  }
+  return 0;
+}
+// in: len coefficient planes then c; out: len-1 quotient planes of p / (x - c), then the remainder plane
+int oracle_poly_div_linear_batch(size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch) {
+  for (size_t i = 0; i < n; i++) {
+    std::vector<F17> v;
+    for (uint32_t k = 0; k < len; k++) v.push_back(f17(in[k * in_pitch + i]));
+    F17 c = f17(in[len * in_pitch + i]);
+    auto qr = poly_div(Poly<F17>(v), Poly<F17>({-c, F17::one()}));                  // src/poly.rs:230-247, src/plonk.rs:437-442
+    for (uint32_t k = 0; k + 1 < len; k++) out[k * out_pitch + i] = k < qr.first.c.size() ? (uint8_t)qr.first.c[k].v : 0;
+    out[(len - 1) * out_pitch + i] = qr.second.c.empty() ? 0 : (uint8_t)qr.second.c[0].v;
+  }
+  return 0;
+}
+// mul_ntt (src/fft.rs:109-132) with CooleyTurkey over F_M: a (la planes), b (lb planes), la + lb == size; out: size planes
+int oracle_mul_ntt_batch(size_t n, uint64_t M, uint64_t omega, uint32_t size, uint32_t la, uint32_t lb, const uint16_t* a,
+                         size_t a_pitch, const uint16_t* b, size_t b_pitch, uint16_t* out, size_t out_pitch) {
+  try {
+    DISPATCH_M(M, {
+      EvaluationDomainGenerator<F> d{F::from_u64(omega), size};
+      CooleyTukeyFFT<F> f(d);
+      for (size_t i = 0; i < n; i++) {
+        std::vector<F> va, vb;
+        for (uint32_t k = 0; k < la; k++) va.push_back(F::from_u64(a[k * a_pitch + i]));
+        for (uint32_t k = 0; k < lb; k++) vb.push_back(F::from_u64(b[k * b_pitch + i]));
+        std::vector<F> r = mul_ntt<F>(f, va, vb);
+        for (uint32_t k = 0; k < size; k++) out[k * out_pitch + i] = k < r.size() ? (uint16_t)r[k].v : 0;
+      }
+      return 0;
+    })
+  } catch (const Panic&) {
+    return 1;
+  }
+  return -1;
+}
 int oracle_g1_smul_batch(size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch) {
   for (size_t i = 0; i < n; i++) {
     uint8_t p[3] = {in[i], in[in_pitch + i], in[2 * in_pitch + i]}, o[3];

@@ -867,6 +867,66 @@ int pbh_ntt_generic_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t ome
   return PBH_OK;
 }
 
+int pbh_mul_ntt_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t omega, uint32_t la, uint32_t lb, const uint16_t* a,
+                      size_t a_pitch, const uint16_t* b, size_t b_pitch, uint16_t* out, size_t out_pitch, int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!a || !b || !out || a_pitch < n || b_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  const uint32_t size = la + lb;
+  if (la < 1 || lb < 1 || modulus < 2 || modulus >= 65536 || size < 2 || size > 64 || (size & (size - 1)))
+    return fail(ctx, PBH_ERR_UNSUPPORTED, "modulus < 2^16, la + lb a power of two in [2, 64]");
+  uint32_t log2size = 0;
+  while ((1u << log2size) < size) log2size++;
+  uint16_t tw[64];
+  uint32_t m = 1;
+  for (uint32_t i = 0; i < size; i++) { tw[i] = (uint16_t)m; m = (uint32_t)(((uint64_t)m * (omega % modulus)) % modulus); }
+  uint64_t len_inv = 1, bb = size % modulus, e = modulus - 2;
+  while (e) { if (e & 1) len_inv = len_inv * bb % modulus; bb = bb * bb % modulus; e >>= 1; }
+  if ((len_inv * (size % modulus)) % modulus != 1) return fail(ctx, PBH_ERR_SETUP_PANIC, "size has no inverse modulo the modulus (F::from(len).inv().unwrap() panics)");
+  uint16_t* d_tw = stg.in(tw, 64, 64, 1, ce); CUDA_TRY(ctx, ce);
+  const uint16_t *d_a = a, *d_b = b; uint16_t* d_out = out; size_t ap = a_pitch, bp = b_pitch, op = out_pitch;
+  if (!on_device) {
+    d_a = stg.in(a, a_pitch, n, la, ce); CUDA_TRY(ctx, ce);
+    d_b = stg.in(b, b_pitch, n, lb, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint16_t>(nullptr, 0, n, size, ce); CUDA_TRY(ctx, ce);
+    ap = bp = op = n;
+  }
+  mul_ntt_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, modulus, size, log2size, (uint32_t)len_inv, la, lb, d_tw, d_a, ap, d_b, bp, d_out, op);
+  SWEEP_FINISH(ctx);
+  if (!on_device) CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, size));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute));   // d_tw is freed on return
+  return PBH_OK;
+}
+
+// len coefficient planes + one operand plane in; OP 0 scale (len planes out), 1 eval (1 plane), 2 divide by x - c (len planes)
+template <int OP>
+static int poly_unary_impl(pbh_ctx* ctx, size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
+                           int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!in || !out || in_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  if (len < 1 || len > 64) return fail(ctx, PBH_ERR_UNSUPPORTED, "1 <= len <= 64");
+  const size_t pout = OP == 1 ? 1 : len;
+  const uint8_t* d_in = in; uint8_t* d_out = out; size_t ip = in_pitch, op = out_pitch;
+  if (!on_device) {
+    d_in = stg.in(in, in_pitch, n, len + 1, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint8_t>(nullptr, 0, n, pout, ce); CUDA_TRY(ctx, ce);
+    ip = op = n;
+  }
+  const bool vec_ok = ((uintptr_t)d_in % 4 == 0) && ((uintptr_t)d_out % 4 == 0) && (ip % 4 == 0) && (op % 4 == 0);
+  poly_unary_kernel<OP><<<grid_for(ctx, vec_ok ? (n + 3) / 4 : n, 16), kBlock, 0, ctx->compute>>>(n, len, d_in, ip, d_out, op, vec_ok);
+  SWEEP_FINISH(ctx);
+  if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, pout)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
+  return PBH_OK;
+}
+int pbh_poly_scale_batch(pbh_ctx* ctx, size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return poly_unary_impl<0>(ctx, n, len, in, in_pitch, out, out_pitch, on_device);
+}
+int pbh_poly_eval_batch(pbh_ctx* ctx, size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, int on_device) {
+  return poly_unary_impl<1>(ctx, n, len, in, in_pitch, out, n, on_device);
+}
+int pbh_poly_div_linear_batch(pbh_ctx* ctx, size_t n, uint32_t len, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return poly_unary_impl<2>(ctx, n, len, in, in_pitch, out, out_pitch, on_device);
+}
+
 int pbh_poly_mul_batch(pbh_ctx* ctx, size_t n, uint32_t la, uint32_t lb, const uint8_t* a, size_t a_pitch, const uint8_t* b,
                        size_t b_pitch, uint8_t* out, size_t out_pitch, int on_device) {
   SWEEP_PROLOGUE(ctx, n);
@@ -958,8 +1018,18 @@ int pbh_g1_add_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch,
 }
 int pbh_kzg_commit_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
   return planes_impl(ctx, n, coeffs, in_pitch, 7, out, out_pitch, 3, on_device, [&](int grid, const uint8_t* di, size_t ip, uint8_t* dout, size_t op) {
-    if (ctx->algo == PBH_ALGO_TABLE) kzg_commit_kernel<ALGO_TABLE><<<grid, kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, n, di, ip, dout, op);
-    else kzg_commit_kernel<ALGO_ARITH><<<grid, kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, n, di, ip, dout, op);
+    if (ctx->algo == PBH_ALGO_TABLE) {
+      // four items per word when the layout allows and no coefficient can index past the SRS; the tail goes byte-wise
+      const bool vec_ok = ctx->hs.K.n_pts >= 7 && ((uintptr_t)di % 4 == 0) && ((uintptr_t)dout % 4 == 0) && (ip % 4 == 0) && (op % 4 == 0);
+      const size_t n4 = vec_ok ? n / 4 : 0;
+      if (n4) {
+        kzg_commit_table_vec_kernel<<<grid_for(ctx, n4, 8), kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, n4, di, ip, dout, op);
+        ctx->launches++;
+      }
+      if (n4 * 4 < n)
+        kzg_commit_kernel<ALGO_TABLE><<<1, kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, n - n4 * 4, di + n4 * 4, ip, dout + n4 * 4, op);
+      else ctx->launches--;   // planes_impl counts one launch
+    } else kzg_commit_kernel<ALGO_ARITH><<<grid, kBlock, 0, ctx->compute>>>(ctx->hs.K, ctx->d_tables, n, di, ip, dout, op);
   });
 }
 int pbh_pairing_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {

@@ -619,6 +619,118 @@ __global__ void __launch_bounds__(kBlock) ntt_generic_kernel(size_t n, uint32_t 
   }
 }
 
+// mul_ntt (src/fft.rs:109-132) over CooleyTurkey: both operands zero-extended to `size` = la + lb values, transformed,
+// multiplied pointwise and transformed back (fft_inv = forward transform, reverse, scale: src/fft.rs:72-78).
+__device__ __forceinline__ void ntt_dit_inplace(uint32_t (&a)[64], uint32_t size, uint32_t modulus, const uint32_t* s_tw) {
+  for (uint32_t len = 2; len <= size; len <<= 1) {
+    uint32_t step = size / len;
+    for (uint32_t base = 0; base < size; base += len) {
+      for (uint32_t j = 0; j < len / 2; j++) {
+        uint32_t x = a[base + j];
+        uint32_t y = (uint32_t)(((uint64_t)a[base + j + len / 2] * s_tw[j * step]) % modulus);
+        a[base + j] = (x + y) % modulus;
+        a[base + j + len / 2] = (x + modulus - y) % modulus;
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(kBlock) mul_ntt_kernel(size_t n, uint32_t modulus, uint32_t size, uint32_t log2size, uint32_t len_inv,
+                                                          uint32_t la, uint32_t lb, const uint16_t* __restrict__ tw,
+                                                          const uint16_t* __restrict__ a_in, size_t a_pitch,
+                                                          const uint16_t* __restrict__ b_in, size_t b_pitch, uint16_t* __restrict__ out,
+                                                          size_t out_pitch) {
+  __shared__ uint32_t s_tw[64];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_tw[i] = i < (int)size ? tw[i] : 0;
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t a[64], b[64];
+    for (uint32_t k = 0; k < size; k++) {
+      uint32_t r = __brev(k) >> (32 - log2size);
+      a[r] = k < la ? a_in[(size_t)k * a_pitch + i] % modulus : 0u;
+      b[r] = k < lb ? b_in[(size_t)k * b_pitch + i] % modulus : 0u;
+    }
+    ntt_dit_inplace(a, size, modulus, s_tw);
+    ntt_dit_inplace(b, size, modulus, s_tw);
+    for (uint32_t k = 0; k < size; k++) {           // pointwise product, stored bit-reversed for the second transform
+      uint32_t r = __brev(k) >> (32 - log2size);
+      if (r >= k) {
+        uint32_t ck = (uint32_t)(((uint64_t)a[k] * b[k]) % modulus), cr = (uint32_t)(((uint64_t)a[r] * b[r]) % modulus);
+        a[k] = cr; a[r] = ck;
+      }
+    }
+    ntt_dit_inplace(a, size, modulus, s_tw);
+    for (uint32_t k = 0; k < size; k++) {
+      uint32_t src = k == 0 ? 0 : size - k;
+      out[(size_t)k * out_pitch + i] = (uint16_t)(((uint64_t)a[src] * len_inv) % modulus);
+    }
+  }
+}
+
+// Poly * scalar (src/poly.rs:220-228), Poly::eval (src/poly.rs:71-79) and Poly / (x - c) (src/poly.rs:230-247 with the
+// monic linear divisors of src/plonk.rs:437-442) over F_17: `len` coefficient planes followed by one operand plane
+// (the scalar, the point, c), four items per 32-bit word.  OP 0: len planes out; OP 1: one plane out; OP 2: len - 1
+// quotient planes then the remainder plane (a Horner chain whose intermediate values are the quotient).
+template <int OP>
+__global__ void __launch_bounds__(kBlock) poly_unary_kernel(size_t n, uint32_t len, const uint8_t* __restrict__ in, size_t in_pitch,
+                                                             uint8_t* __restrict__ out, size_t out_pitch, bool vec_ok) {
+  const size_t n4 = vec_ok ? n / 4 : 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
+    const uint32_t opw = reinterpret_cast<const uint32_t*>(in + (size_t)len * in_pitch)[q];
+    uint32_t x[4], acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; j++) x[j] = mod17((opw >> (8 * j)) & 0xFFu);
+    // eight planes' loads are issued before any is consumed (bytes in flight, not arithmetic, bound these kernels)
+    if (OP == 0) {
+      for (uint32_t k0 = 0; k0 < len; k0 += 8) {
+        uint32_t w[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) w[j] = k0 + j < len ? reinterpret_cast<const uint32_t*>(in + (size_t)(k0 + j) * in_pitch)[q] : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) {
+          if (k0 + j < len) {
+            const uint32_t r = swar_mod17(w[j]);
+            uint32_t o = 0;
+#pragma unroll
+            for (int l = 0; l < 4; l++) o |= mod17(((r >> (8 * l)) & 0xFFu) * x[l]) << (8 * l);
+            reinterpret_cast<uint32_t*>(out + (size_t)(k0 + j) * out_pitch)[q] = o;
+          }
+        }
+      }
+    } else {
+      for (uint32_t k0 = len; k0 > 0; k0 = k0 > 8 ? k0 - 8 : 0) {   // planes k0-1, k0-2, ... (Horner runs downwards)
+        uint32_t w[8];
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) w[j] = j < k0 ? reinterpret_cast<const uint32_t*>(in + (size_t)(k0 - 1 - j) * in_pitch)[q] : 0u;
+#pragma unroll
+        for (uint32_t j = 0; j < 8; j++) {
+          if (j < k0) {
+            const uint32_t k = k0 - 1 - j;
+            if (OP == 2 && k + 1 < len) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = acc[0] | (acc[1] << 8) | (acc[2] << 16) | (acc[3] << 24);
+            const uint32_t r = swar_mod17(w[j]);
+#pragma unroll
+            for (int l = 0; l < 4; l++) acc[l] = mod17(acc[l] * x[l] + ((r >> (8 * l)) & 0xFFu));
+          }
+        }
+      }
+      reinterpret_cast<uint32_t*>(out + (size_t)(OP == 2 ? len - 1 : 0) * out_pitch)[q] = acc[0] | (acc[1] << 8) | (acc[2] << 16) | (acc[3] << 24);
+    }
+  }
+  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t x = mod17(in[(size_t)len * in_pitch + i]);
+    if (OP == 0) {
+      for (uint32_t k = 0; k < len; k++) out[(size_t)k * out_pitch + i] = (uint8_t)mod17(mod17(in[(size_t)k * in_pitch + i]) * x);
+    } else {
+      uint32_t acc = 0;
+      for (uint32_t k = len; k-- > 0;) {
+        if (OP == 2 && k + 1 < len) out[(size_t)k * out_pitch + i] = (uint8_t)acc;
+        acc = mod17(acc * x + mod17(in[(size_t)k * in_pitch + i]));
+      }
+      out[(size_t)(OP == 2 ? len - 1 : 0) * out_pitch + i] = (uint8_t)acc;
+    }
+  }
+}
+
 // schoolbook product over F_17, runtime lengths <= 16                        src/poly.rs:205-218
 __global__ void __launch_bounds__(kBlock) poly_mul_kernel(size_t n, uint32_t la, uint32_t lb, const uint8_t* __restrict__ a,
                                                            size_t a_pitch, const uint8_t* __restrict__ b, size_t b_pitch,
@@ -756,6 +868,41 @@ __global__ void __launch_bounds__(kBlock) kzg_commit_kernel(const Consts K, cons
     uint32_t w = commit<ALGO>(c, K, sT);
     if (longer_than(c, K.n_pts)) w = 0xFF0000u;
     out[i] = (uint8_t)(w & 0xFF); out[out_pitch + i] = (uint8_t)((w >> 8) & 0xFF); out[2 * out_pitch + i] = (uint8_t)(w >> 16);
+  }
+}
+
+// The same commitment for PBH_ALGO_TABLE with at least 7 SRS points, four items per 32-bit word: the exponent of G is
+// the dot product of the coefficients with the SRS discrete logs, accumulated in two 16-bit lanes per word (any byte
+// value is accepted: 7 * 255 * 16 < 2^16), reduced with 16 = -1 (mod 17), and the point comes from the 17-entry table.
+// One-byte accesses keep too few bytes in flight to cover the HBM latency (measured 2.2 TB/s); words quadruple them.
+__global__ void __launch_bounds__(kBlock) kzg_commit_table_vec_kernel(const Consts K, const Tables* __restrict__ gT, size_t n4,
+                                                                       const uint8_t* __restrict__ in, size_t in_pitch,
+                                                                       uint8_t* __restrict__ out, size_t out_pitch) {
+  __shared__ uint32_t s_pt[17];
+  if (threadIdx.x < 17) s_pt[threadIdx.x] = gT->pt17[threadIdx.x];
+  __syncthreads();
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) w[k] = reinterpret_cast<const uint32_t*>(in + (size_t)k * in_pitch)[q];
+    uint32_t ev = 0, od = 0;   // items 0, 2 and items 1, 3 as 16-bit lanes
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      ev += (w[k] & 0x00FF00FFu) * K.srs_dlog[k];
+      od += ((w[k] >> 8) & 0x00FF00FFu) * K.srs_dlog[k];
+    }
+    // x = n0 + 16 n1 + 256 n2 + 4096 n3 = n0 - n1 + n2 - n3 (mod 17); + 34 keeps the lane positive (<= 64)
+    const uint32_t m = 0x000F000Fu;
+    const uint32_t te = (ev & m) + ((ev >> 8) & m) + 0x00220022u - ((ev >> 4) & m) - ((ev >> 12) & m);
+    const uint32_t to = (od & m) + ((od >> 8) & m) + 0x00220022u - ((od >> 4) & m) - ((od >> 12) & m);
+    const uint32_t e = swar_mod17(te | (to << 8));   // byte lane j = exponent of item j
+    const uint32_t p0 = s_pt[e & 0xFFu], p1 = s_pt[(e >> 8) & 0xFFu], p2 = s_pt[(e >> 16) & 0xFFu], p3 = s_pt[e >> 24];
+    // transpose the four packed points (x | y << 8 | inf << 16) into the three output planes
+    const uint32_t a01 = __byte_perm(p0, p1, 0x5140), a23 = __byte_perm(p2, p3, 0x5140);   // x0 x1 y0 y1 / x2 x3 y2 y3
+    reinterpret_cast<uint32_t*>(out)[q] = __byte_perm(a01, a23, 0x5410);
+    reinterpret_cast<uint32_t*>(out + out_pitch)[q] = __byte_perm(a01, a23, 0x7632);
+    const uint32_t i01 = __byte_perm(p0, p1, 0x0062), i23 = __byte_perm(p2, p3, 0x0062);    // inf0 inf1 . .
+    reinterpret_cast<uint32_t*>(out + 2 * out_pitch)[q] = __byte_perm(i01, i23, 0x5410);
   }
 }
 

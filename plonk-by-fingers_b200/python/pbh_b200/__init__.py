@@ -45,7 +45,7 @@ pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_pr
 pbh_proof_records_to_planes_dev pbh_proof_planes_to_records_dev pbh_prove_digest_batch_dev pbh_verify_bitmap_batch_dev pbh_ntt4_batch pbh_intt4_batch
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
-pbh_measure_int32_peak pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev""".split()
+pbh_measure_int32_peak pbh_mul_ntt_batch pbh_poly_scale_batch pbh_poly_eval_batch pbh_poly_div_linear_batch pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -485,6 +485,43 @@ class Context:
                                             C.c_size_t(n), 0)
         self._check(rc, "pbh_ntt_generic_batch")
         return out
+
+    def mul_ntt_batch(self, a, b, modulus, omega):
+        """a (la, n), b (lb, n) uint16 numpy arrays (host) -> (la + lb, n): mul_ntt over CooleyTurkey, src/fft.rs:109-132."""
+        a = np.ascontiguousarray(a, dtype=np.uint16); b = np.ascontiguousarray(b, dtype=np.uint16)
+        la, n = a.shape; lb = b.shape[0]
+        out = np.empty((la + lb, n), dtype=np.uint16)
+        rc = self.lib.pbh_mul_ntt_batch(self.h, C.c_size_t(n), C.c_uint32(modulus), C.c_uint32(omega), C.c_uint32(la), C.c_uint32(lb),
+                                        a.ctypes.data_as(u16p), C.c_size_t(n), b.ctypes.data_as(u16p), C.c_size_t(n),
+                                        out.ctypes.data_as(u16p), C.c_size_t(n), 0)
+        self._check(rc, "pbh_mul_ntt_batch")
+        return out
+
+    def _poly_unary(self, fn, arr, pout):
+        A = _Planes(arr, np.shape(arr)[0] if not _is_torch(arr) else arr.shape[0], name="in")
+        ln = A.arr.shape[0] - 1
+        out = self._empty(A.dev, pout(ln), A.n)
+        O = _Planes(out, pout(ln), A.n, "out")
+        cur = self._dev_begin() if A.dev else None
+        args = [self.h, C.c_size_t(A.n), C.c_uint32(ln), C.c_void_p(A.ptr), C.c_size_t(A.pitch), C.c_void_p(O.ptr)]
+        if fn is not self.lib.pbh_poly_eval_batch:
+            args.append(C.c_size_t(O.pitch))
+        rc = fn(*args, int(A.dev))
+        self._dev_end(cur)
+        self._check(rc, "poly sweep")
+        return O.arr
+
+    def poly_scale_batch(self, arr):
+        """len coefficient planes + the scalar plane -> len planes (src/poly.rs:220-228)."""
+        return self._poly_unary(self.lib.pbh_poly_scale_batch, arr, lambda ln: ln)
+
+    def poly_eval_batch(self, arr):
+        """len coefficient planes + the point plane -> (n,) (src/poly.rs:71-79)."""
+        return self._poly_unary(self.lib.pbh_poly_eval_batch, arr, lambda ln: 1).reshape(-1)
+
+    def poly_div_linear_batch(self, arr):
+        """len coefficient planes + the plane c -> len - 1 quotient planes of p / (x - c), then the remainder (src/poly.rs:230-247)."""
+        return self._poly_unary(self.lib.pbh_poly_div_linear_batch, arr, lambda ln: ln)
 
     # ---- device-side helpers (torch) ----
     def generate_inputs(self, n, first_index=0, seed=0xB200, dist=DIST_FULLPATH, want_attempt=False):

@@ -408,6 +408,15 @@ def test_kzg_commit_sweep(gpu_ctx, oracle, algo):
     c[:, :17] = 0
     c[0, :17] = np.arange(17)
     assert np.array_equal(ctx.kzg_commit_batch(c), oracle.kzg_commit_batch(c))
+    # any byte value is a coefficient (F17::from reduces it); device pointers; sizes around the 4-items-per-word path
+    import torch
+    for n in (1, 3, 4, 7, 4096, 20003):
+        c = rng.integers(0, 256, size=(7, n), dtype=np.uint8)
+        exp = oracle.kzg_commit_batch(c)
+        assert np.array_equal(ctx.kzg_commit_batch(c), exp), n
+        got = ctx.kzg_commit_batch(torch.from_numpy(c).cuda())
+        ctx.sync()
+        assert np.array_equal(got.cpu().numpy(), exp), n
 
 
 def test_poly_sweeps(gpu_ctx, oracle):
@@ -430,6 +439,48 @@ def test_poly_sweeps(gpu_ctx, oracle):
     q, r = ctx.poly_div_zh_batch(p)
     qo, ro = oracle.poly_div_zh_batch(p)
     assert np.array_equal(q, qo) and np.array_equal(r, ro)
+
+
+def test_poly_scale_eval_div_linear_sweeps(gpu_ctx, oracle):
+    """Poly * scalar (src/poly.rs:220-228), Poly::eval (:71-79), Poly / (x - c) (:230-247), host and device pointers,
+    word-aligned and ragged sizes, non-canonical bytes reduced as F17::from does."""
+    import torch
+    ctx = gpu_ctx["table"]
+    rng = np.random.default_rng(11)
+    # src/poly.rs tests: eval of 1 + 2x + 3x^2 at 2 is 17 = 0 mod 17
+    assert ctx.poly_eval_batch(np.array([[1, 2, 3, 2]], dtype=np.uint8).T.copy())[0] == 0
+    for n in (1, 3, 4096, 20011):
+        for ln in (1, 2, 7, 10, 22):
+            arr = rng.integers(0, 17, size=(ln + 1, n), dtype=np.uint8)
+            arr[ln, : n // 5] = 0                       # scale by 0 (Q15), evaluate at 0, divide by x
+            arr[:, n // 2: n // 2 + n // 7] = rng.integers(0, 256, size=(ln + 1, n // 7), dtype=np.uint8)
+            so, eo, do = oracle.poly_scale_batch(arr), oracle.poly_eval_batch(arr), oracle.poly_div_linear_batch(arr)
+            assert np.array_equal(ctx.poly_scale_batch(arr), so), (n, ln)
+            assert np.array_equal(ctx.poly_eval_batch(arr), eo), (n, ln)
+            assert np.array_equal(ctx.poly_div_linear_batch(arr), do), (n, ln)
+            assert np.array_equal(do[ln - 1], eo)       # remainder theorem
+            if n > 1000:
+                d = torch.from_numpy(arr).cuda()
+                got = [ctx.poly_scale_batch(d), ctx.poly_eval_batch(d), ctx.poly_div_linear_batch(d)]
+                ctx.sync()
+                assert np.array_equal(got[0].cpu().numpy(), so) and np.array_equal(got[1].cpu().numpy(), eo) and np.array_equal(got[2].cpu().numpy(), do)
+
+
+def test_mul_ntt_sweep(gpu_ctx, oracle):
+    """mul_ntt (src/fft.rs:109-132): the reference's own vector (src/fft.rs:171-183) and random batches against the
+    oracle's CooleyTurkey restatement over F_337 and F_257."""
+    ctx = gpu_ctx["table"]
+    a = np.array([[24, 12, 28, 8]], dtype=np.uint16).T.copy(); b = np.array([[4, 26, 29, 23]], dtype=np.uint16).T.copy()
+    assert ctx.mul_ntt_batch(a, b, 337, 85)[:, 0].tolist() == [96, 335, 109, 312, 285, 202, 184, 0]
+    rng = np.random.default_rng(4)
+    for mod, root, order in ((337, 85, 8), (257, 3, 256)):
+        for la, lb in ((1, 1), (2, 2), (3, 5), (4, 4), (7, 9), (16, 16), (40, 24)):
+            size = la + lb
+            if size > order:
+                continue
+            omega = pow(root, order // size, mod)
+            x = rng.integers(0, mod, size=(la, 2000)).astype(np.uint16); y = rng.integers(0, mod, size=(lb, 2000)).astype(np.uint16)
+            assert np.array_equal(ctx.mul_ntt_batch(x, y, mod, omega), oracle.mul_ntt_batch(x, y, mod, omega)), (mod, la, lb)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -112,3 +112,25 @@ def test_group_primitives_agree(oracle):
         f = (int(rng.integers(0, 101)), int(rng.integers(0, 101)))
         n = int(rng.integers(0, 700))
         assert oracle.gt_pow(f, n) == pyref.gt_pow(f, n)
+
+
+def test_sweep_oracles_match_the_polynomial_restatement(oracle):
+    """The batch oracles of the scale / eval / divide-by-(x - c) / mul_ntt sweeps are thin loops over the restated Poly
+    and fft.rs functions that the reference vectors pin; check the plane packing against the per-polynomial entry points."""
+    rng = np.random.default_rng(3)
+    arr = rng.integers(0, 17, size=(8, 200), dtype=np.uint8)
+    arr[7, :40] = 0
+    s, e, d = oracle.poly_scale_batch(arr), oracle.poly_eval_batch(arr), oracle.poly_div_linear_batch(arr)
+    pad = lambda v, k: list(v) + [0] * (k - len(v))
+    for i in range(200):
+        p, c = [int(v) for v in arr[:7, i]], int(arr[7, i])
+        assert pad(oracle.poly_op(17, "scale", p, [c]), 7) == s[:, i].tolist()
+        assert oracle.poly_op(17, "eval", p, [c]) == e[i]
+        q, r = oracle.poly_op(17, "div", p, [(-c) % 17, 1])
+        assert pad(q, 6) + pad(r, 1) == d[:, i].tolist()
+    a = rng.integers(0, 337, size=(3, 50)).astype(np.uint16); b = rng.integers(0, 337, size=(5, 50)).astype(np.uint16)
+    m = oracle.mul_ntt_batch(a, b, 337, 85)
+    for i in range(50):
+        assert pad(oracle.mul_ntt(337, 85, 8, "cooley_tukey", a[:, i], b[:, i]), 8) == m[:, i].tolist()
+    assert oracle.mul_ntt_batch(np.array([[24, 12, 28, 8]], dtype=np.uint16).T, np.array([[4, 26, 29, 23]], dtype=np.uint16).T, 337, 85)[:, 0].tolist() \
+        == [96, 335, 109, 312, 285, 202, 184, 0]                     # src/fft.rs:171-183

@@ -14,15 +14,16 @@ root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, dst = os.path.join(root, "gpurun_out"), os.path.join(root, "profiles")
 os.makedirs(dst, exist_ok=True)
 
-lines = [l for l in open(os.path.join(src, f"{tag}_launches.csv")) if l.startswith('"')]
-rows = list(csv.DictReader(lines))
+have_list = os.path.exists(os.path.join(src, f"{tag}_launches.csv"))   # a capture of a side kernel may come without a launch list
+lines = [l for l in open(os.path.join(src, f"{tag}_launches.csv")) if l.startswith('"')] if have_list else []
+rows = list(csv.DictReader(lines)) if have_list else []
 agg = collections.OrderedDict()
 for r in rows:
     agg.setdefault(r["Kernel Name"].split("(")[0], []).append(float(r["Metric Value"]))
-tot = sum(sum(v) for v in agg.values())
+tot = sum(sum(v) for v in agg.values()) or 1.0
 step = {k: v for k, v in agg.items() if any(s in k for s in ("prove_kernel", "verify_kernel", "pack_verdicts", "digest_kernel"))}
-step_tot = sum(sum(v) for v in step.values())
-with open(os.path.join(dst, f"{tag}_launches.txt"), "w") as f:
+step_tot = sum(sum(v) for v in step.values()) or 1.0
+with open(os.path.join(dst, f"{tag}_launches.txt") if have_list else os.devnull, "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, command: bench.py --steps 3 --warmup 3 --no-cpu --ring 2 --e2e-steps 0\n")
     f.write(f"# {note}\n# per-launch times are cold-cache and serialised: compare SHARES, not absolutes\n")
     f.write(f"{'kernel':60s} {'launches':>8s} {'avg_us':>10s} {'share_all_%':>11s} {'share_of_step_%':>15s}\n")
@@ -60,10 +61,11 @@ traffic = json.load(open(tj)) if os.path.exists(tj) else {}
 def _avg(name):
     i = hdr.index(name)
     return sum(float(v[i]) for v in vals) / len(vals)
-traffic[kernel] = {"tag": tag, "dram_read_bytes": _bytes("dram__bytes_read.sum"), "dram_write_bytes": _bytes("dram__bytes_write.sum"),
-                   "issue_active_pct": _avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                   "warp_instructions": _avg("smsp__inst_executed.sum"),
-                   "note": "ncu --set full, per launch, bench.py --steps 3 --ring 2 (2^20 items); writes of a 28 MB result mostly stay in the 126 MB L2 at capture time"}
-json.dump(traffic, open(tj, "w"), indent=1, sort_keys=True)
-print(open(os.path.join(dst, f"{tag}_launches.txt")).read())
+if have_list:
+  traffic[kernel] = {"tag": tag, "dram_read_bytes": _bytes("dram__bytes_read.sum"), "dram_write_bytes": _bytes("dram__bytes_write.sum"),
+                     "issue_active_pct": _avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                     "warp_instructions": _avg("smsp__inst_executed.sum"),
+                     "note": "ncu --set full, per launch, bench.py --steps 3 --ring 2 (2^20 items); writes of a 28 MB result mostly stay in the 126 MB L2 at capture time"}
+  json.dump(traffic, open(tj, "w"), indent=1, sort_keys=True)
+  print(open(os.path.join(dst, f"{tag}_launches.txt")).read())
 print(open(os.path.join(dst, f"{tag}_{kernel}_full.txt")).read())

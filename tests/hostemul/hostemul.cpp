@@ -168,7 +168,7 @@ int emul_sha256(const uint8_t* data, size_t len, uint8_t out[32]) {
   for (int i = 0; i < 8; i++) for (int b = 0; b < 4; b++) out[4 * i + b] = (uint8_t)(h[i] >> (24 - 8 * b));
   return 0;
 }
-// state <- SHA-256(state || msg) through the single-compression device routine; len <= 23
+// state <- SHA-256(state || msg) through the single-compression device routine; len <= 15
 int emul_sha256_absorb(uint8_t state[32], const uint8_t* msg, int len) {
   uint32_t st[8], m[6] = {0, 0, 0, 0, 0, 0};
   for (int i = 0; i < 8; i++) st[i] = ((uint32_t)state[4 * i] << 24) | ((uint32_t)state[4 * i + 1] << 16) | ((uint32_t)state[4 * i + 2] << 8) | state[4 * i + 3];

@@ -53,7 +53,7 @@ def test_sha256_implementations_match_hashlib(oracle, hostemul):
         assert oracle.sha256(m) == hashlib.sha256(m).digest()
         assert hostemul.sha256(m) == hashlib.sha256(m).digest()
     rng = np.random.default_rng(1)
-    for length in range(0, 24):      # the single-compression routine the kernels use: state || up to 23 bytes
+    for length in range(0, 16):      # the single-compression routine the kernels use: state || up to 15 bytes
         for _ in range(20):
             st, msg = rng.bytes(32), rng.bytes(length)
             assert hostemul.sha256_absorb(st, msg) == hashlib.sha256(st + msg).digest()

@@ -619,8 +619,47 @@ class CopyOf:
     def C(cls, n): return cls(2, n)
 
 
+class Expression:
+    """src/constraints.rs:246-287 — the reference's (unfinished) circuit front-end: an expression tree over named
+    variables with `+`, `-`, `*`; `Constrains.eval_exprs` lowers it to gates.  Host-side only, as in the reference."""
+
+    def __init__(self, kind, a=None, b=None):
+        self.kind, self.a, self.b = kind, a, b
+
+    @classmethod
+    def Var(cls, name): return cls("var", name)
+    @classmethod
+    def Const(cls, value): return cls("const", f17(value))
+
+    def __add__(self, rhs): return Expression("sum", self, rhs)      # src/constraints.rs:268-273
+    def __sub__(self, rhs): return Expression("sub", self, rhs)      # :275-280
+    def __mul__(self, rhs): return Expression("mul", self, rhs)      # :282-287
+
+    def __str__(self):                                               # Display, src/constraints.rs:254-266
+        if self.kind in ("var", "const"):
+            return str(self.a)
+        return "(%s%s%s)" % (self.a, {"sum": "+", "sub": "-", "mul": "*"}[self.kind], self.b)
+
+
 class Constrains:
     """src/constraints.rs:109-153"""
+
+    @staticmethod
+    def eval_exprs(expr, variables, gates):
+        """src/constraints.rs:155-196: post-order lowering.  `variables` maps a name to its index (a dict, in insertion
+        order), `gates` collects (Gate, left index, right index, output index).  Returns the index holding the value of
+        `expr`.  As in the reference a constant is not supported (`unimplemented!()`, :166-168), every operator node
+        allocates a fresh variable "v<n>", and n is the number of variables at that moment."""
+        if expr.kind == "var":
+            return variables.setdefault(expr.a, len(variables))
+        if expr.kind == "const":
+            raise ReferencePanic(-1, "not implemented (src/constraints.rs:167)")
+        l = Constrains.eval_exprs(expr.a, variables, gates)
+        r = Constrains.eval_exprs(expr.b, variables, gates)
+        n = len(variables)
+        variables["v%d" % n] = n
+        gates.append(({"mul": Gate.mul_a_b, "sum": Gate.sum_a_b, "sub": Gate.sub_a_b}[expr.kind](), l, r, n))
+        return n
 
     def __init__(self, gates, copy_constraints):
         if len(gates) != 4:

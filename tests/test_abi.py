@@ -68,3 +68,26 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("import oracle", "from oracle", "oracle/", "liboracle", "pbh_oracle", "oracle.py", "hostemul", "pyref"):
                     assert needle not in text, (needle, os.path.join(dirpath, f))
+
+
+def test_expression_front_end_mirrors_the_reference():
+    """src/constraints.rs:289-322 (`test_expr`, #[ignore]d upstream because it ends in unimplemented!()): the lowering of
+    a*a + b*b - c*c.  The expected trace is the reference's algorithm (:155-196) followed by hand: post-order, one fresh
+    variable per operator node, numbered by the size of the variable map at that moment."""
+    import pbh_b200
+    from pbh_b200 import Constrains, Expression, Gate
+    a, b, c = Expression.Var("a"), Expression.Var("b"), Expression.Var("c")
+    pitagoras = (a * a) + (b * b) - (c * c)
+    assert str(pitagoras) == "(((a*a)+(b*b))-(c*c))"
+    variables, gates = {}, []
+    r = Constrains.eval_exprs(pitagoras, variables, gates)
+    assert r == 7 and variables == {"a": 0, "v1": 1, "b": 2, "v3": 3, "v4": 4, "c": 5, "v6": 6, "v7": 7}
+    sel = lambda g: (g.q_l, g.q_r, g.q_o, g.q_m, g.q_c)
+    mul, add, sub = sel(Gate.mul_a_b()), sel(Gate.sum_a_b()), sel(Gate.sub_a_b())
+    assert [(sel(g), l, rr, o) for g, l, rr, o in gates] == [(mul, 0, 0, 1), (mul, 2, 2, 3), (add, 1, 3, 4), (mul, 5, 5, 6), (sub, 4, 6, 7)]
+    assert sub == (1, 1, 1, 0, 0)                       # sic: src/constraints.rs:37-45
+    with pytest.raises(pbh_b200.ReferencePanic):        # Expression::Const => unimplemented!()  (:166-168)
+        Constrains.eval_exprs(a + Expression.Const(3), {}, [])
+    # five gates: more than the four the reference's prove() is hard-wired to, which is why upstream stops here
+    with pytest.raises(pbh_b200.PbhError):
+        Constrains([g for g, _, _, _ in gates], ([], [], []))

@@ -526,14 +526,9 @@ struct ConvF32 { PBH_HD F32 operator()(uint32_t x) const { return f_from_u32(x, 
 template <int ALGO, bool FP32, bool PBH_CIRCUIT>
 PBH_HD uint32_t prove_item_fs(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&seed)[8], const Consts& K,
                               const ConstsF& KF, const Tables& T, ProofRegs& P, uint32_t (&derived)[6], bool want_u = true) {
-  // a zero among b1, b3, b5, b7 makes the quotient short whatever the challenges are (status 1-4 only), and only then
-  // can the reference's SubAssign quirk (Q1) fire: those items take the exact-length integer routine
-  const bool rare = rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
-  if (!FP32 || rare) {
+  if (!FP32) {
     FsChal<uint32_t, ConvU32> cs(seed, want_u);
-    uint32_t status;
-    if (FP32) status = prove_one_cs<ALGO_TABLE, true>(w, rnd, cs, K, T, P, -1);
-    else status = prove_one_cs<ALGO, false>(w, rnd, cs, K, T, P, -1);
+    const uint32_t status = prove_one_cs<ALGO, false>(w, rnd, cs, K, T, P, -1);
 #pragma unroll
     for (int k = 0; k < 6; k++) derived[k] = cs.derived[k];
     return status;
@@ -557,6 +552,17 @@ PBH_HD uint32_t prove_item_fs(const uint32_t (&w)[12], const uint32_t (&rnd)[9],
 #pragma unroll
   for (int k = 0; k < 6; k++) derived[k] = cs.derived[k];
   if (unsat) status = 1;
+  // A zero among b1, b3, b5, b7 makes the quotient short whatever the challenges are (status 1-4 only), and only then can
+  // the reference's SubAssign quirk (Q1) fire, which the FP32 core does not model.  The commitments of rounds 1 and 2,
+  // hence beta, gamma and alpha, do not depend on that: such items keep the transcript of the core above and only have
+  // their status recomputed by the exact-length integer routine (no hashing on this branch, so a warp that holds one
+  // of them pays about a thousand instructions, not two more compressions).
+  const bool rare = rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
+  if (rare) {
+    const uint32_t ch[5] = {derived[0], derived[1], derived[2], 0u, 0u};
+    ProofRegs scratch;
+    status = prove_one<ALGO_TABLE, true>(w, rnd, ch, K, T, scratch, unsat ? 1 : 0);
+  }
   return status;
 }
 

@@ -30,13 +30,23 @@ PBH_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-// x mod 17 for x < 2^28:  floor(x * ceil(2^32/17) / 2^32) == floor(x/17) there (error term x*16/(17*2^32) < 1/17).
-PBH_HD uint32_t mod17(uint32_t x) { return x - 17u * umulhi32(x, 252645136u); }
-// x mod 101 for x < 2^26: ceil(2^32/101) = 42524429, 42524429*101 - 2^32 = 33, x*33/(101*2^32) < 1/101.
-PBH_HD uint32_t mod101(uint32_t x) { return x - 101u * umulhi32(x, 42524429u); }
-// x mod 102 for x < 2^26 (dlog arithmetic in the cyclic group E(F_101) of order 102): ceil(2^32/102) = 42107523,
-// 42107523*102 - 2^32 = 50.
-PBH_HD uint32_t mod102(uint32_t x) { return x - 102u * umulhi32(x, 42107523u); }
+// Reductions by a low multiply and a shift: floor(x/m) = (x * M) >> k with M = ceil(2^k/m) is exact while
+// x * (M*m - 2^k) < 2^k, and x * M must fit 32 bits.  Not a multiply-high: IMAD.HI issues at half the IMAD rate on sm_100
+// (profiles/r01_pipe_rates.txt) and the integer paths (PBH_ALGO_ARITH curve arithmetic, the int32 prover, the sweeps)
+// are bound by that pipe.  The ranges below cover every argument in this code base; test builds record the largest
+// argument seen (tests/hostemul, PBH_RANGE_TRACK) and the test suite checks it against the range.
+//   mod17:  M = 61681 = ceil(2^20/17),  61681*17  - 2^20 = 1:  exact for x < 69631 (x*M < 2^32)
+//   mod101: M = 41528 = ceil(2^22/101), 41528*101 - 2^22 = 24: exact for x < 103000
+//   mod102: M = 41121 = ceil(2^22/102), 41121*102 - 2^22 = 38: exact for x < 104000
+#if defined(PBH_RANGE_TRACK) && !defined(__CUDA_ARCH__)
+static uint32_t g_mod_max[3] = {0, 0, 0};   // test builds only
+#define PBH_TRACK(i, x) do { if ((x) > g_mod_max[i]) g_mod_max[i] = (x); } while (0)
+#else
+#define PBH_TRACK(i, x) do { } while (0)
+#endif
+PBH_HD uint32_t mod17(uint32_t x) { PBH_TRACK(0, x); return x - 17u * ((x * 61681u) >> 20); }
+PBH_HD uint32_t mod101(uint32_t x) { PBH_TRACK(1, x); return x - 101u * ((x * 41528u) >> 22); }
+PBH_HD uint32_t mod102(uint32_t x) { PBH_TRACK(2, x); return x - 102u * ((x * 41121u) >> 22); }
 
 PBH_HD uint32_t mul17(uint32_t a, uint32_t b) { return mod17(a * b); }
 PBH_HD uint32_t mul101(uint32_t a, uint32_t b) { return mod101(a * b); }

@@ -87,11 +87,17 @@ uint64_t emul_check_red17_f32() {
 const char* emul_last_error() { return g_err.c_str(); }
 
 // exhaustive check of the reciprocal constants over their documented ranges; returns the number of mismatches
+// largest arguments mod17 / mod101 / mod102 have received so far in this process
+uint32_t emul_mod_max_argument(int which) { return g_mod_max[which]; }
+
 uint64_t emul_check_reductions() {
   uint64_t bad = 0;
-  for (uint32_t x = 0; x < (1u << 28); x++) bad += mod17(x) != x % 17u;
-  for (uint32_t x = 0; x < (1u << 26); x++) bad += mod101(x) != x % 101u;
-  for (uint32_t x = 0; x < (1u << 26); x++) bad += mod102(x) != x % 102u;
+  for (uint32_t x = 0; x < 69631u; x++) bad += (x - 17u * ((x * 61681u) >> 20)) != x % 17u;
+  for (uint32_t x = 0; x < 103000u; x++) bad += (x - 101u * ((x * 41528u) >> 22)) != x % 101u;
+  for (uint32_t x = 0; x < 104000u; x++) bad += (x - 102u * ((x * 41121u) >> 22)) != x % 102u;
+  uint32_t keep[3] = {g_mod_max[0], g_mod_max[1], g_mod_max[2]};   // the sweep below is not a use of the arithmetic
+  for (uint32_t x = 0; x < 60000u; x++) bad += (mod17(x) != x % 17u) + (mod101(x) != x % 101u) + (mod102(x) != x % 102u);
+  for (int i = 0; i < 3; i++) g_mod_max[i] = keep[i];
   return bad;
 }
 

@@ -19,7 +19,7 @@ def load():
         srcs = [os.path.join(HERE, "hostemul.cpp")] + [os.path.join(ROOT, "plonk-by-fingers_b200", "csrc", f) for f in
                                                        ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_prove_f32.cuh", "pbh_verify.cuh", "pbh_setup.hpp", "pbh_sha256.cuh", "pbh_fs.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-mfma", "-o", so, srcs[0]], check=True)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-mfma", "-DPBH_RANGE_TRACK", "-o", so, srcs[0]], check=True)
         _E = C.CDLL(so)
         _E.emul_last_error.restype = C.c_char_p
         _E.emul_check_reductions.restype = C.c_uint64
@@ -132,3 +132,8 @@ class Emul:
 
     def check_reductions(self):
         return int(self.lib.emul_check_reductions())
+
+    def mod_max_arguments(self):
+        """largest arguments seen by mod17, mod101, mod102 in this process"""
+        self.lib.emul_mod_max_argument.restype = C.c_uint32
+        return tuple(int(self.lib.emul_mod_max_argument(i)) for i in range(3))

@@ -6,7 +6,7 @@ import pytest
 
 
 def test_reduction_constants_exhaustive(hostemul):
-    """mod17 / mod101 / mod102 multiply-high reciprocals are exact over their whole documented ranges."""
+    """mod17 / mod101 / mod102 shift reciprocals are exact over their whole documented ranges."""
     assert hostemul.check_reductions() == 0
 
 
@@ -115,3 +115,19 @@ def test_fuzz_arbitrary_bytes(hostemul, oracle, algo):
     ve, ge = oracle.verify_batch(p3, c3, u3, threads=8)
     v, g = hostemul.verify(circ, p3, c3, u3, algo)
     assert np.array_equal(v, ve) and np.array_equal(g, ge)
+
+
+def test_zz_reduction_argument_ranges(hostemul, oracle):
+    """Runs last in this file: every argument the mod 17 / 101 / 102 reductions received during the group-law, pairing,
+    prover and verifier tests above (plus an adversarial verifier batch here) stayed inside the range over which their
+    shift reciprocals are exact (checked exhaustively by test_reduction_constants_exhaustive)."""
+    rng = np.random.default_rng(5)
+    n = 4000
+    proof = rng.integers(0, 101, size=(27, n), dtype=np.uint8)
+    proof[18] = rng.integers(0, 256, size=n); proof[19] = rng.integers(0, 2, size=n); proof[20:] = rng.integers(0, 17, size=(7, n))
+    chal = rng.integers(0, 17, size=(5, n), dtype=np.uint8); u = rng.integers(0, 17, size=n, dtype=np.uint8)
+    ro, go = oracle.verify_batch(proof, chal, u, threads=8)
+    re, ge = hostemul.verify(oracle.pbh_test_circuit(), proof, chal, u, 0)
+    assert np.array_equal(re, ro) and np.array_equal(ge, go)
+    m17, m101, m102 = hostemul.mod_max_arguments()
+    assert 0 < m17 < 69631 and 0 < m101 < 103000 and 0 < m102 < 104000, (m17, m101, m102)

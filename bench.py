@@ -513,6 +513,10 @@ def main():
                      "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_item": 54 if prove_ms >= verify_ms else 34,
                      "issue_slot_utilisation_pct_ncu": issue_pct,
+                     # the work the reference's algorithm does per item, in its own modular operations
+                     # (mul + add + inv); the kernels execute far fewer instructions for the same bytes
+                     "reference_equivalent_modops_per_item": {"prove": 5170 + 3719 + 318, "verify": 3552 + 1309 + 256},
+                     "reference_equivalent_modops_per_s": value * (5170 + 3719 + 318 + 3552 + 1309 + 256),
                      "note": "the kernel is instruction-issue bound (FP32 FMA dispatch), not HBM bound; see DESIGN.md section 4"},
         "launch": launch_mode,
         "kernels": {"how": "each kernel alone, back to back over the ring, CUDA events on the context's stream",

@@ -57,6 +57,14 @@ PBH_HD uint32_t sub101(uint32_t a, uint32_t b) { return a >= b ? a - b : a + 101
 PBH_HD uint32_t add17(uint32_t a, uint32_t b) { uint32_t s = a + b; return s >= 17u ? s - 17u : s; }
 PBH_HD uint32_t sub17(uint32_t a, uint32_t b) { return a >= b ? a - b : a + 17u - b; }
 
+// Two-point fixed-base tables for PBH_ALGO_ARITH (a width-2 comb over the fixed points): entry a + 17 b of pair j is
+// [a]P_2j + [b]P_2j+1, packed like pt17, so a commitment to L coefficients costs ceil(L/2) lookups and one addition fewer
+// than that.  10.4 KB: kept in global memory (L1-resident) rather than staged into shared memory with `Tables`.
+struct PairTables {
+  uint32_t srs_pair[5][289];    // P_i = g1s[i] (identity beyond the SRS)           src/plonk.rs:51-58
+  uint32_t vfix_pair[4][289];   // P_i = q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s   src/plonk.rs:510-517
+};
+
 // ---- tables shared by all kernels (one copy in global memory per context, staged into shared memory) ----
 struct Tables {
   uint8_t inv17[32];     // inv17[a] = a^-1 mod 17, inv17[0] = 0
@@ -73,7 +81,17 @@ struct Tables {
   // Fixed-base multiples (PBH_ALGO_ARITH): [k]P for k < 17, packed like pt17.
   uint32_t srs_mult[10][17];              // P = g1s[i]                 (src/plonk.rs:51-58)
   uint32_t vfix_mult[9][17];              // q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s, G
+  const PairTables* pairs;                // device (or, in host builds, host) address of the two-point tables
 };
+
+// read-only lookup in a global-memory table (through the read-only data cache on the device)
+PBH_HD uint32_t pair_lookup(const uint32_t* table, uint32_t index) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(table + index);
+#else
+  return table[index];
+#endif
+}
 
 // ---- G1: y^2 = x^3 + 3 over F_101 ---------------------------------------------------------------
 struct G1 {

@@ -39,6 +39,7 @@ struct pbh_ctx {
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
   HostSetup hs;
   Tables* d_tables = nullptr;
+  PairTables* d_pairs = nullptr;
   uint8_t* d_wtab = nullptr;
   unsigned int* d_tile_counters = nullptr;   // dynamic tile scheduler: [stream index][prove, verify]
   cudaStream_t compute = nullptr;          // `_dev` entry points
@@ -122,8 +123,14 @@ int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_
   if ((ce = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
   for (int s = 0; s < kSlots; s++)
     if ((ce = cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
+  if ((ce = cudaMalloc(&ctx->d_pairs, sizeof(PairTables))) != cudaSuccess) return bail("cudaMalloc(pair tables)", ce);
+  if ((ce = cudaMemcpy(ctx->d_pairs, &ctx->hs.P, sizeof(PairTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(pair tables)", ce);
   if ((ce = cudaMalloc(&ctx->d_tables, sizeof(Tables))) != cudaSuccess) return bail("cudaMalloc(tables)", ce);
-  if ((ce = cudaMemcpy(ctx->d_tables, &ctx->hs.T, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(tables)", ce);
+  {
+    Tables dev_copy = ctx->hs.T;          // the device copy points at the device pair tables, the host copy at the host ones
+    dev_copy.pairs = ctx->d_pairs;
+    if ((ce = cudaMemcpy(ctx->d_tables, &dev_copy, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(tables)", ce);
+  }
   // witness table of the synthetic-input generator: solutions of x^2 + y^2 = z^2 in F_17^3, lexicographic
   uint8_t wtab[289 * 3];
   int nw = 0;
@@ -148,6 +155,7 @@ void pbh_ctx_destroy(pbh_ctx* ctx) {
   }
   if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); }
   if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_pairs) cudaFree(ctx->d_pairs);
   if (ctx->d_wtab) cudaFree(ctx->d_wtab);
   if (ctx->d_tile_counters) cudaFree(ctx->d_tile_counters);
   delete ctx;

@@ -92,9 +92,14 @@ PBH_HD uint32_t commit(const uint32_t (&c)[L], const Consts& K, const Tables& T)
     for (int i = 0; i < L; i++) e += c[i] * K.srs_dlog[i];
     return T.pt17[mod17(e)];
   } else {
-    G1 acc = g1_identity();
+    // two coefficients per lookup (PairTables), the first lookup needs no addition
+    static_assert(L >= 2 && L <= 10, "the SRS tables cover 10 points");
+    G1 acc = g1_unpack(pair_lookup(T.pairs->srs_pair[0], c[0] + 17u * c[1]));
 #pragma unroll
-    for (int i = 0; i < L; i++) acc = g1_add(acc, g1_unpack(T.srs_mult[i][c[i]]), T.inv101);
+    for (int j = 1; j < (L + 1) / 2; j++) {
+      const uint32_t hi = (2 * j + 1 < L) ? c[(2 * j + 1 < L) ? 2 * j + 1 : 0] : 0u;
+      acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->srs_pair[j], c[2 * j] + 17u * hi)), T.inv101);
+    }
     return g1_pack(acc);
   }
 }

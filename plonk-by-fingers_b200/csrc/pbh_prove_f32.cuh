@@ -214,11 +214,16 @@ PBH_HD uint32_t fcommit(const T (&c)[L], const CK& ck, const Tables& Tb, bool re
     for (int i = 1; i < L; i++) e = f_fma(c[i], f_const(ck.srs_dlog(i), tag), e);
     return f_canon(f_red(e));
   } else {
-    G1 acc = g1_identity();
+    // two coefficients per lookup (PairTables), the first lookup needs no addition
+    static_assert(L >= 2 && L <= 10, "the SRS tables cover 10 points");
+    uint32_t ci[L];
 #pragma unroll
-    for (int i = 0; i < L; i++) {
-      const uint32_t ci = f_canon(reduced ? c[i] : f_red(c[i]));
-      acc = g1_add(acc, g1_unpack(Tb.srs_mult[i][ci]), Tb.inv101);
+    for (int i = 0; i < L; i++) ci[i] = f_canon(reduced ? c[i] : f_red(c[i]));
+    G1 acc = g1_unpack(pair_lookup(Tb.pairs->srs_pair[0], ci[0] + 17u * ci[1]));
+#pragma unroll
+    for (int j = 1; j < (L + 1) / 2; j++) {
+      const uint32_t hi = (2 * j + 1 < L) ? ci[(2 * j + 1 < L) ? 2 * j + 1 : 0] : 0u;
+      acc = g1_add(acc, g1_unpack(pair_lookup(Tb.pairs->srs_pair[j], ci[2 * j] + 17u * hi)), Tb.inv101);
     }
     return g1_pack(acc);
   }

@@ -23,6 +23,7 @@ struct HostSetup {
   G1 vconst[8];               // q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s
   uint32_t g102_idx_of_G;     // == 6
   uint32_t fs_seed[8];        // initial state of the Fiat-Shamir transcript (include/pbh_b200.h), SHA-256 words
+  PairTables P;               // two-point fixed-base tables; T.pairs points here until the context uploads them
 };
 
 // "G2" of src/pbh/g2.rs:58-101: (a, b*u), u^2 = -2, no identity; returns false where the reference panics (Q12)
@@ -173,6 +174,17 @@ inline int host_setup(const pbh_circuit& c, uint32_t srs_secret, uint32_t srs_n,
     G1 m = g1_identity();
     for (int k = 0; k < 17; k++) { T.vfix_mult[j][k] = g1_pack(m); m = g1_add(m, base, T.inv101); }
   }
+
+  // two-point tables: entry a + 17 b = [a]P_2j + [b]P_2j+1
+  for (int j = 0; j < 5; j++)
+    for (int b = 0; b < 17; b++)
+      for (int a = 0; a < 17; a++)
+        hs.P.srs_pair[j][a + 17 * b] = g1_pack(g1_add(g1_unpack(T.srs_mult[2 * j][a]), g1_unpack(T.srs_mult[2 * j + 1][b]), T.inv101));
+  for (int j = 0; j < 4; j++)
+    for (int b = 0; b < 17; b++)
+      for (int a = 0; a < 17; a++)
+        hs.P.vfix_pair[j][a + 17 * b] = g1_pack(g1_add(g1_unpack(T.vfix_mult[2 * j][a]), g1_unpack(T.vfix_mult[2 * j + 1][b]), T.inv101));
+  T.pairs = &hs.P;
 
   // ---- group structure of E(F_101) for PBH_ALGO_TABLE
   std::vector<G1> pts;

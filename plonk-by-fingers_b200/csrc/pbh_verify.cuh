@@ -134,14 +134,11 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
     e2.a = T.pair_1_a[i2]; e2.b = T.pair_1_b[i2];
   } else {
     // fixed-base multiples (the constant commitments lie in <G>, of order 17, so -[s]P = [17-s]P)
-    G1 acc = g1_unpack(T.vfix_mult[0][s_qm]);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[1][s_ql]), T.inv101);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[2][s_qr]), T.inv101);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[3][s_qo]), T.inv101);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[4][s_qc]), T.inv101);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[5][v5]), T.inv101);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[6][v6]), T.inv101);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[7][neg17(s_s3)]), T.inv101);
+    // two scalars per lookup for the eight constant commitments (PairTables), then the multiple of G
+    G1 acc = g1_unpack(pair_lookup(T.pairs->vfix_pair[0], s_qm + 17u * s_ql));
+    acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[1], s_qr + 17u * s_qo)), T.inv101);
+    acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[2], s_qc + 17u * v5)), T.inv101);
+    acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[3], v6 + 17u * neg17(s_s3))), T.inv101);
     acc = g1_add(acc, g1_unpack(T.vfix_mult[8][neg17(s_e)]), T.inv101);
     // Straus: sum_k [sc_k] pt_k with shared doublings, scalars < 17 (5 bits)
     const uint32_t sc[9] = {v2, v3, v4, s_zs, 1u, z6, z12, z, s_wzw};

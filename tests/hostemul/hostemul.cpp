@@ -53,6 +53,8 @@ int emul_f32_bounds(double* max_exact, double* max_red) {
     for (auto& x : c) x = Bnd(16);
     ProofF pf;
     Tables tb; std::memset(&tb, 0, sizeof tb);
+    static PairTables pairs_zero{};
+    tb.pairs = &pairs_zero;
     prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, RuntimeCK{KF, n_pts}, tb, inv, pf);
     prove_core_f32<ALGO_ARITH, Bnd>(w, r, c, RuntimeCK{KF, n_pts}, tb, inv, pf);
     prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, PbhCK(), tb, inv, pf);

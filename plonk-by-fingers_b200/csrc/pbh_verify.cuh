@@ -140,18 +140,26 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
     acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[2], s_qc + 17u * v5)), T.inv101);
     acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[3], v6 + 17u * neg17(s_s3))), T.inv101);
     acc = g1_add(acc, g1_unpack(T.vfix_mult[8][neg17(s_e)]), T.inv101);
-    // Straus: sum_k [sc_k] pt_k with shared doublings, scalars < 17 (5 bits)
+    // Straus with joint two-point windows: sum_k [sc_k] pt_k with shared doublings, scalars < 17 (5 bits).  The points
+    // are taken in pairs; per bit level one addition of 0, P, Q or P + Q (precomputed) serves both scalars of a pair:
+    // 4 + 21 additions and 4 doublings instead of 44 + 4.  t_lo_s has the scalar 1 (one addition at the last level).
     const uint32_t sc[9] = {v2, v3, v4, s_zs, 1u, z6, z12, z, s_wzw};
+    const int pa[4] = {0, 2, 5, 7}, pb[4] = {1, 3, 6, 8};
+    G1 both[4];
+#pragma unroll
+    for (int p = 0; p < 4; p++) both[p] = g1_add(pt[pa[p]], pt[pb[p]], T.inv101);
     G1 r = g1_identity();
 #pragma unroll
     for (int j = 4; j >= 0; j--) {
       if (j != 4) r = g1_add(r, r, T.inv101);
 #pragma unroll
-      for (int k = 0; k < 9; k++) {
-        if (j == 4 && k == 4) continue;   // the scalar of t_lo_s is 1
-        G1 s = g1_add(r, pt[k], T.inv101);
-        if ((sc[k] >> j) & 1u) r = s;
+      for (int p = 0; p < 4; p++) {
+        const bool ba = (sc[pa[p]] >> j) & 1u, bb = (sc[pb[p]] >> j) & 1u;
+        G1 addend = ba ? (bb ? both[p] : pt[pa[p]]) : pt[pb[p]];
+        G1 s = g1_add(r, addend, T.inv101);
+        if (ba || bb) r = s;
       }
+      if (j == 0) r = g1_add(r, pt[4], T.inv101);
     }
     G1 q2 = g1_add(r, acc, T.inv101);                                        // e_2_q1
     G1 q1 = g1_add(pt[7], g1_smul<5>(pt[8], u, T.inv101), T.inv101);         // e_1_q1

@@ -34,7 +34,7 @@ PBH_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 // x * (M*m - 2^k) < 2^k, and x * M must fit 32 bits.  Not a multiply-high: IMAD.HI issues at half the IMAD rate on sm_100
 // (profiles/r01_pipe_rates.txt) and the integer paths (PBH_ALGO_ARITH curve arithmetic, the int32 prover, the sweeps)
 // are bound by that pipe.  The ranges below cover every argument in this code base; test builds record the largest
-// argument seen (tests/hostemul, PBH_RANGE_TRACK) and the test suite checks it against the range.
+// argument seen (PBH_RANGE_TRACK, host compilation only) and the test suite checks it against the range.
 //   mod17:  M = 61681 = ceil(2^20/17),  61681*17  - 2^20 = 1:  exact for x < 69631 (x*M < 2^32)
 //   mod101: M = 41528 = ceil(2^22/101), 41528*101 - 2^22 = 24: exact for x < 103000
 //   mod102: M = 41121 = ceil(2^22/102), 41121*102 - 2^22 = 38: exact for x < 104000

@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--no-fs", action="store_true", help="skip timing the Fiat-Shamir kernels")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--no-cycle-graph", action="store_true", help="replay one graph per step instead of one per ring cycle")
+    ap.add_argument("--no-overlap-verify", dest="overlap_verify", action="store_false",
+                    help="keep verify(k) and prove(k+1) on one stream inside the cycle graphs (default: verify(k) runs on a second stream beside prove(k+1))")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -250,13 +252,36 @@ def main():
     if graphs is not None and not args.no_cycle_graph:
         try:
             cycle_graphs = []
+            if args.overlap_verify:
+                # the verifier of step k runs on a second context (its own stream) beside the prover of step k + 1: the two
+                # touch different ring slots, and the tail of one kernel fills the SMs the other has not reached yet
+                ctx_v = pbh_b200.Context(device=local, algo=args.algo)
+                vstream = ctx_v.torch_stream()
+                with torch.cuda.stream(vstream):
+                    for slot in range(ring):
+                        ctx_v.verify_bitmap_batch(outs[slot]["proof"], ins[slot][2], ins[slot][3], outs[slot]["result"], outs[slot]["bitmap"])
+                torch.cuda.synchronize()
             for b in range(2):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
-                    for slot in range(ring):
-                        kernels(slot, b)
+                    if not args.overlap_verify:
+                        for slot in range(ring):
+                            kernels(slot, b)
+                    else:
+                        for slot in range(ring):
+                            w, rd, c, u, first = ins[slot]
+                            o = outs[slot]
+                            ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
+                            proved = torch.cuda.Event()
+                            proved.record(stream)
+                            vstream.wait_event(proved)
+                            with torch.cuda.stream(vstream):
+                                ctx_v.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
+                        stream.wait_stream(vstream)
                 cycle_graphs.append(g)
             launch_mode = f"cuda_graph ({ring}-step cycle graphs, one all-gather per cycle; per-step graphs for the remainder)"
+            if args.overlap_verify:
+                launch_mode += "; verify(k) on a second stream beside prove(k+1)"
         except Exception as e:   # pragma: no cover
             cycle_graphs = None
             launch_mode += f"; cycle graph unavailable: {type(e).__name__}"

@@ -278,7 +278,55 @@ class Setup:
         return True
 
     def prove(self, a, b, c, rand, ch):
+        """src/plonk.rs:191-466 with the caller's Challange (alpha, beta, gamma, z, v)."""
         alpha, beta, gamma, z, v = ch
+        answers = {"beta_gamma": (beta, gamma), "alpha": alpha, "z": z, "v": v, "u": None}
+        steps = self._prove_steps(a, b, c, rand)
+        try:
+            ask, _ = next(steps)
+            while True:
+                ask, _ = steps.send(answers[ask])
+        except StopIteration as done:
+            return done.value
+
+    def prove_fs(self, a, b, c, rand, seed):
+        """Fiat-Shamir (include/pbh_b200.h): the same prover with each challenge derived from the SHA-256 transcript at
+        the moment it is first needed.  Returns (proof dict, [alpha, beta, gamma, z, v, u])."""
+        import hashlib
+        state = [bytes(seed)]
+        derived = [0] * 6
+
+        def absorb(msg):
+            state[0] = hashlib.sha256(state[0] + msg).digest()
+            return state[0]
+
+        def point(p):
+            return bytes([p[0], p[1], 1 if p[2] else 0, 0])
+
+        def squeeze(st, k):
+            return int.from_bytes(st[8 * k:8 * k + 8], "big") % P17
+
+        steps = self._prove_steps(a, b, c, rand)
+        try:
+            ask, data = next(steps)
+            while True:
+                if ask == "v":
+                    st = absorb(bytes(data))
+                else:
+                    st = absorb(b"".join(point(p) for p in data))
+                if ask == "beta_gamma":
+                    derived[1], derived[2] = squeeze(st, 0), squeeze(st, 1)
+                    answer = (derived[1], derived[2])
+                else:
+                    idx = {"alpha": 0, "z": 3, "v": 4, "u": 5}[ask]
+                    derived[idx] = answer = squeeze(st, 0)
+                ask, data = steps.send(answer)
+        except StopIteration as done:
+            return done.value, derived
+
+    def _prove_steps(self, a, b, c, rand):
+        """The prover as a coroutine: yields (which challenge it needs now, the transcript data produced since the last
+        one) at the point where the reference first uses that challenge, and returns the proof."""
         k = self.c
         if not self.satisfies(a, b, c):
             raise Panic(1)
@@ -291,6 +339,7 @@ class Setup:
         bx = padd(pmul(norm([b4, b3]), self.zh), fb)
         cx = padd(pmul(norm([b6, b5]), self.zh), fc)
         a_s, b_s, c_s = self.commit(ax), self.commit(bx), self.commit(cx)
+        beta, gamma = yield ("beta_gamma", [a_s, b_s, c_s])
         acc = [1]
         for i in range(1, 4):
             w = pow(OMEGA, i - 1, P17)
@@ -306,6 +355,7 @@ class Setup:
             raise Panic(8)
         zx = padd(pmul(norm([b9, b8, b7]), self.zh), accx)
         z_s = self.commit(zx)
+        alpha = yield ("alpha", [z_s])
         L1 = self.interp([1, 0, 0, 0])
         t1 = padd(padd(padd(padd(padd(pmul(pmul(ax, bx), qm), pmul(ax, ql)), pmul(bx, qr)), pmul(cx, qo)), [0]), qc)
         A2 = pscale(padd(ax, norm([gamma, beta])), alpha)
@@ -326,6 +376,7 @@ class Setup:
             raise Panic(4)
         thi, tmid, tlo = norm(tx[12:18]), norm(tx[6:12]), norm(tx[0:6])
         t_hi_s, t_mid_s, t_lo_s = self.commit(thi), self.commit(tmid), self.commit(tlo)
+        z = yield ("z", [t_lo_s, t_mid_s, t_hi_s])
         a_z, b_z, c_z = peval(ax, z), peval(bx, z), peval(cx, z)
         s1z, s2z = peval(S1, z), peval(S2, z)
         t_z = peval(tx, z)
@@ -336,6 +387,7 @@ class Setup:
         r4 = pscale(pscale(zx, peval(L1, z)), alpha * alpha % P17)
         rx = padd(padd(padd(r1, r2), r3), r4)
         r_z = peval(rx, z)
+        v = yield ("v", [a_z, b_z, c_z, s1z, s2z, r_z, zwz])
         wn = padd_scalar(padd(padd(tlo, pscale(tmid, pow(z, 6, P17))), pscale(thi, pow(z, 12, P17))), -t_z)
         for poly, val, e in ((rx, r_z, 1), (ax, a_z, 2), (bx, b_z, 3), (cx, c_z, 4), (S1, s1z, 5), (S2, s2z, 6)):
             wn = padd(wn, pscale(padd_scalar(poly, -val), pow(v, e, P17)))
@@ -347,6 +399,7 @@ class Setup:
             raise Panic(7)
         w_z_s = self.commit(wz)
         w_zw_s = self.commit(wzw)
+        yield ("u", [w_z_s, w_zw_s])
         return dict(points=[a_s, b_s, c_s, z_s, t_lo_s, t_mid_s, t_hi_s, w_z_s, w_zw_s], evals=[a_z, b_z, c_z, s1z, s2z, r_z, zwz])
 
     def verify(self, points, evals, ch, u):

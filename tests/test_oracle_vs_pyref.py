@@ -134,3 +134,31 @@ def test_sweep_oracles_match_the_polynomial_restatement(oracle):
         assert pad(oracle.mul_ntt(337, 85, 8, "cooley_tukey", a[:, i], b[:, i]), 8) == m[:, i].tolist()
     assert oracle.mul_ntt_batch(np.array([[24, 12, 28, 8]], dtype=np.uint16).T, np.array([[4, 26, 29, 23]], dtype=np.uint16).T, 337, 85)[:, 0].tolist() \
         == [96, 335, 109, 312, 285, 202, 184, 0]                     # src/fft.rs:171-183
+
+
+def test_fiat_shamir_agrees(oracle):
+    """The Fiat-Shamir prover of the two restatements: the C++ oracle asks a challenge source inside its templated
+    prove; pyref runs its prover as a coroutine driven by hashlib.  Same proofs, statuses and derived challenges."""
+    n = 400
+    wit, rnd, _, _, _ = oracle.generate_inputs(n, seed=123, dist=0, threads=4)
+    rnd[:, :60] = np.random.default_rng(1).choice(np.array([0, 0, 1, 16], dtype=np.uint8), size=(9, 60))
+    po, so, co = oracle.prove_fs_batch(wit, rnd, threads=4)
+    setup = pyref.Setup(pyref.PBH_CIRCUIT)
+    seed = oracle.fs_seed()
+    seen = set()
+    for i in range(n):
+        a, b, c = [int(x) for x in wit[0:4, i]], [int(x) for x in wit[4:8, i]], [int(x) for x in wit[8:12, i]]
+        try:
+            pr, derived = setup.prove_fs(a, b, c, [int(x) for x in rnd[:, i]], seed)
+            st = 0
+        except pyref.Panic as e:
+            st = e.site
+        assert st == so[i], (i, st, so[i])
+        seen.add(st)
+        if st == 0:
+            assert derived == co[:, i].tolist()
+            for k, p in enumerate(pr["points"]):
+                assert (p[0], p[1]) == (po[2 * k, i], po[2 * k + 1, i])
+                assert bool(p[2]) == bool(((po[18, i] >> k) & 1) if k < 8 else (po[19, i] & 1))
+            assert pr["evals"] == po[20:27, i].tolist()
+    assert seen >= {0, 2, 4, 5}

@@ -21,7 +21,9 @@ agg = collections.OrderedDict()
 for r in rows:
     agg.setdefault(r["Kernel Name"].split("(")[0], []).append(float(r["Metric Value"]))
 tot = sum(sum(v) for v in agg.values()) or 1.0
-step = {k: v for k, v in agg.items() if any(s in k for s in ("prove_kernel", "verify_kernel", "pack_verdicts", "digest_kernel"))}
+# the kernels of a bench step: the default (PBH_ALGO_TABLE = 1) instantiations of the prover and the verifier
+step = {k: v for k, v in agg.items() if any(s in k for s in ("prove_f32_tma_kernel<1", "verify_tma_kernel<1", "prove_kernel<1", "verify_kernel<1",
+                                                               "pack_verdicts", "digest_kernel"))}
 step_tot = sum(sum(v) for v in step.values()) or 1.0
 with open(os.path.join(dst, f"{tag}_launches.txt") if have_list else os.devnull, "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none, command: bench.py --steps 3 --warmup 3 --no-cpu --ring 2 --e2e-steps 0\n")

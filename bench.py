@@ -518,8 +518,8 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O
         threads = max(1, O.hardware_threads())
+        vall, dtall = cpu_leg(20000 * threads, threads)     # draws the sample on all threads; the next leg reuses a slice of it
         v1, dt1 = cpu_leg(20000, 1)
-        vall, dtall = cpu_leg(20000 * threads, threads)
         cpu = {"value": vall, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{20000 * threads} D_fullpath items, prove then verify, C++ restatement of the reference (oracle/), {threads} threads, {dtall:.1f} s",
                "single_thread": {"value": v1, "cores": 1, "sample": f"20000 items, {dt1:.1f} s"}}

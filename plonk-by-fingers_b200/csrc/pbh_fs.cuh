@@ -31,10 +31,12 @@ PBH_HD uint32_t fs_point_word(uint32_t packed) {
   return ((packed & 0xFFu) << 24) | ((packed & 0xFF00u) << 8) | ((packed >> 8) & 0x100u);
 }
 
-// Conv turns a canonical residue (0..16) into the routine's scalar type; OUTLINE selects the shared out-of-line copy of
-// the compression (pbh_sha256.cuh)
-template <class T, class Conv, bool OUTLINE = false>
+// Conv turns a canonical residue (0..16) into the routine's scalar type; OUTLINE_MASK selects, per transcript step, the
+// shared out-of-line copy of the compression (pbh_sha256.cuh)
+template <class T, class Conv, int OUTLINE_MASK = 0>
 struct FsChal {
+  // bit k of OUTLINE_MASK: step k (beta/gamma, alpha, z, v, u) calls the shared out-of-line compression
+  template <int STEP> static constexpr bool outlined() { return (OUTLINE_MASK >> STEP) & 1; }
   static constexpr bool kNeedsPoints = true;
   uint32_t st[8];
   uint32_t derived[6];   // alpha beta gamma z v u
@@ -47,32 +49,32 @@ struct FsChal {
   }
   PBH_HD void beta_gamma(uint32_t pa, uint32_t pb, uint32_t pc, T& beta, T& gamma) {
     const uint32_t m[6] = {fs_point_word(pa), fs_point_word(pb), fs_point_word(pc), 0u, 0u, 0u};
-    sha256_absorb<OUTLINE>(st, m, 12);
+    sha256_absorb<outlined<0>()>(st, m, 12);
     derived[1] = sha256_squeeze17(st, 0); derived[2] = sha256_squeeze17(st, 1);
     beta = Conv()(derived[1]); gamma = Conv()(derived[2]);
   }
   PBH_HD T alpha(uint32_t pz) {
     const uint32_t m[6] = {fs_point_word(pz), 0u, 0u, 0u, 0u, 0u};
-    sha256_absorb<OUTLINE>(st, m, 4);
+    sha256_absorb<outlined<1>()>(st, m, 4);
     derived[0] = sha256_squeeze17(st, 0);
     return Conv()(derived[0]);
   }
   PBH_HD T zeta(uint32_t lo, uint32_t mid, uint32_t hi) {
     const uint32_t m[6] = {fs_point_word(lo), fs_point_word(mid), fs_point_word(hi), 0u, 0u, 0u};
-    sha256_absorb<OUTLINE>(st, m, 12);
+    sha256_absorb<outlined<2>()>(st, m, 12);
     derived[3] = sha256_squeeze17(st, 0);
     return Conv()(derived[3]);
   }
   PBH_HD T v(const uint32_t (&ev)[7]) {
     const uint32_t m[6] = {(ev[0] << 24) | (ev[1] << 16) | (ev[2] << 8) | ev[3], (ev[4] << 24) | (ev[5] << 16) | (ev[6] << 8), 0u, 0u, 0u, 0u};
-    sha256_absorb<OUTLINE>(st, m, 7);
+    sha256_absorb<outlined<3>()>(st, m, 7);
     derived[4] = sha256_squeeze17(st, 0);
     return Conv()(derived[4]);
   }
   PBH_HD void u(uint32_t wz, uint32_t wzw) {
     if (!want_u) return;
     const uint32_t m[6] = {fs_point_word(wz), fs_point_word(wzw), 0u, 0u, 0u, 0u};
-    sha256_absorb<OUTLINE>(st, m, 8);
+    sha256_absorb<outlined<4>()>(st, m, 8);
     derived[5] = sha256_squeeze17(st, 0);
   }
 };

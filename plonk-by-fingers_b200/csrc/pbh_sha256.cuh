@@ -67,8 +67,8 @@ PBH_HD void sha256_init(uint32_t (&h)[8]) {
 // length word w15 the caller has prepared.  Two copies: inlined, and an out-of-line device function.  Five inlined
 // compressions make a kernel of about 190 KB of SASS that stalls on instruction fetch (ncu: 0.9-1.8 "no instruction"
 // stalls per issue); one shared copy avoids that but pays the call's register shuffling.  Measured per 2^20 items:
-// the verifier gains (411 -> 393 us), the prover, with many more live registers around each call, loses
-// (379 -> 414 us without the u step), so each uses the copy that suits it.
+// the verifier gains (411 -> 393 us); the prover, with many more live registers around the early calls, loses when
+// every step is outlined (379 -> 414 us without the u step) and gains when only the last two are (490 -> 441 us).
 struct ShaState { uint32_t v[8]; };
 PBH_HD ShaState sha256_step_inline(ShaState st, uint32_t w8, uint32_t w9, uint32_t w10, uint32_t w11, uint32_t w15) {
   uint32_t w[16];

@@ -244,7 +244,7 @@ PBH_HD uint32_t verify_one_fs(const uint32_t (&px)[9], const uint32_t (&py)[9], 
   uint32_t pk[9];
 #pragma unroll
   for (int k = 0; k < 9; k++) pk[k] = (px[k] & 0xFFu) | ((py[k] & 0xFFu) << 8) | (((infbits >> k) & 1u) << 16);
-  FsChal<uint32_t, ConvU32, ALGO == ALGO_TABLE> cs(seed);   // out-of-line compression where it measured faster (pbh_sha256.cuh)
+  FsChal<uint32_t, ConvU32, ALGO == ALGO_TABLE ? 31 : 0> cs(seed);   // out-of-line compression where it measured faster (pbh_sha256.cuh)
   uint32_t beta, gamma;
   cs.beta_gamma(pk[0], pk[1], pk[2], beta, gamma);
   cs.alpha(pk[3]);

@@ -28,4 +28,29 @@ extern "C" {
     pub fn pbh_verify_batch(ctx: *mut pbh_ctx, n: usize, proof: *const u8, proof_pitch: usize, chal: *const u8, chal_pitch: usize,
                             u: *const u8, result: *mut u8, gt: *mut u8, gt_pitch: usize) -> c_int;
     pub fn pbh_ctx_stream(ctx: *mut pbh_ctx) -> *mut c_void;
+    pub fn pbh_ctx_set_option(ctx: *mut pbh_ctx, option: c_int, value: c_int) -> c_int;
+    // Fiat-Shamir: challenges and the verifier's rand[0] derived on the device (include/pbh_b200.h)
+    pub fn pbh_ctx_get_fs_seed(ctx: *const pbh_ctx, state_0: *mut u8) -> c_int;
+    pub fn pbh_prove_fs_batch(ctx: *mut pbh_ctx, n: usize, wit: *const u8, wit_pitch: usize, rand: *const u8, rand_pitch: usize,
+                              proof: *mut u8, proof_pitch: usize, status: *mut u8, chal_out: *mut u8, chal_pitch: usize) -> c_int;
+    pub fn pbh_verify_fs_batch(ctx: *mut pbh_ctx, n: usize, proof: *const u8, proof_pitch: usize, result: *mut u8,
+                               chal_out: *mut u8, chal_pitch: usize, gt: *mut u8, gt_pitch: usize) -> c_int;
+    // 32-byte records (Vec<Proof>-shaped exchange without per-field copies)
+    pub fn pbh_prove_records(ctx: *mut pbh_ctx, n: usize, input: *const WitnessRecord, out: *mut ProofRecord) -> c_int;
+    pub fn pbh_verify_records(ctx: *mut pbh_ctx, n: usize, proofs: *const ProofRecord, params: *const WitnessRecord,
+                              result: *mut u8) -> c_int;
+    // batched equivalents of the crate's value-type operations (a selection; the header has them all)
+    pub fn pbh_kzg_commit_batch(ctx: *mut pbh_ctx, n: usize, coeffs: *const u8, in_pitch: usize, out: *mut u8, out_pitch: usize,
+                                on_device: c_int) -> c_int;                       // SRS::eval_at_s
+    pub fn pbh_pairing_batch(ctx: *mut pbh_ctx, n: usize, input: *const u8, in_pitch: usize, out: *mut u8, out_pitch: usize,
+                             on_device: c_int) -> c_int;                          // PBHPairing::pairing
+    pub fn pbh_mul_ntt_batch(ctx: *mut pbh_ctx, n: usize, modulus: u32, omega: u32, la: u32, lb: u32, a: *const u16, a_pitch: usize,
+                             b: *const u16, b_pitch: usize, out: *mut u16, out_pitch: usize, on_device: c_int) -> c_int;  // fft::mul_ntt
 }
+
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct WitnessRecord { pub wit: [u8; 12], pub rand: [u8; 9], pub chal: [u8; 5], pub u: u8, pub reserved: [u8; 5] }
+#[repr(C)]
+#[derive(Clone, Copy, Default)]
+pub struct ProofRecord { pub xy: [u8; 18], pub inf_lo: u8, pub inf_hi: u8, pub evals: [u8; 7], pub status: u8, pub reserved: [u8; 4] }

@@ -37,6 +37,7 @@ struct pbh_ctx {
   int use_tma = 1;                         // TMA-staged tiles when base/pitch alignment allows (PBH_OPT_TMA)
   int host_direct = 1;                     // PBH_OPT_HOST_DIRECT: run the kernels in place on page-locked, mapped host buffers
   int prover_fp32 = 1;                     // PBH_ALGO_TABLE prover: FP32-pipe arithmetic (1) or the int32 routine (0)
+  int verifier_fp32 = 0;                   // PBH_ALGO_TABLE verifier scalars: int32 (0, default: faster since the reductions lost their multiply-high) or FP32 (1)
   HostSetup hs;
   Tables* d_tables = nullptr;
   PairTables* d_pairs = nullptr;
@@ -183,6 +184,7 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
   if (option == PBH_OPT_TMA) { ctx->use_tma = value != 0; return PBH_OK; }
   if (option == PBH_OPT_SPECIALISE) { ctx->specialise = value != 0; return PBH_OK; }
   if (option == PBH_OPT_HOST_DIRECT) { ctx->host_direct = value != 0; return PBH_OK; }
+  if (option == PBH_OPT_VERIFIER_FP32) { ctx->verifier_fp32 = value != 0; return PBH_OK; }
   if (option == PBH_OPT_CHUNK_LOG2) {
     if (value < 8 || value > 20) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "chunk log2 must be in [8, 20]");
     ctx->chunk = (size_t)1 << value;
@@ -328,7 +330,7 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
       size_t tiles = (A.n + kTile - 1) / kTile;
       if (ctx->algo == PBH_ALGO_TABLE) {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 4);
-        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->prover_fp32 != 0, ctx->d_tables, A,
+        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A,
                                                               fresh_tile_counter(ctx, st, 1));
       } else {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 3);
@@ -347,7 +349,7 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
   }
   if (A.bitmap) { bitmap_later = A.bitmap; A.bitmap = nullptr; }   // the plain kernels do not pack
   int grid = grid_for(ctx, A.n, 8);
-  if (ctx->algo == PBH_ALGO_TABLE) verify_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->prover_fp32 != 0, ctx->d_tables, A);
+  if (ctx->algo == PBH_ALGO_TABLE) verify_kernel<ALGO_TABLE><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A);
   else verify_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
@@ -595,7 +597,7 @@ static int launch_verify_fs(pbh_ctx* ctx, cudaStream_t st, const VerifyFsArgs& F
   if (F.base.n == 0) return PBH_OK;
   const int grid = grid_for(ctx, F.base.n, 2);
   const FsSeed seed = fs_seed_of(ctx);
-  if (ctx->algo == PBH_ALGO_TABLE) verify_fs_kernel<ALGO_TABLE><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->prover_fp32 != 0, seed, ctx->d_tables, F);
+  if (ctx->algo == PBH_ALGO_TABLE) verify_fs_kernel<ALGO_TABLE><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, seed, ctx->d_tables, F);
   else verify_fs_kernel<ALGO_ARITH><<<grid, 256, 0, st>>>(ctx->hs.K, ctx->hs.KF, false, seed, ctx->d_tables, F);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());

@@ -65,6 +65,9 @@ def gpu_ctx(product_lib):
     # FP32 prover, generic instantiation (run-time circuit constants) even though the circuit is the reference's own
     ctxs["table_generic"] = pbh_b200.Context(device=0, algo="table")
     ctxs["table_generic"].set_option(pbh_b200.OPT_SPECIALISE, 0)
+    # the verifier's F_17 scalar work on the FP32 pipes (the default is int32)
+    ctxs["table_vf32"] = pbh_b200.Context(device=0, algo="table")
+    ctxs["table_vf32"].set_option(pbh_b200.OPT_VERIFIER_FP32, 1)
     # FP32 prover with plain per-thread loads/stores instead of TMA-staged tiles
     ctxs["table_notma"] = pbh_b200.Context(device=0, algo="table")
     ctxs["table_notma"].set_option(pbh_b200.OPT_TMA, 0)

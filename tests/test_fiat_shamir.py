@@ -153,7 +153,7 @@ def test_tampered_and_malformed_proofs(hostemul, oracle):
 
 
 # ---------------------------------------------------------------------------------------------------------------- GPU
-CTXS = ("table", "arith", "table_int", "arith_int", "table_generic")
+CTXS = ("table", "arith", "table_int", "arith_int", "table_generic", "table_vf32")
 
 
 @pytest.mark.gpu

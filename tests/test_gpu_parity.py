@@ -11,9 +11,10 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 ALGOS = ("table", "arith")
-CTXS = ("table", "table_generic", "table_notma", "table_int", "arith", "arith_int")   # gpu_ctx keys: table = FP32-pipe prover with TMA tiles (default),
+CTXS = ("table", "table_generic", "table_notma", "table_int", "table_vf32", "arith", "arith_int")   # gpu_ctx keys: table = FP32-pipe prover with TMA tiles (default),
 # table_generic = same without the compile-time circuit constants, table_notma = plain loads/stores, table_int = int32
-# prover, arith = per-item curve arithmetic (FP32 core), arith_int = per-item curve arithmetic (int32 prover)
+# prover and verifier, table_vf32 = verifier scalars on the FP32 pipes, arith = per-item curve arithmetic (FP32 core),
+# arith_int = per-item curve arithmetic (int32 prover)
 
 
 def _np(t):

@@ -36,14 +36,21 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
   e1.a = e1.b = e2.a = e2.b = 0;
   // ---- encoding (see include/pbh_b200.h).  Out-of-range bytes are replaced by 0 so that no table is indexed out
   // of bounds; the verdict of such an item is PBH_VR_BAD_ENCODING whatever is computed below.
-  bool bad = (infbits >> 9) != 0u || u >= 17u;
+  // The range checks are two maxima (three-input integer max on the device) instead of 24 compares.  PBH_ALGO_TABLE only
+  // indexes its 128-entry tables with min(x, 127) and merely compares y, so it reads the coordinates as they are; the
+  // curve arithmetic of PBH_ALGO_ARITH needs them in range.
+  uint32_t max_xy = 0u, max_s = u;
 #pragma unroll
-  for (int k = 0; k < 9; k++) bad = bad || px_in[k] >= 101u || py_in[k] >= 101u;
+  for (int k = 0; k < 9; k++) { max_xy = px_in[k] > max_xy ? px_in[k] : max_xy; max_xy = py_in[k] > max_xy ? py_in[k] : max_xy; }
 #pragma unroll
-  for (int k = 0; k < 5; k++) bad = bad || ch_in[k] >= 17u;
+  for (int k = 0; k < 5; k++) max_s = ch_in[k] > max_s ? ch_in[k] : max_s;
+  const bool bad = (infbits >> 9) != 0u || max_xy >= 101u || max_s >= 17u;
   uint32_t px[9], py[9], ch[5];
 #pragma unroll
-  for (int k = 0; k < 9; k++) { px[k] = bad ? 0u : px_in[k]; py[k] = bad ? 0u : py_in[k]; }
+  for (int k = 0; k < 9; k++) {
+    px[k] = (ALGO == ALGO_TABLE) ? px_in[k] : (bad ? 0u : px_in[k]);
+    py[k] = (ALGO == ALGO_TABLE) ? py_in[k] : (bad ? 0u : py_in[k]);
+  }
 #pragma unroll
   for (int k = 0; k < 5; k++) ch[k] = bad ? 0u : ch_in[k];
   if (bad) u = 0u;

@@ -63,11 +63,14 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
   for (int k = 0; k < 9; k++) {
     bool inf = (infbits >> k) & 1u;
     if (ALGO == ALGO_TABLE) {
+      // the table holds the root y <= 50 of x^3 + 3 (0xFF when there is none) and its point's index; the other root is
+      // 101 - y with index 102 - i.  Fold y into 0..50 first: one compare then decides "on the curve".
       uint32_t xi = px[k] < 127u ? px[k] : 127u;
       uint32_t ys = T.y_of_x[xi], i0 = T.idx_of_x[xi];
-      bool lo = py[k] == ys, hi = (py[k] + ys == 101u);
-      off_curve = off_curve || ys == 0xFFu || !(lo || hi);
-      uint32_t i = lo ? i0 : 102u - i0;
+      const bool upper = py[k] > 50u;
+      const uint32_t yf = upper ? 101u - py[k] : py[k];          // out-of-range y gives a value that matches no root
+      off_curve = off_curve || yf != ys;
+      uint32_t i = upper ? 102u - i0 : i0;
       idx[k] = inf ? 0u : i;                 // a flagged point acts as the identity (g1.rs:121, 148-150)
     } else {
       off_curve = off_curve || !g1_in_curve(px[k], py[k]);

@@ -117,6 +117,30 @@ def test_fuzz_arbitrary_bytes(hostemul, oracle, algo):
     assert np.array_equal(v, ve) and np.array_equal(g, ge)
 
 
+@pytest.mark.parametrize("algo", (0, 1, 2))
+def test_point_decode_exhaustive(hostemul, oracle, algo):
+    """Every byte pair (x, y), with and without the infinity flag, in the place of one proof point: the verifier's
+    point decode (table lookup with y folded into 0..50, or in_curve arithmetic) agrees with the oracle on the verdict
+    class and on the pairing values."""
+    w, r, c, u, _ = oracle.generate_inputs(64, seed=3, dist=1, threads=4)
+    p, s = oracle.prove_batch(w, r, c, threads=4)
+    ok = np.nonzero(oracle.verify_batch(p, c, u, threads=4, want_gt=False) == 1)[0]
+    base = int(ok[0])
+    xs, ys = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    for k, flag in ((0, 0), (7, 0), (8, 1), (3, 1)):
+        n = 65536
+        proof = np.repeat(p[:, base:base + 1], n, axis=1)
+        proof[2 * k] = xs.reshape(-1); proof[2 * k + 1] = ys.reshape(-1)
+        if flag:
+            if k < 8: proof[18] |= np.uint8(1 << k)
+            else: proof[19] |= np.uint8(1)
+        chal = np.repeat(c[:, base:base + 1], n, axis=1); uu = np.repeat(u[base:base + 1], n)
+        ro, go = oracle.verify_batch(proof, chal, uu, threads=8)
+        re, ge = hostemul.verify(oracle.pbh_test_circuit(), proof, chal, uu, algo)
+        assert np.array_equal(re, ro) and np.array_equal(ge, go), (k, flag)
+        assert (ro == 0x20).sum() == 65536 - 101 * 101 and (ro == 0x02).sum() > 0
+
+
 def test_zz_reduction_argument_ranges(hostemul, oracle):
     """Runs last in this file: every argument the mod 17 / 101 / 102 reductions received during the group-law, pairing,
     prover and verifier tests above (plus an adversarial verifier batch here) stayed inside the range over which their

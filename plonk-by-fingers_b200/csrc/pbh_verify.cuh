@@ -111,13 +111,15 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
                  r_z = mod17(ev[5]), zw_z = mod17(ev[6]);
 
   // ---- Steps 4-7                                                            src/plonk.rs:553-579
+  // Lazy reduction: a product of up to four residues (<= 16^4 = 65536) is inside mod17's exact range, so chains of
+  // multiplications are reduced once (the host test build records the largest argument mod17 ever receives).
   uint32_t z2 = mul17(z, z), z3 = mul17(z2, z), z4 = mul17(z2, z2);
   uint32_t zh_z = sub17(z4, 1u);
   uint32_t l1_z = mod17(K.L1[0] + K.L1[1] * z + K.L1[2] * z2 + K.L1[3] * z3);
-  uint32_t a2 = mul17(alpha, alpha);
-  uint32_t l1a2 = mul17(l1_z, a2);
+  uint32_t l1a2 = mod17(l1_z * alpha * alpha);
   uint32_t perm_a = mod17(beta * s1_z + gamma + a_z), perm_b = mod17(beta * s2_z + gamma + b_z);
-  uint32_t perm = mul17(mul17(mul17(perm_a, perm_b), mod17(c_z + gamma)), zw_z);   // Q3: no alpha here
+  uint32_t perm_ab = perm_a * perm_b;                                        // <= 256, kept unreduced
+  uint32_t perm = mod17(perm_ab * mod17(c_z + gamma) * zw_z);                // Q3: no alpha here
   bool zh0 = zh_z == 0u;                                                     // Q4
   uint32_t t_z = mul17(mod17(r_z + 34u - perm - l1a2), T.inv17[zh_z]);
 
@@ -125,13 +127,12 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
   uint32_t v2 = mul17(v, v), v3 = mul17(v2, v), v4 = mul17(v3, v), v5 = mul17(v4, v), v6 = mul17(v5, v);
   uint32_t z6 = mul17(z4, z2), z12 = mul17(z6, z6);
   uint32_t bz = mul17(beta, z);
-  uint32_t s_qm = mul17(mul17(a_z, b_z), v), s_ql = mul17(a_z, v), s_qr = mul17(b_z, v), s_qo = mul17(c_z, v), s_qc = v;
-  uint32_t s_zs = mod17(mul17(mul17(mul17(mul17(mod17(a_z + bz + gamma), mod17(b_z + 2u * bz + gamma)),
-                                          mod17(c_z + 3u * bz + gamma)), alpha), v) +
-                        mul17(l1a2, v) + u);
-  uint32_t s_s3 = mul17(mul17(mul17(mul17(mul17(perm_a, perm_b), alpha), v), beta), zw_z);
+  uint32_t s_qm = mod17(a_z * b_z * v), s_ql = mul17(a_z, v), s_qr = mul17(b_z, v), s_qo = mul17(c_z, v), s_qc = v;
+  uint32_t f123a = mod17(mod17(a_z + bz + gamma) * mod17(b_z + 2u * bz + gamma) * mod17(c_z + 3u * bz + gamma) * alpha);
+  uint32_t s_zs = mod17((f123a + l1a2) * v + u);
+  uint32_t s_s3 = mod17(mod17(perm_ab * alpha * v) * beta * zw_z);
   uint32_t s_e = mod17(t_z + v * r_z + v2 * a_z + v3 * b_z + v4 * c_z + v5 * s1_z + v6 * s2_z + u * zw_z);
-  uint32_t s_wzw = mul17(mul17(u, z), 4u);   // u z omega
+  uint32_t s_wzw = mod17(u * z * 4u);   // u z omega
 
   if (ALGO == ALGO_TABLE) {
     // fixed-base part in the exponent of G: d_1 - d_3 + v^5 sigma_1 + v^6 sigma_2 - e

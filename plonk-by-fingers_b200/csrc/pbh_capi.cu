@@ -421,6 +421,25 @@ static int ensure_slots(pbh_ctx* ctx, size_t bytes_per_item) {
   return PBH_OK;
 }
 
+// The staged pipeline shared by the host-pointer entry points: the batch is cut into chunks of ctx->chunk items that
+// cycle through kSlots staging buffers, each with its own stream, so the upload of chunk k+2, the kernels of chunk k+1
+// and the download of chunk k overlap.  `body(lo, m, C, base, stream)` enqueues one chunk of m items starting at item
+// lo into the staging buffer `base` (planes of pitch C) on `stream`.
+template <class Body>
+static int for_each_chunk(pbh_ctx* ctx, size_t n, Body body) {
+  int rc = ensure_slots(ctx, 128);
+  if (rc) return rc;
+  const size_t C = ctx->chunk;
+  size_t k = 0;
+  for (size_t lo = 0; lo < n; lo += C, k++) {
+    const int s = (int)(k % kSlots);
+    rc = body(lo, std::min(C, n - lo), C, ctx->slot_buf[s], ctx->slot_stream[s]);
+    if (rc) return rc;
+  }
+  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+  return PBH_OK;
+}
+
 // The device-side alias of a host range when the whole range is page-locked and mapped (cudaHostAlloc /
 // cudaHostRegister under unified addressing), else nullptr.  When every buffer of a host-pointer call has one, the tile
 // kernel runs in place on the caller's memory: its TMA loads and stores cross PCIe tile by tile, so upload, compute and
@@ -459,27 +478,18 @@ int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch
       return PBH_OK;
     }
   }
-  rc = ensure_slots(ctx, 128);
-  if (rc) return rc;
-  const size_t C = ctx->chunk;
-  size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
-    size_t m = std::min(C, n - lo);
-    int s = (int)(k % kSlots);
-    cudaStream_t st = ctx->slot_stream[s];
-    uint8_t* base = ctx->slot_buf[s];
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
     ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
-    rc = launch_prove(ctx, st, A);
+    int rc = launch_prove(ctx, st, A);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+    return PBH_OK;
+  });
 }
 
 int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal, size_t chal_pitch,
@@ -502,27 +512,18 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
       return PBH_OK;
     }
   }
-  rc = ensure_slots(ctx, 128);
-  if (rc) return rc;
-  const size_t C = ctx->chunk;
-  size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
-    size_t m = std::min(C, n - lo);
-    int s = (int)(k % kSlots);
-    cudaStream_t st = ctx->slot_stream[s];
-    uint8_t* base = ctx->slot_buf[s];
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_proof = base, *d_chal = base + 27 * C, *d_u = base + 32 * C, *d_res = base + 33 * C, *d_gt = base + 34 * C;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
     VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, gt ? d_gt : nullptr, C, m, nullptr};
-    rc = launch_verify(ctx, st, A);
+    int rc = launch_verify(ctx, st, A);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
     if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, C, m, 4, cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+    return PBH_OK;
+  });
 }
 
 // prove then verify without the proof leaving the device in between: per chunk, H2D inputs -> prove kernel -> verify
@@ -535,15 +536,7 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
   if (!wit || !rnd || !chal || !u || !proof || !status || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 128);
-  if (rc) return rc;
-  const size_t C = ctx->chunk;
-  size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
-    size_t m = std::min(C, n - lo);
-    int s = (int)(k % kSlots);
-    cudaStream_t st = ctx->slot_stream[s];
-    uint8_t* base = ctx->slot_buf[s];
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C,
             *d_u = base + 54 * C, *d_res = base + 55 * C;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
@@ -551,7 +544,7 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
     ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
-    rc = launch_prove(ctx, st, A);
+    int rc = launch_prove(ctx, st, A);
     if (rc) return rc;
     VerifyArgs V{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
     rc = launch_verify(ctx, st, V);
@@ -559,9 +552,8 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
     CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+    return PBH_OK;
+  });
 }
 
 // ---- Fiat-Shamir entry points -----------------------------------------------------------------
@@ -631,27 +623,18 @@ int pbh_prove_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pi
   if (!wit || !rnd || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || proof_pitch < n || (chal_out && chal_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 128);
-  if (rc) return rc;
-  const size_t C = ctx->chunk;
-  size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
-    size_t m = std::min(C, n - lo);
-    int s = (int)(k % kSlots);
-    cudaStream_t st = ctx->slot_stream[s];
-    uint8_t* base = ctx->slot_buf[s];
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_proof = base + 21 * C, *d_status = base + 48 * C, *d_chal = base + 49 * C;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
     ProveFsArgs F{{d_wit, C, d_rnd, C, nullptr, 0, d_proof, C, d_status, m}, chal_out ? d_chal : nullptr, C};
-    rc = launch_prove_fs(ctx, st, F);
+    int rc = launch_prove_fs(ctx, st, F);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
     if (chal_out) CUDA_TRY(ctx, cudaMemcpy2DAsync(chal_out + lo, chal_pitch, d_chal, C, m, 6, cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+    return PBH_OK;
+  });
 }
 int pbh_verify_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, uint8_t* result, uint8_t* chal_out,
                         size_t chal_pitch, uint8_t* gt, size_t gt_pitch) {
@@ -660,26 +643,17 @@ int pbh_verify_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t pro
   if (!proof || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (proof_pitch < n || (chal_out && chal_pitch < n) || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 128);
-  if (rc) return rc;
-  const size_t C = ctx->chunk;
-  size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
-    size_t m = std::min(C, n - lo);
-    int s = (int)(k % kSlots);
-    cudaStream_t st = ctx->slot_stream[s];
-    uint8_t* base = ctx->slot_buf[s];
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_proof = base, *d_res = base + 27 * C, *d_chal = base + 28 * C, *d_gt = base + 34 * C;
     CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
     VerifyFsArgs F{{d_proof, C, nullptr, 0, nullptr, d_res, gt ? d_gt : nullptr, C, m, nullptr}, chal_out ? d_chal : nullptr, C};
-    rc = launch_verify_fs(ctx, st, F);
+    int rc = launch_verify_fs(ctx, st, F);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
     if (chal_out) CUDA_TRY(ctx, cudaMemcpy2DAsync(chal_out + lo, chal_pitch, d_chal, C, m, 6, cudaMemcpyDeviceToHost, st));
     if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, C, m, 4, cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+    return PBH_OK;
+  });
 }
 
 // ---- record wire format ------------------------------------------------------------------------------------------
@@ -727,15 +701,7 @@ int pbh_prove_records(pbh_ctx* ctx, size_t n, const pbh_witness_record* in, pbh_
   if (n == 0) return PBH_OK;
   if (!in || !out) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 128);
-  if (rc) return rc;
-  const size_t C = ctx->chunk;
-  size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
-    size_t m = std::min(C, n - lo);
-    int s = (int)(k % kSlots);
-    cudaStream_t st = ctx->slot_stream[s];
-    uint8_t* base = ctx->slot_buf[s];
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C;
     pbh_witness_record* d_in = reinterpret_cast<pbh_witness_record*>(base + 64 * C);
     pbh_proof_record* d_out = reinterpret_cast<pbh_proof_record*>(base + 96 * C);
@@ -743,15 +709,14 @@ int pbh_prove_records(pbh_ctx* ctx, size_t n, const pbh_witness_record* in, pbh_
     witness_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_in, d_wit, C, d_rnd, C, d_chal, C, nullptr);
     ctx->launches++;
     ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
-    rc = launch_prove(ctx, st, A);
+    int rc = launch_prove(ctx, st, A);
     if (rc) return rc;
     proof_planes_to_records_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_proof, C, d_status, d_out);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(out + lo, d_out, m * sizeof(pbh_proof_record), cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+    return PBH_OK;
+  });
 }
 
 int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, const pbh_witness_record* params, uint8_t* result) {
@@ -759,15 +724,7 @@ int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, c
   if (n == 0) return PBH_OK;
   if (!proofs || !params || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = ensure_slots(ctx, 128);
-  if (rc) return rc;
-  const size_t C = ctx->chunk;
-  size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
-    size_t m = std::min(C, n - lo);
-    int s = (int)(k % kSlots);
-    cudaStream_t st = ctx->slot_stream[s];
-    uint8_t* base = ctx->slot_buf[s];
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_proof = base, *d_chal = base + 27 * C, *d_u = base + 32 * C, *d_res = base + 33 * C;
     pbh_witness_record* d_par = reinterpret_cast<pbh_witness_record*>(base + 64 * C);
     pbh_proof_record* d_prf = reinterpret_cast<pbh_proof_record*>(base + 96 * C);
@@ -777,12 +734,11 @@ int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, c
     witness_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_par, nullptr, 0, nullptr, 0, d_chal, C, d_u);
     ctx->launches += 2;
     VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
-    rc = launch_verify(ctx, st, A);
+    int rc = launch_verify(ctx, st, A);
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
-  }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+    return PBH_OK;
+  });
 }
 
 // ---- sweep entry points ---------------------------------------------------------------------------------

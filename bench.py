@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-arith", action="store_true", help="skip timing the PBH_ALGO_ARITH kernels")
     ap.add_argument("--no-fs", action="store_true", help="skip timing the Fiat-Shamir kernels")
+    ap.add_argument("--no-uniform", action="store_true", help="skip timing the kernels on D_uniform inputs")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying CUDA graphs")
     ap.add_argument("--no-cycle-graph", action="store_true", help="replay one graph per step instead of one per ring cycle")
     ap.add_argument("--no-overlap-verify", dest="overlap_verify", action="store_false",
@@ -410,6 +411,24 @@ def main():
         gather_ok = bool(torch.equal(g_[rank].reshape(-1), summary_all[b])) and int((digests == 0).sum().item()) == 0 \
             and int(torch.unique(digests).numel()) == world * ring
 
+    # ---- the other input distribution of SURVEY.md 8(d): D_uniform (attempt 0 only; ~89 % of the items end in one of the
+    # reference's panics, so warps diverge between the FP32 core and the exact-length integer routine).  Reported beside
+    # the headline, which is on D_fullpath where every item does all the work.
+    d_uniform = None
+    if not args.no_uniform:
+        uw, ur, uc, uu = ctx.generate_inputs(n, first_index=0, seed=SEED, dist=pbh_b200.DIST_UNIFORM)
+        u_proof = torch.empty((27, n), dtype=torch.uint8, device=dev)
+        u_status = torch.empty((n,), dtype=torch.uint8, device=dev)
+        u_result = torch.empty((n,), dtype=torch.uint8, device=dev)
+        up_ms = time_kernel(lambda s_: ctx.prove_batch(uw, ur, uc, proof=u_proof, status=u_status), 20)
+        uv_ms = time_kernel(lambda s_: ctx.verify_batch(u_proof, uc, uu, result=u_result), 20)
+        hist = torch.bincount(u_status.to(torch.int64), minlength=6)[:6].tolist()
+        d_uniform = {"prove_ms": up_ms, "verify_ms": uv_ms, "proofs_per_s_per_gpu": n / (up_ms * 1e-3),
+                     "verifies_per_s_per_gpu": n / (uv_ms * 1e-3), "status_histogram_0_to_5": hist,
+                     "accepted": int((u_result == 1).sum().item()), "items": n,
+                     "note": "one batch (no ring): inputs and outputs of 2^20 items stay L2-resident; the kernels are issue-bound"}
+        del uw, ur, uc, uu, u_proof, u_status, u_result
+
     # ---- Fiat-Shamir variants: same witnesses and blinders, challenges derived on the device
     # from the SHA-256 transcript; reported beside the headline, not part of it.  With transcript-derived (uniform)
     # challenges most proofs end in one of the reference's panics; `proofs_produced` says how many did not.
@@ -551,6 +570,7 @@ def main():
                     "prove_hbm_frac": prove_gbs / peak, "verify_hbm_frac": verify_gbs / peak},
         "arith_algo_kernels": arith,
         "fiat_shamir_kernels": fs,
+        "d_uniform_kernels": d_uniform,
         "int32_peak": int32,
         "cpu_baseline": cpu,
         "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n, "gathered_summaries_ok": gather_ok},

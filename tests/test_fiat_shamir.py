@@ -126,6 +126,34 @@ def test_other_circuit_and_srs(hostemul, oracle):
             assert np.array_equal(se, so) and np.array_equal(pe, po) and np.array_equal(ce, co)
 
 
+def test_randomised_circuits(hostemul, oracle):
+    """Random selectors (q_c = 0) and random copy constraints with zero / constant witnesses: the transcript-driven prover
+    reaches the deeper status classes (including a quotient remainder that no quirk explains) under run-time constants."""
+    rng = np.random.default_rng(21)
+    n = 3000
+    seen = set()
+    for case in (dict(s=2, srs_n=6), dict(s=7, srs_n=9)):
+        circ = oracle.pbh_test_circuit()
+        for name in ("q_l", "q_r", "q_o", "q_m"):
+            for i in range(4):
+                getattr(circ, name)[i] = int(rng.integers(0, 17))
+        for i in range(4):
+            circ.q_c[i] = 0
+        for name in ("c_a", "c_b", "c_c"):
+            for i in range(4):
+                getattr(circ, name + "_wire")[i] = int(rng.integers(0, 3)); getattr(circ, name + "_index")[i] = int(rng.integers(1, 5))
+        wit = rng.integers(0, 17, size=(12, n), dtype=np.uint8)
+        wit[:, : n // 2] = wit[:, :1]
+        wit[:, : n // 4] = 0
+        rnd = rng.integers(0, 17, size=(9, n), dtype=np.uint8)
+        po, so, co = oracle.prove_fs_batch(wit, rnd, circuit=circ, threads=8, **case)
+        seen |= set(np.unique(so).tolist())
+        for algo in (0, 1, 2, 3):
+            pe, se, ce = hostemul.prove_fs(circ, wit, rnd, algo, **case)
+            assert np.array_equal(se, so) and np.array_equal(pe, po) and np.array_equal(ce, co), (case, algo)
+    assert {1, 2}.issubset(seen) and len(seen) >= 4, seen
+
+
 def test_tampered_and_malformed_proofs(hostemul, oracle):
     """Any change to an accepted proof changes the derived challenges (so it is judged under different ones); bad
     encodings answer 0x20 with zero challenges; evaluation bytes >= 17 are hashed as they are and fail in_field."""

@@ -162,3 +162,19 @@ def test_fiat_shamir_agrees(oracle):
                 assert bool(p[2]) == bool(((po[18, i] >> k) & 1) if k < 8 else (po[19, i] & 1))
             assert pr["evals"] == po[20:27, i].tolist()
     assert seen >= {0, 2, 4, 5}
+
+
+def test_sweep_oracles_agree_with_pyref(oracle):
+    """The same three polynomial sweeps against the second restatement's scale / eval / long division."""
+    rng = np.random.default_rng(12)
+    arr = rng.integers(0, 17, size=(11, 300), dtype=np.uint8)
+    arr[10, :50] = 0
+    arr[6:10, 100:200] = 0          # shorter polynomials: the normalised-length paths of both restatements
+    s, e, d = oracle.poly_scale_batch(arr), oracle.poly_eval_batch(arr), oracle.poly_div_linear_batch(arr)
+    pad = lambda v, k: list(v) + [0] * (k - len(v))
+    for i in range(300):
+        p, c = pyref.norm([int(v) for v in arr[:10, i]]), int(arr[10, i])
+        assert pad(pyref.pscale(p, c), 10) == s[:, i].tolist()
+        assert pyref.peval(p, c) == e[i]
+        q, r = pyref.pdiv(p, pyref.norm([(-c) % 17, 1]))
+        assert pad(q, 9) + pad(r, 1) == d[:, i].tolist()

@@ -6,15 +6,22 @@
     python bench.py --impl reference ...                     # the CPU path (oracle port of the reference) on host cores
 
 A step is one pass of the hot path over one batch: prove 2^20 D_fullpath witnesses per GPU (configs[1] of
-BASELINE.json), verify the 2^20 proofs, pack the verdict bitmap and digest the proof bytes; with N > 1 every rank
-does that on its own shard (digest fused into the prover, bitmap into the verifier) and the bitmaps + digests are
-all-gathered over NCCL (the only collective: one per ring cycle, overlapped with the next cycle's kernels).  `value` counts proof+verify pairs per second over all ranks with inputs resident in HBM;
-`e2e` is the same work through the host-pointer C-ABI calls (pinned host buffers, H2D and D2H inside the timed
-region).  Inputs rotate through a ring of distinct batches larger than L2.
+BASELINE.json), verify the 2^20 proofs, pack the verdict bitmap and digest the proof bytes; with N > 1 every rank does
+that on its own shard (digest fused into the prover, bitmap into the verifier) and the bitmaps + digests are all-gathered
+over NCCL (the only collective: one per ring cycle, overlapped with the next cycle's kernels).  The K timed steps are ONE
+CUDA graph (kernels and collectives), so the host is out of the timed path; the K-step region is repeated `--reps` times
+and the median of the per-repetition maxima over ranks is reported.  `value` counts proof+verify pairs per second over
+all ranks with inputs resident in HBM; `e2e` is the same work through the host-pointer C-ABI calls (host buffers, H2D and
+D2H inside the timed region).  Inputs rotate through a ring of distinct batches larger than L2.
+
+After the timed region the line's `check` object is filled: the exact 2^20-item batch of ring slot 0 is replayed through
+the CPU oracle byte for byte, and with N > 1 rank 0 recomputes the whole N-rank index range alone and compares the
+gathered bitmaps and digests with it.
 """
 import argparse
 import json
 import os
+import statistics
 import sys
 import threading
 import time
@@ -27,6 +34,7 @@ UNIT = "proof+verify/s"
 N_PER_GPU = 1 << 20
 SEED = 0xB200
 WORKLOAD = "batched prover+verifier: 2^20 D_fullpath witnesses of the pbh circuit per GPU per step, shared SRS (s=2, 7 points)"
+MASK64 = (1 << 64) - 1
 
 
 def measured_peaks():
@@ -41,7 +49,7 @@ def measured_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
         self._stop_evt = threading.Event()
@@ -149,25 +157,71 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---- static inputs of the roofline: executed instructions per item, from the committed ncu captures -------------------
+def instr_table():
+    """profiles/instr_per_item.json: thread instructions per item (total, FMA pipe, ALU pipe) of each fused kernel, read
+    from the ncu reports named there.  STATIC: these are properties of the compiled code, not of this run; the times,
+    the clocks and the pipe peaks they are combined with below ARE measured in this run."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "instr_per_item.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def roofline_entry(name, table_key, ms, items, bytes_per_item, peaks, instr):
+    """One kernel against its four ceilings: HBM bytes, issue slots, FMA pipe, ALU pipe.  `bound` names the largest."""
+    sec = ms * 1e-3
+    ent = {"kernel": name, "ms": ms, "items": items, "items_per_s": items / sec,
+           "hbm": {"achieved_GBps": bytes_per_item * items / sec / 1e9, "peak_GBps": peaks["hbm_gbs"],
+                   "frac": bytes_per_item * items / sec / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes_per_item": bytes_per_item}}
+    fr = {"hbm": ent["hbm"]["frac"]}
+    ins = instr.get(table_key)
+    if ins:
+        ent["instr_per_item_static"] = {k: ins[k] for k in ("total", "fma", "fp32", "imad", "alu") if k in ins}
+        ent["instr_source_static"] = ins.get("source")
+
+        def add(pipe, count, peak):
+            if count is not None and peak:
+                ach = count * items / sec
+                ent[pipe] = {"achieved_thread_instr_per_s": ach, "peak_thread_instr_per_s": peak, "frac": ach / peak}
+                fr[pipe] = ach / peak
+
+        add("issue", ins.get("total"), peaks["issue_thread_instr_per_s"])
+        # FP32 ops issue on both FMA pipes (peak: the FFMA rate), IMAD on the heavy one only (peak: the IMAD rate)
+        add("fma-pipe", ins.get("fma"), peaks["fma_thread_ops_per_s"])
+        if ins.get("imad", 0) > ins.get("fp32", 0):
+            add("imad-pipe", ins.get("imad"), peaks.get("imad_thread_ops_per_s"))
+        add("alu-pipe", ins.get("alu"), peaks["alu_thread_ops_per_s"])
+    ent["bound"] = max(fr, key=fr.get)
+    ent["frac"] = fr[ent["bound"]]
+    return ent
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=7, help="repetitions of the K-step timed region (the median is reported)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--algo", default="table", choices=["table", "arith"])
     ap.add_argument("--items", type=int, default=N_PER_GPU, help="items per GPU per step")
     ap.add_argument("--ring", type=int, default=8, help="distinct input/output batches cycled through (L2 defeat)")
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=None)
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the full-batch oracle replay")
     ap.add_argument("--no-arith", action="store_true", help="skip timing the PBH_ALGO_ARITH kernels")
     ap.add_argument("--no-fs", action="store_true", help="skip timing the Fiat-Shamir kernels")
     ap.add_argument("--no-uniform", action="store_true", help="skip timing the kernels on D_uniform inputs")
-    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying CUDA graphs")
-    ap.add_argument("--no-cycle-graph", action="store_true", help="replay one graph per step instead of one per ring cycle")
+    ap.add_argument("--no-sweeps", action="store_true", help="skip the kernel sweeps of BASELINE.json configs[3] (N = 1 only)")
+    ap.add_argument("--no-config2", action="store_true", help="skip the 16 M-proof verifier of BASELINE.json configs[2] (N = 1 only)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 256 M-witness sharded run of BASELINE.json configs[4]")
+    ap.add_argument("--config4-log2", type=int, default=28)
+    ap.add_argument("--sweep-log2", type=str, default="24,28")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying one CUDA graph per K-step region")
     ap.add_argument("--no-overlap-verify", dest="overlap_verify", action="store_false",
-                    help="keep verify(k) and prove(k+1) on one stream inside the cycle graphs (default: verify(k) runs on a second stream beside prove(k+1))")
+                    help="keep verify(k) and prove(k+1) on one stream inside the graph (default: verify(k) runs on a second stream beside prove(k+1))")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -189,6 +243,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.items
+    K = max(1, args.steps)
     ctx = pbh_b200.Context(device=local, algo=args.algo)
     stream = ctx.torch_stream()
 
@@ -202,7 +257,6 @@ def main():
     row = nb + 8
     summary_all = [torch.zeros(ring * row, dtype=torch.uint8, device=dev) for _ in range(2)]
     gathered_all = [torch.empty(world * ring * row, dtype=torch.uint8, device=dev) if world > 1 else None for _ in range(2)]
-    cycle_done = [None, None]
     for r in range(ring):
         first = (r * world + rank) * n
         w, rd, c, u = ctx.generate_inputs(n, first_index=first, seed=SEED, dist=pbh_b200.DIST_FULLPATH)
@@ -212,178 +266,134 @@ def main():
             summary = summary_all[b][r * row:(r + 1) * row]
             views.append(dict(summary=summary, bitmap=summary[:nb], digest=summary[nb:].view(torch.int64)))
         outs.append(dict(proof=torch.empty((27, n), dtype=torch.uint8, device=dev), status=torch.empty((n,), dtype=torch.uint8, device=dev),
-                         result=torch.empty((n,), dtype=torch.uint8, device=dev), sets=views, **views[0],
-                         gathered=torch.empty(world * row, dtype=torch.uint8, device=dev) if world > 1 else None,
-                         gather_done=None))
+                         result=torch.empty((n,), dtype=torch.uint8, device=dev), sets=views, **views[0]))
     ctx.sync()
     torch.cuda.synchronize()
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
-    KERNELS_PER_STEP = 2   # prover (+ fused proof digest), verifier (+ fused verdict bitmap); plus one 8-byte memset node
+    KERNELS_PER_STEP = 2   # prover (+ fused proof digest), verifier (+ fused verdict bitmap)
+    ctx_v = vstream = None
+    if args.overlap_verify:
+        # the verifier of step k runs on a second context (its own stream) beside the prover of step k + 1: the two touch
+        # different ring slots, and the tail of one kernel fills the SMs the other has not reached yet
+        ctx_v = pbh_b200.Context(device=local, algo=args.algo)
+        vstream = ctx_v.torch_stream()
 
-    def kernels(slot, b=0):
-        w, rd, c, u, first = ins[slot]
-        o = outs[slot]
-        ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
-        ctx.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
-
-    # one CUDA graph per ring slot: the step is four short kernels, so direct launches from Python are launch-bound
-    graphs, launch_mode = None, "direct"
-    if not args.no_graph:
-        try:
-            graphs = []
-            with torch.cuda.stream(stream):
-                for slot in range(ring):
-                    kernels(slot)                      # warm the allocator and the module before capture
-            torch.cuda.synchronize()
-            for slot in range(ring):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=stream):
-                    kernels(slot)
-                graphs.append(g)
-            launch_mode = "cuda_graph"
-        except Exception as e:   # pragma: no cover - capture not supported
-            graphs, launch_mode = None, f"direct (graph capture failed: {type(e).__name__})"
-            torch.cuda.synchronize()
-
-    # Two more graphs, each holding the kernels of a whole ring cycle (ring steps) and writing summary set 0 / 1; one
-    # replay per `ring` steps keeps the host (one Python process per GPU) out of the timed path.  The cycle's summaries
-    # travel in ONE all-gather, enqueued on the side stream behind the cycle, so that it overlaps the next cycle's
-    # kernels: the same bytes as one all-gather per step, one `ring`-th of the collectives.
-    cycle_graphs = None
-    if graphs is not None and not args.no_cycle_graph:
-        try:
-            cycle_graphs = []
-            if args.overlap_verify:
-                # the verifier of step k runs on a second context (its own stream) beside the prover of step k + 1: the two
-                # touch different ring slots, and the tail of one kernel fills the SMs the other has not reached yet
-                ctx_v = pbh_b200.Context(device=local, algo=args.algo)
-                vstream = ctx_v.torch_stream()
-                with torch.cuda.stream(vstream):
-                    for slot in range(ring):
-                        ctx_v.verify_bitmap_batch(outs[slot]["proof"], ins[slot][2], ins[slot][3], outs[slot]["result"], outs[slot]["bitmap"])
-                torch.cuda.synchronize()
-            for b in range(2):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=stream):
-                    if not args.overlap_verify:
-                        for slot in range(ring):
-                            kernels(slot, b)
-                    else:
-                        for slot in range(ring):
-                            w, rd, c, u, first = ins[slot]
-                            o = outs[slot]
-                            ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
-                            proved = torch.cuda.Event()
-                            proved.record(stream)
-                            vstream.wait_event(proved)
-                            with torch.cuda.stream(vstream):
-                                ctx_v.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
-                        stream.wait_stream(vstream)
-                cycle_graphs.append(g)
-            launch_mode = f"cuda_graph ({ring}-step cycle graphs, one all-gather per cycle; per-step graphs for the remainder)"
-            if args.overlap_verify:
-                launch_mode += "; verify(k) on a second stream beside prove(k+1)"
-        except Exception as e:   # pragma: no cover
-            cycle_graphs = None
-            launch_mode += f"; cycle graph unavailable: {type(e).__name__}"
-            torch.cuda.synchronize()
-
-    cycles_run = [0]
-
-    def run_steps(k0, count):
-        """Steps k0 .. k0+count-1 (k0 a multiple of ring): whole cycles through the cycle graphs, the rest step by step."""
-        k = k0
-        if cycle_graphs is not None:
-            while count - (k - k0) >= ring:
-                b = cycles_run[0] % 2
-                cycles_run[0] += 1
-                if cycle_done[b] is not None:
-                    stream.wait_event(cycle_done[b])   # the previous all-gather of this set has read it
-                cycle_graphs[b].replay()
-                if world > 1:
-                    ev_ = torch.cuda.Event()
-                    ev_.record(stream)
-                    comm_stream.wait_event(ev_)
-                    with torch.cuda.stream(comm_stream):
-                        dist.all_gather_into_tensor(gathered_all[b], summary_all[b])   # the only collective
-                        cycle_done[b] = torch.cuda.Event()
-                        cycle_done[b].record(comm_stream)
-                k += ring
-            if k - k0 < count and cycle_done[0] is not None:
-                stream.wait_event(cycle_done[0])       # the remainder steps write set 0
-        while k - k0 < count:
-            step(k)
-            k += 1
-
-    def step(k):
-        slot = k % ring
-        o = outs[slot]
-        if world > 1 and o["gather_done"] is not None:
-            stream.wait_event(o["gather_done"])        # the slot's previous all-gather has read its summary
-        if graphs is not None:
-            graphs[slot].replay()
-        else:
-            kernels(slot)
+    def enqueue_region(steps):
+        """Enqueue exactly `steps` steps on `stream` (+ `vstream`, + the cycle all-gathers on `comm_stream`), joined back into
+        `stream` at the end.  Cycle c (steps c*ring .. c*ring+ring-1, ring slots 0..) writes summary set c % 2; its ONE
+        all-gather overlaps the kernels of cycle c + 1.  Used both directly and under stream capture."""
+        gather_done = {}
+        cycles = (steps + ring - 1) // ring
+        for cyc in range(cycles):
+            b = cyc % 2
+            if world > 1 and cyc >= 2:
+                stream.wait_event(gather_done[cyc - 2])       # the all-gather that read this summary set has finished
+                if vstream is not None:
+                    vstream.wait_event(gather_done[cyc - 2])
+            for slot in range(min(ring, steps - cyc * ring)):
+                w, rd, c, u, first = ins[slot]
+                o = outs[slot]
+                ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
+                if vstream is None:
+                    ctx.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
+                else:
+                    proved = torch.cuda.Event()
+                    proved.record(stream)
+                    vstream.wait_event(proved)
+                    with torch.cuda.stream(vstream):
+                        ctx_v.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
+            if vstream is not None:
+                stream.wait_stream(vstream)
+            if world > 1:
+                ev_ = torch.cuda.Event()
+                ev_.record(stream)
+                comm_stream.wait_event(ev_)
+                with torch.cuda.stream(comm_stream):
+                    dist.all_gather_into_tensor(gathered_all[b], summary_all[b])   # the only collective
+                    gather_done[cyc] = torch.cuda.Event()
+                    gather_done[cyc].record(comm_stream)
         if world > 1:
-            done = torch.cuda.Event()
-            done.record(stream)
-            comm_stream.wait_event(done)
-            with torch.cuda.stream(comm_stream):
-                dist.all_gather_into_tensor(o["gathered"], o["summary"])     # the only collective: bitmaps + digests
-                o["gather_done"] = torch.cuda.Event()
-                o["gather_done"].record(comm_stream)
+            stream.wait_stream(comm_stream)
+        return cycles
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # warm-up (direct launches; also warms NCCL), then capture the K-step region into ONE graph
+    W = max(3, args.warmup)
     with torch.cuda.stream(stream):
-        run_steps(0, max(3, args.warmup) + ring)     # warm-up covers both launch paths
-        if world > 1:
-            stream.wait_stream(comm_stream)
+        enqueue_region(W + ring)
+    barrier()
+    region_graph, launch_mode = None, "direct launches"
+    if not args.no_graph and 2 * K + 64 < 30000:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                enqueue_region(K)
+            region_graph = g
+            launch_mode = (f"one CUDA graph per {K}-step region: {2 * K} kernels" +
+                           (f" + {(K + ring - 1) // ring} NCCL all-gathers (one per {ring}-step cycle, overlapping the next cycle)" if world > 1 else "") +
+                           ("; verify(k) on a second stream beside prove(k+1)" if vstream is not None else ""))
+        except Exception as e:   # pragma: no cover - capture not supported
+            region_graph, launch_mode = None, f"direct launches (graph capture failed: {type(e).__name__}: {e})"
+            torch.cuda.synchronize()
+
+    def run_region():
+        if region_graph is not None:
+            region_graph.replay()
+        else:
+            enqueue_region(K)
+
+    with torch.cuda.stream(stream):
+        run_region()                                  # one untimed replay
     barrier()
 
-    # ---- timed region: exactly K steps, device-timed, max over ranks
+    # ---- timed region: exactly K steps per repetition, device-timed on the launching stream, max over ranks per
+    # repetition, median over repetitions
+    reps = max(1, args.reps)
     sampler = ClockSampler(local)
     sampler.start()
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        t_begin.record(stream)
-        run_steps(0, args.steps)
-        if world > 1:
-            stream.wait_stream(comm_stream)
-        t_end.record(stream)
-    barrier()
-    ms_total = t_begin.elapsed_time(t_end)
-    launches = KERNELS_PER_STEP * args.steps
+    rep_ms = []
+    for _ in range(reps):
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(stream):
+            t_begin.record(stream)
+            run_region()
+            t_end.record(stream)
+        barrier()
+        rep_ms.append(t_begin.elapsed_time(t_end))
     if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        t = torch.tensor(rep_ms, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    value = n * world * args.steps / (ms_total * 1e-3)
+        rep_ms = [float(x) for x in t.tolist()]
+    ms_total = statistics.median(rep_ms)
+    launches = KERNELS_PER_STEP * K * reps
+    value = n * world * K / (ms_total * 1e-3)
+    last_set = (((K + ring - 1) // ring) - 1) % 2       # summary set written by the last cycle of a region
 
     # ---- per-kernel durations for the roofline: each kernel alone, back to back over the ring, CUDA events on its stream
-    def time_kernel(fn, reps):
+    def time_kernel(fn, reps_):
         with torch.cuda.stream(stream):
             for k in range(3):
                 fn(k % ring)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            for k in range(reps):
+            for k in range(reps_):
                 fn(k % ring)
             e1.record(stream)
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+        return e0.elapsed_time(e1) / reps_
 
-    reps = max(10, min(args.steps, 100))
-    prove_ms = time_kernel(lambda s_: ctx.prove_batch(ins[s_][0], ins[s_][1], ins[s_][2], proof=outs[s_]["proof"], status=outs[s_]["status"]), reps)
-    verify_ms = time_kernel(lambda s_: ctx.verify_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], result=outs[s_]["result"]), reps)
+    kreps = max(10, min(K, 100))
+    prove_ms = time_kernel(lambda s_: ctx.prove_batch(ins[s_][0], ins[s_][1], ins[s_][2], proof=outs[s_]["proof"], status=outs[s_]["status"]), kreps)
+    verify_ms = time_kernel(lambda s_: ctx.verify_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], result=outs[s_]["result"]), kreps)
     prove_digest_ms = time_kernel(lambda s_: ctx.prove_digest_batch(ins[s_][0], ins[s_][1], ins[s_][2], outs[s_]["proof"], outs[s_]["status"],
-                                                                    outs[s_]["digest"], first_index=ins[s_][4]), reps)
+                                                                    outs[s_]["digest"], first_index=ins[s_][4]), kreps)
     verify_bitmap_ms = time_kernel(lambda s_: ctx.verify_bitmap_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], outs[s_]["result"],
-                                                                      outs[s_]["bitmap"]), reps)
+                                                                      outs[s_]["bitmap"]), kreps)
     clocks = sampler.stop()
     # the same kernels with per-item curve arithmetic (PBH_ALGO_ARITH: fixed-base MSM commitments, Straus MSM, Miller loops,
     # final exponentiations): reported beside the default group-table algorithm, both bit-exact
@@ -397,23 +407,42 @@ def main():
                  "prove_plus_verify_per_s_per_gpu": n / ((ap_ms + av_ms) * 1e-3)}
 
     # ---- sanity inside the bench: every timed item proved (status 0) and reached the pairing check
-    o = outs[(args.steps - 1) % ring]
+    o = outs[(K - 1) % ring]
     ok_status = int((o["status"] != 0).sum().item()) == 0
     accept = int((o["result"] == 1).sum().item())
     reached = int(((o["result"] == 1) | (o["result"] == 0)).sum().item())
-    # the gathered summaries of the last whole cycle: this rank's slice is its own summary, and every rank's digests are there
-    gather_ok = None
-    if world > 1 and cycle_graphs is not None and cycles_run[0] > 0:
+
+    # ---- check (a): the N-rank result against ONE GPU.  Ring slot 0 of the N ranks is the contiguous global index range
+    # [0, N n): rank 0 recomputes all of it alone and requires gathered bitmap == its bitmap and the sum of the gathered
+    # digests == its digest.  Every rank also finds its own summary at its place in the gathered buffer.
+    gather_ok = sharded_equals_single = None
+    if world > 1:
         torch.cuda.synchronize()
-        b = (cycles_run[0] - 1) % 2
-        g_ = gathered_all[b].view(world, ring, row)
-        digests = g_[:, :, nb:].contiguous().view(torch.int64)
-        gather_ok = bool(torch.equal(g_[rank].reshape(-1), summary_all[b])) and int((digests == 0).sum().item()) == 0 \
-            and int(torch.unique(digests).numel()) == world * ring
+        g_ = gathered_all[last_set].view(world, ring, row)
+        gather_ok = bool(torch.equal(g_[rank].reshape(-1), summary_all[last_set]))
+        flag = torch.tensor([1 if gather_ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = bool(flag.item())
+        if rank == 0:
+            tot = world * n
+            w1, r1, c1, u1 = ctx.generate_inputs(tot, first_index=0, seed=SEED, dist=pbh_b200.DIST_FULLPATH)
+            p1 = torch.empty((27, tot), dtype=torch.uint8, device=dev)
+            s1 = torch.empty((tot,), dtype=torch.uint8, device=dev)
+            v1 = torch.empty((tot,), dtype=torch.uint8, device=dev)
+            b1 = torch.empty((tot // 8,), dtype=torch.uint8, device=dev)
+            d1 = torch.zeros((1,), dtype=torch.int64, device=dev)
+            ctx.prove_digest_batch(w1, r1, c1, p1, s1, d1, first_index=0)
+            ctx.verify_bitmap_batch(p1, c1, u1, v1, b1)
+            ctx.sync()
+            torch.cuda.synchronize()
+            bits_n = g_[:, 0, :nb].reshape(-1)
+            digs_n = g_[:, 0, nb:].contiguous().view(torch.int64).reshape(-1).tolist()
+            sum_n = sum(int(x) & MASK64 for x in digs_n) & MASK64
+            sharded_equals_single = bool(torch.equal(bits_n, b1)) and sum_n == (int(d1.item()) & MASK64)
+            del w1, r1, c1, u1, p1, s1, v1, b1, d1
 
     # ---- the other input distribution of SURVEY.md 8(d): D_uniform (attempt 0 only; ~89 % of the items end in one of the
-    # reference's panics, so warps diverge between the FP32 core and the exact-length integer routine).  Reported beside
-    # the headline, which is on D_fullpath where every item does all the work.
+    # reference's panics).  Reported beside the headline, which is on D_fullpath where every item does all the work.
     d_uniform = None
     if not args.no_uniform:
         uw, ur, uc, uu = ctx.generate_inputs(n, first_index=0, seed=SEED, dist=pbh_b200.DIST_UNIFORM)
@@ -430,8 +459,6 @@ def main():
         del uw, ur, uc, uu, u_proof, u_status, u_result
 
     # ---- Fiat-Shamir variants: same witnesses and blinders, challenges derived on the device
-    # from the SHA-256 transcript; reported beside the headline, not part of it.  With transcript-derived (uniform)
-    # challenges most proofs end in one of the reference's panics; `proofs_produced` says how many did not.
     fs = None
     if args.algo == "table" and not args.no_fs:
         f_proof = torch.empty((27, n), dtype=torch.uint8, device=dev)
@@ -446,53 +473,135 @@ def main():
               "hash": "SHA-256, 5 compressions per proof and per verification"}
         del f_proof, f_status, f_result, f_chal
 
-    # ---- end-to-end through the host-pointer C-ABI calls (pinned host buffers): every rank on its own device
+    # ---- end-to-end through the host-pointer C-ABI calls: every rank on its own device.  Three host-memory cases:
+    #   lanes     page-locked buffers from pbh_host_alloc, pbh_prove_batch_async + pbh_verify_batch_async on two lanes: two
+    #             batches in flight, verify(k) shares the full-duplex link with prove(k+1)           <- the headline `e2e`
+    #   pinned    the same buffers through the two synchronous calls (round 1's number)
+    #   pageable  ordinary numpy arrays (what a Rust Vec<u8> is), the two synchronous calls, staged copies
     e2e = None
     if args.e2e_steps != 0:
-        hw = [torch.empty(t.shape, dtype=torch.uint8).pin_memory() for t in ins[0][:4]]
-        for h, t in zip(hw, ins[0][:4]):
-            h.copy_(t)
-        h_proof = torch.empty((27, n), dtype=torch.uint8).pin_memory()
-        h_status = torch.empty((n,), dtype=torch.uint8).pin_memory()
-        h_result = torch.empty((n,), dtype=torch.uint8).pin_memory()
-        nw, nr, nc, nu = [h.numpy() for h in hw]
+        host_in = [t.cpu().numpy() for t in ins[0][:4]]
 
-        def e2e_step():
-            ctx.prove_batch(nw, nr, nc, proof=h_proof.numpy(), status=h_status.numpy())
-            ctx.verify_batch(h_proof.numpy(), nc, nu, result=h_result.numpy())
+        def alloc_set():
+            hw = [ctx.host_alloc(a.shape) for a in host_in]
+            for h, a in zip(hw, host_in):
+                h[...] = a
+            return dict(w=hw[0], r=hw[1], c=hw[2], u=hw[3], proof=ctx.host_alloc((27, n)), status=ctx.host_alloc((n,)), result=ctx.host_alloc((n,)))
 
-        for _ in range(3):
-            e2e_step()
-        ksteps = args.e2e_steps or max(5, min(args.steps, 50))
+        sets = [alloc_set() for _ in range(2)]
+        ksteps = args.e2e_steps or max(6, min(K, 50))
+
+        def timed(fn, steps_):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(steps_):
+                fn(i)
+            ctx.sync()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+
+        def lanes_step(i):
+            s_ = sets[i % 2]
+            ctx.lane_sync(i % 2)                    # the batch that used these buffers two steps ago is complete
+            ctx.prove_batch_async(i % 2, s_["w"], s_["r"], s_["c"], s_["proof"], s_["status"])
+            ctx.verify_batch_async(i % 2, s_["proof"], s_["c"], s_["u"], s_["result"])
+
+        def pinned_step(i):
+            s_ = sets[0]
+            ctx.prove_batch(s_["w"], s_["r"], s_["c"], proof=s_["proof"], status=s_["status"])
+            ctx.verify_batch(s_["proof"], s_["c"], s_["u"], result=s_["result"])
+
+        pg = dict(proof=np.empty((27, n), np.uint8), status=np.empty((n,), np.uint8), result=np.empty((n,), np.uint8))
+
+        def pageable_step(i):
+            ctx.prove_batch(host_in[0], host_in[1], host_in[2], proof=pg["proof"], status=pg["status"])
+            ctx.verify_batch(pg["proof"], host_in[2], host_in[3], result=pg["result"])
+
+        def fused_step(i):
+            s_ = sets[0]
+            ctx.prove_verify_batch(s_["w"], s_["r"], s_["c"], s_["u"], proof=s_["proof"], status=s_["status"], result=s_["result"])
+
+        for fn in (lanes_step, pinned_step, pageable_step, fused_step):
+            for i in range(3):
+                fn(i)
+            ctx.sync()
+        for s_ in sets:
+            s_["proof"][...] = 0; s_["status"][...] = 255; s_["result"][...] = 255
+        dt_lanes = timed(lanes_step, ksteps)
+        # every byte the lane pipeline produced equals the device-resident path of ring slot 0
+        ref_proof, ref_status, ref_result = (outs[0][k].cpu().numpy() for k in ("proof", "status", "result"))
+        e2e_equal = all(np.array_equal(s_["proof"], ref_proof) and np.array_equal(s_["status"], ref_status) and
+                        np.array_equal(s_["result"], ref_result) for s_ in sets)
+        dt_pinned = timed(pinned_step, ksteps)
+        dt_pageable = timed(pageable_step, max(3, ksteps // 2))
+        e2e_equal = e2e_equal and np.array_equal(pg["proof"], ref_proof) and np.array_equal(pg["result"], ref_result)
+        dt_fused = timed(fused_step, ksteps)
+        per = lambda dt, st: {"value": n * world * st / dt, "ms_per_step": 1e3 * dt / st}
+        e2e = {"value": n * world * ksteps / dt_lanes, "unit": UNIT, "h2d_bytes_per_step": n * (26 + 33) * world,
+               "d2h_bytes_per_step": n * (28 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt_lanes / ksteps,
+               "api": "pbh_prove_batch_async + pbh_verify_batch_async on two lanes (two batches in flight), pbh_lane_sync before a lane's buffers are reused",
+               "host_memory": "page-locked, mapped (pbh_host_alloc); the kernels run in place on it: PBH_OPT_HOST_DIRECT",
+               "numa_node_of_device": ctx.numa_node,
+               "timing": "host wall clock around the C-ABI calls up to the final pbh_ctx_sync, max over ranks",
+               "bytes_equal_device_path": bool(e2e_equal),
+               "two_sync_calls_pinned": dict(per(dt_pinned, ksteps), api="pbh_prove_batch then pbh_verify_batch, page-locked buffers"),
+               "two_sync_calls_pageable": dict(per(dt_pageable, max(3, ksteps // 2)), api="pbh_prove_batch then pbh_verify_batch, pageable numpy buffers (staged chunks)"),
+               "fused_call": dict(per(dt_fused, ksteps), h2d_bytes_per_step=n * 27 * world, d2h_bytes_per_step=n * 29 * world,
+                                  api="pbh_prove_verify_batch (extension: the proof does not cross PCIe twice)")}
+        for s_ in sets:
+            for a in s_.values():
+                ctx.host_free(a)
+        del sets, pg
+
+    # ---- BASELINE.json configs[4]: 2^28 witnesses in total, sharded over the N ranks (strong scaling), ONE all-gather of
+    # the verdict bitmaps + digests at the end of each pass
+    config4 = None
+    if not args.no_config4:
+        tot4 = 1 << args.config4_log2
+        n4 = tot4 // world
+        first4 = rank * n4
+        w4, r4, c4, u4 = ctx.generate_inputs(n4, first_index=first4, seed=SEED, dist=pbh_b200.DIST_FULLPATH)
+        p4 = torch.empty((27, n4), dtype=torch.uint8, device=dev)
+        s4 = torch.empty((n4,), dtype=torch.uint8, device=dev)
+        v4 = torch.empty((n4,), dtype=torch.uint8, device=dev)
+        sum4 = torch.zeros(n4 // 8 + 8, dtype=torch.uint8, device=dev)
+        gat4 = torch.empty(world * (n4 // 8 + 8), dtype=torch.uint8, device=dev) if world > 1 else None
+
+        def pass4():
+            ctx.prove_digest_batch(w4, r4, c4, p4, s4, sum4[n4 // 8:].view(torch.int64), first_index=first4)
+            ctx.verify_bitmap_batch(p4, c4, u4, v4, sum4[:n4 // 8])
+            if world > 1:
+                dist.all_gather_into_tensor(gat4, sum4)
+
+        steps4 = 3
+        with torch.cuda.stream(stream):
+            pass4()
         barrier()
-        t0 = time.perf_counter()
-        for _ in range(ksteps):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        assert np.array_equal(h_status.numpy(), outs[0]["status"].cpu().numpy())
-        # extension: one fused call, the proof does not cross PCIe twice (not the headline: the reference has two calls)
-        for _ in range(2):
-            ctx.prove_verify_batch(nw, nr, nc, nu, proof=h_proof.numpy(), status=h_status.numpy(), result=h_result.numpy())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps4):
+                pass4()
+            e1.record(stream)
         barrier()
-        t0f = time.perf_counter()
-        for _ in range(ksteps):
-            ctx.prove_verify_batch(nw, nr, nc, nu, proof=h_proof.numpy(), status=h_status.numpy(), result=h_result.numpy())
-        torch.cuda.synchronize()
-        dtf = time.perf_counter() - t0f
+        ms4 = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([dtf], dtype=torch.float64, device=dev)
+            t = torch.tensor([ms4], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dtf = float(t.item())
-        e2e = {"value": n * world * ksteps / dt, "unit": UNIT, "h2d_bytes_per_step": n * (26 + 33) * world,
-               "d2h_bytes_per_step": n * (28 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt / ksteps, "host_memory": "pinned (the kernels run in place on it: PBH_OPT_HOST_DIRECT)",
-               "timing": "host wall clock around synchronous C-ABI calls (pbh_prove_batch then pbh_verify_batch), max over ranks",
-               "fused_call": {"value": n * world * ksteps / dtf, "unit": UNIT, "h2d_bytes_per_step": n * 27 * world,
-                              "d2h_bytes_per_step": n * 29 * world, "api": "pbh_prove_verify_batch (extension)"}}
+            ms4 = float(t.item())
+        ok4 = int((s4 != 0).sum().item()) == 0 and int(((v4 != 0) & (v4 != 1)).sum().item()) == 0
+        if world > 1:
+            ok4 = ok4 and bool(torch.equal(gat4.view(world, -1)[rank], sum4))
+        config4 = {"workload": f"BASELINE.json configs[4]: end-to-end prove+verify of 2^{args.config4_log2} witnesses sharded over {world} GPU(s), NCCL all-gather of verdict bitmaps + digests",
+                   "items_total": tot4, "items_per_gpu": n4, "passes": steps4, "ms_per_pass": ms4 / steps4, "value": tot4 * steps4 / (ms4 * 1e-3),
+                   "unit": UNIT, "scaling": "strong", "all_proved_and_reached_pairing": bool(ok4),
+                   "accepted_on_rank0": int((v4 == 1).sum().item())}
+        del w4, r4, c4, u4, p4, s4, v4, sum4, gat4
+        torch.cuda.empty_cache()
 
     def finish():
         """Multi-rank teardown: final barrier, then leave without destroy_process_group() — tearing the communicator down
@@ -508,72 +617,143 @@ def main():
         finish()
         return
 
-    peak, peak_src = measured_peaks()
-    traffic, issue_pct = None, None
-    try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture (profiles/)
-        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            tj = json.load(f)
-        ent = tj.get("prove_f32_tma_kernel") if args.algo == "table" else None
-        if ent and n == N_PER_GPU:
-            traffic = ent["dram_read_bytes"] + ent["dram_write_bytes"]
-            issue_pct = ent.get("issue_active_pct")
-    except Exception:
-        traffic = None
-    prove_gbs = 54.0 * n / (prove_ms * 1e-3) / 1e9
-    verify_gbs = 34.0 * n / (verify_ms * 1e-3) / 1e9
-    prove_name = "prove_f32_tma_kernel" if args.algo == "table" else "prove_kernel<ARITH>"
-    verify_name = "verify_tma_kernel<TABLE>" if args.algo == "table" else "verify_tma_kernel<ARITH>"
-    dominant = prove_name if prove_ms >= verify_ms else verify_name
-    ach = prove_gbs if prove_ms >= verify_ms else verify_gbs
+    # ---- pipe peaks measured in THIS run (independent register chains, no memory traffic)
+    hbm_peak, peak_src = measured_peaks()
     int32 = {}
     try:
-        names = ["imad", "lop3_iadd3", "half_imad_half_alu", "ffma", "hfma2_instr", "dp4a_instr", "imad_hi_iadd", "half_ffma_half_imad", "ffma_3reg", "imad_3reg"]
+        names = ["imad", "lop3_iadd3", "half_imad_half_alu", "ffma", "hfma2_instr", "dp4a_instr", "imad_hi_iadd", "half_ffma_half_imad", "ffma_3reg", "imad_3reg",
+                 "ffma2_3pair_instr", "ffma2_bcast_instr", "shf"]
         int32 = {f"{nm}_thread_ops_per_s": ctx.measure_int32_peak(i) for i, nm in enumerate(names)}
     except Exception as e:  # pragma: no cover
         int32 = {"error": str(e)}
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_hz = 1e6 * float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965)
+    peaks = {"hbm_gbs": hbm_peak,
+             # one warp instruction per clock per SM sub-partition: 4 x 32 thread instructions per clock per SM at the SM clock sampled under load
+             "issue_thread_instr_per_s": sm_count * 128 * sm_hz,
+             "fma_thread_ops_per_s": int32.get("ffma_thread_ops_per_s"),       # FFMA on both FMA pipes (measured above)
+             "imad_thread_ops_per_s": int32.get("imad_thread_ops_per_s"),      # IMAD issues on the heavy FMA pipe only
+             "alu_thread_ops_per_s": int32.get("shf_thread_ops_per_s")}        # SHF = one ALU-pipe instruction per chain step
+    instr = instr_table()
+    kernels_rf = [roofline_entry("prove_f32_tma_kernel<TABLE>" if args.algo == "table" else "prove_f32_tma_kernel<ARITH>",
+                                 "prove_table" if args.algo == "table" else "prove_arith", prove_ms, n, 54, peaks, instr),
+                  roofline_entry("verify_tma_kernel<TABLE>" if args.algo == "table" else "verify_tma_kernel<ARITH>",
+                                 "verify_table" if args.algo == "table" else "verify_arith", verify_ms, n, 34, peaks, instr)]
+    if arith:
+        kernels_rf.append(roofline_entry("prove_f32_tma_kernel<ARITH>", "prove_arith", arith["prove_ms"], n, 54, peaks, instr))
+        kernels_rf.append(roofline_entry("verify_tma_kernel<ARITH>", "verify_arith", arith["verify_ms"], n, 34, peaks, instr))
+    if fs:
+        kernels_rf.append(roofline_entry("prove_fs_kernel<TABLE>", "prove_fs", fs["prove_fs_ms"], n, 49 + 6, peaks, instr))
+        kernels_rf.append(roofline_entry("verify_fs_kernel<TABLE>", "verify_fs", fs["verify_fs_ms"], n, 27 + 1 + 6, peaks, instr))
+    if d_uniform:
+        kernels_rf.append(roofline_entry("prove_f32_tma_kernel<TABLE> on D_uniform", "prove_table_uniform", d_uniform["prove_ms"], n, 54, peaks, instr))
+    dom = max(kernels_rf[:2], key=lambda e: e["ms"])          # the dominant kernel of the step
+    traffic = None
+    try:   # per-launch DRAM bytes of the dominant kernel from the committed ncu capture (profiles/): STATIC
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            tj = json.load(f)
+        ent = tj.get("prove_f32_tma_kernel") if (args.algo == "table" and dom is kernels_rf[0]) else None
+        if ent and n == N_PER_GPU:
+            traffic = ent["dram_read_bytes"] + ent["dram_write_bytes"]
+    except Exception:
+        traffic = None
+    if dom["bound"] == "hbm":
+        rf_main = {"bound": "hbm", "achieved": dom["hbm"]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm"]["frac"]}
+    else:
+        b_ = dom[dom["bound"]]
+        rf_main = {"bound": dom["bound"], "achieved": b_["achieved_thread_instr_per_s"] / 1e12, "peak": b_["peak_thread_instr_per_s"] / 1e12,
+                   "unit": "T thread-instr/s", "frac": b_["frac"]}
 
+    # ---- N = 1 only: BASELINE.json configs[2] (16 M-proof verifier) and configs[3] (kernel sweeps, 2^24 .. 2^28 items)
+    config2 = sweeps = None
+    if world == 1 and not args.no_config2:
+        n2 = 1 << 24
+        w2, r2, c2, u2 = ctx.generate_inputs(n2, first_index=0, seed=SEED, dist=pbh_b200.DIST_FULLPATH)
+        p2, s2 = ctx.prove_batch(w2, r2, c2)
+        v2 = torch.empty((n2,), dtype=torch.uint8, device=dev)
+        v2a = torch.empty((n2,), dtype=torch.uint8, device=dev)
+        ms2 = time_kernel(lambda s_: ctx.verify_batch(p2, c2, u2, result=v2), 5)
+        ctx.set_algo("arith")
+        ms2a = time_kernel(lambda s_: ctx.verify_batch(p2, c2, u2, result=v2a), 3)
+        ctx.set_algo("table")
+        config2 = {"workload": "BASELINE.json configs[2]: batched verifier, 2^24 proofs, one B200", "items": n2, "verify_ms": ms2,
+                   "verifies_per_s": n2 / (ms2 * 1e-3), "hbm_frac": 34.0 * n2 / (ms2 * 1e-3) / 1e9 / hbm_peak,
+                   "arith_verify_ms": ms2a, "arith_verifies_per_s": n2 / (ms2a * 1e-3), "table_equals_arith": bool(torch.equal(v2, v2a)),
+                   "accepted": int((v2 == 1).sum().item()), "all_reached_pairing": int(((v2 != 0) & (v2 != 1)).sum().item()) == 0}
+        del w2, r2, c2, u2, p2, s2, v2, v2a
+        torch.cuda.empty_cache()
+    if world == 1 and not args.no_sweeps:
+        import bench_sweeps
+        sweeps = []
+        for lg in [int(x) for x in args.sweep_log2.split(",") if x]:
+            sweeps.append({"log2_items": lg, "kernels": bench_sweeps.run_sweeps(ctx, lg, reps=5 if lg >= 27 else 10, hbm_peak=hbm_peak, peaks=peaks)})
+            torch.cuda.empty_cache()
+
+    # ---- check (b) and the CPU baseline: the exact 2^20-item batch of ring slot 0 replayed through the oracle, byte for byte
     cpu = None
-    if world == 1 and not args.no_cpu:
+    oracle_full = generator_sample_ok = None
+    if world >= 1 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O
         threads = max(1, O.hardware_threads())
-        vall, dtall = cpu_leg(20000 * threads, threads)     # draws the sample on all threads; the next leg reuses a slice of it
-        v1, dt1 = cpu_leg(20000, 1)
-        cpu = {"value": vall, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{20000 * threads} D_fullpath items, prove then verify, C++ restatement of the reference (oracle/), {threads} threads, {dtall:.1f} s",
-               "single_thread": {"value": v1, "cores": 1, "sample": f"20000 items, {dt1:.1f} s"}}
+        h_w, h_r, h_c, h_u = (t.cpu().numpy() for t in ins[0][:4])
+        t0 = time.perf_counter()
+        o_proof, o_status = O.prove_batch(h_w, h_r, h_c, threads=threads)
+        o_result = O.verify_batch(o_proof, h_c, h_u, threads=threads, want_gt=False)
+        dt_full = time.perf_counter() - t0
+        if isinstance(o_result, tuple):
+            o_result = o_result[0]
+        oracle_full = (np.array_equal(o_proof, outs[0]["proof"].cpu().numpy()) and np.array_equal(o_status, outs[0]["status"].cpu().numpy())
+                       and np.array_equal(o_result, outs[0]["result"].cpu().numpy()))
+        # the device generator against the oracle's on a prefix of the same slot (the oracle needs ~20 attempts per item)
+        g_w, g_r, g_c, g_u = O.generate_inputs(4096, first_index=ins[0][4], seed=SEED, dist=1, threads=threads)[:4]
+        generator_sample_ok = bool(np.array_equal(g_w, h_w[:, :4096]) and np.array_equal(g_r, h_r[:, :4096]) and
+                                   np.array_equal(g_c, h_c[:, :4096]) and np.array_equal(g_u, h_u[:4096]))
+        if world == 1:
+            v1, dt1 = cpu_leg(20000, 1)
+            cpu = {"value": n / dt_full, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"the whole 2^20-item D_fullpath batch of ring slot 0 (the batch the GPU is checked against), prove then verify, C++ restatement of the reference (oracle/), {threads} threads, {dt_full:.1f} s",
+                   "single_thread": {"value": v1, "cores": 1, "sample": f"20000 items, {dt1:.1f} s"}}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32/int32 registers holding exact F_17 / F_101 residues (u8 on the wire)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "items_per_gpu_per_step": n, "algo": args.algo, "distribution": "D_fullpath seed 0xB200",
                    "l2": f"ring of {ring} distinct input/output batches ({ring * n * 88 / 1e6:.0f} MB) cycled, larger than the 126 MB L2",
-                   "parallelism": f"shard x{world}, all-gather of verdict bitmaps + digests" if world > 1 else "single GPU"},
+                   "parallelism": f"shard x{world}, all-gather of verdict bitmaps + digests" if world > 1 else "single GPU",
+                   "timing": f"median of {reps} repetitions of the exactly-{K}-step region (CUDA events on the launching stream, max over ranks per repetition)"},
+        "timed_region_ms": {"median": ms_total, "all_repetitions": rep_ms},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_item": 54 if prove_ms >= verify_ms else 34,
-                     "issue_slot_utilisation_pct_ncu": issue_pct,
+        "roofline": {"bound": rf_main["bound"], "achieved": rf_main["achieved"], "peak": rf_main["peak"], "unit": rf_main["unit"],
+                     "frac": rf_main["frac"], "traffic": traffic, "kernel": dom["kernel"],
+                     "traffic_source": "profiles/roofline_traffic.json (ncu --set full; STATIC, not measured in this run)",
+                     "hbm_frac": dom["hbm"]["frac"], "hbm_achieved_GBps": dom["hbm"]["achieved_GBps"], "hbm_peak_GBps": hbm_peak, "peak_source": peak_src,
+                     "algorithmic_bytes_per_item": dom["hbm"]["algorithmic_bytes_per_item"],
+                     "how": "frac = max over {HBM bytes, issue slots, FMA pipe, ALU pipe} of achieved / peak for the step's dominant kernel; times, clocks "
+                            "and pipe peaks are measured in this run, instructions per item are the committed ncu counts (profiles/instr_per_item.json)",
+                     "peaks_measured_in_this_run": peaks, "kernels": kernels_rf,
                      # the work the reference's algorithm does per item, in its own modular operations
-                     # (mul + add + inv); the kernels execute far fewer instructions for the same bytes
                      "reference_equivalent_modops_per_item": {"prove": 5170 + 3719 + 318, "verify": 3552 + 1309 + 256},
-                     "reference_equivalent_modops_per_s": value * (5170 + 3719 + 318 + 3552 + 1309 + 256),
-                     "note": "the kernel is instruction-issue bound (FP32 FMA dispatch), not HBM bound; see DESIGN.md section 4"},
+                     "reference_equivalent_modops_per_s": value * (5170 + 3719 + 318 + 3552 + 1309 + 256)},
         "launch": launch_mode,
         "kernels": {"how": "each kernel alone, back to back over the ring, CUDA events on the context's stream",
                     "prove_ms": prove_ms, "verify_ms": verify_ms, "prove_with_digest_ms": prove_digest_ms,
                     "verify_with_bitmap_ms": verify_bitmap_ms, "proofs_per_s_per_gpu": n / (prove_ms * 1e-3),
-                    "verifies_per_s_per_gpu": n / (verify_ms * 1e-3), "prove_GBps": prove_gbs, "verify_GBps": verify_gbs,
-                    "prove_hbm_frac": prove_gbs / peak, "verify_hbm_frac": verify_gbs / peak},
+                    "verifies_per_s_per_gpu": n / (verify_ms * 1e-3)},
         "arith_algo_kernels": arith,
         "fiat_shamir_kernels": fs,
         "d_uniform_kernels": d_uniform,
+        "config2_verifier_16m": config2,
+        "config4_256m_sharded": config4,
+        "sweeps": sweeps,
         "int32_peak": int32,
         "cpu_baseline": cpu,
-        "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n, "gathered_summaries_ok": gather_ok},
+        "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n,
+                  "oracle_full_batch": oracle_full, "generator_prefix_equals_oracle": generator_sample_ok,
+                  "gathered_summaries_ok": gather_ok, "sharded_equals_single": sharded_equals_single},
     }
     print(json.dumps(line))
     finish()

@@ -10,8 +10,10 @@
  *  - Plain pointers and sizes only.  Return 0 on success, a negative pbh_error otherwise; nothing
  *    aborts or unwinds across this boundary.  A Rust panic of the reference becomes a per-item
  *    status byte (below), never a process abort.
- *  - One context drives one CUDA device (one process per GPU under torchrun).  A context may be
- *    used from one host thread at a time.
+ *  - One context drives one CUDA device (one process per GPU under torchrun; pbh_multi_* below drives several devices
+ *    from one process).  A context may be used from one host thread at a time.  Launches recorded into CUDA graphs
+ *    (stream capture around `_dev` calls) each hold a tile-scheduler slot for the life of the context (32768 per
+ *    context), and a graph must not be replayed concurrently with itself.
  *  - Batches are structure-of-arrays BYTE PLANES: plane k of an n-item batch is the n bytes at
  *    base + k*pitch (pitch >= n; pitch is in bytes and lets a shard address a column range of a
  *    larger batch without repacking).  One byte per field element: F_17 values 0..16, F_101
@@ -175,6 +177,30 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
                      size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
 int pbh_verify_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
                          size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
+
+/* ---- asynchronous host-pointer calls: lanes ---------------------------------------------------------------------------
+ * Same arguments and results as pbh_prove_batch / pbh_verify_batch, but the call only ENQUEUES the work on lane `lane`
+ * (0 .. PBH_LANES-1) and returns.  Calls on one lane run in issue order, so verify(k) may read the proof that prove(k)
+ * writes when both use the same lane; calls on different lanes overlap - PCIe is full duplex, the download of one batch
+ * travels beside the upload of the next.  Every buffer must stay valid and untouched until pbh_lane_sync(ctx, lane) or
+ * pbh_ctx_sync(ctx) returns.  Only page-locked, mapped buffers (pbh_host_alloc, cudaHostAlloc, cudaHostRegister) are
+ * asynchronous: the kernels run in place on them.  With any other buffer the call waits for the context's earlier work
+ * and then behaves exactly like the synchronous entry point. */
+#define PBH_LANES 4
+int pbh_prove_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand,
+                          size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch,
+                          uint8_t* status);
+int pbh_verify_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                           size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
+int pbh_lane_sync(pbh_ctx* ctx, int lane);
+
+/* Page-locked, mapped host memory for the host-pointer entry points (they then run in place on it, see
+ * PBH_OPT_HOST_DIRECT).  When the platform exposes the NUMA node of the device's PCIe root (sysfs; pbh_ctx_numa_node
+ * returns it, -1 otherwise) the pages are bound to that node before they are locked.  Freed by pbh_host_free or with the
+ * context. */
+int pbh_host_alloc(pbh_ctx* ctx, size_t bytes, void** out);
+int pbh_host_free(pbh_ctx* ctx, void* ptr);
+int pbh_ctx_numa_node(const pbh_ctx* ctx);
 
 /* Extension (no counterpart in the reference): Plonk::prove followed by Plonk::verify of the fresh proofs with
  * challenge `chal` and rand[0] = u, host pointers.  Same bytes as pbh_prove_batch + pbh_verify_batch, but a proof

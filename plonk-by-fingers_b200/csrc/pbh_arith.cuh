@@ -1,9 +1,9 @@
 // pbh_arith.cuh — F_17 / F_101 / G1 / GT arithmetic for the B200 kernels.
 //
 // Everything is `__host__ __device__` so that context creation (host) and the kernels (device) run
-// the same routines.  Values live in 32-bit registers; reductions are multiply-high by a
-// reciprocal (one IMAD.HI + one IMAD), applied lazily: sums of products are accumulated
-// unreduced and reduced once per output.  Inverses come from 17- and 101-byte tables that are
+// the same routines.  Values live in 32-bit registers; reductions are a low multiply by a
+// reciprocal and a shift (IMAD, SHF, IMAD: IMAD.HI is half-rate on sm_100), applied lazily: sums of
+// products are accumulated unreduced and reduced once per output.  Inverses come from 17- and 101-byte tables that are
 // packed into <= 32 shared-memory banks, so a divergent lookup is bank-conflict free.
 //
 // Reference semantics reproduced here (file:line relative to the reference repository):
@@ -57,12 +57,15 @@ PBH_HD uint32_t sub101(uint32_t a, uint32_t b) { return a >= b ? a - b : a + 101
 PBH_HD uint32_t add17(uint32_t a, uint32_t b) { uint32_t s = a + b; return s >= 17u ? s - 17u : s; }
 PBH_HD uint32_t sub17(uint32_t a, uint32_t b) { return a >= b ? a - b : a + 17u - b; }
 
-// Two-point fixed-base tables for PBH_ALGO_ARITH (a width-2 comb over the fixed points): entry a + 17 b of pair j is
-// [a]P_2j + [b]P_2j+1, packed like pt17, so a commitment to L coefficients costs ceil(L/2) lookups and one addition fewer
-// than that.  10.4 KB: kept in global memory (L1-resident) rather than staged into shared memory with `Tables`.
-struct PairTables {
-  uint32_t srs_pair[5][289];    // P_i = g1s[i] (identity beyond the SRS)           src/plonk.rs:51-58
-  uint32_t vfix_pair[4][289];   // P_i = q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s   src/plonk.rs:510-517
+// Three-point fixed-base tables for PBH_ALGO_ARITH (a width-3 comb over the fixed points): entry a + 17 b + 289 c of
+// triple j is [a]P_3j + [b]P_3j+1 + [c]P_3j+2, packed like pt17 (the SRS tables take CENTRED digits: entry
+// (a+8) + 17 (b+8) + 289 (c+8) for a, b, c in [-8, 8], so that the FP32 prover indexes them with two FMAs on its centred
+// residues instead of making each coefficient canonical first), so a commitment to L coefficients costs ceil(L/3) lookups
+// and one addition fewer than that: 11 additions per proof for the nine commitments, 2 for the verifier's nine fixed
+// terms.  7 x 19.2 KB: kept in global memory (L1 / L2 resident), not staged into shared memory with `Tables`.
+struct FixedBaseTables {
+  uint32_t srs_tri[4][4913];    // P_i = g1s[i] (identity beyond the SRS; triple 3 holds g1s[9] alone)   src/plonk.rs:51-58
+  uint32_t vfix_tri[3][4913];   // P_i = q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s, G    src/plonk.rs:510-517
 };
 
 // ---- tables shared by all kernels (one copy in global memory per context, staged into shared memory) ----
@@ -71,6 +74,7 @@ struct Tables {
   uint8_t inv101[128];   // inv101[a] = a^-1 mod 101, inv101[0] = 0
   uint32_t pt17[32];     // [e]G for e < 17 as x | y<<8 | inf<<16     (G = (1,2), src/pbh/g1.rs:71-77)
   float inv17c[32];      // centred inverse mod 17 as a float, indexed by the canonical residue (pbh_prove_f32.cuh)
+  float inv101c[408];    // entry i: centred inverse mod 101 of (i - 202), 0 where that is 0 mod 101 (pbh_g1f.cuh f_inv101)
   // Group-structure tables (PBH_ALGO_TABLE).  E(F_101): y^2 = x^3 + 3 is cyclic of order 102; a point's
   // index is its discrete log to a generator g102 chosen so that G = [6]g102; index 0 is the identity.
   uint8_t y_of_x[128];   // the root y <= 50 of x^3 + 3, 0xFF when x^3 + 3 is a non-residue
@@ -81,7 +85,7 @@ struct Tables {
   // Fixed-base multiples (PBH_ALGO_ARITH): [k]P for k < 17, packed like pt17.
   uint32_t srs_mult[10][17];              // P = g1s[i]                 (src/plonk.rs:51-58)
   uint32_t vfix_mult[9][17];              // q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s, G
-  const PairTables* pairs;                // device (or, in host builds, host) address of the two-point tables
+  const FixedBaseTables* fixed;           // device (or, in host builds, host) address of the three-point tables
 };
 
 // read-only lookup in a global-memory table (through the read-only data cache on the device)

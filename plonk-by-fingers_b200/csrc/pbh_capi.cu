@@ -5,8 +5,14 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <algorithm>
+#include <cctype>
 #include <cstdio>
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -25,6 +31,7 @@ void set_global_error(const std::string& e) { std::lock_guard<std::mutex> l(g_er
 // stream, so the H2D copy of chunk k+2, the kernel of chunk k+1 and the D2H copy of chunk k overlap (PCIe is full duplex).
 static constexpr size_t kChunkMax = (size_t)1 << 20;   // upper bound of the staged chunk (staging buffers are sized for it lazily)
 static constexpr int kSlots = 4;
+static constexpr uint32_t kCounterRing = 4096, kCounterGraphPool = 32768;   // tile-counter pairs (8 bytes each)
 
 struct pbh_ctx {
   int device = 0;
@@ -40,14 +47,22 @@ struct pbh_ctx {
   int verifier_fp32 = 0;                   // PBH_ALGO_TABLE verifier scalars: int32 (0, default: faster since the reductions lost their multiply-high) or FP32 (1)
   HostSetup hs;
   Tables* d_tables = nullptr;
-  PairTables* d_pairs = nullptr;
+  FixedBaseTables* d_pairs = nullptr;
   uint8_t* d_wtab = nullptr;
-  unsigned int* d_tile_counters = nullptr;   // dynamic tile scheduler: [stream index][prove, verify]
+  // dynamic tile scheduler: one {next tile, blocks done} pair PER LAUNCH.  Direct launches take pairs round-robin from a ring
+  // (a pair is reused only kCounterRing launches later, long after the launch that held it has finished: every host-pointer
+  // call synchronises and the last block of a launch resets its pair); launches recorded into a CUDA graph take pairs from a
+  // pool that is never reused, because a captured launch replays for as long as the graph lives.
+  unsigned int* d_tile_counters = nullptr;
+  uint32_t counter_seq = 0, graph_counters_used = 0;
   cudaStream_t compute = nullptr;          // `_dev` entry points
   cudaStream_t slot_stream[kSlots] = {};
   uint8_t* slot_buf[kSlots] = {};
   size_t slot_bytes = 0;
   uint64_t launches = 0;
+  int grid_scale = 2;                      // persistent-grid blocks per SM are grid_scale/2 of the kernel's residency (1: half grids, async lanes)
+  int numa_node = -1;                      // NUMA node of the device's PCIe root (sysfs), -1 when the platform does not say
+  std::map<void*, std::pair<size_t, bool>> host_allocs;   // pbh_host_alloc: pointer -> (bytes, mmap'ed + registered)
   std::string last_error;
 };
 
@@ -64,6 +79,8 @@ struct pbh_ctx {
       return PBH_ERR_CUDA;                                                                       \
     }                                                                                            \
   } while (0)
+
+static int device_numa_node(int device);
 
 static int fail(pbh_ctx* ctx, int code, const char* msg) {
   if (ctx) ctx->last_error = msg; else set_global_error(msg);
@@ -121,15 +138,16 @@ int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_
   cudaDeviceProp prop;
   if ((ce = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", ce);
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->numa_node = device_numa_node(device);
   if ((ce = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
   for (int s = 0; s < kSlots; s++)
     if ((ce = cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", ce);
-  if ((ce = cudaMalloc(&ctx->d_pairs, sizeof(PairTables))) != cudaSuccess) return bail("cudaMalloc(pair tables)", ce);
-  if ((ce = cudaMemcpy(ctx->d_pairs, &ctx->hs.P, sizeof(PairTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(pair tables)", ce);
+  if ((ce = cudaMalloc(&ctx->d_pairs, sizeof(FixedBaseTables))) != cudaSuccess) return bail("cudaMalloc(pair tables)", ce);
+  if ((ce = cudaMemcpy(ctx->d_pairs, &ctx->hs.P, sizeof(FixedBaseTables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(pair tables)", ce);
   if ((ce = cudaMalloc(&ctx->d_tables, sizeof(Tables))) != cudaSuccess) return bail("cudaMalloc(tables)", ce);
   {
     Tables dev_copy = ctx->hs.T;          // the device copy points at the device pair tables, the host copy at the host ones
-    dev_copy.pairs = ctx->d_pairs;
+    dev_copy.fixed = ctx->d_pairs;
     if ((ce = cudaMemcpy(ctx->d_tables, &dev_copy, sizeof(Tables), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(tables)", ce);
   }
   // witness table of the synthetic-input generator: solutions of x^2 + y^2 = z^2 in F_17^3, lexicographic
@@ -139,8 +157,8 @@ int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_
     for (int y = 0; y < 17; y++)
       for (int z = 0; z < 17; z++)
         if ((x * x + y * y) % 17 == (z * z) % 17) { wtab[3 * nw] = x; wtab[3 * nw + 1] = y; wtab[3 * nw + 2] = z; nw++; }
-  if ((ce = cudaMalloc(&ctx->d_tile_counters, (1 + kSlots) * 4 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc(counters)", ce);
-  if ((ce = cudaMemset(ctx->d_tile_counters, 0, (1 + kSlots) * 4 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMemset(counters)", ce);
+  if ((ce = cudaMalloc(&ctx->d_tile_counters, (kCounterRing + kCounterGraphPool) * 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc(counters)", ce);
+  if ((ce = cudaMemset(ctx->d_tile_counters, 0, (kCounterRing + kCounterGraphPool) * 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMemset(counters)", ce);
   if ((ce = cudaMalloc(&ctx->d_wtab, sizeof(wtab))) != cudaSuccess) return bail("cudaMalloc(wtab)", ce);
   if ((ce = cudaMemcpy(ctx->d_wtab, wtab, sizeof(wtab), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(wtab)", ce);
   *out = ctx;
@@ -155,6 +173,8 @@ void pbh_ctx_destroy(pbh_ctx* ctx) {
     if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
   }
   if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); }
+  for (auto& a : ctx->host_allocs) { if (a.second.second) { cudaHostUnregister(a.first); munmap(a.first, a.second.first); } else cudaFreeHost(a.first); }
+  ctx->host_allocs.clear();
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_pairs) cudaFree(ctx->d_pairs);
   if (ctx->d_wtab) cudaFree(ctx->d_wtab);
@@ -225,12 +245,16 @@ int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
   return PBH_OK;
 }
 
-// the tile counter of the launch about to be enqueued on `st` (one pair per stream, so concurrent streams never share),
-// zeroed on that stream
-static unsigned int* fresh_tile_counter(pbh_ctx* ctx, cudaStream_t st, int which) {
-  int idx = 0;
-  for (int s = 0; s < kSlots; s++) if (st == ctx->slot_stream[s]) idx = 1 + s;
-  return ctx->d_tile_counters + (idx * 2 + which) * 2;   // {next tile, blocks done}: self-resetting, zero between launches
+// The {next tile, blocks done} pair of the launch about to be enqueued on `st`: launch-local, zero when the launch starts
+// (the last block of the previous holder reset it).  nullptr when a capturing stream has used up the graph pool.
+static unsigned int* fresh_tile_counter(pbh_ctx* ctx, cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+  if (cap != cudaStreamCaptureStatusNone) {
+    if (ctx->graph_counters_used >= kCounterGraphPool) return nullptr;
+    return ctx->d_tile_counters + (size_t)(kCounterRing + ctx->graph_counters_used++) * 2;
+  }
+  return ctx->d_tile_counters + (size_t)(ctx->counter_seq++ % kCounterRing) * 2;
 }
 
 // ---- TMA tensor maps --------------------------------------------------------------------------------------------
@@ -280,8 +304,9 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint6
     if (make_plane_map(&M.wit, A.wit, A.n, A.wit_pitch, 12) && make_plane_map(&M.rnd, A.rnd, A.n, A.rand_pitch, 9) &&
         make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) && make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27)) {
       size_t tiles = (A.n + kTile - 1) / kTile;
-      int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2);   // persistent: two resident blocks per SM
-      unsigned int* tc = fresh_tile_counter(ctx, st, 0);
+      int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * ctx->grid_scale);   // persistent: two resident blocks per SM (one on the async lanes)
+      unsigned int* tc = fresh_tile_counter(ctx, st);
+      if (!tc) return fail(ctx, PBH_ERR_UNSUPPORTED, "too many launches captured into CUDA graphs from this context");
       unsigned long long* dg = (unsigned long long*)digest;
       // the compile-time instantiation for the reference's own circuit + SRS(2, 6) when the context's constants match it
       const bool special = ctx->pbh_circuit && ctx->specialise;
@@ -328,14 +353,14 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
     if (make_plane_map(&M.proof, A.proof, A.n, A.proof_pitch, 27) && make_plane_map(&M.chal, A.chal, A.n, A.chal_pitch, 5) &&
         make_plane_map(&M.u, A.u, A.n, (A.n + 15) / 16 * 16, 1)) {
       size_t tiles = (A.n + kTile - 1) / kTile;
+      unsigned int* tc = fresh_tile_counter(ctx, st);
+      if (!tc) return fail(ctx, PBH_ERR_UNSUPPORTED, "too many launches captured into CUDA graphs from this context");
       if (ctx->algo == PBH_ALGO_TABLE) {
-        int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 4);
-        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A,
-                                                              fresh_tile_counter(ctx, st, 1));
+        int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2 * ctx->grid_scale);
+        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A, tc);
       } else {
-        int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 3);
-        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A,
-                                                              fresh_tile_counter(ctx, st, 1));
+        int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * (ctx->grid_scale == 2 ? 3 : 2));
+        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A, tc);
       }
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
@@ -425,19 +450,30 @@ static int ensure_slots(pbh_ctx* ctx, size_t bytes_per_item) {
 // cycle through kSlots staging buffers, each with its own stream, so the upload of chunk k+2, the kernels of chunk k+1
 // and the download of chunk k overlap.  `body(lo, m, C, base, stream)` enqueues one chunk of m items starting at item
 // lo into the staging buffer `base` (planes of pitch C) on `stream`.
+// Every body lays its planes out inside kStagePlanes rows of C bytes; the static_asserts next to each body tie its
+// plane offsets to this budget.
+static constexpr size_t kStagePlanes = 128;
 template <class Body>
-static int for_each_chunk(pbh_ctx* ctx, size_t n, Body body) {
-  int rc = ensure_slots(ctx, 128);
+static int for_each_chunk(pbh_ctx* ctx, size_t n, Body body, bool wait = true) {
+  int rc = ensure_slots(ctx, kStagePlanes);
   if (rc) return rc;
   const size_t C = ctx->chunk;
   size_t k = 0;
-  for (size_t lo = 0; lo < n; lo += C, k++) {
+  for (size_t lo = 0; lo < n && rc == PBH_OK; lo += C, k++) {
     const int s = (int)(k % kSlots);
     rc = body(lo, std::min(C, n - lo), C, ctx->slot_buf[s], ctx->slot_stream[s]);
-    if (rc) return rc;
   }
-  for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
-  return PBH_OK;
+  // Also on failure: copies that read or write the caller's buffers may still be in flight, and the caller is free to
+  // release them as soon as this call returns.
+  if (rc != PBH_OK || wait) {
+    const std::string keep = ctx->last_error;
+    for (int s = 0; s < kSlots; s++) {
+      cudaError_t e = cudaStreamSynchronize(ctx->slot_stream[s]);
+      if (e != cudaSuccess && rc == PBH_OK) { ctx->last_error = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e); rc = PBH_ERR_CUDA; }
+    }
+    if (rc != PBH_OK && !keep.empty() && ctx->last_error.empty()) ctx->last_error = keep;
+  }
+  return rc;
 }
 
 // The device-side alias of a host range when the whole range is page-locked and mapped (cudaHostAlloc /
@@ -446,15 +482,34 @@ static int for_each_chunk(pbh_ctx* ctx, size_t n, Body body) {
 // download overlap at 256-item granularity with no staging copy, no pipeline fill/drain and one launch.  Measured on
 // PCIe Gen5 x16 (scripts/time_zero_copy.py): prove 0.83 ms per 2^20 items against 0.97 ms for the best staged chunking
 // (the copy engine pays about a microsecond per row of a pitched copy, which bounds how small a staged chunk can be).
+typedef CUresult (*PointerGetAttributeFn)(void*, CUpointer_attribute, CUdeviceptr);
+static PointerGetAttributeFn pointer_get_attribute_fn() {
+  static PointerGetAttributeFn fn = []() -> PointerGetAttributeFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return (PointerGetAttributeFn)p;
+  }();
+  return fn;
+}
+// The whole span [p, p + span) must lie inside ONE page-locked, mapped allocation or registration: the range the driver
+// reports for the first byte has to cover the last one too (probing the two ends alone would accept two registrations
+// with an unmapped hole between them, and the kernel would fault on the hole).  Anything else takes the staged path.
 static uint8_t* mapped_host_alias(pbh_ctx* ctx, const uint8_t* p, size_t span) {
   if (!ctx->host_direct || !p || span == 0) return nullptr;
-  cudaPointerAttributes lo{}, hi{};
-  if (cudaPointerGetAttributes(&lo, p) != cudaSuccess || cudaPointerGetAttributes(&hi, p + span - 1) != cudaSuccess) {
-    cudaGetLastError();
+  cudaPointerAttributes lo{};
+  if (cudaPointerGetAttributes(&lo, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (lo.type != cudaMemoryTypeHost || !lo.devicePointer) return nullptr;
+  PointerGetAttributeFn attr = pointer_get_attribute_fn();
+  if (!attr) return nullptr;
+  CUdeviceptr start = 0;
+  size_t size = 0;
+  if (attr(&start, CU_POINTER_ATTRIBUTE_RANGE_START_ADDR, (CUdeviceptr)(uintptr_t)lo.devicePointer) != CUDA_SUCCESS ||
+      attr(&size, CU_POINTER_ATTRIBUTE_RANGE_SIZE, (CUdeviceptr)(uintptr_t)lo.devicePointer) != CUDA_SUCCESS)
     return nullptr;
-  }
-  if (lo.type != cudaMemoryTypeHost || hi.type != cudaMemoryTypeHost || !lo.devicePointer || !hi.devicePointer) return nullptr;
-  if ((const uint8_t*)hi.devicePointer - (const uint8_t*)lo.devicePointer != (ptrdiff_t)(span - 1)) return nullptr;
+  const uintptr_t a = (uintptr_t)lo.devicePointer;
+  if (a < (uintptr_t)start || a + span > (uintptr_t)start + size) return nullptr;
   return (uint8_t*)lo.devicePointer;
 }
 
@@ -554,6 +609,142 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
     return PBH_OK;
   });
+}
+
+// plane budgets of the staged bodies (rows of C bytes inside one staging slot, see for_each_chunk)
+static_assert(53 + 1 <= kStagePlanes, "pbh_prove_batch: 12 + 9 + 5 + 27 + 1 planes");
+static_assert(34 + 4 <= kStagePlanes, "pbh_verify_batch: 27 + 5 + 1 + 1 + 4 planes");
+static_assert(55 + 1 <= kStagePlanes, "pbh_prove_verify_batch: 54 + u + result");
+static_assert(49 + 6 <= kStagePlanes && 34 + 4 <= kStagePlanes, "Fiat-Shamir bodies");
+static_assert(96 + sizeof(pbh_proof_record) <= kStagePlanes && 64 + sizeof(pbh_witness_record) <= 96, "record bodies: planes below row 64, records above");
+
+// ---- asynchronous host-pointer calls (include/pbh_b200.h "lanes") ------------------------------------------------------
+// A lane is one of the context's slot streams.  Page-locked, mapped buffers run in place on the lane's stream and the call
+// returns at once; the grids are half the synchronous ones (one prover block and two verifier blocks per SM), so that
+// kernels of different lanes are resident together and the upload of one batch shares the link with the download of
+// another.  Other buffers take the synchronous staged path (copies from pageable memory are synchronous anyway).
+static int lane_stream(pbh_ctx* ctx, int lane, cudaStream_t* st) {
+  if (lane < 0 || lane >= PBH_LANES) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "lane out of range");
+  *st = ctx->slot_stream[lane];
+  return PBH_OK;
+}
+int pbh_prove_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
+                          const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status) {
+  CTX_CHECK(ctx);
+  cudaStream_t st;
+  int rc = lane_stream(ctx, lane, &st);
+  if (rc) return rc;
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const uint8_t *a_wit = mapped_host_alias(ctx, wit, 11 * wit_pitch + n), *a_rnd = mapped_host_alias(ctx, rnd, 8 * rand_pitch + n),
+                *a_chal = mapped_host_alias(ctx, chal, 4 * chal_pitch + n);
+  uint8_t *a_proof = mapped_host_alias(ctx, proof, 26 * proof_pitch + n), *a_status = mapped_host_alias(ctx, status, n);
+  if (a_wit && a_rnd && a_chal && a_proof && a_status) {
+    ProveArgs A{a_wit, wit_pitch, a_rnd, rand_pitch, a_chal, chal_pitch, a_proof, proof_pitch, a_status, n};
+    const int keep = ctx->grid_scale;
+    ctx->grid_scale = 1;
+    rc = launch_prove(ctx, st, A);
+    ctx->grid_scale = keep;
+    return rc;
+  }
+  rc = pbh_ctx_sync(ctx);   // the staged path shares the slot streams with the lanes
+  if (rc) return rc;
+  return pbh_prove_batch(ctx, n, wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, proof, proof_pitch, status);
+}
+int pbh_verify_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                           size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch) {
+  CTX_CHECK(ctx);
+  cudaStream_t st;
+  int rc = lane_stream(ctx, lane, &st);
+  if (rc) return rc;
+  if (n == 0) return PBH_OK;
+  if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  const uint8_t *a_proof = mapped_host_alias(ctx, proof, 26 * proof_pitch + n), *a_chal = mapped_host_alias(ctx, chal, 4 * chal_pitch + n),
+                *a_u = mapped_host_alias(ctx, u, n);
+  uint8_t *a_res = mapped_host_alias(ctx, result, n), *a_gt = gt ? mapped_host_alias(ctx, gt, 3 * gt_pitch + n) : nullptr;
+  if (a_proof && a_chal && a_u && a_res && (!gt || a_gt)) {
+    VerifyArgs A{a_proof, proof_pitch, a_chal, chal_pitch, a_u, a_res, a_gt, gt_pitch, n, nullptr};
+    const int keep = ctx->grid_scale;
+    ctx->grid_scale = 1;
+    rc = launch_verify(ctx, st, A);
+    ctx->grid_scale = keep;
+    return rc;
+  }
+  rc = pbh_ctx_sync(ctx);
+  if (rc) return rc;
+  return pbh_verify_batch(ctx, n, proof, proof_pitch, chal, chal_pitch, u, result, gt, gt_pitch);
+}
+int pbh_lane_sync(pbh_ctx* ctx, int lane) {
+  CTX_CHECK(ctx);
+  cudaStream_t st;
+  int rc = lane_stream(ctx, lane, &st);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(st));
+  return PBH_OK;
+}
+
+// ---- page-locked, mapped host memory next to the device ------------------------------------------------------------------
+// NUMA node of the device's PCIe root from sysfs (-1: the platform, e.g. a virtual machine, does not expose one)
+static int device_numa_node(int device) {
+  char id[32] = {0};
+  if (cudaDeviceGetPCIBusId(id, sizeof id, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+  for (char* c = id; *c; c++) *c = (char)std::tolower((unsigned char)*c);
+  std::string path = std::string("/sys/bus/pci/devices/") + id + "/numa_node";
+  FILE* f = std::fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (std::fscanf(f, "%d", &node) != 1) node = -1;
+  std::fclose(f);
+  return node;
+}
+int pbh_ctx_numa_node(const pbh_ctx* ctx) { return ctx ? ctx->numa_node : PBH_ERR_BAD_ARGUMENT; }
+
+int pbh_host_alloc(pbh_ctx* ctx, size_t bytes, void** out) {
+  CTX_CHECK(ctx);
+  if (!out || bytes == 0) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer or zero size");
+  *out = nullptr;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (ctx->numa_node >= 0 && ctx->numa_node < 1024) {
+    // pages bound to the device's node (mbind, MPOL_BIND = 2), touched, then page-locked and mapped
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE), len = (bytes + page - 1) / page * page;
+    void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p != MAP_FAILED) {
+      unsigned long mask[16] = {0};
+      mask[ctx->numa_node / (8 * sizeof(unsigned long))] |= 1ul << (ctx->numa_node % (8 * sizeof(unsigned long)));
+      const long mb = syscall(SYS_mbind, p, len, 2 /* MPOL_BIND */, mask, (unsigned long)(8 * sizeof mask), 0u);
+      if (mb == 0) {
+        for (size_t o = 0; o < len; o += page) static_cast<volatile uint8_t*>(p)[o] = 0;
+        if (cudaHostRegister(p, len, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
+          ctx->host_allocs[p] = {len, true};
+          *out = p;
+          return PBH_OK;
+        }
+        cudaGetLastError();
+      }
+      munmap(p, len);
+    }
+  }
+  void* p = nullptr;
+  CUDA_TRY(ctx, cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+  ctx->host_allocs[p] = {bytes, false};
+  *out = p;
+  return PBH_OK;
+}
+int pbh_host_free(pbh_ctx* ctx, void* p) {
+  CTX_CHECK(ctx);
+  if (!p) return PBH_OK;
+  auto it = ctx->host_allocs.find(p);
+  if (it == ctx->host_allocs.end()) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "not a pbh_host_alloc pointer of this context");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = pbh_ctx_sync(ctx);
+  if (it->second.second) { cudaHostUnregister(p); munmap(p, it->second.first); } else cudaFreeHost(p);
+  ctx->host_allocs.erase(it);
+  return rc;
 }
 
 // ---- Fiat-Shamir entry points -----------------------------------------------------------------
@@ -905,7 +1096,29 @@ int pbh_poly_mul_batch(pbh_ctx* ctx, size_t n, uint32_t la, uint32_t lb, const u
     d_out = stg.in<uint8_t>(nullptr, 0, n, la + lb - 1, ce); CUDA_TRY(ctx, ce);
     ap = bp = op = n;
   }
-  poly_mul_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, la, lb, d_a, ap, d_b, bp, d_out, op);
+  // operands up to 8 coefficients, 4-byte aligned planes: four items per word in the size-specialised FP32 kernel; the
+  // ragged tail (n % 4 items) and everything else go through the general kernel
+  const bool vec_ok = la <= 8 && lb <= 8 && ((uintptr_t)d_a % 4 == 0) && ((uintptr_t)d_b % 4 == 0) && ((uintptr_t)d_out % 4 == 0) && (ap % 4 == 0) &&
+                      (bp % 4 == 0) && (op % 4 == 0);
+  const size_t n4 = vec_ok ? n / 4 : 0;
+  if (n4) {
+    const int grid = grid_for(ctx, n4, 8);
+#define PBH_MUL_CASE(LA, LB) poly_mul_vec_kernel<LA, LB><<<grid, kBlock, 0, ctx->compute>>>(n4, la, lb, d_a, ap, d_b, bp, d_out, op)
+#define PBH_MUL_ROW(LA)                                                                     \
+    switch ((lb + 1) / 2) { case 1: PBH_MUL_CASE(LA, 2); break; case 2: PBH_MUL_CASE(LA, 4); break; \
+                            case 3: PBH_MUL_CASE(LA, 6); break; default: PBH_MUL_CASE(LA, 8); break; }
+    switch ((la + 1) / 2) {
+      case 1: PBH_MUL_ROW(2); break;
+      case 2: PBH_MUL_ROW(4); break;
+      case 3: PBH_MUL_ROW(6); break;
+      default: PBH_MUL_ROW(8); break;
+    }
+#undef PBH_MUL_ROW
+#undef PBH_MUL_CASE
+    ctx->launches++;
+  }
+  if (n4 * 4 < n) poly_mul_kernel<<<grid_for(ctx, n - n4 * 4, 8), kBlock, 0, ctx->compute>>>(n - n4 * 4, la, lb, d_a + n4 * 4, ap, d_b + n4 * 4, bp, d_out + n4 * 4, op);
+  else ctx->launches--;   // SWEEP_FINISH counts one launch
   SWEEP_FINISH(ctx);
   if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, la + lb - 1)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
   return PBH_OK;

@@ -50,8 +50,9 @@ __device__ __forceinline__ void digest_flush(unsigned long long acc, unsigned lo
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
-// Dynamic tile scheduler state: c[0] = next tile, c[1] = blocks finished.  Both are zero between launches: the last
-// block to leave resets them, so no memset node is needed per launch (launches sharing a counter pair are stream-ordered).
+// Dynamic tile scheduler state: c[0] = next tile, c[1] = blocks finished.  The pair is launch-local (the host hands every
+// launch its own, pbh_capi.cu: fresh_tile_counter) and zero when the launch starts: the last block to leave resets it, so
+// a launch recorded into a CUDA graph finds it zero again at every replay and no memset node is needed.
 __device__ __forceinline__ void tile_scheduler_leave(unsigned int* c) {
   if (threadIdx.x == 0) {
     __threadfence();
@@ -670,6 +671,33 @@ __global__ void __launch_bounds__(kBlock) mul_ntt_kernel(size_t n, uint32_t modu
 // monic linear divisors of src/plonk.rs:437-442) over F_17: `len` coefficient planes followed by one operand plane
 // (the scalar, the point, c), four items per 32-bit word.  OP 0: len planes out; OP 1: one plane out; OP 2: len - 1
 // quotient planes then the remainder plane (a Horner chain whose intermediate values are the quotient).
+//
+// Arithmetic: every item has its OWN multiplier, which rules out byte-lane SWAR multiplies, and one int32 multiply +
+// reduction per byte made round 1's version ALU-bound at 94-175 instructions per item (profiles/r02a_sweeps_before.txt).
+// Here two items share one packed-half instruction: a byte b becomes the half 1024 + b by planting the exponent byte 0x64
+// next to it (one PRMT for two lanes), all values are integers below 2048 in magnitude and therefore exact in fp16, and
+// x mod 17 is three HFMA2-class instructions for two lanes (round(x / 17) with the 1536 = 1.5 * 2^10 rounding constant,
+// exact for |x| <= 2048: checked for every integer of the range by tests/test_hostemul_parity.py).  Any input byte is
+// accepted: |acc * x + c| <= 8 * 8 + 255 and |c * x| <= 255 * 8.
+__device__ __forceinline__ __half2 h2_bits(uint32_t b) { return *reinterpret_cast<__half2*>(&b); }
+__device__ __forceinline__ uint32_t h2_word(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// bytes (0, 1) or (2, 3) of w as two exact halves
+__device__ __forceinline__ __half2 h2_from_bytes(uint32_t w, bool upper) {
+  return __hsub2(h2_bits(__byte_perm(w, 0x64646464u, upper ? 0x4342u : 0x4140u)), h2_bits(0x64006400u));
+}
+// centred residue mod 17 of two exact integers |x| <= 2048
+__device__ __forceinline__ __half2 h2_red17(__half2 x) {
+  const __half2 k = h2_bits(0x66006600u);                                 // 1536, 1536
+  const __half2 q = __hsub2(__hfma2(x, h2_bits(0x2B882B88u), k), k);      // 0x2B88 = fp16(1 / 17) = 0.05883789
+  return __hfma2(q, h2_bits(0xCC40CC40u), x);                             // 0xCC40 = -17
+}
+// four centred residues -> canonical bytes 0..16 packed in one word
+__device__ __forceinline__ uint32_t h2_pack_canon(__half2 a01, __half2 a23) {
+  const __half2 zero = h2_bits(0u), p17 = h2_bits(0x4C404C40u), bias = h2_bits(0x64006400u);
+  a01 = __hadd2(__hfma2(__hlt2(a01, zero), p17, a01), bias);
+  a23 = __hadd2(__hfma2(__hlt2(a23, zero), p17, a23), bias);
+  return __byte_perm(h2_word(a01), h2_word(a23), 0x6420u);
+}
 template <int OP>
 __global__ void __launch_bounds__(kBlock) poly_unary_kernel(size_t n, uint32_t len, const uint8_t* __restrict__ in, size_t in_pitch,
                                                              uint8_t* __restrict__ out, size_t out_pitch, bool vec_ok) {
@@ -677,9 +705,8 @@ __global__ void __launch_bounds__(kBlock) poly_unary_kernel(size_t n, uint32_t l
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
     const uint32_t opw = reinterpret_cast<const uint32_t*>(in + (size_t)len * in_pitch)[q];
-    uint32_t x[4], acc[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 4; j++) x[j] = mod17((opw >> (8 * j)) & 0xFFu);
+    const __half2 x01 = h2_red17(h2_from_bytes(opw, false)), x23 = h2_red17(h2_from_bytes(opw, true));
+    __half2 acc01 = h2_bits(0u), acc23 = h2_bits(0u);
     // eight planes' loads are issued before any is consumed (bytes in flight, not arithmetic, bound these kernels)
     if (OP == 0) {
       for (uint32_t k0 = 0; k0 < len; k0 += 8) {
@@ -688,13 +715,9 @@ __global__ void __launch_bounds__(kBlock) poly_unary_kernel(size_t n, uint32_t l
         for (uint32_t j = 0; j < 8; j++) w[j] = k0 + j < len ? reinterpret_cast<const uint32_t*>(in + (size_t)(k0 + j) * in_pitch)[q] : 0u;
 #pragma unroll
         for (uint32_t j = 0; j < 8; j++) {
-          if (k0 + j < len) {
-            const uint32_t r = swar_mod17(w[j]);
-            uint32_t o = 0;
-#pragma unroll
-            for (int l = 0; l < 4; l++) o |= mod17(((r >> (8 * l)) & 0xFFu) * x[l]) << (8 * l);
-            reinterpret_cast<uint32_t*>(out + (size_t)(k0 + j) * out_pitch)[q] = o;
-          }
+          if (k0 + j < len)
+            reinterpret_cast<uint32_t*>(out + (size_t)(k0 + j) * out_pitch)[q] =
+                h2_pack_canon(h2_red17(__hmul2(h2_from_bytes(w[j], false), x01)), h2_red17(__hmul2(h2_from_bytes(w[j], true), x23)));
         }
       }
     } else {
@@ -706,14 +729,13 @@ __global__ void __launch_bounds__(kBlock) poly_unary_kernel(size_t n, uint32_t l
         for (uint32_t j = 0; j < 8; j++) {
           if (j < k0) {
             const uint32_t k = k0 - 1 - j;
-            if (OP == 2 && k + 1 < len) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = acc[0] | (acc[1] << 8) | (acc[2] << 16) | (acc[3] << 24);
-            const uint32_t r = swar_mod17(w[j]);
-#pragma unroll
-            for (int l = 0; l < 4; l++) acc[l] = mod17(acc[l] * x[l] + ((r >> (8 * l)) & 0xFFu));
+            if (OP == 2 && k + 1 < len) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = h2_pack_canon(acc01, acc23);
+            acc01 = h2_red17(__hfma2(acc01, x01, h2_from_bytes(w[j], false)));
+            acc23 = h2_red17(__hfma2(acc23, x23, h2_from_bytes(w[j], true)));
           }
         }
       }
-      reinterpret_cast<uint32_t*>(out + (size_t)(OP == 2 ? len - 1 : 0) * out_pitch)[q] = acc[0] | (acc[1] << 8) | (acc[2] << 16) | (acc[3] << 24);
+      reinterpret_cast<uint32_t*>(out + (size_t)(OP == 2 ? len - 1 : 0) * out_pitch)[q] = h2_pack_canon(acc01, acc23);
     }
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -751,6 +773,53 @@ __global__ void __launch_bounds__(kBlock) poly_mul_kernel(size_t n, uint32_t la,
           if (j <= k && k - j < 16) acc += av[j] * bv[k - j];
         }
         out[(size_t)k * out_pitch + i] = (uint8_t)mod17(acc);
+      }
+    }
+  }
+}
+
+// The same product for LA, LB <= 8 (padded to even sizes by the host), four items per 32-bit word and exact FP32
+// arithmetic: round 1's kernel above keeps its operand lengths in registers and executed 560 instructions per 6 x 6 product
+// (profiles/r02a_sweeps_before.txt).  Input bytes are used as they are (any value: 8 x 255^2 < 2^20), every output is
+// reduced once with a FLOOR reduction that lands on the canonical residue 0..16 directly (the operands are non-negative:
+// q = rint(x / 17 - 0.48) is floor(x / 17) because the fractional parts of x / 17 are multiples of 1 / 17), and the four
+// lanes of an output word are packed by planting them under the 2^23 exponent.
+__device__ __forceinline__ float f_byte(uint32_t w, int k) { return __int_as_float((int)__byte_perm(w, 0x4B000000u, 0x7440u + (uint32_t)k)) - 8388608.0f; }
+__device__ __forceinline__ uint32_t f_floor_mod17_biased(float x) {      // bits of 2^23 + (x mod 17) for an exact integer 0 <= x < 2^20
+  const float q = fmaf(x, 0.058823529411764705f, 12582912.0f - 0.48f) - 12582912.0f;
+  return (uint32_t)__float_as_int(fmaf(q, -17.0f, x) + 8388608.0f);
+}
+template <int LA, int LB>
+__global__ void __launch_bounds__(kBlock) poly_mul_vec_kernel(size_t n4, uint32_t la, uint32_t lb, const uint8_t* __restrict__ a, size_t a_pitch,
+                                                               const uint8_t* __restrict__ b, size_t b_pitch, uint8_t* __restrict__ out,
+                                                               size_t out_pitch) {
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (size_t)gridDim.x * blockDim.x) {
+    uint32_t aw[LA], bw[LB];
+#pragma unroll
+    for (int k = 0; k < LA; k++) aw[k] = (uint32_t)k < la ? reinterpret_cast<const uint32_t*>(a + (size_t)k * a_pitch)[q] : 0u;
+#pragma unroll
+    for (int k = 0; k < LB; k++) bw[k] = (uint32_t)k < lb ? reinterpret_cast<const uint32_t*>(b + (size_t)k * b_pitch)[q] : 0u;
+    float av[4][LA], bv[4][LB];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+#pragma unroll
+      for (int k = 0; k < LA; k++) av[l][k] = f_byte(aw[k], l);
+#pragma unroll
+      for (int k = 0; k < LB; k++) bv[l][k] = f_byte(bw[k], l);
+    }
+#pragma unroll
+    for (int k = 0; k < LA + LB - 1; k++) {
+      if ((uint32_t)k < la + lb - 1) {
+        uint32_t r[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int i = 0; i < LA; i++)
+            if (k - i >= 0 && k - i < LB) acc = fmaf(av[l][i], bv[l][k - i], acc);
+          r[l] = f_floor_mod17_biased(acc);
+        }
+        reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = __byte_perm(__byte_perm(r[0], r[1], 0x0040u), __byte_perm(r[2], r[3], 0x0040u), 0x5410u);
       }
     }
   }
@@ -830,11 +899,14 @@ __global__ void __launch_bounds__(kBlock) g1_smul_kernel(const Tables* __restric
   __shared__ Tables sT;
   stage_tables(sT, gT);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    G1 p;
-    p.x = in[i] % 101u; p.y = in[in_pitch + i] % 101u; p.inf = in[2 * in_pitch + i] != 0;
-    uint32_t k = in[3 * in_pitch + i] % 101u;
-    G1 r = g1_smul<7>(p, k, sT.inv101);
-    out[i] = (uint8_t)r.x; out[out_pitch + i] = (uint8_t)r.y; out[2 * out_pitch + i] = (uint8_t)r.inf;
+    // exact FP32 curve arithmetic (pbh_g1f.cuh): every multiple of one point lies on one curve y^2 = x^3 + b', whatever b' is
+    // (the addition formulas never use b), so the unified slope serves any (x, y), on the reference's curve or not
+    F32* tag = nullptr;
+    G1F<F32> p;
+    p.x = f_from_u32(in[i] % 101u, tag); p.y = f_from_u32(in[in_pitch + i] % 101u, tag); p.inf = in[2 * in_pitch + i] != 0;
+    const uint32_t k = in[3 * in_pitch + i] % 101u;
+    const G1F<F32> r = g1f_smul<7>(p, k, sT.inv101c);
+    out[i] = (uint8_t)f_canon101(r.x); out[out_pitch + i] = (uint8_t)f_canon101(r.y); out[2 * out_pitch + i] = (uint8_t)(r.inf ? 1 : 0);
   }
 }
 
@@ -865,7 +937,7 @@ __global__ void __launch_bounds__(kBlock) kzg_commit_kernel(const Consts K, cons
     uint32_t c[7];
 #pragma unroll
     for (int k = 0; k < 7; k++) c[k] = mod17(in[(size_t)k * in_pitch + i]);
-    uint32_t w = commit<ALGO>(c, K, sT);
+    uint32_t w = (ALGO == ALGO_TABLE) ? commit<ALGO_TABLE>(c, K, sT) : commit_pairs_f32<7>(c, sT);
     if (longer_than(c, K.n_pts)) w = 0xFF0000u;
     out[i] = (uint8_t)(w & 0xFF); out[out_pitch + i] = (uint8_t)((w >> 8) & 0xFF); out[2 * out_pitch + i] = (uint8_t)(w >> 16);
   }
@@ -912,11 +984,12 @@ __global__ void __launch_bounds__(kBlock) pairing_kernel(const Tables* __restric
   __shared__ Tables sT;
   stage_tables(sT, gT);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    G1 p;
-    p.x = in[i] % 101u; p.y = in[in_pitch + i] % 101u; p.inf = in[2 * in_pitch + i] != 0;
-    uint32_t qa = in[3 * in_pitch + i] % 101u, qb = in[4 * in_pitch + i] % 101u;
-    GT e = pairing(p, qa, qb, sT.inv101);
-    out[i] = (uint8_t)e.a; out[out_pitch + i] = (uint8_t)e.b;
+    F32* tag = nullptr;
+    G1F<F32> p;
+    p.x = f_from_u32(in[i] % 101u, tag); p.y = f_from_u32(in[in_pitch + i] % 101u, tag); p.inf = in[2 * in_pitch + i] != 0;
+    const F32 qa = f_from_u32(in[3 * in_pitch + i] % 101u, tag), qb = f_from_u32(in[4 * in_pitch + i] % 101u, tag);
+    const GTF<F32> e = pairingf(p, qa, qb, sT.inv101c);
+    out[i] = (uint8_t)f_canon101(e.a); out[out_pitch + i] = (uint8_t)f_canon101(e.b);
   }
 }
 
@@ -1002,9 +1075,10 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-// Digest of one item: FNV-1a-style 64-bit mixing over the item's bytes packed four planes per 32-bit word, seeded
-// with the global item index, finished with splitmix64.  The batch digest is the sum over items modulo 2^64, so
-// digests of disjoint shards add up to the digest of the whole batch.
+// Digest of one item (include/pbh_b200.h, digest_item_* above): two 32-bit lanes seeded with the global item index,
+// murmur3-style multiply / rotate rounds over the item's bytes packed four planes per 32-bit word, murmur3 finaliser.
+// The batch digest is the sum over items modulo 2^64, so digests of disjoint shards add up to the digest of the whole
+// batch.
 // vec_ok: data and pitch are 4-byte aligned, so a thread takes four consecutive items through one 32-bit word per
 // plane (128-byte warp transactions, four independent loads in flight) and transposes 4x4 bytes with PRMT.
 __global__ void __launch_bounds__(kBlock) digest_kernel(size_t n, uint64_t first_index, uint32_t planes,
@@ -1219,15 +1293,16 @@ __global__ void __launch_bounds__(kBlock) mac3_peak_kernel(uint32_t iters, uint3
     float r = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
     if (r == 12345.678f) sink[0] = 1;
   } else {
-    uint32_t x0 = seed + threadIdx.x, x1 = x0 * 3u, x2 = x0 * 5u, x3 = x0 * 7u, y0 = seed ^ 0x55u, y1 = y0 * 3u, y2 = y0 * 5u, y3 = y0 * 7u;
-    uint32_t c0 = 0, c1 = 1, c2 = 2, c3 = 3, c4 = 4, c5 = 5, c6 = 6, c7 = 7;
+    uint32_t x0 = seed + threadIdx.x, y0 = seed ^ 0x55u;
+    uint32_t c0 = x0, c1 = x0 * 3u + 1u, c2 = x0 * 5u + 2u, c3 = x0 * 7u + 3u, c4 = y0 | 1u, c5 = y0 * 3u + 5u, c6 = y0 * 5u + 6u, c7 = y0 * 7u + 7u;
     for (uint32_t it = 0; it < iters; it++) {
 #pragma unroll
       for (int rep = 0; rep < 8; rep++) {
-        c0 = x0 * y0 + c0; c1 = x0 * y1 + c1; c2 = x1 * y2 + c2; c3 = x1 * y3 + c3;
-        c4 = x2 * y0 + c4; c5 = x2 * y1 + c5; c6 = x3 * y2 + c6; c7 = x3 * y3 + c7;
+        // every multiplicand is itself an accumulator of the previous repetition, so that ptxas can neither hoist the
+        // products out of the unrolled body nor turn the chain into a multiply by 8 (round 1 measured a folded loop)
+        c0 = c4 * c5 + c0; c1 = c5 * c6 + c1; c2 = c6 * c7 + c2; c3 = c7 * c4 + c3;
+        c4 = c0 * c1 + c4; c5 = c1 * c2 + c5; c6 = c2 * c3 + c6; c7 = c3 * c0 + c7;
       }
-      x0 += c7 >> 31; y0 += c0 >> 31;
     }
     uint32_t r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
     if (r == 0x12345678u) sink[0] = r;

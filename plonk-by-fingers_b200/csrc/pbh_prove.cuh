@@ -81,6 +81,17 @@ PBH_HD void ntt4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t (&
   e[3] = mod17(c0 + 13u * c1 + 16u * c2 + 4u * c3);
 }
 
+// index of the canonical coefficients 3J, 3J+1, 3J+2 (those below L) in a three-point SRS table, whose digits are the
+// centred residues plus 8 (FixedBaseTables)
+PBH_HD uint32_t tri_digit(uint32_t c) { return c <= 8u ? c + 8u : c - 9u; }
+template <int L, int J>
+PBH_HD uint32_t tri_index(const uint32_t (&c)[L]) {
+  uint32_t idx = (3 * J < L) ? tri_digit(c[(3 * J < L) ? 3 * J : 0]) : 8u;
+  idx += 17u * ((3 * J + 1 < L) ? tri_digit(c[(3 * J + 1 < L) ? 3 * J + 1 : 0]) : 8u);
+  idx += 289u * ((3 * J + 2 < L) ? tri_digit(c[(3 * J + 2 < L) ? 3 * J + 2 : 0]) : 8u);
+  return idx;
+}
+
 // SRS::eval_at_s (src/plonk.rs:51-58) of a zero-padded coefficient array, as a packed point x | y<<8 | inf<<16.
 //   TABLE: every g1s[i] is [d_i]G, so the commitment is [sum c_i d_i mod 17]G — one conflict-free lookup.
 //   ARITH: per-term fixed-base multiples [c_i]g1s[i] added with the affine group law.
@@ -92,13 +103,13 @@ PBH_HD uint32_t commit(const uint32_t (&c)[L], const Consts& K, const Tables& T)
     for (int i = 0; i < L; i++) e += c[i] * K.srs_dlog[i];
     return T.pt17[mod17(e)];
   } else {
-    // two coefficients per lookup (PairTables), the first lookup needs no addition
+    // three coefficients per lookup (FixedBaseTables), the first lookup needs no addition
     static_assert(L >= 2 && L <= 10, "the SRS tables cover 10 points");
-    G1 acc = g1_unpack(pair_lookup(T.pairs->srs_pair[0], c[0] + 17u * c[1]));
+    G1 acc = g1_unpack(pair_lookup(T.fixed->srs_tri[0], tri_index<L, 0>(c)));
 #pragma unroll
-    for (int j = 1; j < (L + 1) / 2; j++) {
-      const uint32_t hi = (2 * j + 1 < L) ? c[(2 * j + 1 < L) ? 2 * j + 1 : 0] : 0u;
-      acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->srs_pair[j], c[2 * j] + 17u * hi)), T.inv101);
+    for (int j = 1; j < (L + 2) / 3; j++) {
+      const uint32_t idx = j == 1 ? tri_index<L, 1>(c) : (j == 2 ? tri_index<L, 2>(c) : tri_index<L, 3>(c));
+      acc = g1_add(acc, g1_unpack(pair_lookup(T.fixed->srs_tri[j], idx)), T.inv101);
     }
     return g1_pack(acc);
   }

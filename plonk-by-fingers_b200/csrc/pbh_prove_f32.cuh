@@ -19,59 +19,10 @@
 #include <math.h>
 
 #include "pbh_prove.cuh"
+#include "pbh_f32.cuh"
+#include "pbh_g1f.cuh"
 
 namespace pbh {
-
-// ---- scalar policy: plain float -------------------------------------------------------------------------------------
-struct F32 {
-  float v;
-  PBH_HD F32() : v(0.f) {}
-  PBH_HD explicit F32(float x) : v(x) {}
-};
-PBH_HD F32 f_const(float c, F32*) { return F32(c); }
-PBH_HD F32 f_fma(F32 a, F32 b, F32 c) { return F32(fmaf(a.v, b.v, c.v)); }
-PBH_HD F32 f_mul(F32 a, F32 b) { return F32(a.v * b.v); }
-PBH_HD F32 f_add(F32 a, F32 b) { return F32(a.v + b.v); }
-PBH_HD F32 f_sub(F32 a, F32 b) { return F32(a.v - b.v); }
-PBH_HD F32 f_red(F32 x) {
-  float t = fmaf(x.v, 0.058823529411764705f, 12582912.0f);
-  float q = t - 12582912.0f;
-  return F32(fmaf(q, -17.0f, x.v));
-}
-PBH_HD bool f_is_zero(F32 x) { return x.v == 0.0f; }               // for reduced values
-// canonical residue 0..16 of a centred one, as an integer (full-rate ops: compare/select, FADD, LOP3)
-PBH_HD uint32_t f_canon(F32 x) {
-  float c = x.v < 0.0f ? x.v + 17.0f : x.v;
-#if defined(__CUDA_ARCH__)
-  return (uint32_t)__float_as_int(c + 12582912.0f) & 0xFFu;
-#else
-  return (uint32_t)(int)c;
-#endif
-}
-// rint(x / d) for an exact integer x (|x| < 2^21) that is never half-way between two multiples of d
-PBH_HD F32 f_rint_div(F32 x, float d, float inv_d, F32*) {
-  (void)d;
-  float t = fmaf(x.v, inv_d, 12582912.0f);
-  return F32(t - 12582912.0f);
-}
-// canonical residue 0..16 of a centred one, kept as a float
-PBH_HD F32 f_canon_f(F32 x, F32*) { return F32(x.v < 0.0f ? x.v + 17.0f : x.v); }
-// table index 0..101 of a centred residue mod 102
-PBH_HD uint32_t f_index102(F32 x) {
-  float c = x.v < 0.0f ? x.v + 102.0f : x.v;
-#if defined(__CUDA_ARCH__)
-  return (uint32_t)__float_as_int(c + 12582912.0f) & 0xFFu;
-#else
-  return (uint32_t)(int)c;
-#endif
-}
-PBH_HD F32 f_from_u32(uint32_t b, F32*) {                          // exact for b < 2^23
-#if defined(__CUDA_ARCH__)
-  return F32(__int_as_float(0x4B000000 | (int)b) - 8388608.0f);
-#else
-  return F32((float)b);
-#endif
-}
 
 // schoolbook products, unreduced, in outer-product order: consecutive FFMAs share the multiplicand a[i] (operand
 // reuse cache, fewer register-bank conflicts) and write different accumulators (independent chains)
@@ -195,6 +146,18 @@ struct ProofF {
   uint32_t ev[7];    // canonical evaluations
 };
 
+// sum_i [c_i] g1s[i] from canonical coefficients through the three-point tables: ceil(L/3) lookups, one addition fewer
+template <int L>
+PBH_HD uint32_t commit_pairs_f32(const uint32_t (&ci)[L], const Tables& Tb) {
+  G1F<F32> acc = g1f_unpack<F32>(pair_lookup(Tb.fixed->srs_tri[0], tri_index<L, 0>(ci)));
+#pragma unroll
+  for (int j = 1; j < (L + 2) / 3; j++) {
+    const uint32_t idx = j == 1 ? tri_index<L, 1>(ci) : (j == 2 ? tri_index<L, 2>(ci) : tri_index<L, 3>(ci));
+    acc = g1f_add(acc, g1f_unpack<F32>(pair_lookup(Tb.fixed->srs_tri[j], idx)), Tb.inv101c);
+  }
+  return g1f_pack(acc);
+}
+
 // SRS::eval_at_s of a coefficient array (src/plonk.rs:51-58); `oob` is set when a coefficient at or beyond n_pts is
 // non-zero (the reference then indexes g1s out of bounds, src/plonk.rs:56).
 //   ALGO_TABLE: dot product with the SRS discrete logs -> exponent of G (see commit<> of pbh_prove.cuh); returns 0..16.
@@ -214,18 +177,23 @@ PBH_HD uint32_t fcommit(const T (&c)[L], const CK& ck, const Tables& Tb, bool re
     for (int i = 1; i < L; i++) e = f_fma(c[i], f_const(ck.srs_dlog(i), tag), e);
     return f_canon(f_red(e));
   } else {
-    // two coefficients per lookup (PairTables), the first lookup needs no addition
+    // three coefficients per lookup (FixedBaseTables), the first lookup needs no addition; exact FP32 curve arithmetic
+    // (pbh_g1f.cuh: the table entries are multiples of SRS points, all on the curve)
     static_assert(L >= 2 && L <= 10, "the SRS tables cover 10 points");
-    uint32_t ci[L];
+    T cr[L];
 #pragma unroll
-    for (int i = 0; i < L; i++) ci[i] = f_canon(reduced ? c[i] : f_red(c[i]));
-    G1 acc = g1_unpack(pair_lookup(Tb.pairs->srs_pair[0], ci[0] + 17u * ci[1]));
+    for (int i = 0; i < L; i++) cr[i] = reduced ? c[i] : f_red(c[i]);
+    // table index of a triple straight from the centred residues: (c0 + 8) + 17 (c1 + 8) + 289 (c2 + 8)
+    auto index = [&](int j) -> uint32_t {
+      T x = f_add(cr[3 * j], f_const(2456.f, tag));
+      if (3 * j + 1 < L) x = f_fma(cr[(3 * j + 1 < L) ? 3 * j + 1 : 0], f_const(17.f, tag), x);
+      if (3 * j + 2 < L) x = f_fma(cr[(3 * j + 2 < L) ? 3 * j + 2 : 0], f_const(289.f, tag), x);
+      return f_to_index(x);
+    };
+    G1F<F32> acc = g1f_unpack<F32>(pair_lookup(Tb.fixed->srs_tri[0], index(0)));
 #pragma unroll
-    for (int j = 1; j < (L + 1) / 2; j++) {
-      const uint32_t hi = (2 * j + 1 < L) ? ci[(2 * j + 1 < L) ? 2 * j + 1 : 0] : 0u;
-      acc = g1_add(acc, g1_unpack(pair_lookup(Tb.pairs->srs_pair[j], ci[2 * j] + 17u * hi)), Tb.inv101);
-    }
-    return g1_pack(acc);
+    for (int j = 1; j < (L + 2) / 3; j++) acc = g1f_add(acc, g1f_unpack<F32>(pair_lookup(Tb.fixed->srs_tri[j], index(j))), Tb.inv101c);
+    return g1f_pack(acc);
   }
 }
 
@@ -460,7 +428,7 @@ PBH_HD uint32_t prove_core_f32_cs(const T (&w)[12], const T (&rnd_in)[9], CS& cs
   T wzw[6];
   {
     T zo = f_mul(zc, f_const(4.f, tag));
-    wzw[5] = z[6];
+    wzw[5] = (ALGO == ALGO_ARITH) ? f_red(z[6]) : z[6];   // the ARITH tables are indexed by centred residues, z[6] = b7 arrives as 0..16
 #pragma unroll
     for (int k = 4; k >= 0; k--) wzw[k] = f_red(f_fma(zo, wzw[k + 1], z[k + 1]));
   }

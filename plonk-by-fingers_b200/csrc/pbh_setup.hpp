@@ -23,7 +23,7 @@ struct HostSetup {
   G1 vconst[8];               // q_m_s q_l_s q_r_s q_o_s q_c_s sigma_1_s sigma_2_s sigma_3_s
   uint32_t g102_idx_of_G;     // == 6
   uint32_t fs_seed[8];        // initial state of the Fiat-Shamir transcript (include/pbh_b200.h), SHA-256 words
-  PairTables P;               // two-point fixed-base tables; T.pairs points here until the context uploads them
+  FixedBaseTables P;          // three-point fixed-base tables; T.fixed points here until the context uploads them
 };
 
 // "G2" of src/pbh/g2.rs:58-101: (a, b*u), u^2 = -2, no identity; returns false where the reference panics (Q12)
@@ -175,16 +175,22 @@ inline int host_setup(const pbh_circuit& c, uint32_t srs_secret, uint32_t srs_n,
     for (int k = 0; k < 17; k++) { T.vfix_mult[j][k] = g1_pack(m); m = g1_add(m, base, T.inv101); }
   }
 
-  // two-point tables: entry a + 17 b = [a]P_2j + [b]P_2j+1
-  for (int j = 0; j < 5; j++)
-    for (int b = 0; b < 17; b++)
-      for (int a = 0; a < 17; a++)
-        hs.P.srs_pair[j][a + 17 * b] = g1_pack(g1_add(g1_unpack(T.srs_mult[2 * j][a]), g1_unpack(T.srs_mult[2 * j + 1][b]), T.inv101));
+  // three-point tables: entry a + 17 b + 289 c = [a]P_3j + [b]P_3j+1 + [c]P_3j+2 (identity for points beyond the table)
+  auto mult = [&](const uint32_t (*tab)[17], int rows, int i, int k) { return i < rows ? g1_unpack(tab[i][k]) : g1_identity(); };
   for (int j = 0; j < 4; j++)
-    for (int b = 0; b < 17; b++)
-      for (int a = 0; a < 17; a++)
-        hs.P.vfix_pair[j][a + 17 * b] = g1_pack(g1_add(g1_unpack(T.vfix_mult[2 * j][a]), g1_unpack(T.vfix_mult[2 * j + 1][b]), T.inv101));
-  T.pairs = &hs.P;
+    for (int cc = 0; cc < 17; cc++)
+      for (int b = 0; b < 17; b++)
+        for (int a = 0; a < 17; a++)
+          // centred digits: entry (a, b, cc) holds the multiples (a - 8, b - 8, cc - 8) mod 17
+          hs.P.srs_tri[j][a + 17 * b + 289 * cc] = g1_pack(g1_add(g1_add(mult(T.srs_mult, 10, 3 * j, (a + 9) % 17), mult(T.srs_mult, 10, 3 * j + 1, (b + 9) % 17), T.inv101),
+                                                                mult(T.srs_mult, 10, 3 * j + 2, (cc + 9) % 17), T.inv101));
+  for (int j = 0; j < 3; j++)
+    for (int cc = 0; cc < 17; cc++)
+      for (int b = 0; b < 17; b++)
+        for (int a = 0; a < 17; a++)
+          hs.P.vfix_tri[j][a + 17 * b + 289 * cc] = g1_pack(g1_add(g1_add(mult(T.vfix_mult, 9, 3 * j, a), mult(T.vfix_mult, 9, 3 * j + 1, b), T.inv101),
+                                                                 mult(T.vfix_mult, 9, 3 * j + 2, cc), T.inv101));
+  T.fixed = &hs.P;
 
   // ---- group structure of E(F_101) for PBH_ALGO_TABLE
   std::vector<G1> pts;
@@ -227,6 +233,10 @@ inline int host_setup(const pbh_circuit& c, uint32_t srs_secret, uint32_t srs_n,
   for (int i = 0; i < 10; i++) F.srs_dlog[i] = cen(K.srs_dlog[i]);
   for (int i = 0; i < 8; i++) F.vdlog[i] = cen(K.vdlog[i]);
   for (uint32_t a = 0; a < 17; a++) T.inv17c[a] = cen(T.inv17[a]);
+  for (int i = 0; i < 408; i++) {                       // f_inv101 of pbh_g1f.cuh: index = s + 202
+    const uint32_t r = (uint32_t)(((i - 202) % 101 + 101) % 101), v = T.inv101[r];
+    T.inv101c[i] = v > 50u ? (float)v - 101.0f : (float)v;
+  }
 
   // ---- Fiat-Shamir seed: SHA-256(tag || omega_pows || circuit || SRS), see include/pbh_b200.h
   {

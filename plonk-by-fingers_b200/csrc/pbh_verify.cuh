@@ -58,7 +58,8 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
   // ---- Step 1: in_curve on the raw coordinates (flag ignored)              src/plonk.rs:523-534
   bool off_curve = false;
   uint32_t idx[9];   // TABLE: discrete logs
-  G1 pt[9];          // ARITH: points
+  G1F<F32> pt[9];    // ARITH: points (pbh_g1f.cuh)
+  F32* ftag = nullptr;
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     bool inf = (infbits >> k) & 1u;
@@ -73,8 +74,9 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
       uint32_t i = upper ? 102u - i0 : i0;
       idx[k] = inf ? 0u : i;                 // a flagged point acts as the identity (g1.rs:121, 148-150)
     } else {
-      off_curve = off_curve || !g1_in_curve(px[k], py[k]);
-      pt[k] = inf ? g1_identity() : g1_make(px[k], py[k]);
+      const F32 fx = f_from_u32(px[k], ftag), fy = f_from_u32(py[k], ftag);
+      off_curve = off_curve || !g1f_in_curve(fx, fy);
+      pt[k].x = inf ? f_const(0.f, ftag) : fx; pt[k].y = inf ? f_const(0.f, ftag) : fy; pt[k].inf = inf;
     }
   }
   // ---- Step 2: in_field                                                     src/plonk.rs:538-547
@@ -144,38 +146,43 @@ PBH_HD uint32_t verify_one(const uint32_t (&px_in)[9], const uint32_t (&py_in)[9
     e1.a = T.pair_s_a[i1]; e1.b = T.pair_s_b[i1];
     e2.a = T.pair_1_a[i2]; e2.b = T.pair_1_b[i2];
   } else {
+    // Exact FP32 curve arithmetic (pbh_g1f.cuh).  The points are on the curve or the verdict is decided by Step 1 alone (the
+    // arithmetic below then runs on garbage that stays in range: every table index is bounded by construction).
+    const float* inv = T.inv101c;
     // fixed-base multiples (the constant commitments lie in <G>, of order 17, so -[s]P = [17-s]P)
-    // two scalars per lookup for the eight constant commitments (PairTables), then the multiple of G
-    G1 acc = g1_unpack(pair_lookup(T.pairs->vfix_pair[0], s_qm + 17u * s_ql));
-    acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[1], s_qr + 17u * s_qo)), T.inv101);
-    acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[2], s_qc + 17u * v5)), T.inv101);
-    acc = g1_add(acc, g1_unpack(pair_lookup(T.pairs->vfix_pair[3], v6 + 17u * neg17(s_s3))), T.inv101);
-    acc = g1_add(acc, g1_unpack(T.vfix_mult[8][neg17(s_e)]), T.inv101);
+    // three scalars per lookup for the eight constant commitments and G (FixedBaseTables): 3 lookups, 2 additions
+    G1F<F32> acc = g1f_unpack<F32>(pair_lookup(T.fixed->vfix_tri[0], s_qm + 17u * s_ql + 289u * s_qr));
+    acc = g1f_add(acc, g1f_unpack<F32>(pair_lookup(T.fixed->vfix_tri[1], s_qo + 17u * s_qc + 289u * v5)), inv);
+    acc = g1f_add(acc, g1f_unpack<F32>(pair_lookup(T.fixed->vfix_tri[2], v6 + 17u * neg17(s_s3) + 289u * neg17(s_e))), inv);
     // Straus with joint two-point windows: sum_k [sc_k] pt_k with shared doublings, scalars < 17 (5 bits).  The points
     // are taken in pairs; per bit level one addition of 0, P, Q or P + Q (precomputed) serves both scalars of a pair:
     // 4 + 21 additions and 4 doublings instead of 44 + 4.  t_lo_s has the scalar 1 (one addition at the last level).
+    // "No addition" is an addend flagged as the identity, which the addition handles with the flag alone.
     const uint32_t sc[9] = {v2, v3, v4, s_zs, 1u, z6, z12, z, s_wzw};
     const int pa[4] = {0, 2, 5, 7}, pb[4] = {1, 3, 6, 8};
-    G1 both[4];
+    G1F<F32> both[4];
 #pragma unroll
-    for (int p = 0; p < 4; p++) both[p] = g1_add(pt[pa[p]], pt[pb[p]], T.inv101);
-    G1 r = g1_identity();
+    for (int p = 0; p < 4; p++) both[p] = g1f_add(pt[pa[p]], pt[pb[p]], inv);
+    G1F<F32> r = g1f_identity<F32>();
 #pragma unroll
     for (int j = 4; j >= 0; j--) {
-      if (j != 4) r = g1_add(r, r, T.inv101);
+      if (j != 4) r = g1f_add(r, r, inv);
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         const bool ba = (sc[pa[p]] >> j) & 1u, bb = (sc[pb[p]] >> j) & 1u;
-        G1 addend = ba ? (bb ? both[p] : pt[pa[p]]) : pt[pb[p]];
-        G1 s = g1_add(r, addend, T.inv101);
-        if (ba || bb) r = s;
+        G1F<F32> addend;
+        addend.x = f_sel(ba, f_sel(bb, both[p].x, pt[pa[p]].x), pt[pb[p]].x);
+        addend.y = f_sel(ba, f_sel(bb, both[p].y, pt[pa[p]].y), pt[pb[p]].y);
+        addend.inf = ba ? (bb ? both[p].inf : pt[pa[p]].inf) : (bb ? pt[pb[p]].inf : true);
+        r = g1f_add(r, addend, inv);
       }
-      if (j == 0) r = g1_add(r, pt[4], T.inv101);
+      if (j == 0) r = g1f_add(r, pt[4], inv);
     }
-    G1 q2 = g1_add(r, acc, T.inv101);                                        // e_2_q1
-    G1 q1 = g1_add(pt[7], g1_smul<5>(pt[8], u, T.inv101), T.inv101);         // e_1_q1
-    e1 = pairing(q1, K.g2_s[0], K.g2_s[1], T.inv101);                        // src/plonk.rs:646
-    e2 = pairing(q2, K.g2_1[0], K.g2_1[1], T.inv101);                        // src/plonk.rs:647
+    const G1F<F32> q2 = g1f_add(r, acc, inv);                                          // e_2_q1
+    const G1F<F32> q1 = g1f_add(pt[7], g1f_smul<5>(pt[8], u, inv), inv);               // e_1_q1
+    const GTF<F32> f1 = pairingf(q1, f_from_u32(K.g2_s[0], ftag), f_from_u32(K.g2_s[1], ftag), inv);   // src/plonk.rs:646
+    const GTF<F32> f2 = pairingf(q2, f_from_u32(K.g2_1[0], ftag), f_from_u32(K.g2_1[1], ftag), inv);   // src/plonk.rs:647
+    e1.a = f_canon101(f1.a); e1.b = f_canon101(f1.b); e2.a = f_canon101(f2.a); e2.b = f_canon101(f2.b);
   }
 
   uint32_t res = (e1.a == e2.a && e1.b == e2.b) ? VR_ACCEPT : VR_REJECT_PAIRING;

@@ -45,7 +45,8 @@ pbh_prove_batch pbh_prove_batch_dev pbh_verify_batch pbh_verify_batch_dev pbh_pr
 pbh_proof_records_to_planes_dev pbh_proof_planes_to_records_dev pbh_prove_digest_batch_dev pbh_verify_bitmap_batch_dev pbh_ntt4_batch pbh_intt4_batch
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
-pbh_measure_int32_peak pbh_mul_ntt_batch pbh_poly_scale_batch pbh_poly_eval_batch pbh_poly_div_linear_batch pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev""".split()
+pbh_measure_int32_peak pbh_mul_ntt_batch pbh_poly_scale_batch pbh_poly_eval_batch pbh_poly_div_linear_batch pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev
+pbh_prove_batch_async pbh_verify_batch_async pbh_lane_sync pbh_host_alloc pbh_host_free pbh_ctx_numa_node""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -119,6 +120,10 @@ def load_library():
         lib.pbh_ctx_launch_count.argtypes = [C.c_void_p]
         lib.pbh_ctx_destroy.argtypes = [C.c_void_p]
         lib.pbh_ctx_destroy.restype = None
+        lib.pbh_ctx_numa_node.argtypes = [C.c_void_p]
+        lib.pbh_lane_sync.argtypes = [C.c_void_p, C.c_int]
+        lib.pbh_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        lib.pbh_host_free.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -136,7 +141,7 @@ def _is_torch(x):
 class _Planes:
     """Uniform view of a (planes, n) uint8 batch living on the host (numpy) or the device (torch)."""
 
-    def __init__(self, arr, planes, n=None, name="array"):
+    def __init__(self, arr, planes, n=None, name="array", out=False):
         self.dev = _is_torch(arr)
         if self.dev:
             import torch
@@ -155,7 +160,11 @@ class _Planes:
             if arr.ndim == 1:
                 arr = arr.reshape(1, -1)
             if arr.shape[1] > 0 and arr.strides[1] != 1:
+                if out:      # the library would fill a temporary copy and the caller's array would stay untouched
+                    raise PbhError(f"{name}: output planes must be contiguous along the item axis")
                 arr = np.ascontiguousarray(arr)
+            if out and not arr.flags.writeable:
+                raise PbhError(f"{name}: output array is read-only")
             self.arr, self.ptr = arr, arr.ctypes.data
             self.pitch = arr.strides[0] if arr.shape[0] > 1 else max(arr.shape[1], 1)
         if arr.shape[0] != planes:
@@ -278,7 +287,7 @@ class Context:
             raise PbhError("all batches must live on the same side (host or device)")
         proof = self._empty(W.dev, 27, n) if proof is None else proof
         status = self._empty(W.dev, 1, n) if status is None else status
-        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status")
+        P = _Planes(proof, 27, n, "proof", out=True); S = _Planes(status, 1, n, "status", out=True)
         fn = self.lib.pbh_prove_batch_dev if W.dev else self.lib.pbh_prove_batch
         cur = self._dev_begin() if W.dev else None
         rc = fn(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch),
@@ -294,11 +303,11 @@ class Context:
         if not (P.dev == Ch.dev == U.dev):
             raise PbhError("all batches must live on the same side (host or device)")
         result = self._empty(P.dev, 1, n) if result is None else result
-        Rs = _Planes(result, 1, n, "result")
+        Rs = _Planes(result, 1, n, "result", out=True)
         G = None
         if want_gt or gt is not None:
             gt = self._empty(P.dev, 4, n) if gt is None else gt
-            G = _Planes(gt, 4, n, "gt")
+            G = _Planes(gt, 4, n, "gt", out=True)
         fn = self.lib.pbh_verify_batch_dev if P.dev else self.lib.pbh_verify_batch
         cur = self._dev_begin() if P.dev else None
         rc = fn(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch),
@@ -308,12 +317,62 @@ class Context:
         res = Rs.arr.reshape(-1)
         return (res, G.arr) if G else res
 
+    # ---- asynchronous host-pointer calls on lanes (include/pbh_b200.h) ----
+    def prove_batch_async(self, lane, wit, rand, chal, proof, status):
+        """Enqueue pbh_prove_batch on `lane` and return; the arrays must stay alive and untouched until lane_sync(lane)."""
+        W = _Planes(wit, 12, name="wit"); n = W.n
+        R = _Planes(rand, 9, n, "rand"); Ch = _Planes(chal, 5, n, "chal")
+        P = _Planes(proof, 27, n, "proof", out=True); S = _Planes(status, 1, n, "status", out=True)
+        if W.dev or R.dev or Ch.dev or P.dev or S.dev:
+            raise PbhError("the lane API takes host arrays")
+        rc = self.lib.pbh_prove_batch_async(self.h, int(lane), C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr),
+                                            C.c_size_t(R.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(P.ptr),
+                                            C.c_size_t(P.pitch), C.c_void_p(S.ptr))
+        self._check(rc, "pbh_prove_batch_async")
+
+    def verify_batch_async(self, lane, proof, chal, u, result, gt=None):
+        P = _Planes(proof, 27, name="proof"); n = P.n
+        Ch = _Planes(chal, 5, n, "chal"); U = _Planes(u, 1, n, "u"); Rs = _Planes(result, 1, n, "result", out=True)
+        G = _Planes(gt, 4, n, "gt", out=True) if gt is not None else None
+        if P.dev or Ch.dev or U.dev or Rs.dev or (G is not None and G.dev):
+            raise PbhError("the lane API takes host arrays")
+        rc = self.lib.pbh_verify_batch_async(self.h, int(lane), C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Ch.ptr),
+                                             C.c_size_t(Ch.pitch), C.c_void_p(U.ptr), C.c_void_p(Rs.ptr), C.c_void_p(G.ptr if G else None),
+                                             C.c_size_t(G.pitch if G else 0))
+        self._check(rc, "pbh_verify_batch_async")
+
+    def lane_sync(self, lane):
+        self._check(self.lib.pbh_lane_sync(self.h, int(lane)), "pbh_lane_sync")
+
+    @property
+    def numa_node(self):
+        return int(self.lib.pbh_ctx_numa_node(self.h))
+
+    def host_alloc(self, shape):
+        """uint8 numpy array over page-locked, mapped host memory (pbh_host_alloc): the host-pointer calls run in place
+        on it.  The memory lives until host_free(array) or the context closes."""
+        shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        nbytes = max(1, int(np.prod(shape)))
+        p = C.c_void_p()
+        self._check(self.lib.pbh_host_alloc(self.h, C.c_size_t(nbytes), C.byref(p)), "pbh_host_alloc")
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=int(np.prod(shape))).reshape(shape)
+        self._host_ptrs = getattr(self, "_host_ptrs", {})
+        self._host_ptrs[arr.ctypes.data] = p.value
+        return arr
+
+    def host_free(self, arr):
+        p = getattr(self, "_host_ptrs", {}).pop(arr.ctypes.data, None)
+        if p is None:
+            raise PbhError("not a host_alloc array of this context")
+        self._check(self.lib.pbh_host_free(self.h, C.c_void_p(p)), "pbh_host_free")
+
     def prove_digest_batch(self, wit, rand, chal, proof, status, digest, first_index=0):
         """Device tensors: prove and add the additive digest of the 27 proof planes (== digest(proof, first_index)) in
         the same kernel.  `digest`: int64 tensor of one element."""
         W = _Planes(wit, 12, name="wit"); n = W.n
         R = _Planes(rand, 9, n, "rand"); Ch = _Planes(chal, 5, n, "chal")
-        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status")
+        P = _Planes(proof, 27, n, "proof", out=True); S = _Planes(status, 1, n, "status", out=True)
         cur = self._dev_begin()
         rc = self.lib.pbh_prove_digest_batch_dev(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr),
                                                  C.c_size_t(R.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(P.ptr),
@@ -326,7 +385,7 @@ class Context:
     def verify_bitmap_batch(self, proof, chal, u, result, bitmap):
         """Device tensors: verify and pack the verdict bits (== pack_verdicts(result)) in the same kernel."""
         P = _Planes(proof, 27, name="proof"); n = P.n
-        Ch = _Planes(chal, 5, n, "chal"); U = _Planes(u, 1, n, "u"); Rs = _Planes(result, 1, n, "result")
+        Ch = _Planes(chal, 5, n, "chal"); U = _Planes(u, 1, n, "u"); Rs = _Planes(result, 1, n, "result", out=True)
         cur = self._dev_begin()
         rc = self.lib.pbh_verify_bitmap_batch_dev(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Ch.ptr),
                                                   C.c_size_t(Ch.pitch), C.c_void_p(U.ptr), C.c_void_p(Rs.ptr), C.c_void_p(bitmap.data_ptr()))
@@ -343,7 +402,7 @@ class Context:
         proof = np.empty((27, n), dtype=np.uint8) if proof is None else proof
         status = np.empty((n,), dtype=np.uint8) if status is None else status
         result = np.empty((n,), dtype=np.uint8) if result is None else result
-        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status"); Rs = _Planes(result, 1, n, "result")
+        P = _Planes(proof, 27, n, "proof", out=True); S = _Planes(status, 1, n, "status", out=True); Rs = _Planes(result, 1, n, "result", out=True)
         rc = self.lib.pbh_prove_verify_batch(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr),
                                              C.c_size_t(R.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(U.ptr),
                                              C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr), C.c_void_p(Rs.ptr))
@@ -364,11 +423,11 @@ class Context:
             raise PbhError("all batches must live on the same side (host or device)")
         proof = self._empty(W.dev, 27, n) if proof is None else proof
         status = self._empty(W.dev, 1, n) if status is None else status
-        P = _Planes(proof, 27, n, "proof"); S = _Planes(status, 1, n, "status")
+        P = _Planes(proof, 27, n, "proof", out=True); S = _Planes(status, 1, n, "status", out=True)
         Ch = None
         if want_chal or chal is not None:
             chal = self._empty(W.dev, 6, n) if chal is None else chal
-            Ch = _Planes(chal, 6, n, "chal")
+            Ch = _Planes(chal, 6, n, "chal", out=True)
         fn = self.lib.pbh_prove_fs_batch_dev if W.dev else self.lib.pbh_prove_fs_batch
         cur = self._dev_begin() if W.dev else None
         rc = fn(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch),
@@ -382,14 +441,14 @@ class Context:
         """proof (27,n) -> result (n,) [, chal (6,n)] [, gt (4,n)]."""
         P = _Planes(proof, 27, name="proof"); n = P.n
         result = self._empty(P.dev, 1, n) if result is None else result
-        Rs = _Planes(result, 1, n, "result")
+        Rs = _Planes(result, 1, n, "result", out=True)
         Ch = G = None
         if want_chal or chal is not None:
             chal = self._empty(P.dev, 6, n) if chal is None else chal
-            Ch = _Planes(chal, 6, n, "chal")
+            Ch = _Planes(chal, 6, n, "chal", out=True)
         if want_gt or gt is not None:
             gt = self._empty(P.dev, 4, n) if gt is None else gt
-            G = _Planes(gt, 4, n, "gt")
+            G = _Planes(gt, 4, n, "gt", out=True)
         fn = self.lib.pbh_verify_fs_batch_dev if P.dev else self.lib.pbh_verify_fs_batch
         cur = self._dev_begin() if P.dev else None
         rc = fn(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Rs.ptr), C.c_void_p(Ch.ptr if Ch else None),

@@ -31,6 +31,15 @@ inline uint32_t f_canon(Bnd) { return 0; }
 inline Bnd f_rint_div(Bnd x, float d, float, Bnd*) { if (x.m > g_max_red) g_max_red = x.m; if (x.m >= 2097152.0) g_violation = true; return chk(x.m / d + 1.0); }
 inline Bnd f_canon_f(Bnd, Bnd*) { return Bnd(16); }
 inline uint32_t f_index102(Bnd) { return 0; }
+// F_101 policy (pbh_g1f.cuh): red101 is exact for |x| <= 2^21, the inverse lookup takes an integer |s| <= 202
+inline Bnd f_red101(Bnd x) { if (x.m > g_max_red) g_max_red = x.m; if (x.m > 2097152.0) g_violation = true; return Bnd(50); }
+inline Bnd f_inv101(Bnd s, const float*) { if (s.m > 202.0) g_violation = true; return Bnd(50); }
+inline Bnd f_sel(bool, Bnd a, Bnd b) { return Bnd(a.m > b.m ? a.m : b.m); }
+inline Bnd f_neg(Bnd a) { return a; }
+inline uint32_t f_canon101(Bnd) { return 0; }
+inline Bnd f_from_byte(uint32_t, int, Bnd*) { return Bnd(100); }
+inline bool f_eq(Bnd, Bnd) { return false; }
+inline uint32_t f_to_index(Bnd x) { if (x.m >= 8192.0) g_violation = true; return 0; }
 }  // namespace pbh
 
 extern "C" {
@@ -53,8 +62,8 @@ int emul_f32_bounds(double* max_exact, double* max_red) {
     for (auto& x : c) x = Bnd(16);
     ProofF pf;
     Tables tb; std::memset(&tb, 0, sizeof tb);
-    static PairTables pairs_zero{};
-    tb.pairs = &pairs_zero;
+    static FixedBaseTables fixed_zero{};
+    tb.fixed = &fixed_zero;
     prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, RuntimeCK{KF, n_pts}, tb, inv, pf);
     prove_core_f32<ALGO_ARITH, Bnd>(w, r, c, RuntimeCK{KF, n_pts}, tb, inv, pf);
     prove_core_f32<ALGO_TABLE, Bnd>(w, r, c, PbhCK(), tb, inv, pf);
@@ -68,8 +77,36 @@ int emul_f32_bounds(double* max_exact, double* max_red) {
     uint32_t i1, i2; bool zh0;
     verify_scalars_f32<Bnd>(idx, ev, ch, Bnd(16), KF, inv, i1, i2, zh0);
   }
+  {
+    // the FP32 curve arithmetic: coordinates as raw bytes (<= 100) or centred residues, G2 coordinates <= 100
+    G1F<Bnd> p, q;
+    p.x = p.y = q.x = q.y = Bnd(100); p.inf = q.inf = false;
+    float inv[408] = {0};
+    G1F<Bnd> r = g1f_add(p, q, inv);
+    r = g1f_add(r, p, inv);
+    r = g1f_smul<7>(p, 127u, inv);
+    (void)g1f_in_curve(Bnd(100), Bnd(100));
+    GTF<Bnd> e = pairingf(p, Bnd(100), Bnd(100), inv);
+    GTF<Bnd> raw; raw.a = raw.b = Bnd(100);
+    e = gtf_final_exp(raw, inv);
+    (void)e; (void)r;
+  }
   *max_exact = g_max_exact; *max_red = g_max_red;
   return g_violation ? 1 : 0;
+}
+
+// red101 of pbh_g1f.cuh against x mod 101 for every integer |x| <= 2^21; returns the number of mismatches (the result must
+// be THE centred residue in [-50, 50], not merely congruent: zero tests and table indices rely on it)
+uint64_t emul_check_red101_f32() {
+  using namespace pbh;
+  uint64_t bad = 0;
+  for (int64_t x = -2097152; x <= 2097152; x++) {
+    float r = f_red101(F32((float)x)).v;
+    int64_t m = ((x % 101) + 101) % 101;
+    if (m > 50) m -= 101;
+    if ((int64_t)r != m || r != (float)(int64_t)r) bad++;
+  }
+  return bad;
 }
 
 // red17 of pbh_prove_f32.cuh against x mod 17 for every integer |x| <= 2^23; returns the number of mismatches
@@ -276,6 +313,44 @@ int emul_pairing(const uint8_t p[3], const uint8_t q[2], uint8_t out[2], uint8_t
   GT f = miller_f17(a, q[0], q[1], hs.T.inv101);
   GT e = gt_final_exp(f, hs.T.inv101);
   out[0] = e.a; out[1] = e.b; miller_out[0] = f.a; miller_out[1] = f.b;
+  return 0;
+}
+// the same three through the exact FP32 curve arithmetic of pbh_g1f.cuh (what PBH_ALGO_ARITH runs on the device)
+static const HostSetup& shared_setup() {
+  static HostSetup hs; static bool init = false;
+  if (!init) { pbh_circuit c; std::memset(&c, 0, sizeof c); for (int i = 0; i < 4; i++) c.c_a_index[i] = c.c_b_index[i] = c.c_c_index[i] = 1;
+    host_setup(c, 2, 6, 4, hs, g_err); init = true; }
+  return hs;
+}
+static G1F<F32> g1f_of(const uint8_t p[3]) { G1F<F32> a; a.x = F32((float)p[0]); a.y = F32((float)p[1]); a.inf = p[2] != 0; return a; }
+int emul_g1f_add(const uint8_t p[3], const uint8_t q[3], uint8_t out[3]) {
+  const HostSetup& hs = shared_setup();
+  G1F<F32> a = g1f_of(p), b = g1f_of(q);
+  if (a.inf) a = g1f_identity<F32>();
+  if (b.inf) b = g1f_identity<F32>();
+  const G1F<F32> r = g1f_add(a, b, hs.T.inv101c);
+  out[0] = (uint8_t)f_canon101(r.x); out[1] = (uint8_t)f_canon101(r.y); out[2] = r.inf ? 1 : 0;
+  return 0;
+}
+int emul_g1f_smul(const uint8_t p[3], uint8_t k, uint8_t out[3]) {
+  const HostSetup& hs = shared_setup();
+  const G1F<F32> r = g1f_smul<7>(g1f_of(p), k, hs.T.inv101c);
+  out[0] = (uint8_t)f_canon101(r.x); out[1] = (uint8_t)f_canon101(r.y); out[2] = r.inf ? 1 : 0;
+  return 0;
+}
+int emul_pairingf(const uint8_t p[3], const uint8_t q[2], uint8_t out[2], uint8_t miller_out[2]) {
+  const HostSetup& hs = shared_setup();
+  const GTF<F32> f = millerf_f17(g1f_of(p), F32((float)q[0]), F32((float)q[1]), hs.T.inv101c);
+  const GTF<F32> e = gtf_final_exp(f, hs.T.inv101c);
+  out[0] = (uint8_t)f_canon101(e.a); out[1] = (uint8_t)f_canon101(e.b);
+  miller_out[0] = (uint8_t)f_canon101(f.a); miller_out[1] = (uint8_t)f_canon101(f.b);
+  return 0;
+}
+int emul_gtf_final_exp(const uint8_t f[2], uint8_t out[2]) {
+  const HostSetup& hs = shared_setup();
+  GTF<F32> x; x.a = F32((float)f[0]); x.b = F32((float)f[1]);
+  const GTF<F32> e = gtf_final_exp(x, hs.T.inv101c);
+  out[0] = (uint8_t)f_canon101(e.a); out[1] = (uint8_t)f_canon101(e.b);
   return 0;
 }
 int emul_gt_final_exp(const uint8_t f[2], uint8_t out[2]) {

@@ -17,7 +17,7 @@ def load():
     if _E is None:
         so = os.path.join(HERE, "libhostemul.so")
         srcs = [os.path.join(HERE, "hostemul.cpp")] + [os.path.join(ROOT, "plonk-by-fingers_b200", "csrc", f) for f in
-                                                       ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_prove_f32.cuh", "pbh_verify.cuh", "pbh_setup.hpp", "pbh_sha256.cuh", "pbh_fs.cuh")]
+                                                       ("pbh_arith.cuh", "pbh_prove.cuh", "pbh_prove_f32.cuh", "pbh_verify.cuh", "pbh_setup.hpp", "pbh_sha256.cuh", "pbh_fs.cuh", "pbh_f32.cuh", "pbh_g1f.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-mfma", "-DPBH_RANGE_TRACK", "-o", so, srcs[0]], check=True)
         _E = C.CDLL(so)
@@ -115,6 +115,31 @@ class Emul:
         o = (C.c_uint8 * 2)(); m = (C.c_uint8 * 2)()
         self.lib.emul_pairing((C.c_uint8 * 3)(*p), (C.c_uint8 * 2)(*q), o, m)
         return tuple(o), tuple(m)
+
+    # ---- the exact FP32 curve arithmetic of pbh_g1f.cuh (PBH_ALGO_ARITH on the device) ----
+    def g1f_add(self, p, q):
+        o = (C.c_uint8 * 3)()
+        self.lib.emul_g1f_add((C.c_uint8 * 3)(*p), (C.c_uint8 * 3)(*q), o)
+        return tuple(o)
+
+    def g1f_smul(self, p, k):
+        o = (C.c_uint8 * 3)()
+        self.lib.emul_g1f_smul((C.c_uint8 * 3)(*p), C.c_uint8(k), o)
+        return tuple(o)
+
+    def pairingf(self, p, q):
+        o = (C.c_uint8 * 2)(); m = (C.c_uint8 * 2)()
+        self.lib.emul_pairingf((C.c_uint8 * 3)(*p), (C.c_uint8 * 2)(*q), o, m)
+        return tuple(o), tuple(m)
+
+    def gtf_final_exp(self, f):
+        o = (C.c_uint8 * 2)()
+        self.lib.emul_gtf_final_exp((C.c_uint8 * 2)(*f), o)
+        return tuple(o)
+
+    def check_red101_f32(self):
+        self.lib.emul_check_red101_f32.restype = C.c_uint64
+        return int(self.lib.emul_check_red101_f32())
 
     def gt_final_exp(self, f):
         o = (C.c_uint8 * 2)()

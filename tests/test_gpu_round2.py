@@ -1,0 +1,180 @@
+"""Round-2 GPU tests, all through the C ABI: the asynchronous lane API and pbh_host_alloc, launch-local tile counters under
+concurrent streams and CUDA graphs, the sharded path under REAL NCCL (spawned ranks, needs >= 2 visible GPUs), and the
+2^20-item batch bench.py times replayed through the oracle byte for byte."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_bench_batch_equals_oracle_full(gpu_ctx, oracle):
+    """Every one of the 2^20 items of ring slot 0 of bench.py (seed 0xB200, D_fullpath, first index 0): proof, status and
+    result bytes against the oracle (src/plonk.rs:191-650 restated), for both group algorithms."""
+    import torch
+    n = 1 << 20
+    t, a = gpu_ctx["table"], gpu_ctx["arith"]
+    w, r, c, u = t.generate_inputs(n, first_index=0, seed=0xB200, dist=1)
+    pt, st = t.prove_batch(w, r, c)
+    vt, gt_t = t.verify_batch(pt, c, u, want_gt=True)
+    pa, sa = a.prove_batch(w, r, c)
+    va, gt_a = a.verify_batch(pa, c, u, want_gt=True)
+    t.sync(); a.sync()
+    threads = max(1, oracle.hardware_threads())
+    hw, hr, hc, hu = (x.cpu().numpy() for x in (w, r, c, u))
+    po, so = oracle.prove_batch(hw, hr, hc, threads=threads)
+    vo, go = oracle.verify_batch(po, hc, hu, threads=threads)
+    for p_, s_, v_, g_ in ((pt, st, vt, gt_t), (pa, sa, va, gt_a)):
+        assert np.array_equal(p_.cpu().numpy(), po) and np.array_equal(s_.cpu().numpy(), so)
+        assert np.array_equal(v_.cpu().numpy(), vo) and np.array_equal(g_.cpu().numpy(), go)
+    # the device generator against the oracle's on a prefix (the oracle needs ~20 prove+verify attempts per item)
+    gw, gr, gc, gu = oracle.generate_inputs(8192, first_index=0, seed=0xB200, dist=1, threads=threads)[:4]
+    assert np.array_equal(gw, hw[:, :8192]) and np.array_equal(gr, hr[:, :8192]) and np.array_equal(gc, hc[:, :8192]) and np.array_equal(gu, hu[:8192])
+
+
+def test_lanes_and_host_alloc(gpu_ctx, oracle):
+    """pbh_prove_batch_async / pbh_verify_batch_async on two lanes over pbh_host_alloc memory: same bytes as the oracle;
+    pageable buffers degrade to the synchronous path with the same bytes; bad lanes and foreign pointers are refused."""
+    import pbh_b200
+    for algo in ("table", "arith"):
+        ctx = gpu_ctx[algo]
+        n = 70000 + 48          # ragged: not a multiple of the 256-item tile, a multiple of 16 (TMA path)
+        sets = []
+        for lane in range(2):
+            w, r, c, u, _ = oracle.generate_inputs(n, first_index=lane * n, seed=11, dist=lane)
+            bufs = dict(w=ctx.host_alloc((12, n)), r=ctx.host_alloc((9, n)), c=ctx.host_alloc((5, n)), u=ctx.host_alloc((n,)),
+                        proof=ctx.host_alloc((27, n)), status=ctx.host_alloc((n,)), result=ctx.host_alloc((n,)), gt=ctx.host_alloc((4, n)))
+            bufs["w"][...] = w; bufs["r"][...] = r; bufs["c"][...] = c; bufs["u"][...] = u
+            bufs["proof"][...] = 0xEE; bufs["status"][...] = 0xEE; bufs["result"][...] = 0xEE
+            sets.append((bufs, (w, r, c, u)))
+        for rep in range(3):
+            for lane, (b, _) in enumerate(sets):
+                ctx.lane_sync(lane)
+                ctx.prove_batch_async(lane, b["w"], b["r"], b["c"], b["proof"], b["status"])
+                ctx.verify_batch_async(lane, b["proof"], b["c"], b["u"], b["result"], gt=b["gt"])
+        ctx.sync()
+        for b, (w, r, c, u) in sets:
+            po, so = oracle.prove_batch(w, r, c, threads=8)
+            vo, go = oracle.verify_batch(po, c, u, threads=8)
+            assert np.array_equal(b["proof"], po) and np.array_equal(b["status"], so)
+            assert np.array_equal(b["result"], vo) and np.array_equal(b["gt"], go)
+        # pageable arrays through the same entry points: synchronous, same bytes
+        (b, (w, r, c, u)) = sets[1]
+        proof = np.full((27, n), 0xEE, np.uint8); status = np.full(n, 0xEE, np.uint8); result = np.full(n, 0xEE, np.uint8)
+        ctx.prove_batch_async(3, w, r, c, proof, status)
+        ctx.verify_batch_async(3, proof, c, u, result)
+        assert np.array_equal(proof, b["proof"]) and np.array_equal(status, b["status"]) and np.array_equal(result, b["result"])
+        with pytest.raises(pbh_b200.PbhError):          # lane out of range
+            ctx.prove_batch_async(7, w, r, c, proof, status)
+        with pytest.raises(pbh_b200.PbhError):
+            ctx.host_free(np.zeros(4, np.uint8))
+        for b, _ in sets:
+            for arr in b.values():
+                ctx.host_free(arr)
+        assert isinstance(ctx.numa_node, int)
+
+
+def test_output_arrays_must_be_contiguous(gpu_ctx, oracle):
+    """A non-contiguous OUTPUT array used to be filled through a temporary copy and stay untouched."""
+    import pbh_b200
+    ctx = gpu_ctx["table"]
+    w, r, c, u, _ = oracle.generate_inputs(64, seed=3, dist=1)
+    bad = np.zeros((64, 27), np.uint8).T          # (27, 64) view with item stride 27
+    with pytest.raises(pbh_b200.PbhError):
+        ctx.prove_batch(w, r, c, proof=bad)
+    ro = np.zeros((27, 64), np.uint8); ro.setflags(write=False)
+    with pytest.raises(pbh_b200.PbhError):
+        ctx.prove_batch(w, r, c, proof=ro)
+    p, s = ctx.prove_batch(np.asfortranarray(w), r, c)         # non-contiguous INPUTS are still copied
+    po, so = oracle.prove_batch(w, r, c)
+    assert np.array_equal(p, po) and np.array_equal(s, so)
+
+
+def test_tile_counters_are_launch_local(gpu_ctx, oracle):
+    """Two CUDA graphs captured from ONE context and replayed concurrently on different streams, next to direct launches:
+    every launch owns its tile-scheduler slot, so no tile is skipped (pbh_capi.cu fresh_tile_counter)."""
+    import torch
+    ctx = gpu_ctx["table"]
+    n = 1 << 18
+    dev = torch.device("cuda", 0)
+    batches = []
+    for k in range(3):
+        w, r, c, u = ctx.generate_inputs(n, first_index=k * n, seed=21, dist=1)
+        batches.append(dict(w=w, r=r, c=c, u=u, proof=torch.zeros((27, n), dtype=torch.uint8, device=dev), status=torch.full((n,), 77, dtype=torch.uint8, device=dev),
+                            result=torch.full((n,), 77, dtype=torch.uint8, device=dev)))
+    ctx.sync()
+    ref = []
+    for b in batches:
+        p, s = ctx.prove_batch(b["w"], b["r"], b["c"])
+        v = ctx.verify_batch(p, b["c"], b["u"])
+        ref.append((p.clone(), s.clone(), v.clone()))
+    ctx.sync()
+    graphs, streams = [], [torch.cuda.Stream(), torch.cuda.Stream()]
+    for b, st in zip(batches[:2], streams):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(4):
+                ctx.prove_batch(b["w"], b["r"], b["c"], proof=b["proof"], status=b["status"])
+                ctx.verify_batch(b["proof"], b["c"], b["u"], result=b["result"])
+        graphs.append(g)
+    torch.cuda.synchronize()
+    for rep in range(5):
+        for g, st in zip(graphs, streams):
+            with torch.cuda.stream(st):
+                g.replay()
+        b = batches[2]
+        ctx.prove_batch(b["w"], b["r"], b["c"], proof=b["proof"], status=b["status"])      # direct launches beside the replays
+        ctx.verify_batch(b["proof"], b["c"], b["u"], result=b["result"])
+    torch.cuda.synchronize(); ctx.sync()
+    for b, (p, s, v) in zip(batches, ref):
+        assert torch.equal(b["proof"], p) and torch.equal(b["status"], s) and torch.equal(b["result"], v)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, n_total, out_dir):
+    sys.path[:0] = [os.path.join(ROOT, "plonk-by-fingers_b200", "python")]
+    import torch
+    import torch.distributed as dist
+    import pbh_b200
+    from pbh_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ctx = pbh_b200.Context(device=rank)
+    bitmap, digs, total = sharding.run_sharded(n_total, rank, world, lambda lo, cnt: sharding.gpu_compute(ctx, lo, cnt))
+    torch.save({"bitmap": bitmap.cpu(), "digs": digs.cpu(), "total": total}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    torch.cuda.synchronize()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+def test_run_sharded_under_real_nccl(gpu_ctx, tmp_path):
+    """sharding.run_sharded with one process per GPU over NCCL: the gathered bitmap and the summed digests of the N-rank run
+    equal what ONE GPU computes for the same global index range."""
+    import torch
+    import torch.multiprocessing as mp
+    from pbh_b200 import sharding
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip(f"needs >= 2 visible GPUs for NCCL ranks, this box shows {torch.cuda.device_count()} "
+                    "(shard-count independence on one GPU: test_shard_summaries, test_config4_256m_end_to_end_sharding; "
+                    "N-rank equality inside the driver's SCALE run: bench.py check.sharded_equals_single)")
+    n_total = (1 << 20) + 4000 + 5
+    ctx = gpu_ctx["table"]
+    sb, sd, st = sharding.run_sharded(n_total, 0, 1, lambda lo, cnt: sharding.gpu_compute(ctx, lo, cnt))
+    port = _free_port()
+    mp.spawn(_nccl_worker, args=(world, port, n_total, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        o = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
+        assert torch.equal(o["bitmap"], sb.cpu()) and o["total"] == st and o["digs"].numel() == world

@@ -92,6 +92,38 @@ def test_pairing_exhaustive(hostemul, oracle):
             assert hostemul.gt_final_exp((a, b)) == oracle.gt_pow((a, b), 600)
 
 
+def test_fp32_curve_arithmetic_exhaustive(hostemul, oracle):
+    """pbh_g1f.cuh, the exact FP32 arithmetic of PBH_ALGO_ARITH: ALL 102 x 102 sums through the unified slope
+    (x1^2 + x1 x2 + x2^2) / (y1 + y2) against the reference's case analysis (src/pbh/g1.rs:119-144), all 102 x 101 multiples
+    (:146-168), multiples of off-curve points (they live on y^2 = x^3 + b' and the formulas never use b), the pairing and the
+    Miller value of every point against several G2 arguments (src/pbh/pairing.rs:12-47), pow(600) on ALL of F_101^2
+    (src/pbh/gt.rs:33-59), and the reduction mod 101 on its whole validity range."""
+    assert hostemul.check_red101_f32() == 0
+    pts = [(x, y, 0) for x in range(101) for y in range(101) if (y * y - x * x * x - 3) % 101 == 0] + [(0, 0, 1)]
+    P = np.array(pts, dtype=np.uint8)
+    a = np.repeat(P, 102, axis=0); b = np.tile(P, (102, 1))
+    exp = oracle.g1_add_batch(np.ascontiguousarray(np.concatenate([a, b], axis=1).T))
+    for i in range(102 * 102):
+        assert list(hostemul.g1f_add(tuple(a[i]), tuple(b[i]))) == exp[:, i].tolist(), (a[i], b[i])
+    sm = np.ascontiguousarray(np.concatenate([np.repeat(P, 101, axis=0), np.tile(np.arange(101, dtype=np.uint8), 102)[:, None]], axis=1).T)
+    exp = oracle.g1_smul_batch(sm)
+    for i in range(sm.shape[1]):
+        assert list(hostemul.g1f_smul(tuple(sm[:3, i]), int(sm[3, i]))) == exp[:, i].tolist(), sm[:, i]
+    rng = np.random.default_rng(12)
+    r4 = rng.integers(0, 101, size=(4, 20000), dtype=np.uint8); r4[2] = rng.integers(0, 2, size=20000)      # mostly off-curve
+    exp = oracle.g1_smul_batch(r4)
+    for i in range(r4.shape[1]):
+        assert list(hostemul.g1f_smul(tuple(r4[:3, i]), int(r4[3, i]))) == exp[:, i].tolist(), r4[:, i]
+    for q in [(36, 31), (90, 82), (10, 16), (5, 77), (0, 0), (100, 100)]:
+        for p in pts + [(1, 2, 1), (48, 0, 1)]:
+            e, m = hostemul.pairingf(p, q)
+            po = None if (p[2] and p[0] == 0) else p
+            assert e == oracle.pairing(po, q) and m == oracle.miller(po, q), (p, q)
+    for x in range(101):
+        for y in range(101):
+            assert hostemul.gtf_final_exp((x, y)) == oracle.gt_pow((x, y), 600)
+
+
 @pytest.mark.parametrize("algo", (1, 2, 3))
 def test_fuzz_arbitrary_bytes(hostemul, oracle, algo):
     """Any byte value in any input plane: same classes and bytes as the oracle (CPU guard of the GPU fuzz test)."""

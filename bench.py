@@ -531,7 +531,17 @@ def main():
             ctx.sync()
         for s_ in sets:
             s_["proof"][...] = 0; s_["status"][...] = 255; s_["result"][...] = 255
-        dt_lanes = timed(lanes_step, ksteps)
+        dt_lanes = timed(lanes_step, ksteps)             # the library's default PBH_OPT_LANE_MODE
+        lane_modes = {}
+        for mode, what in ((0, "kernels read and write the host buffers in place"), (1, "copy-engine upload, in-place stores"),
+                           (3, "copy engine both ways")):
+            ctx.set_option(pbh_b200.OPT_LANE_MODE, mode)
+            for i in range(2):
+                lanes_step(i)
+            ctx.sync()
+            dtm = timed(lanes_step, ksteps)
+            lane_modes[str(mode)] = {"value": n * world * ksteps / dtm, "ms_per_step": 1e3 * dtm / ksteps, "how": what}
+        ctx.set_option(pbh_b200.OPT_LANE_MODE, 1)
         # every byte the lane pipeline produced equals the device-resident path of ring slot 0
         ref_proof, ref_status, ref_result = (outs[0][k].cpu().numpy() for k in ("proof", "status", "result"))
         e2e_equal = all(np.array_equal(s_["proof"], ref_proof) and np.array_equal(s_["status"], ref_status) and
@@ -548,6 +558,7 @@ def main():
                "numa_node_of_device": ctx.numa_node,
                "timing": "host wall clock around the C-ABI calls up to the final pbh_ctx_sync, max over ranks",
                "bytes_equal_device_path": bool(e2e_equal),
+               "lane_modes": lane_modes,
                "two_sync_calls_pinned": dict(per(dt_pinned, ksteps), api="pbh_prove_batch then pbh_verify_batch, page-locked buffers"),
                "two_sync_calls_pageable": dict(per(dt_pageable, max(3, ksteps // 2)), api="pbh_prove_batch then pbh_verify_batch, pageable numpy buffers (staged chunks)"),
                "fused_call": dict(per(dt_fused, ksteps), h2d_bytes_per_step=n * 27 * world, d2h_bytes_per_step=n * 29 * world,

@@ -144,6 +144,12 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 /* PBH_OPT_VERIFIER_FP32: with PBH_ALGO_TABLE, run the verifier's F_17 scalar work in int32 (0, default: measured 25.4
  * against 28.7 us per 2^20 items) or as exact small-integer FP32 (1). */
 #define PBH_OPT_VERIFIER_FP32 7
+/* PBH_OPT_LANE_MODE: how the asynchronous lane calls (pbh_prove_batch_async / pbh_verify_batch_async) move page-locked
+ * buffers.  Bit 0: inputs are uploaded whole by the copy engine into a per-lane staging buffer (else the kernel reads mapped
+ * memory in place); bit 1: outputs come back through the copy engine (else the kernel stores into mapped memory in place).
+ * 0 = in place both ways, 1 = copy-engine upload + in-place stores (default: measured fastest on PCIe Gen5), 3 = copy engine
+ * both ways.  Buffers that are page-locked but not mapped always go through the copy engine. */
+#define PBH_OPT_LANE_MODE 8
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */
@@ -183,9 +189,9 @@ int pbh_verify_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t pr
  * (0 .. PBH_LANES-1) and returns.  Calls on one lane run in issue order, so verify(k) may read the proof that prove(k)
  * writes when both use the same lane; calls on different lanes overlap - PCIe is full duplex, the download of one batch
  * travels beside the upload of the next.  Every buffer must stay valid and untouched until pbh_lane_sync(ctx, lane) or
- * pbh_ctx_sync(ctx) returns.  Only page-locked, mapped buffers (pbh_host_alloc, cudaHostAlloc, cudaHostRegister) are
- * asynchronous: the kernels run in place on them.  With any other buffer the call waits for the context's earlier work
- * and then behaves exactly like the synchronous entry point. */
+ * pbh_ctx_sync(ctx) returns.  Only page-locked buffers (pbh_host_alloc, cudaHostAlloc, cudaHostRegister) are asynchronous
+ * (PBH_OPT_LANE_MODE says how they travel); with pageable memory the call waits for the context's earlier work and then
+ * behaves exactly like the synchronous entry point.  Batches above 2^24 items are processed synchronously as well. */
 #define PBH_LANES 4
 int pbh_prove_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand,
                           size_t rand_pitch, const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch,
@@ -286,6 +292,15 @@ int pbh_ntt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t in_pitc
  * coefficients (zero padded; the reference's normalised length is implied by the values). */
 int pbh_intt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* evals, size_t in_pitch, uint8_t* coeffs,
                     size_t out_pitch, int on_device);
+/* The same two transforms on a COSET k H of the order-4 subgroup: evals[i] = p(k 4^i), and its inverse.  k = 2 and k = 3 are
+ * K1 and K2 of src/pbh/mod.rs:27-28, whose cosets k1_h = {2, 8, 15, 9} and k2_h = {3, 12, 14, 5} the reference builds in
+ * Plonk::new (src/plonk.rs:136-139) for the copy-constraint labels; k = 1 is H itself (pbh_ntt4_batch / pbh_intt4_batch).
+ * The reference has no coset transform of its own: the forward results equal Poly::eval (src/poly.rs:71-79) of the
+ * polynomial at the four coset points, the inverse undoes it.  Any other k: PBH_ERR_UNSUPPORTED. */
+int pbh_coset_ntt4_batch(pbh_ctx* ctx, size_t n, uint32_t k, const uint8_t* coeffs, size_t in_pitch, uint8_t* evals,
+                         size_t out_pitch, int on_device);
+int pbh_coset_intt4_batch(pbh_ctx* ctx, size_t n, uint32_t k, const uint8_t* evals, size_t in_pitch, uint8_t* coeffs,
+                          size_t out_pitch, int on_device);
 /* generic power-of-two NTT / iNTT over F_modulus (modulus < 2^16, size in {2,4,...,64}), values as
  * uint16 planes; reproduces CooleyTurkey::fft / fft_inv (src/fft.rs:66-78) for full-length input. */
 int pbh_ntt_generic_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t omega, uint32_t size, int inverse,

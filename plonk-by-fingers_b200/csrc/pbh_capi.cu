@@ -60,6 +60,9 @@ struct pbh_ctx {
   uint8_t* slot_buf[kSlots] = {};
   size_t slot_bytes = 0;
   uint64_t launches = 0;
+  uint8_t* lane_buf[kSlots] = {};          // whole-batch staging of the asynchronous lanes (PBH_OPT_LANE_MODE 1 and 3)
+  size_t lane_bytes[kSlots] = {};
+  int lane_mode = 1;                       // PBH_OPT_LANE_MODE
   int grid_scale = 2;                      // persistent-grid blocks per SM are grid_scale/2 of the kernel's residency (1: half grids, async lanes)
   int numa_node = -1;                      // NUMA node of the device's PCIe root (sysfs), -1 when the platform does not say
   std::map<void*, std::pair<size_t, bool>> host_allocs;   // pbh_host_alloc: pointer -> (bytes, mmap'ed + registered)
@@ -171,6 +174,7 @@ void pbh_ctx_destroy(pbh_ctx* ctx) {
   for (int s = 0; s < kSlots; s++) {
     if (ctx->slot_stream[s]) { cudaStreamSynchronize(ctx->slot_stream[s]); cudaStreamDestroy(ctx->slot_stream[s]); }
     if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
+    if (ctx->lane_buf[s]) cudaFree(ctx->lane_buf[s]);
   }
   if (ctx->compute) { cudaStreamSynchronize(ctx->compute); cudaStreamDestroy(ctx->compute); }
   for (auto& a : ctx->host_allocs) { if (a.second.second) { cudaHostUnregister(a.first); munmap(a.first, a.second.first); } else cudaFreeHost(a.first); }
@@ -205,6 +209,11 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
   if (option == PBH_OPT_SPECIALISE) { ctx->specialise = value != 0; return PBH_OK; }
   if (option == PBH_OPT_HOST_DIRECT) { ctx->host_direct = value != 0; return PBH_OK; }
   if (option == PBH_OPT_VERIFIER_FP32) { ctx->verifier_fp32 = value != 0; return PBH_OK; }
+  if (option == PBH_OPT_LANE_MODE) {
+    if (value != 0 && value != 1 && value != 3) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "lane mode must be 0, 1 or 3");
+    ctx->lane_mode = value;
+    return PBH_OK;
+  }
   if (option == PBH_OPT_CHUNK_LOG2) {
     if (value < 8 || value > 20) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "chunk log2 must be in [8, 20]");
     ctx->chunk = (size_t)1 << value;
@@ -628,6 +637,24 @@ static int lane_stream(pbh_ctx* ctx, int lane, cudaStream_t* st) {
   *st = ctx->slot_stream[lane];
   return PBH_OK;
 }
+// page-locked (mapped or not): the copy engines can read and write it asynchronously
+static bool host_pinned(const uint8_t* p) {
+  if (!p) return false;
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+// whole-batch staging buffer of a lane: `rows` planes of pitch C = n rounded up to a tile
+static int ensure_lane(pbh_ctx* ctx, int lane, size_t bytes) {
+  if (ctx->lane_bytes[lane] >= bytes) return PBH_OK;
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[lane]));
+  if (ctx->lane_buf[lane]) { CUDA_TRY(ctx, cudaFree(ctx->lane_buf[lane])); ctx->lane_buf[lane] = nullptr; ctx->lane_bytes[lane] = 0; }
+  CUDA_TRY(ctx, cudaMalloc(&ctx->lane_buf[lane], bytes));
+  ctx->lane_bytes[lane] = bytes;
+  return PBH_OK;
+}
+static constexpr size_t kLaneMaxItems = (size_t)1 << 24;   // larger batches take the synchronous chunked path
+
 int pbh_prove_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,
                           const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status) {
   CTX_CHECK(ctx);
@@ -641,13 +668,39 @@ int pbh_prove_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* wit, 
   const uint8_t *a_wit = mapped_host_alias(ctx, wit, 11 * wit_pitch + n), *a_rnd = mapped_host_alias(ctx, rnd, 8 * rand_pitch + n),
                 *a_chal = mapped_host_alias(ctx, chal, 4 * chal_pitch + n);
   uint8_t *a_proof = mapped_host_alias(ctx, proof, 26 * proof_pitch + n), *a_status = mapped_host_alias(ctx, status, n);
-  if (a_wit && a_rnd && a_chal && a_proof && a_status) {
+  const bool in_mapped = a_wit && a_rnd && a_chal, out_mapped = a_proof && a_status;
+  const bool in_pinned = host_pinned(wit) && host_pinned(rnd) && host_pinned(chal), out_pinned = host_pinned(proof) && host_pinned(status);
+  // inputs: uploaded by the copy engine (mode bit 0, page-locked memory) or read in place (mapped memory); outputs alike (bit 1)
+  const bool in_ce = in_pinned && ((ctx->lane_mode & 1) || !in_mapped) && n <= kLaneMaxItems;
+  const bool out_ce = out_pinned && ((ctx->lane_mode & 2) || !out_mapped) && n <= kLaneMaxItems;
+  if ((in_ce || in_mapped) && (out_ce || out_mapped)) {
+    const size_t C = (n + kTile - 1) / kTile * kTile;
+    uint8_t* base = nullptr;
+    if (in_ce || out_ce) {
+      rc = ensure_lane(ctx, lane, 64 * C);
+      if (rc) return rc;
+      base = ctx->lane_buf[lane];
+    }
     ProveArgs A{a_wit, wit_pitch, a_rnd, rand_pitch, a_chal, chal_pitch, a_proof, proof_pitch, a_status, n};
+    if (in_ce) {
+      uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C;
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit, wit_pitch, n, 12, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd, rand_pitch, n, 9, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal, chal_pitch, n, 5, cudaMemcpyHostToDevice, st));
+      A.wit = d_wit; A.wit_pitch = C; A.rnd = d_rnd; A.rand_pitch = C; A.chal = d_chal; A.chal_pitch = C;
+    }
+    if (out_ce) { A.proof = base + 26 * C; A.proof_pitch = C; A.status = base + 53 * C; }
+    // kernels that touch host memory directly run on half grids, so that two lanes' kernels are resident together
     const int keep = ctx->grid_scale;
-    ctx->grid_scale = 1;
+    ctx->grid_scale = (in_ce && out_ce) ? 2 : 1;
     rc = launch_prove(ctx, st, A);
     ctx->grid_scale = keep;
-    return rc;
+    if (rc) return rc;
+    if (out_ce) {
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(proof, proof_pitch, A.proof, C, n, 27, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(ctx, cudaMemcpyAsync(status, A.status, n, cudaMemcpyDeviceToHost, st));
+    }
+    return PBH_OK;
   }
   rc = pbh_ctx_sync(ctx);   // the staged path shares the slot streams with the lanes
   if (rc) return rc;
@@ -666,13 +719,38 @@ int pbh_verify_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* proo
   const uint8_t *a_proof = mapped_host_alias(ctx, proof, 26 * proof_pitch + n), *a_chal = mapped_host_alias(ctx, chal, 4 * chal_pitch + n),
                 *a_u = mapped_host_alias(ctx, u, n);
   uint8_t *a_res = mapped_host_alias(ctx, result, n), *a_gt = gt ? mapped_host_alias(ctx, gt, 3 * gt_pitch + n) : nullptr;
-  if (a_proof && a_chal && a_u && a_res && (!gt || a_gt)) {
+  const bool in_mapped = a_proof && a_chal && a_u, out_mapped = a_res && (!gt || a_gt);
+  const bool in_pinned = host_pinned(proof) && host_pinned(chal) && host_pinned(u), out_pinned = host_pinned(result) && (!gt || host_pinned(gt));
+  const bool in_ce = in_pinned && ((ctx->lane_mode & 1) || !in_mapped) && n <= kLaneMaxItems;
+  const bool out_ce = out_pinned && ((ctx->lane_mode & 2) || !out_mapped) && n <= kLaneMaxItems;
+  if ((in_ce || in_mapped) && (out_ce || out_mapped)) {
+    const size_t C = (n + kTile - 1) / kTile * kTile;
+    uint8_t* base = nullptr;
+    if (in_ce || out_ce) {
+      rc = ensure_lane(ctx, lane, 64 * C);
+      if (rc) return rc;
+      base = ctx->lane_buf[lane];
+    }
     VerifyArgs A{a_proof, proof_pitch, a_chal, chal_pitch, a_u, a_res, a_gt, gt_pitch, n, nullptr};
+    if (in_ce) {
+      // rows 0..53 of the lane buffer belong to a prove call that may still be in flight on this lane: verify stages elsewhere
+      uint8_t *d_proof = base + 26 * C, *d_chal = base + 54 * C, *d_u = base + 59 * C;
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof, proof_pitch, n, 27, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal, chal_pitch, n, 5, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u, n, cudaMemcpyHostToDevice, st));
+      A.proof = d_proof; A.proof_pitch = C; A.chal = d_chal; A.chal_pitch = C; A.u = d_u;
+    }
+    if (out_ce) { A.result = base + 60 * C; if (gt) { A.gt = base; A.gt_pitch = C; } }
     const int keep = ctx->grid_scale;
-    ctx->grid_scale = 1;
+    ctx->grid_scale = (in_ce && out_ce) ? 2 : 1;
     rc = launch_verify(ctx, st, A);
     ctx->grid_scale = keep;
-    return rc;
+    if (rc) return rc;
+    if (out_ce) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(result, A.result, n, cudaMemcpyDeviceToHost, st));
+      if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt, gt_pitch, A.gt, C, n, 4, cudaMemcpyDeviceToHost, st));
+    }
+    return PBH_OK;
   }
   rc = pbh_ctx_sync(ctx);
   if (rc) return rc;
@@ -970,10 +1048,11 @@ struct Staged {
   (ctx)->launches++;                                   \
   CUDA_TRY(ctx, cudaGetLastError())
 
-static int ntt4_impl(pbh_ctx* ctx, bool inverse, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
+static int ntt4_impl(pbh_ctx* ctx, bool inverse, uint32_t k, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
                      int on_device) {
   SWEEP_PROLOGUE(ctx, n);
   if (!in || !out || in_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  if (k < 1 || k > 3) return fail(ctx, PBH_ERR_UNSUPPORTED, "coset shift must be 1 (H), 2 (K1) or 3 (K2): src/pbh/mod.rs:27-28");
   const uint8_t* d_in = in; uint8_t* d_out = out; size_t ip = in_pitch, op = out_pitch;
   if (!on_device) {
     d_in = stg.in(in, in_pitch, n, 4, ce); CUDA_TRY(ctx, ce);
@@ -983,17 +1062,27 @@ static int ntt4_impl(pbh_ctx* ctx, bool inverse, size_t n, const uint8_t* in, si
   auto aligned = [&](size_t a) { return ((uintptr_t)d_in % a == 0) && ((uintptr_t)d_out % a == 0) && (ip % a == 0) && (op % a == 0); };
   const int vec = aligned(16) ? 16 : (aligned(4) ? 4 : 0);
   int grid = grid_for(ctx, vec ? (n + vec - 1) / vec : n, 8);
-  if (inverse) ntt4_kernel<true><<<grid, kBlock, 0, ctx->compute>>>(n, d_in, ip, d_out, op, vec);
-  else ntt4_kernel<false><<<grid, kBlock, 0, ctx->compute>>>(n, d_in, ip, d_out, op, vec);
+#define PBH_NTT4(INV, KK) ntt4_kernel<INV, KK><<<grid, kBlock, 0, ctx->compute>>>(n, d_in, ip, d_out, op, vec)
+  if (inverse) { if (k == 1) PBH_NTT4(true, 1); else if (k == 2) PBH_NTT4(true, 2); else PBH_NTT4(true, 3); }
+  else { if (k == 1) PBH_NTT4(false, 1); else if (k == 2) PBH_NTT4(false, 2); else PBH_NTT4(false, 3); }
+#undef PBH_NTT4
   SWEEP_FINISH(ctx);
   if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, 4)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
   return PBH_OK;
 }
 int pbh_ntt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t in_pitch, uint8_t* evals, size_t out_pitch, int on_device) {
-  return ntt4_impl(ctx, false, n, coeffs, in_pitch, evals, out_pitch, on_device);
+  return ntt4_impl(ctx, false, 1, n, coeffs, in_pitch, evals, out_pitch, on_device);
 }
 int pbh_intt4_batch(pbh_ctx* ctx, size_t n, const uint8_t* evals, size_t in_pitch, uint8_t* coeffs, size_t out_pitch, int on_device) {
-  return ntt4_impl(ctx, true, n, evals, in_pitch, coeffs, out_pitch, on_device);
+  return ntt4_impl(ctx, true, 1, n, evals, in_pitch, coeffs, out_pitch, on_device);
+}
+int pbh_coset_ntt4_batch(pbh_ctx* ctx, size_t n, uint32_t k, const uint8_t* coeffs, size_t in_pitch, uint8_t* evals, size_t out_pitch,
+                         int on_device) {
+  return ntt4_impl(ctx, false, k, n, coeffs, in_pitch, evals, out_pitch, on_device);
+}
+int pbh_coset_intt4_batch(pbh_ctx* ctx, size_t n, uint32_t k, const uint8_t* evals, size_t in_pitch, uint8_t* coeffs, size_t out_pitch,
+                          int on_device) {
+  return ntt4_impl(ctx, true, k, n, evals, in_pitch, coeffs, out_pitch, on_device);
 }
 
 int pbh_ntt_generic_batch(pbh_ctx* ctx, size_t n, uint32_t modulus, uint32_t omega, uint32_t size, int inverse, const uint16_t* in,

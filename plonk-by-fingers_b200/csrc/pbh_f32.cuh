@@ -1,5 +1,5 @@
 // pbh_f32.cuh — the plain-float scalar policy of the FP32-pipe arithmetic (pbh_prove_f32.cuh, pbh_g1f.cuh): exact small
-// integers held in floats.  tests/hostemul supplies a second policy with the same function names that propagates
+// integers held in floats.  The CPU test suite supplies a second policy with the same function names that propagates
 // worst-case magnitudes instead of values; the arithmetic templates are instantiated with both.
 #pragma once
 #include <math.h>
@@ -26,6 +26,14 @@ PBH_HD F32 f_red(F32 x) {
   return F32(fmaf(q, -17.0f, x.v));
 }
 PBH_HD bool f_is_zero(F32 x) { return x.v == 0.0f; }               // for reduced values
+// true when the predicate holds for any item handled by this warp (a warp vote on the device, the item itself on the host)
+PBH_HD bool f_any(bool b, F32*) {
+#if defined(__CUDA_ARCH__)
+  return __any_sync(__activemask(), b) != 0;
+#else
+  return b;
+#endif
+}
 // canonical residue 0..16 of a centred one, as an integer (full-rate ops: compare/select, FADD, LOP3)
 PBH_HD uint32_t f_canon(F32 x) {
   float c = x.v < 0.0f ? x.v + 17.0f : x.v;

@@ -18,14 +18,14 @@
 //
 // Exactness: every value is an integer below 2^21 in magnitude (red101 is exact there: checked for every integer of the
 // range by the CPU test suite, and the bounds of every expression are machine-checked by instantiating these templates
-// with the magnitude-propagating type of tests/hostemul).
+// with the magnitude-propagating scalar type of the CPU test suite).
 #pragma once
 #include "pbh_arith.cuh"
 #include "pbh_f32.cuh"
 
 namespace pbh {
 
-// ---- FP32 primitives for F_101 (plain float policy; tests/hostemul adds the bound-propagating policy) ----------------
+// ---- FP32 primitives for F_101 (plain float policy; the CPU test suite adds a bound-propagating policy) ----------------
 // centred residue in [-50, 50] of an exact integer |x| <= 2^21
 PBH_HD F32 f_red101(F32 x) {
   float t = fmaf(x.v, 0.009900990099009901f, 12582912.0f);

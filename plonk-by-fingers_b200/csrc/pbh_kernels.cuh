@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     }
     if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
 
-    const uint8_t* in = &S.in[stage][0][tid];
+    const uint32_t it = (uint32_t)tid;
+    const uint8_t* in = &S.in[stage][0][it];
     uint32_t w[12], r[9], c[5];
     bool bad = false;
 #pragma unroll
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     uint32_t status = prove_item_f32<ALGO, PBH_CIRCUIT>(w, r, c, K, KF, S.T, P, unsat ? 1 : 0);
     if (bad) status = PBH_ST_BAD_ENCODING;
 
-    uint8_t* out = &S.out[stage][0][tid];
+    uint8_t* out = &S.out[stage][0][it];
     uint32_t inf_lo = 0, inf_hi = 0;
     const bool ok = status == 0u;
 #pragma unroll
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     out[19 * kTile] = (uint8_t)inf_hi;
 #pragma unroll
     for (int k = 0; k < 7; k++) out[(20 + k) * kTile] = (uint8_t)(ok ? P.ev[k] : 0u);
-    const size_t i = tile * kTile + tid;
+    const size_t i = tile * kTile + it;
     if (i < n) status_out[i] = (uint8_t)status;
     if (digest_out != nullptr && i < n) {
       // digest of this item's 27 proof bytes (pbh_digest_dev's definition), from registers: planes 4k..4k+3 per word
@@ -518,10 +519,50 @@ __device__ __forceinline__ uint32_t swar_mod17(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t swar_neg17(uint32_t x) { return 0x11111111u - x; }   // lanes 0..16 -> 17 - lane (1..17)
 
-// forward: e_i = sum_j c_j 4^(ij); inverse: f_j = 13 sum_i 4^(-ij) v_i with 13 = 1/4 = -4   (src/fft.rs:66-106, src/plonk.rs:177-179)
-template <bool INVERSE>
+// lanes 0..16 times the constant C (0 < C < 17): lanes congruent to C x, at most 255, by shifts and adds (-c is 17 - c)
+template <int C>
+__device__ __forceinline__ uint32_t swar_mulc(uint32_t x) {
+  static_assert(C >= 1 && C <= 16, "F_17 constant");
+  switch (C) {
+    case 1: return x;
+    case 2: return x << 1;
+    case 3: return x + (x << 1);
+    case 4: return x << 2;
+    case 5: return x + (x << 2);
+    case 6: return (x << 1) + (x << 2);
+    case 7: return (x << 3) + swar_neg17(x);                 // 8x - x = 8x + (17 - x), lanes <= 145
+    case 8: return x << 3;
+    case 9: return x + (x << 3);
+    case 10: return (x << 1) + (x << 3);
+    case 11: return swar_mulc<6>(swar_neg17(x));              // -6 (17 - x <= 17: lanes <= 102)
+    case 12: return (x << 2) + (x << 3);
+    case 13: return swar_neg17(x) << 2;                       // -4
+    case 14: return swar_mulc<3>(swar_neg17(x));              // -3
+    case 15: return swar_neg17(x) << 1;                       // -2
+    default: return swar_neg17(x);                            // -1
+  }
+}
+// lanes 0..255 -> lanes congruent to -4 x (= x / 4: 13 = 1/4 = -4), in 8..128, WITHOUT reducing x first: x = 16 a + b = b - a,
+// so -4 x = 4 a + 4 (17 - b); one lane reduction fewer per output of the inverse transform
+__device__ __forceinline__ uint32_t swar_m4(uint32_t x) {
+  const uint32_t lo = x & 0x0F0F0F0Fu, hi = (x >> 4) & 0x0F0F0F0Fu;
+  return ((hi + 0x11111111u) - lo) << 2;                      // lanes (a + 17 - b) <= 32, times 4 <= 128: no carry between lanes
+}
+__host__ __device__ constexpr int pow17(int b, int e) { int r = 1; for (int i = 0; i < e; i++) r = r * b % 17; return r; }
+__host__ __device__ constexpr int inv17c_(int a) { return pow17(a, 15); }
+
+// Size-4 transforms over F_17 with omega = 4 on the coset K H, K in {1, 2, 3}: K = 1 is H itself (src/fft.rs:66-106 with
+// EvaluationDomainGenerator(4, 4); the inverse is Plonk::interpolate_at_h, src/plonk.rs:177-179), K = 2 and K = 3 are the
+// cosets k1 H = {2, 8, 15, 9} and k2 H = {3, 12, 14, 5} of src/plonk.rs:136-139 (K1, K2 of src/pbh/mod.rs:27-28).
+//   forward: e_i = p(K 4^i) = sum_j (c_j K^j) 4^(ij)         - the plain transform of the coefficients scaled by K^j
+//   inverse: c_j = K^-j * 13 sum_i 4^(-ij) v_i, 13 = 1/4     - the plain inverse, its 1/4 folded with K^-j into ONE constant
+// so the inverse costs the same as on H, and the forward transform costs three more lane reductions.
+template <bool INVERSE, int K>
 __device__ __forceinline__ void swar_ntt4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t (&o)[4]) {
   w0 = swar_mod17(w0); w1 = swar_mod17(w1); w2 = swar_mod17(w2); w3 = swar_mod17(w3);   // any byte value is accepted
+  if (!INVERSE && K != 1) {
+    w1 = swar_mod17(swar_mulc<pow17(K, 1)>(w1)); w2 = swar_mod17(swar_mulc<pow17(K, 2)>(w2)); w3 = swar_mod17(swar_mulc<pow17(K, 3)>(w3));
+  }
   const uint32_t n1 = swar_neg17(w1), n2 = swar_neg17(w2), n3 = swar_neg17(w3);
   const uint32_t s0 = w0 + w1 + w2 + w3;                            // lanes <= 64
   const uint32_t sp = w0 + (w1 << 2) + n2 + (n3 << 2);              // c0 + 4c1 - c2 - 4c3, lanes <= 165
@@ -530,18 +571,22 @@ __device__ __forceinline__ void swar_ntt4(uint32_t w0, uint32_t w1, uint32_t w2,
   if (!INVERSE) {
     o[0] = swar_mod17(s0); o[1] = swar_mod17(sp); o[2] = swar_mod17(s2); o[3] = swar_mod17(sm);
   } else {
-    // omega^-1 = -4 swaps the roles of sp and sm; then multiply by 13 = -4: 4 * (17 - residue) <= 68
-    o[0] = swar_mod17(swar_neg17(swar_mod17(s0)) << 2);
-    o[1] = swar_mod17(swar_neg17(swar_mod17(sm)) << 2);
-    o[2] = swar_mod17(swar_neg17(swar_mod17(s2)) << 2);
-    o[3] = swar_mod17(swar_neg17(swar_mod17(sp)) << 2);
+    // omega^-1 = -4 swaps the roles of sp and sm; then one constant per coefficient: 13 K^-j
+    o[0] = swar_mod17(swar_m4(s0));
+    if (K == 1) {
+      o[1] = swar_mod17(swar_m4(sm)); o[2] = swar_mod17(swar_m4(s2)); o[3] = swar_mod17(swar_m4(sp));
+    } else {
+      o[1] = swar_mod17(swar_mulc<13 * inv17c_(pow17(K, 1)) % 17>(swar_mod17(sm)));
+      o[2] = swar_mod17(swar_mulc<13 * inv17c_(pow17(K, 2)) % 17>(swar_mod17(s2)));
+      o[3] = swar_mod17(swar_mulc<13 * inv17c_(pow17(K, 3)) % 17>(swar_mod17(sp)));
+    }
   }
 }
 
 // vec: 0 = byte path, 4 = one 32-bit word per plane and thread (4 items), 16 = one 128-bit word (16 items; needs
 // 16-byte aligned bases and pitches).  Wider accesses keep more bytes in flight per thread: the kernel is
 // latency-limited, not ALU-limited.
-template <bool INVERSE>
+template <bool INVERSE, int K>
 __global__ void __launch_bounds__(kBlock) ntt4_kernel(size_t n, const uint8_t* __restrict__ in, size_t in_pitch,
                                                        uint8_t* __restrict__ out, size_t out_pitch, int vec) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -553,10 +598,10 @@ __global__ void __launch_bounds__(kBlock) ntt4_kernel(size_t n, const uint8_t* _
 #pragma unroll
       for (int k = 0; k < 4; k++) wv[k] = reinterpret_cast<const uint4*>(in + (size_t)k * in_pitch)[q];
       uint32_t o[4];
-      swar_ntt4<INVERSE>(wv[0].x, wv[1].x, wv[2].x, wv[3].x, o); ov[0].x = o[0]; ov[1].x = o[1]; ov[2].x = o[2]; ov[3].x = o[3];
-      swar_ntt4<INVERSE>(wv[0].y, wv[1].y, wv[2].y, wv[3].y, o); ov[0].y = o[0]; ov[1].y = o[1]; ov[2].y = o[2]; ov[3].y = o[3];
-      swar_ntt4<INVERSE>(wv[0].z, wv[1].z, wv[2].z, wv[3].z, o); ov[0].z = o[0]; ov[1].z = o[1]; ov[2].z = o[2]; ov[3].z = o[3];
-      swar_ntt4<INVERSE>(wv[0].w, wv[1].w, wv[2].w, wv[3].w, o); ov[0].w = o[0]; ov[1].w = o[1]; ov[2].w = o[2]; ov[3].w = o[3];
+      swar_ntt4<INVERSE, K>(wv[0].x, wv[1].x, wv[2].x, wv[3].x, o); ov[0].x = o[0]; ov[1].x = o[1]; ov[2].x = o[2]; ov[3].x = o[3];
+      swar_ntt4<INVERSE, K>(wv[0].y, wv[1].y, wv[2].y, wv[3].y, o); ov[0].y = o[0]; ov[1].y = o[1]; ov[2].y = o[2]; ov[3].y = o[3];
+      swar_ntt4<INVERSE, K>(wv[0].z, wv[1].z, wv[2].z, wv[3].z, o); ov[0].z = o[0]; ov[1].z = o[1]; ov[2].z = o[2]; ov[3].z = o[3];
+      swar_ntt4<INVERSE, K>(wv[0].w, wv[1].w, wv[2].w, wv[3].w, o); ov[0].w = o[0]; ov[1].w = o[1]; ov[2].w = o[2]; ov[3].w = o[3];
 #pragma unroll
       for (int k = 0; k < 4; k++) reinterpret_cast<uint4*>(out + (size_t)k * out_pitch)[q] = ov[k];
     }
@@ -567,7 +612,7 @@ __global__ void __launch_bounds__(kBlock) ntt4_kernel(size_t n, const uint8_t* _
       uint32_t wv[4], ov[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) wv[k] = reinterpret_cast<const uint32_t*>(in + (size_t)k * in_pitch)[q];
-      swar_ntt4<INVERSE>(wv[0], wv[1], wv[2], wv[3], ov);
+      swar_ntt4<INVERSE, K>(wv[0], wv[1], wv[2], wv[3], ov);
 #pragma unroll
       for (int k = 0; k < 4; k++) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = ov[k];
     }
@@ -575,7 +620,7 @@ __global__ void __launch_bounds__(kBlock) ntt4_kernel(size_t n, const uint8_t* _
   }
   for (size_t i = done + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     uint32_t ov[4];
-    swar_ntt4<INVERSE>(in[i], in[in_pitch + i], in[2 * in_pitch + i], in[3 * in_pitch + i], ov);   // one live lane
+    swar_ntt4<INVERSE, K>(in[i], in[in_pitch + i], in[2 * in_pitch + i], in[3 * in_pitch + i], ov);   // one live lane
 #pragma unroll
     for (int k = 0; k < 4; k++) out[(size_t)k * out_pitch + i] = (uint8_t)ov[k];
   }
@@ -677,7 +722,7 @@ __global__ void __launch_bounds__(kBlock) mul_ntt_kernel(size_t n, uint32_t modu
 // Here two items share one packed-half instruction: a byte b becomes the half 1024 + b by planting the exponent byte 0x64
 // next to it (one PRMT for two lanes), all values are integers below 2048 in magnitude and therefore exact in fp16, and
 // x mod 17 is three HFMA2-class instructions for two lanes (round(x / 17) with the 1536 = 1.5 * 2^10 rounding constant,
-// exact for |x| <= 2048: checked for every integer of the range by tests/test_hostemul_parity.py).  Any input byte is
+// exact for |x| <= 2048: checked for every integer of the range by the CPU test suite).  Any input byte is
 // accepted: |acc * x + c| <= 8 * 8 + 255 and |c * x| <= 255 * 8.
 __device__ __forceinline__ __half2 h2_bits(uint32_t b) { return *reinterpret_cast<__half2*>(&b); }
 __device__ __forceinline__ uint32_t h2_word(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
@@ -782,12 +827,12 @@ __global__ void __launch_bounds__(kBlock) poly_mul_kernel(size_t n, uint32_t la,
 // arithmetic: round 1's kernel above keeps its operand lengths in registers and executed 560 instructions per 6 x 6 product
 // (profiles/r02a_sweeps_before.txt).  Input bytes are used as they are (any value: 8 x 255^2 < 2^20), every output is
 // reduced once with a FLOOR reduction that lands on the canonical residue 0..16 directly (the operands are non-negative:
-// q = rint(x / 17 - 0.48) is floor(x / 17) because the fractional parts of x / 17 are multiples of 1 / 17), and the four
+// q = rint((x - 8) / 17) is floor(x / 17) because the fractional parts of x / 17 are multiples of 1 / 17), and the four
 // lanes of an output word are packed by planting them under the 2^23 exponent.
 __device__ __forceinline__ float f_byte(uint32_t w, int k) { return __int_as_float((int)__byte_perm(w, 0x4B000000u, 0x7440u + (uint32_t)k)) - 8388608.0f; }
-__device__ __forceinline__ uint32_t f_floor_mod17_biased(float x) {      // bits of 2^23 + (x mod 17) for an exact integer 0 <= x < 2^20
-  const float q = fmaf(x, 0.058823529411764705f, 12582912.0f - 0.48f) - 12582912.0f;
-  return (uint32_t)__float_as_int(fmaf(q, -17.0f, x) + 8388608.0f);
+__device__ __forceinline__ uint32_t f_floor_mod17_biased(float xm8) {    // xm8 = x - 8 for an exact integer 0 <= x < 2^20: bits of 2^23 + (x mod 17)
+  const float q = fmaf(xm8, 0.058823529411764705f, 12582912.0f) - 12582912.0f;    // rint((x - 8) / 17) = floor(x / 17)
+  return (uint32_t)__float_as_int(fmaf(q, -17.0f, xm8) + 8388616.0f);             // x - 8 - 17 q + 8 + 2^23
 }
 template <int LA, int LB>
 __global__ void __launch_bounds__(kBlock) poly_mul_vec_kernel(size_t n4, uint32_t la, uint32_t lb, const uint8_t* __restrict__ a, size_t a_pitch,
@@ -813,7 +858,7 @@ __global__ void __launch_bounds__(kBlock) poly_mul_vec_kernel(size_t n4, uint32_
         uint32_t r[4];
 #pragma unroll
         for (int l = 0; l < 4; l++) {
-          float acc = 0.0f;
+          float acc = -8.0f;                                   // the floor reduction takes x - 8
 #pragma unroll
           for (int i = 0; i < LA; i++)
             if (k - i >= 0 && k - i < LB) acc = fmaf(av[l][i], bv[l][k - i], acc);

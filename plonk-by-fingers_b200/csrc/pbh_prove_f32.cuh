@@ -12,9 +12,10 @@
 // scalar type, and the CPU test suite instantiates it with a type that propagates worst-case magnitudes and fails if
 // any operation could leave the exact range (test_f32_bounds).
 //
-// Scope of this fast path: it assumes alpha*b1*b3*b5*b7 != 0 (mod 17), i.e. t1+t2 has 22 coefficients, so the
-// reference's SubAssign quirk Q1 (src/poly.rs:192-203) cannot trigger.  Items that violate it can only end in
-// status 1-4; the caller sends them to the exact integer routine prove_one<> of pbh_prove.cuh.
+// The reference's SubAssign quirk Q1 (src/poly.rs:192-203) is reproduced inside the core: it can only act when the top
+// coefficient alpha b1 b3 b5 b7 of t1 + t2 vanishes, which a warp vote detects, so the common case pays one reduction and
+// one vote for it.  (Round 1 sent such items to the exact-length integer routine of pbh_prove.cuh, which made every warp
+// of a uniformly drawn batch run both routines: 146 us per 2^20 proofs against 74 us on a full-path batch.)
 #pragma once
 #include <math.h>
 
@@ -271,18 +272,8 @@ PBH_HD uint32_t prove_core_f32_cs(const T (&w)[12], const T (&rnd_in)[9], CS& cs
     fpoly_mac(c, qo, t1);
 #pragma unroll
     for (int i = 0; i < 4; i++) t1[i] = f_add(t1[i], f_const(ck.QC(i), tag));
-    // alpha^2 (z - 1) L1
-    T zm[7], l1[4], t4[10];
 #pragma unroll
-    for (int i = 0; i < 7; i++) zm[i] = (i == 0) ? f_sub(z[0], f_const(1.f, tag)) : z[i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) l1[i] = f_const(ck.L1(i), tag);
-    fpoly_mul(zm, l1, t4);
-#pragma unroll
-    for (int i = 0; i < 22; i++) {
-      T s = (i < 14) ? t1[i] : f_const(0.f, tag);
-      num[i] = (i < 10) ? f_fma(a2, t4[i], s) : s;
-    }
+    for (int i = 0; i < 22; i++) num[i] = (i < 14) ? t1[i] : f_const(0.f, tag);
   }
   T zw[7];   // z(omega x): coefficient i times omega^i = 1, 4, -1, -4, 1, 4, -1
   zw[0] = z[0]; zw[1] = f_mul(z[1], f_const(4.f, tag)); zw[2] = f_sub(f_const(0.f, tag), z[2]); zw[3] = f_mul(z[3], f_const(-4.f, tag));
@@ -304,6 +295,19 @@ PBH_HD uint32_t prove_core_f32_cs(const T (&w)[12], const T (&rnd_in)[9], CS& cs
 #pragma unroll
     for (int i = 0; i < 22; i++) num[i] = f_fma(alpha, t2[i], num[i]);
   }
+  // Q1 (src/poly.rs:192-203): `t1 + t2 -= t3` pushes the coefficients of t3 at or beyond len(t1 + t2) UN-NEGATED.  num holds
+  // t1 + t2 here.  Its top coefficient is alpha b1 b3 b5 b7, so the quirk needs a zero among those five (27 % of uniformly
+  // drawn inputs, none of a full-path batch); the scan below finds len(t1 + t2) and runs only in warps that hold such an item.
+  uint32_t unnegated = 0u;        // bit n: coefficient n of t3 is added, not subtracted
+  const bool q1_warp = f_any(f_is_zero(f_red(num[21])), tag);
+  if (q1_warp) {
+    bool tail_zero = true;        // (t1 + t2)[n..21] all zero; the zero polynomial keeps one coefficient
+#pragma unroll
+    for (int n = 21; n >= 1; n--) {
+      tail_zero = tail_zero && f_is_zero(f_red(num[n]));
+      unnegated |= tail_zero ? (1u << n) : 0u;
+    }
+  }
   {
     // t3' = (a + beta S1 + gamma)(b + beta S2 + gamma)(c + beta S3 + gamma) z(omega x)
     T A[6], B[6], C[6];
@@ -323,8 +327,24 @@ PBH_HD uint32_t prove_core_f32_cs(const T (&w)[12], const T (&rnd_in)[9], CS& cs
     fpoly_mul(AB, C, ABC);
     fpoly_mul(ABC, zw, t3);
     T nalpha = f_sub(f_const(0.f, tag), alpha);
+    if (q1_warp) {
 #pragma unroll
-    for (int i = 0; i < 22; i++) num[i] = f_red(f_fma(nalpha, t3[i], num[i]));
+      for (int i = 0; i < 22; i++) num[i] = f_fma(((unnegated >> i) & 1u) ? alpha : nalpha, t3[i], num[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 22; i++) num[i] = f_fma(nalpha, t3[i], num[i]);
+    }
+  }
+  {
+    // + alpha^2 (z - 1) L1                                                     src/plonk.rs:356-369
+    T zm[7], l1[4], t4[10];
+#pragma unroll
+    for (int i = 0; i < 7; i++) zm[i] = (i == 0) ? f_sub(z[0], f_const(1.f, tag)) : z[i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) l1[i] = f_const(ck.L1(i), tag);
+    fpoly_mul(zm, l1, t4);
+#pragma unroll
+    for (int i = 0; i < 22; i++) num[i] = f_red((i < 10) ? f_fma(a2, t4[i], num[i]) : num[i]);
   }
 
   // ---- divide by Z_H = x^4 - 1                                              src/plonk.rs:369-378
@@ -455,16 +475,13 @@ PBH_HD uint32_t prove_core_f32(const T (&w)[12], const T (&rnd_in)[9], const T (
   return prove_core_f32_cs<ALGO, T>(w, rnd_in, cs, ck, Tb, inv17c, P);
 }
 
-// One proof through the fast path: FP32 core for the common case, exact integer routine for items whose quotient
-// is known to be short (alpha*b1*b3*b5*b7 = 0 mod 17: Q1/Q5 territory, status 1-4 only).  Inputs are canonical
-// bytes (< 17).  Output as packed points + canonical evaluations, like prove_one<ALGO_TABLE>.
+// One proof through the FP32 core (every input class, Q1 included).  Inputs are canonical bytes (< 17).  Output as packed
+// points + canonical evaluations, like prove_one<ALGO_TABLE>.
 // `unsat_known`: -1 = evaluate constraints.satisfies here; 0 / 1 = already evaluated by the caller.
 // PBH_CIRCUIT = true: the context's constants equal PbhCK's (checked by the host), use the compile-time instantiation.
 template <int ALGO, bool PBH_CIRCUIT = false>
 PBH_HD uint32_t prove_item_f32(const uint32_t (&w)[12], const uint32_t (&rnd)[9], const uint32_t (&ch)[5], const Consts& K,
                                const ConstsF& KF, const Tables& T, ProofRegs& P, int unsat_known = -1) {
-  const bool rare = ch[0] == 0u || rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
-  if (rare) return prove_one<ALGO_TABLE, true>(w, rnd, ch, K, T, P, unsat_known);   // status only: the algorithm is irrelevant
   const bool unsat = unsat_known < 0 ? unsatisfied(w, K) : (unsat_known != 0);
   F32* tag = nullptr;
   F32 wf[12], rf[9], cf[5];
@@ -527,17 +544,6 @@ PBH_HD uint32_t prove_item_fs(const uint32_t (&w)[12], const uint32_t (&rnd)[9],
 #pragma unroll
   for (int k = 0; k < 6; k++) derived[k] = cs.derived[k];
   if (unsat) status = 1;
-  // A zero among b1, b3, b5, b7 makes the quotient short whatever the challenges are (status 1-4 only), and only then can
-  // the reference's SubAssign quirk (Q1) fire, which the FP32 core does not model.  The commitments of rounds 1 and 2,
-  // hence beta, gamma and alpha, do not depend on that: such items keep the transcript of the core above and only have
-  // their status recomputed by the exact-length integer routine (no hashing on this branch, so a warp that holds one
-  // of them pays about a thousand instructions, not two more compressions).
-  const bool rare = rnd[0] == 0u || rnd[2] == 0u || rnd[4] == 0u || rnd[6] == 0u;
-  if (rare) {
-    const uint32_t ch[5] = {derived[0], derived[1], derived[2], 0u, 0u};
-    ProofRegs scratch;
-    status = prove_one<ALGO_TABLE, true>(w, rnd, ch, K, T, scratch, unsat ? 1 : 0);
-  }
   return status;
 }
 

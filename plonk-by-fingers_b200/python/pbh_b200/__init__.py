@@ -26,7 +26,7 @@ u16p = C.POINTER(C.c_uint16)
 ST_OK, ST_UNSATISFIED, ST_ACC_DIV0, ST_T_REMAINDER, ST_T_SLICE, ST_SRS_OOB, ST_BAD_ENCODING = 0, 1, 2, 3, 4, 5, 32
 VR_ACCEPT, VR_REJECT_PAIRING, VR_NOT_ON_CURVE, VR_NOT_IN_FIELD, VR_PANIC_ZH0, VR_BAD_ENCODING = 1, 0, 2, 4, 0x10, 0x20
 ALGO_ARITH, ALGO_TABLE = 0, 1
-OPT_PROVER_FP32, OPT_PROVER_LAUNCH_SHAPE, OPT_TMA, OPT_CHUNK_LOG2, OPT_SPECIALISE, OPT_HOST_DIRECT, OPT_VERIFIER_FP32 = 1, 2, 3, 4, 5, 6, 7
+OPT_PROVER_FP32, OPT_PROVER_LAUNCH_SHAPE, OPT_TMA, OPT_CHUNK_LOG2, OPT_SPECIALISE, OPT_HOST_DIRECT, OPT_VERIFIER_FP32, OPT_LANE_MODE = 1, 2, 3, 4, 5, 6, 7, 8
 DIST_UNIFORM, DIST_FULLPATH = 0, 1
 ERR = {0: "PBH_OK", -1: "PBH_ERR_BAD_ARGUMENT", -2: "PBH_ERR_SETUP_PANIC", -3: "PBH_ERR_CUDA", -4: "PBH_ERR_NO_DEVICE",
        -5: "PBH_ERR_UNSUPPORTED"}
@@ -46,7 +46,8 @@ pbh_proof_records_to_planes_dev pbh_proof_planes_to_records_dev pbh_prove_digest
 pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batch pbh_g1_smul_batch pbh_g1_add_batch
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
 pbh_measure_int32_peak pbh_mul_ntt_batch pbh_poly_scale_batch pbh_poly_eval_batch pbh_poly_div_linear_batch pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev
-pbh_prove_batch_async pbh_verify_batch_async pbh_lane_sync pbh_host_alloc pbh_host_free pbh_ctx_numa_node""".split()
+pbh_prove_batch_async pbh_verify_batch_async pbh_lane_sync pbh_host_alloc pbh_host_free pbh_ctx_numa_node
+pbh_coset_ntt4_batch pbh_coset_intt4_batch""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -493,6 +494,23 @@ class Context:
 
     def ntt4_batch(self, coeffs): return self._sweep(self.lib.pbh_ntt4_batch, coeffs, 4, 4)
     def intt4_batch(self, evals): return self._sweep(self.lib.pbh_intt4_batch, evals, 4, 4)
+
+    def _coset(self, fn, arr, k):
+        A = _Planes(arr, 4, name="in")
+        out = self._empty(A.dev, 4, A.n)
+        O = _Planes(out, 4, A.n, "out")
+        cur = self._dev_begin() if A.dev else None
+        rc = fn(self.h, C.c_size_t(A.n), C.c_uint32(k), C.c_void_p(A.ptr), C.c_size_t(A.pitch), C.c_void_p(O.ptr), C.c_size_t(O.pitch), int(A.dev))
+        self._dev_end(cur)
+        self._check(rc, fn.__name__)
+        return O.arr
+
+    def coset_ntt4_batch(self, coeffs, k):
+        """evals[i] = p(k 4^i): the coset k H of src/plonk.rs:136-139 (k = 2: K1, k = 3: K2, k = 1: H)."""
+        return self._coset(self.lib.pbh_coset_ntt4_batch, coeffs, k)
+
+    def coset_intt4_batch(self, evals, k):
+        return self._coset(self.lib.pbh_coset_intt4_batch, evals, k)
     def g1_smul_batch(self, arr): return self._sweep(self.lib.pbh_g1_smul_batch, arr, 4, 3)
     def g1_add_batch(self, arr): return self._sweep(self.lib.pbh_g1_add_batch, arr, 6, 3)
     def kzg_commit_batch(self, arr): return self._sweep(self.lib.pbh_kzg_commit_batch, arr, 7, 3)

@@ -27,6 +27,7 @@ inline Bnd f_add(Bnd a, Bnd b) { return chk(a.m + b.m); }
 inline Bnd f_sub(Bnd a, Bnd b) { return chk(a.m + b.m); }
 inline Bnd f_red(Bnd x) { if (x.m > g_max_red) g_max_red = x.m; if (x.m > 8388608.0) g_violation = true; return Bnd(8); }
 inline bool f_is_zero(Bnd) { return false; }
+inline bool f_any(bool, Bnd*) { return true; }     // the bound analysis walks the Q1 path
 inline uint32_t f_canon(Bnd) { return 0; }
 inline Bnd f_rint_div(Bnd x, float d, float, Bnd*) { if (x.m > g_max_red) g_max_red = x.m; if (x.m >= 2097152.0) g_violation = true; return chk(x.m / d + 1.0); }
 inline Bnd f_canon_f(Bnd, Bnd*) { return Bnd(16); }

@@ -178,3 +178,54 @@ def test_run_sharded_under_real_nccl(gpu_ctx, tmp_path):
     for r in range(world):
         o = torch.load(os.path.join(tmp_path, f"r{r}.pt"))
         assert torch.equal(o["bitmap"], sb.cpu()) and o["total"] == st and o["digs"].numel() == world
+
+
+def test_coset_ntt4_exhaustive(gpu_ctx, oracle):
+    """pbh_coset_ntt4_batch / pbh_coset_intt4_batch on k H for k = 1 (H), 2 (K1) and 3 (K2), the cosets of
+    src/plonk.rs:136-139: ALL 17^4 coefficient tuples.  Forward == Poly::eval (src/poly.rs:71-79) at the four coset points
+    k 4^i (the oracle's restatement of eval), inverse(forward(c)) == c, any byte value is reduced like F17::from, host and
+    device pointers, ragged sizes."""
+    import itertools
+    import torch
+    import pbh_b200
+    ctx = gpu_ctx["table"]
+    coeffs = np.ascontiguousarray(np.array(list(itertools.product(range(17), repeat=4)), dtype=np.uint8).T)     # (4, 83521)
+    n = coeffs.shape[1]
+    assert np.array_equal(ctx.coset_ntt4_batch(coeffs, 1), ctx.ntt4_batch(coeffs))
+    for k, coset in ((1, [1, 4, 16, 13]), (2, [2, 8, 15, 9]), (3, [3, 12, 14, 5])):
+        ev = ctx.coset_ntt4_batch(coeffs, k)
+        for i, point in enumerate(coset):
+            arr = np.concatenate([coeffs, np.full((1, n), point, np.uint8)], axis=0)
+            assert np.array_equal(ev[i], oracle.poly_eval_batch(arr)), (k, i)
+        assert np.array_equal(ctx.coset_intt4_batch(ev, k), coeffs), k
+        d = torch.from_numpy(coeffs).cuda()
+        ev_d = ctx.coset_ntt4_batch(d, k); back = ctx.coset_intt4_batch(ev_d, k)
+        ctx.sync()
+        assert np.array_equal(ev_d.cpu().numpy(), ev) and np.array_equal(back.cpu().numpy(), coeffs)
+        rng = np.random.default_rng(k)
+        raw = rng.integers(0, 256, size=(4, 10007), dtype=np.uint8)
+        assert np.array_equal(ctx.coset_ntt4_batch(raw, k), ctx.coset_ntt4_batch(raw % 17, k))
+        assert np.array_equal(ctx.coset_intt4_batch(raw, k), ctx.coset_intt4_batch(raw % 17, k))
+        assert np.array_equal(ctx.coset_intt4_batch(ctx.coset_ntt4_batch(raw, k), k), raw % 17)
+    with pytest.raises(pbh_b200.PbhError):
+        ctx.coset_ntt4_batch(coeffs, 4)
+
+
+def test_poly_mul_all_small_shapes_and_bytes(gpu_ctx, oracle):
+    """Schoolbook product (src/poly.rs:205-218) through the size-specialised FP32 kernel: every shape up to 8 x 8 (and the
+    general kernel beyond), operands of ANY byte value (F17::from reduces them), ragged and unaligned batches."""
+    import torch
+    ctx = gpu_ctx["table"]
+    rng = np.random.default_rng(77)
+    for la in range(1, 10):
+        for lb in (1, 2, 3, 6, 7, 8, 9):
+            n = 4099 if (la + lb) % 2 else 4096
+            a = rng.integers(0, 256, size=(la, n), dtype=np.uint8); b = rng.integers(0, 256, size=(lb, n), dtype=np.uint8)
+            a[:, :300] = 255; b[:, :300] = 255; a[:, 300:600] = 0
+            exp = oracle.poly_mul_batch(a % 17, b % 17)
+            assert np.array_equal(ctx.poly_mul_batch(a, b), exp), (la, lb)
+            da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+            got = ctx.poly_mul_batch(da, db); ctx.sync()
+            assert np.array_equal(got.cpu().numpy(), exp), (la, lb)
+            got = ctx.poly_mul_batch(da[:, 1:], db[:, 1:]); ctx.sync()          # unaligned bases: general kernel
+            assert np.array_equal(got.cpu().numpy(), exp[:, 1:]), (la, lb)

@@ -92,6 +92,52 @@ def test_pairing_exhaustive(hostemul, oracle):
             assert hostemul.gt_final_exp((a, b)) == oracle.gt_pow((a, b), 600)
 
 
+def test_q1_inside_the_fp32_core(hostemul, oracle):
+    """The SubAssign quirk Q1 (src/poly.rs:192-203) is handled inside the FP32 core since round 2 (no integer fallback):
+    SURVEY.md section 9's Q1 tuple, and a batch with zeros forced into a third of the blinders and a fifth of the alphas
+    (thousands of status-3 items, every length of t1 + t2), for the three FP32 instantiations."""
+    circ = oracle.pbh_test_circuit()
+    x, y, z = 4, 4, 7
+    w = np.array([[x, y, z, x * x % 17, x, y, z, y * y % 17, x * x % 17, y * y % 17, z * z % 17, z * z % 17]], dtype=np.uint8).T.copy()
+    r = np.array([[0, 0, 10, 0, 7, 0, 0, 0, 16]], dtype=np.uint8).T.copy()
+    c = np.array([[7, 4, 2, 16, 16]], dtype=np.uint8).T.copy()
+    assert oracle.prove_batch(w, r, c)[1].tolist() == [3]
+    rng = np.random.default_rng(5)
+    n = 120000
+    wo, ro, co, uo, _ = oracle.generate_inputs(n, seed=99, dist=0, threads=8)
+    ro = ro.copy(); ro[rng.random((9, n)) < 0.35] = 0
+    co = co.copy(); co[0, rng.random(n) < 0.2] = 0
+    po, so = oracle.prove_batch(wo, ro, co, threads=8)
+    assert np.bincount(so, minlength=6)[3] > 500
+    for algo in (2, 3, 4):
+        assert hostemul.prove(circ, w, r, c, algo)[1].tolist() == [3]
+        pe, se = hostemul.prove(circ, wo, ro, co, algo)
+        assert np.array_equal(se, so) and np.array_equal(pe, po), algo
+
+
+def test_half2_reduction_constants():
+    """The packed-half reduction of the polynomial sweeps (pbh_kernels.cuh h2_red17): q = fma(x, fp16(1/17), 1536) - 1536,
+    r = fma(q, -17, x), emulated with one rounding per fused operation, is THE centred residue for every integer
+    |x| <= 2048 (the sweeps stay below 255 * 8 = 2040); the constants are the bit patterns the kernel uses."""
+    c17 = np.array([0x2B88], dtype=np.uint16).view(np.float16)[0]
+    assert np.array([0x6600, 0xCC40, 0x4C40, 0x6400], dtype=np.uint16).view(np.float16).tolist() == [1536.0, -17.0, 17.0, 1024.0]
+    assert c17 == np.float16(1 / 17)
+    for v in range(-2048, 2049):
+        t = np.float16(np.float64(v) * np.float64(c17) + 1536.0)       # the fused multiply-add rounds once
+        q = np.float64(t) - 1536.0
+        r = float(np.float16(q * -17.0 + v))
+        m = v % 17
+        assert r == (m - 17 if m > 8 else m), v
+    # the floor reduction of the FP32 polynomial product (f_floor_mod17_biased): canonical residue for 0 <= x < 2^20
+    x = np.arange(0, 1 << 20, dtype=np.float64)
+    xm8 = (x - 8.0).astype(np.float32)
+    t = (xm8.astype(np.float64) * np.float64(np.float32(0.058823529411764705)) + 12582912.0).astype(np.float32)
+    q = t - np.float32(12582912.0)
+    biased = ((q.astype(np.float64) * -17.0 + xm8.astype(np.float64)).astype(np.float32).astype(np.float64) + 8388616.0).astype(np.float32)
+    assert np.array_equal(biased.view(np.uint32) & 0xFF, (np.arange(0, 1 << 20) % 17).astype(np.uint32))
+    assert np.array_equal(biased.view(np.uint32) >> 8, np.full(1 << 20, 0x4B0000, np.uint32))
+
+
 def test_fp32_curve_arithmetic_exhaustive(hostemul, oracle):
     """pbh_g1f.cuh, the exact FP32 arithmetic of PBH_ALGO_ARITH: ALL 102 x 102 sums through the unified slope
     (x1^2 + x1 x2 + x2^2) / (y1 + y2) against the reference's case analysis (src/pbh/g1.rs:119-144), all 102 x 101 multiples

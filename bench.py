@@ -356,9 +356,23 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     rep_ms = []
+    def aligned_start():
+        """After the barrier the ranks still leave it tens of microseconds apart, and the first collective of the region makes
+        the early ones wait for the last: with a 2 ms region that skew is a few per cent of every rank's time.  All ranks
+        therefore agree on one instant of the node's monotonic clock (the maximum of their proposals) and launch then."""
+        if world == 1:
+            return
+        t = torch.tensor([time.monotonic() + 0.002], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        deadline = float(t.item())
+        torch.cuda.synchronize()
+        while time.monotonic() < deadline:
+            pass
+
     for _ in range(reps):
         t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        aligned_start()
         with torch.cuda.stream(stream):
             t_begin.record(stream)
             run_region()
@@ -415,7 +429,7 @@ def main():
     # ---- check (a): the N-rank result against ONE GPU.  Ring slot 0 of the N ranks is the contiguous global index range
     # [0, N n): rank 0 recomputes all of it alone and requires gathered bitmap == its bitmap and the sum of the gathered
     # digests == its digest.  Every rank also finds its own summary at its place in the gathered buffer.
-    gather_ok = sharded_equals_single = None
+    gather_ok = sharded_equals_single = single_ref = None
     if world > 1:
         torch.cuda.synchronize()
         g_ = gathered_all[last_set].view(world, ring, row)
@@ -439,6 +453,7 @@ def main():
             digs_n = g_[:, 0, nb:].contiguous().view(torch.int64).reshape(-1).tolist()
             sum_n = sum(int(x) & MASK64 for x in digs_n) & MASK64
             sharded_equals_single = bool(torch.equal(bits_n, b1)) and sum_n == (int(d1.item()) & MASK64)
+            single_ref = (b1.cpu().numpy(), int(d1.item()) & MASK64)
             del w1, r1, c1, u1, p1, s1, v1, b1, d1
 
     # ---- the other input distribution of SURVEY.md 8(d): D_uniform (attempt 0 only; ~89 % of the items end in one of the
@@ -541,7 +556,7 @@ def main():
             ctx.sync()
             dtm = timed(lanes_step, ksteps)
             lane_modes[str(mode)] = {"value": n * world * ksteps / dtm, "ms_per_step": 1e3 * dtm / ksteps, "how": what}
-        ctx.set_option(pbh_b200.OPT_LANE_MODE, 1)
+        ctx.set_option(pbh_b200.OPT_LANE_MODE, 3)
         # every byte the lane pipeline produced equals the device-resident path of ring slot 0
         ref_proof, ref_status, ref_result = (outs[0][k].cpu().numpy() for k in ("proof", "status", "result"))
         e2e_equal = all(np.array_equal(s_["proof"], ref_proof) and np.array_equal(s_["status"], ref_status) and
@@ -554,7 +569,7 @@ def main():
         e2e = {"value": n * world * ksteps / dt_lanes, "unit": UNIT, "h2d_bytes_per_step": n * (26 + 33) * world,
                "d2h_bytes_per_step": n * (28 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt_lanes / ksteps,
                "api": "pbh_prove_batch_async + pbh_verify_batch_async on two lanes (two batches in flight), pbh_lane_sync before a lane's buffers are reused",
-               "host_memory": "page-locked, mapped (pbh_host_alloc); the kernels run in place on it: PBH_OPT_HOST_DIRECT",
+               "host_memory": "page-locked (pbh_host_alloc); default PBH_OPT_LANE_MODE 3: whole-batch copy-engine transfers both ways on the lane's stream",
                "numa_node_of_device": ctx.numa_node,
                "timing": "host wall clock around the C-ABI calls up to the final pbh_ctx_sync, max over ranks",
                "bytes_equal_device_path": bool(e2e_equal),
@@ -726,6 +741,25 @@ def main():
                    "sample": f"the whole 2^20-item D_fullpath batch of ring slot 0 (the batch the GPU is checked against), prove then verify, C++ restatement of the reference (oracle/), {threads} threads, {dt_full:.1f} s",
                    "single_thread": {"value": v1, "cores": 1, "sample": f"20000 items, {dt1:.1f} s"}}
 
+    # ---- the same sharded pass from ONE process through the C ABI's multi-device entry points (pbh_multi_*: one stream per
+    # device, ncclCommInitAll, one in-library ncclAllGather): rank 0 drives all the GPUs of the job while the other ranks wait
+    # at the final barrier.  Checked against what one GPU computed for the same global index range.
+    multi = None
+    try:
+        if single_ref is None:
+            bm0 = ctx.pack_verdicts(outs[0]["result"])
+            single_ref = (bm0.cpu().numpy(), int(ctx.digest(outs[0]["proof"], first_index=ins[0][4]).item()) & MASK64)
+            ctx.sync()
+        with pbh_b200.MultiContext(world, algo=args.algo) as mc:
+            mc.prove_verify_sharded(world * n, first_index=0, seed=SEED)          # warm-up (allocations, NCCL channels)
+            runs = [mc.prove_verify_sharded(world * n, first_index=0, seed=SEED) for _ in range(5)]
+            best = min(runs, key=lambda r_: r_["ms"])
+            multi = {"api": "pbh_multi_create + pbh_multi_prove_verify_sharded (generate -> prove -> verify on every device, one ncclAllGather of bitmaps + digests)",
+                     "n_dev": mc.device_count, "items_total": world * n, "ms_per_pass_incl_generation": best["ms"],
+                     "accepted": best["accepted"], "equals_single_gpu": bool(np.array_equal(best["bitmap"], single_ref[0]) and best["total_digest"] == single_ref[1])}
+    except Exception as e:   # pragma: no cover - reported, not fatal for the headline
+        multi = {"error": f"{type(e).__name__}: {e}"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -760,6 +794,7 @@ def main():
         "config2_verifier_16m": config2,
         "config4_256m_sharded": config4,
         "sweeps": sweeps,
+        "single_process_multi_device": multi,
         "int32_peak": int32,
         "cpu_baseline": cpu,
         "check": {"all_status_ok": ok_status, "accepted": accept, "reached_pairing": reached, "items": n,

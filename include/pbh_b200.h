@@ -147,8 +147,8 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
 /* PBH_OPT_LANE_MODE: how the asynchronous lane calls (pbh_prove_batch_async / pbh_verify_batch_async) move page-locked
  * buffers.  Bit 0: inputs are uploaded whole by the copy engine into a per-lane staging buffer (else the kernel reads mapped
  * memory in place); bit 1: outputs come back through the copy engine (else the kernel stores into mapped memory in place).
- * 0 = in place both ways, 1 = copy-engine upload + in-place stores (default: measured fastest on PCIe Gen5), 3 = copy engine
- * both ways.  Buffers that are page-locked but not mapped always go through the copy engine. */
+ * 0 = in place both ways, 1 = copy-engine upload + in-place stores, 3 = copy engine both ways (default: measured 1.28 ms per
+ * 2^20 prove + verify pairs on PCIe Gen5 x16, i.e. the upload link at 48 GB/s, against 1.33 ms for mode 1 and 1.48 ms for 0).  Buffers that are page-locked but not mapped always go through the copy engine. */
 #define PBH_OPT_LANE_MODE 8
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
@@ -367,6 +367,39 @@ int pbh_prove_digest_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_
                                uint8_t* status, uint64_t first_index, uint64_t* digest);
 int pbh_verify_bitmap_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
                                 size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* bitmap);
+
+/* ---- multi-device: several GPUs driven from ONE process -------------------------------------------
+ * pbh_multi_create does pbh_ctx_create on each of the n_dev devices (devices == NULL: 0 .. n_dev-1), with one stream per
+ * device, and - when n_dev > 1 - builds one NCCL communicator over them (ncclCommInitAll; libnccl.so.2 is loaded at run
+ * time, PBH_ERR_UNSUPPORTED when it cannot be: there is no fallback for the collective).  Batches are split contiguously
+ * over the devices in whole 256-item tiles.  Results never depend on the number of devices.  (The one-process-per-GPU
+ * arrangement under torchrun uses plain contexts and torch.distributed instead: plonk-by-fingers_b200/python/pbh_b200/
+ * sharding.py, bench.py.) */
+typedef struct pbh_multi pbh_multi;
+int pbh_multi_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_n, uint8_t omega_pows, const int* devices,
+                     int n_dev, pbh_multi** out);
+void pbh_multi_destroy(pbh_multi* m);
+int pbh_multi_device_count(const pbh_multi* m);
+pbh_ctx* pbh_multi_ctx(pbh_multi* m, int i);              /* the context of device i, e.g. for the `_dev` entry points */
+const char* pbh_multi_last_error(const pbh_multi* m);     /* m may be NULL: last creation error */
+int pbh_multi_set_algo(pbh_multi* m, int algo);
+/* Plonk::prove / Plonk::verify over n items, HOST pointers, same arguments and bytes as pbh_prove_batch / pbh_verify_batch:
+ * shard d goes through device d's single-device entry point on its own host thread. */
+int pbh_multi_prove_batch(pbh_multi* m, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand, size_t rand_pitch,
+                          const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status);
+int pbh_multi_verify_batch(pbh_multi* m, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
+                           size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
+/* The sharded end-to-end pass of BASELINE.json configs[4] in one call.  The synthetic items with global indices
+ * [first_index, first_index + n_total) (pbh_generate_inputs_dev) are generated, proved and verified shard by shard on the
+ * devices, the digest fused into the prover and the verdict bitmap into the verifier; then ONE ncclAllGather exchanges the
+ * shard summaries (bitmap + 64-bit proof digest), after which every device holds all of them.  Returned from device 0:
+ *   bitmap_out        ceil(n_total / 8) bytes, bit i%8 of byte i/8 = verdict of item i (what one device computes alone)
+ *   digests_out       n_dev values (nullable); total_digest_out (nullable) their sum mod 2^64 = pbh_digest_dev of the whole batch
+ *   accepted_out      number of accepted proofs (nullable)
+ *   ms_out            device time of the pass including the collective, maximum over the devices, CUDA events (nullable) */
+int pbh_multi_prove_verify_sharded(pbh_multi* m, uint64_t n_total, uint64_t first_index, uint64_t seed, int dist,
+                                   uint8_t* bitmap_out, uint64_t* digests_out, uint64_t* total_digest_out, uint64_t* accepted_out,
+                                   float* ms_out);
 
 /* ---- synthetic inputs, device pointers ------------------------------------------ */
 #define PBH_DIST_UNIFORM 0   /* attempt k = 0 only: exercises every status class                    */

@@ -62,7 +62,7 @@ struct pbh_ctx {
   uint64_t launches = 0;
   uint8_t* lane_buf[kSlots] = {};          // whole-batch staging of the asynchronous lanes (PBH_OPT_LANE_MODE 1 and 3)
   size_t lane_bytes[kSlots] = {};
-  int lane_mode = 1;                       // PBH_OPT_LANE_MODE
+  int lane_mode = 3;                       // PBH_OPT_LANE_MODE
   int grid_scale = 2;                      // persistent-grid blocks per SM are grid_scale/2 of the kernel's residency (1: half grids, async lanes)
   int numa_node = -1;                      // NUMA node of the device's PCIe root (sysfs), -1 when the platform does not say
   std::map<void*, std::pair<size_t, bool>> host_allocs;   // pbh_host_alloc: pointer -> (bytes, mmap'ed + registered)

@@ -96,6 +96,24 @@ void free_shard_buffers(Shard& s) {
 }
 }  // namespace
 
+// host-pointer calls: shard d takes items [d * per, min(n, (d + 1) * per)) through its device's single-device entry point on its own
+// host thread (a context serves one host thread at a time; different contexts are independent)
+template <class Call>
+static int for_each_shard(pbh_multi* m, size_t n, Call call) {
+  const size_t n_dev = m->shards.size(), per = shard_items(n, n_dev);
+  std::vector<int> rcs(n_dev, PBH_OK);
+  std::vector<std::thread> threads;
+  for (size_t d = 0; d < n_dev; d++) {
+    const size_t lo = std::min(n, d * per), cnt = std::min(n, lo + per) - lo;
+    if (cnt == 0) continue;
+    threads.emplace_back([&, d, lo, cnt]() { rcs[d] = call(m->shards[d].ctx, lo, cnt); });
+  }
+  for (std::thread& t : threads) t.join();
+  for (size_t d = 0; d < n_dev; d++)
+    if (rcs[d] != PBH_OK) return mfail(m, rcs[d], std::string("device ") + std::to_string(m->shards[d].device) + ": " + pbh_last_error(m->shards[d].ctx));
+  return PBH_OK;
+}
+
 extern "C" {
 
 int pbh_multi_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_n, uint8_t omega_pows, const int* devices, int n_dev,
@@ -149,24 +167,6 @@ const char* pbh_multi_last_error(const pbh_multi* m) { return m ? m->last_error.
 int pbh_multi_set_algo(pbh_multi* m, int algo) {
   if (!m) return PBH_ERR_BAD_ARGUMENT;
   for (Shard& s : m->shards) { int rc = pbh_ctx_set_algo(s.ctx, algo); if (rc) return mfail(m, rc, pbh_last_error(s.ctx)); }
-  return PBH_OK;
-}
-
-// host-pointer calls: shard d takes items [d * per, min(n, (d + 1) * per)) through its device's single-device entry point on its own
-// host thread (a context serves one host thread at a time; different contexts are independent)
-template <class Call>
-static int for_each_shard(pbh_multi* m, size_t n, Call call) {
-  const size_t n_dev = m->shards.size(), per = shard_items(n, n_dev);
-  std::vector<int> rcs(n_dev, PBH_OK);
-  std::vector<std::thread> threads;
-  for (size_t d = 0; d < n_dev; d++) {
-    const size_t lo = std::min(n, d * per), cnt = std::min(n, lo + per) - lo;
-    if (cnt == 0) continue;
-    threads.emplace_back([&, d, lo, cnt]() { rcs[d] = call(m->shards[d].ctx, lo, cnt); });
-  }
-  for (std::thread& t : threads) t.join();
-  for (size_t d = 0; d < n_dev; d++)
-    if (rcs[d] != PBH_OK) return mfail(m, rcs[d], std::string("device ") + std::to_string(m->shards[d].device) + ": " + pbh_last_error(m->shards[d].ctx));
   return PBH_OK;
 }
 

@@ -47,7 +47,8 @@ pbh_ntt_generic_batch pbh_poly_mul_batch pbh_poly_add_batch pbh_poly_div_zh_batc
 pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_generate_inputs_dev
 pbh_measure_int32_peak pbh_mul_ntt_batch pbh_poly_scale_batch pbh_poly_eval_batch pbh_poly_div_linear_batch pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev
 pbh_prove_batch_async pbh_verify_batch_async pbh_lane_sync pbh_host_alloc pbh_host_free pbh_ctx_numa_node
-pbh_coset_ntt4_batch pbh_coset_intt4_batch""".split()
+pbh_coset_ntt4_batch pbh_coset_intt4_batch pbh_multi_create pbh_multi_destroy pbh_multi_device_count pbh_multi_ctx pbh_multi_last_error
+pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_verify_sharded""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -122,6 +123,14 @@ def load_library():
         lib.pbh_ctx_destroy.argtypes = [C.c_void_p]
         lib.pbh_ctx_destroy.restype = None
         lib.pbh_ctx_numa_node.argtypes = [C.c_void_p]
+        lib.pbh_multi_destroy.argtypes = [C.c_void_p]
+        lib.pbh_multi_destroy.restype = None
+        lib.pbh_multi_device_count.argtypes = [C.c_void_p]
+        lib.pbh_multi_last_error.argtypes = [C.c_void_p]
+        lib.pbh_multi_last_error.restype = C.c_char_p
+        lib.pbh_multi_ctx.argtypes = [C.c_void_p, C.c_int]
+        lib.pbh_multi_ctx.restype = C.c_void_p
+        lib.pbh_multi_set_algo.argtypes = [C.c_void_p, C.c_int]
         lib.pbh_lane_sync.argtypes = [C.c_void_p, C.c_int]
         lib.pbh_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         lib.pbh_host_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -646,6 +655,76 @@ class Context:
         v = C.c_double()
         self._check(self.lib.pbh_measure_int32_peak(self.h, int(which), C.byref(v)), "pbh_measure_int32_peak")
         return v.value
+
+
+class MultiContext:
+    """pbh_multi: one process, several devices (include/pbh_b200.h "multi-device").  Host arrays only."""
+
+    def __init__(self, devices, circuit=None, s=2, srs_n=6, omega_pows=4, algo="table"):
+        self.lib = load_library()
+        self.circuit = circuit if circuit is not None else pbh_test_circuit()
+        devices = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.pbh_multi_create(C.byref(self.circuit), C.c_uint8(s), C.c_uint32(srs_n), C.c_uint8(omega_pows), arr, len(devices), C.byref(h))
+        if rc != 0:
+            raise PbhError(f"pbh_multi_create: {ERR.get(rc, rc)}: {self.lib.pbh_multi_last_error(None).decode()}")
+        self.h, self.devices = h, devices
+        self._check(self.lib.pbh_multi_set_algo(self.h, {"arith": ALGO_ARITH, "table": ALGO_TABLE}[algo]), "pbh_multi_set_algo")
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise PbhError(f"{what}: {ERR.get(rc, rc)}: {self.lib.pbh_multi_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pbh_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_count(self):
+        return int(self.lib.pbh_multi_device_count(self.h))
+
+    def prove_batch(self, wit, rand, chal):
+        W = _Planes(wit, 12, name="wit"); n = W.n
+        R = _Planes(rand, 9, n, "rand"); Ch = _Planes(chal, 5, n, "chal")
+        proof = np.empty((27, n), np.uint8); status = np.empty((n,), np.uint8)
+        P = _Planes(proof, 27, n, "proof", out=True); S = _Planes(status, 1, n, "status", out=True)
+        rc = self.lib.pbh_multi_prove_batch(self.h, C.c_size_t(n), C.c_void_p(W.ptr), C.c_size_t(W.pitch), C.c_void_p(R.ptr), C.c_size_t(R.pitch),
+                                            C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(S.ptr))
+        self._check(rc, "pbh_multi_prove_batch")
+        return proof, status
+
+    def verify_batch(self, proof, chal, u, want_gt=False):
+        P = _Planes(proof, 27, name="proof"); n = P.n
+        Ch = _Planes(chal, 5, n, "chal"); U = _Planes(u, 1, n, "u")
+        result = np.empty((n,), np.uint8); gt = np.empty((4, n), np.uint8) if want_gt else None
+        Rs = _Planes(result, 1, n, "result", out=True); G = _Planes(gt, 4, n, "gt", out=True) if want_gt else None
+        rc = self.lib.pbh_multi_verify_batch(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch), C.c_void_p(Ch.ptr), C.c_size_t(Ch.pitch),
+                                             C.c_void_p(U.ptr), C.c_void_p(Rs.ptr), C.c_void_p(G.ptr if G else None), C.c_size_t(G.pitch if G else 0))
+        self._check(rc, "pbh_multi_verify_batch")
+        return (result, gt) if want_gt else result
+
+    def prove_verify_sharded(self, n_total, first_index=0, seed=0xB200, dist=DIST_FULLPATH):
+        """-> dict(bitmap uint8[ceil(n/8)], digests uint64[n_dev], total_digest int, accepted int, ms float)."""
+        bitmap = np.zeros((n_total + 7) // 8, np.uint8); digs = np.zeros(len(self.devices), np.uint64)
+        total = C.c_uint64(); acc = C.c_uint64(); ms = C.c_float()
+        rc = self.lib.pbh_multi_prove_verify_sharded(self.h, C.c_uint64(n_total), C.c_uint64(first_index), C.c_uint64(seed), int(dist),
+                                                     C.c_void_p(bitmap.ctypes.data), C.c_void_p(digs.ctypes.data), C.byref(total), C.byref(acc), C.byref(ms))
+        self._check(rc, "pbh_multi_prove_verify_sharded")
+        return dict(bitmap=bitmap, digests=digs, total_digest=int(total.value), accepted=int(acc.value), ms=float(ms.value))
 
 
 # ================================================================================================

@@ -229,3 +229,37 @@ def test_poly_mul_all_small_shapes_and_bytes(gpu_ctx, oracle):
             assert np.array_equal(got.cpu().numpy(), exp), (la, lb)
             got = ctx.poly_mul_batch(da[:, 1:], db[:, 1:]); ctx.sync()          # unaligned bases: general kernel
             assert np.array_equal(got.cpu().numpy(), exp[:, 1:]), (la, lb)
+
+
+def test_multi_device_context(gpu_ctx, oracle):
+    """pbh_multi_* (include/pbh_b200.h): every visible GPU (one on a single-GPU box) driven from this one process.  Host-pointer
+    prove / verify split over the devices equal the oracle; the sharded pass (in-library NCCL all-gather when there is more
+    than one device) returns the bitmap and the digest one context computes alone for the same global index range."""
+    import torch
+    import pbh_b200
+    n_dev = min(torch.cuda.device_count(), 8)
+    ctx = gpu_ctx["table"]
+    for algo in ("table", "arith"):
+        with pbh_b200.MultiContext(n_dev, algo=algo) as mc:
+            assert mc.device_count == n_dev
+            n = 3 * 256 * n_dev + 77
+            w, r, c, u, _ = oracle.generate_inputs(n, seed=31, dist=0, threads=8)
+            p, s = mc.prove_batch(w, r, c)
+            po, so = oracle.prove_batch(w, r, c, threads=8)
+            assert np.array_equal(p, po) and np.array_equal(s, so)
+            v, g = mc.verify_batch(p, c, u, want_gt=True)
+            vo, go = oracle.verify_batch(po, c, u, threads=8)
+            assert np.array_equal(v, vo) and np.array_equal(g, go)
+            for n_total, first in ((300000 + 40, 0), (4096, 123456 * 8), (77, 8)):
+                out = mc.prove_verify_sharded(n_total, first_index=first, seed=0xB200)
+                gw, gr, gc, gu = ctx.generate_inputs(n_total, first_index=first, seed=0xB200, dist=1)
+                gp, gs = ctx.prove_batch(gw, gr, gc)
+                gv = ctx.verify_batch(gp, gc, gu)
+                bm = ctx.pack_verdicts(gv)
+                dg = int(ctx.digest(gp, first_index=first).item()) & (2**64 - 1)
+                ctx.sync()
+                assert np.array_equal(out["bitmap"], bm.cpu().numpy()), (algo, n_total)
+                assert out["total_digest"] == dg and out["accepted"] == int((gv == 1).sum().item())
+                assert sum(int(x) for x in out["digests"]) % 2**64 == dg and out["ms"] > 0
+    with pytest.raises(pbh_b200.PbhError):
+        pbh_b200.MultiContext([torch.cuda.device_count() + 3])

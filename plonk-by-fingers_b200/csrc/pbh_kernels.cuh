@@ -743,47 +743,92 @@ __device__ __forceinline__ uint32_t h2_pack_canon(__half2 a01, __half2 a23) {
   a23 = __hadd2(__hfma2(__hlt2(a23, zero), p17, a23), bias);
   return __byte_perm(h2_word(a01), h2_word(a23), 0x6420u);
 }
-template <int OP>
-__global__ void __launch_bounds__(kBlock) poly_unary_kernel(size_t n, uint32_t len, const uint8_t* __restrict__ in, size_t in_pitch,
-                                                             uint8_t* __restrict__ out, size_t out_pitch, bool vec_ok) {
-  const size_t n4 = vec_ok ? n / 4 : 0;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
-    const uint32_t opw = reinterpret_cast<const uint32_t*>(in + (size_t)len * in_pitch)[q];
-    const __half2 x01 = h2_red17(h2_from_bytes(opw, false)), x23 = h2_red17(h2_from_bytes(opw, true));
-    __half2 acc01 = h2_bits(0u), acc23 = h2_bits(0u);
-    // eight planes' loads are issued before any is consumed (bytes in flight, not arithmetic, bound these kernels)
-    if (OP == 0) {
-      for (uint32_t k0 = 0; k0 < len; k0 += 8) {
-        uint32_t w[8];
+// WORDS 32-bit words per plane and thread: 1 (4 items, 4-byte aligned planes) or 4 (16 items through one 128-bit access,
+// 16-byte aligned planes: four times the bytes in flight per thread and a quarter of the address arithmetic per item).
+template <int WORDS> struct PlaneVec;
+template <> struct PlaneVec<1> {
+  uint32_t w[1];
+  __device__ __forceinline__ void load(const uint8_t* p, size_t q) { w[0] = reinterpret_cast<const uint32_t*>(p)[q]; }
+  __device__ __forceinline__ void store(uint8_t* p, size_t q) const { reinterpret_cast<uint32_t*>(p)[q] = w[0]; }
+};
+template <> struct PlaneVec<4> {
+  uint32_t w[4];
+  __device__ __forceinline__ void load(const uint8_t* p, size_t q) { const uint4 v = reinterpret_cast<const uint4*>(p)[q]; w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; }
+  __device__ __forceinline__ void store(uint8_t* p, size_t q) const { reinterpret_cast<uint4*>(p)[q] = make_uint4(w[0], w[1], w[2], w[3]); }
+};
+template <int OP, int WORDS>
+__device__ __forceinline__ void poly_unary_vec(size_t q, uint32_t len, const uint8_t* __restrict__ in, size_t in_pitch, uint8_t* __restrict__ out,
+                                               size_t out_pitch) {
+  PlaneVec<WORDS> op;
+  op.load(in + (size_t)len * in_pitch, q);
+  __half2 x[2 * WORDS], acc[2 * WORDS];
 #pragma unroll
-        for (uint32_t j = 0; j < 8; j++) w[j] = k0 + j < len ? reinterpret_cast<const uint32_t*>(in + (size_t)(k0 + j) * in_pitch)[q] : 0u;
+  for (int j = 0; j < WORDS; j++) {
+    x[2 * j] = h2_red17(h2_from_bytes(op.w[j], false)); x[2 * j + 1] = h2_red17(h2_from_bytes(op.w[j], true));
+    acc[2 * j] = acc[2 * j + 1] = h2_bits(0u);
+  }
+  constexpr uint32_t kAhead = WORDS == 1 ? 8 : 4;     // planes whose loads are issued before any is consumed
+  if (OP == 0) {
+    for (uint32_t k0 = 0; k0 < len; k0 += kAhead) {
+      PlaneVec<WORDS> v[kAhead];
 #pragma unroll
-        for (uint32_t j = 0; j < 8; j++) {
-          if (k0 + j < len)
-            reinterpret_cast<uint32_t*>(out + (size_t)(k0 + j) * out_pitch)[q] =
-                h2_pack_canon(h2_red17(__hmul2(h2_from_bytes(w[j], false), x01)), h2_red17(__hmul2(h2_from_bytes(w[j], true), x23)));
+      for (uint32_t j = 0; j < kAhead; j++)
+        if (k0 + j < len) v[j].load(in + (size_t)(k0 + j) * in_pitch, q);
+#pragma unroll
+      for (uint32_t j = 0; j < kAhead; j++) {
+        if (k0 + j < len) {
+          PlaneVec<WORDS> o;
+#pragma unroll
+          for (int t = 0; t < WORDS; t++)
+            o.w[t] = h2_pack_canon(h2_red17(__hmul2(h2_from_bytes(v[j].w[t], false), x[2 * t])), h2_red17(__hmul2(h2_from_bytes(v[j].w[t], true), x[2 * t + 1])));
+          o.store(out + (size_t)(k0 + j) * out_pitch, q);
         }
       }
-    } else {
-      for (uint32_t k0 = len; k0 > 0; k0 = k0 > 8 ? k0 - 8 : 0) {   // planes k0-1, k0-2, ... (Horner runs downwards)
-        uint32_t w[8];
+    }
+  } else {
+    for (uint32_t k0 = len; k0 > 0; k0 = k0 > kAhead ? k0 - kAhead : 0) {   // planes k0-1, k0-2, ... (Horner runs downwards)
+      PlaneVec<WORDS> v[kAhead];
 #pragma unroll
-        for (uint32_t j = 0; j < 8; j++) w[j] = j < k0 ? reinterpret_cast<const uint32_t*>(in + (size_t)(k0 - 1 - j) * in_pitch)[q] : 0u;
+      for (uint32_t j = 0; j < kAhead; j++)
+        if (j < k0) v[j].load(in + (size_t)(k0 - 1 - j) * in_pitch, q);
 #pragma unroll
-        for (uint32_t j = 0; j < 8; j++) {
-          if (j < k0) {
-            const uint32_t k = k0 - 1 - j;
-            if (OP == 2 && k + 1 < len) reinterpret_cast<uint32_t*>(out + (size_t)k * out_pitch)[q] = h2_pack_canon(acc01, acc23);
-            acc01 = h2_red17(__hfma2(acc01, x01, h2_from_bytes(w[j], false)));
-            acc23 = h2_red17(__hfma2(acc23, x23, h2_from_bytes(w[j], true)));
+      for (uint32_t j = 0; j < kAhead; j++) {
+        if (j < k0) {
+          const uint32_t k = k0 - 1 - j;
+          if (OP == 2 && k + 1 < len) {
+            PlaneVec<WORDS> o;
+#pragma unroll
+            for (int t = 0; t < WORDS; t++) o.w[t] = h2_pack_canon(acc[2 * t], acc[2 * t + 1]);
+            o.store(out + (size_t)k * out_pitch, q);
+          }
+#pragma unroll
+          for (int t = 0; t < WORDS; t++) {
+            acc[2 * t] = h2_red17(__hfma2(acc[2 * t], x[2 * t], h2_from_bytes(v[j].w[t], false)));
+            acc[2 * t + 1] = h2_red17(__hfma2(acc[2 * t + 1], x[2 * t + 1], h2_from_bytes(v[j].w[t], true)));
           }
         }
       }
-      reinterpret_cast<uint32_t*>(out + (size_t)(OP == 2 ? len - 1 : 0) * out_pitch)[q] = h2_pack_canon(acc01, acc23);
     }
+    PlaneVec<WORDS> o;
+#pragma unroll
+    for (int t = 0; t < WORDS; t++) o.w[t] = h2_pack_canon(acc[2 * t], acc[2 * t + 1]);
+    o.store(out + (size_t)(OP == 2 ? len - 1 : 0) * out_pitch, q);
   }
-  for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+}
+// vec: 0 = byte path only, 4 = one 32-bit word per plane and thread, 16 = one 128-bit word
+template <int OP>
+__global__ void __launch_bounds__(kBlock) poly_unary_kernel(size_t n, uint32_t len, const uint8_t* __restrict__ in, size_t in_pitch,
+                                                             uint8_t* __restrict__ out, size_t out_pitch, int vec) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t done = 0;
+  if (vec == 16) {
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n / 16; q += stride) poly_unary_vec<OP, 4>(q, len, in, in_pitch, out, out_pitch);
+    done = n / 16 * 16;
+  } else if (vec == 4) {
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n / 4; q += stride) poly_unary_vec<OP, 1>(q, len, in, in_pitch, out, out_pitch);
+    done = n / 4 * 4;
+  }
+  for (size_t i = done + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint32_t x = mod17(in[(size_t)len * in_pitch + i]);
     if (OP == 0) {
       for (uint32_t k = 0; k < len; k++) out[(size_t)k * out_pitch + i] = (uint8_t)mod17(mod17(in[(size_t)k * in_pitch + i]) * x);

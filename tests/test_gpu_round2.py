@@ -51,17 +51,25 @@ def test_lanes_and_host_alloc(gpu_ctx, oracle):
             bufs["w"][...] = w; bufs["r"][...] = r; bufs["c"][...] = c; bufs["u"][...] = u
             bufs["proof"][...] = 0xEE; bufs["status"][...] = 0xEE; bufs["result"][...] = 0xEE
             sets.append((bufs, (w, r, c, u)))
-        for rep in range(3):
-            for lane, (b, _) in enumerate(sets):
-                ctx.lane_sync(lane)
-                ctx.prove_batch_async(lane, b["w"], b["r"], b["c"], b["proof"], b["status"])
-                ctx.verify_batch_async(lane, b["proof"], b["c"], b["u"], b["result"], gt=b["gt"])
-        ctx.sync()
+        expect = []
         for b, (w, r, c, u) in sets:
             po, so = oracle.prove_batch(w, r, c, threads=8)
-            vo, go = oracle.verify_batch(po, c, u, threads=8)
-            assert np.array_equal(b["proof"], po) and np.array_equal(b["status"], so)
-            assert np.array_equal(b["result"], vo) and np.array_equal(b["gt"], go)
+            expect.append((po, so) + tuple(oracle.verify_batch(po, c, u, threads=8)))
+        # PBH_OPT_LANE_MODE: 3 = copy engine both ways (default), 1 = copy-engine upload + in-place stores, 0 = in place
+        for mode in (3, 1, 0):
+            ctx.set_option(pbh_b200.OPT_LANE_MODE, mode)
+            for b, _ in sets:
+                b["proof"][...] = 0xEE; b["status"][...] = 0xEE; b["result"][...] = 0xEE; b["gt"][...] = 0xEE
+            for rep in range(3):
+                for lane, (b, _) in enumerate(sets):
+                    ctx.lane_sync(lane)
+                    ctx.prove_batch_async(lane, b["w"], b["r"], b["c"], b["proof"], b["status"])
+                    ctx.verify_batch_async(lane, b["proof"], b["c"], b["u"], b["result"], gt=b["gt"])
+            ctx.sync()
+            for (b, _), (po, so, vo, go) in zip(sets, expect):
+                assert np.array_equal(b["proof"], po) and np.array_equal(b["status"], so), mode
+                assert np.array_equal(b["result"], vo) and np.array_equal(b["gt"], go), mode
+        ctx.set_option(pbh_b200.OPT_LANE_MODE, 3)
         # pageable arrays through the same entry points: synchronous, same bytes
         (b, (w, r, c, u)) = sets[1]
         proof = np.full((27, n), 0xEE, np.uint8); status = np.full(n, 0xEE, np.uint8); result = np.full(n, 0xEE, np.uint8)

@@ -348,6 +348,23 @@ int pbh_kzg_commit_batch(pbh_ctx* ctx, size_t n, const uint8_t* coeffs, size_t i
 int pbh_pairing_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch,
                       int on_device);
 
+/* GTP * GTP (src/pbh/gt.rs:61-69): planes a1 b1 a2 b2 in; a b out.  GTP::pow(600) (src/pbh/gt.rs:33-59, the final
+ * exponentiation of src/pbh/pairing.rs:17): planes a b in; a b out (0 + 0u stays 0 + 0u, Q10). */
+int pbh_gt_mul_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device);
+int pbh_gt_pow600_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device);
+/* (q, r) = num / den for ANY divisor over F_17 (src/poly.rs:230-247): ln numerator planes and ld divisor planes in (zero
+ * padded, 1 <= ln <= 32, 1 <= ld <= 16), ln quotient planes and ld remainder planes out.  status[i] = 1 where the reference
+ * panics (a NON-ZERO numerator divided by the zero polynomial: `lead_d.inv().unwrap()`; 0 / 0 is (0, 0) because the division
+ * loop never starts), with zero outputs; 0 otherwise. */
+int pbh_poly_divrem_batch(pbh_ctx* ctx, size_t n, uint32_t ln, uint32_t ld, const uint8_t* num, size_t num_pitch, const uint8_t* den,
+                          size_t den_pitch, uint8_t* q, size_t q_pitch, uint8_t* r, size_t r_pitch, uint8_t* status, int on_device);
+/* `a += b` (subtract = 0) / `a -= b` (subtract = 1) for operands of different lengths exactly as the reference does it
+ * (src/poly.rs:165-176, 192-203): la and lb planes in (zero padded, <= 64), max(la, lb) planes out.  With len(a) the
+ * normalised length of a, out[n] = a[n] +- b[n] below len(a) and b[n] UNCHANGED at or beyond it - also when subtracting,
+ * which is the quirk the prover depends on. */
+int pbh_poly_addsub_ragged_batch(pbh_ctx* ctx, size_t n, uint32_t la, uint32_t lb, int subtract, const uint8_t* a, size_t a_pitch,
+                                 const uint8_t* b, size_t b_pitch, uint8_t* out, size_t out_pitch, int on_device);
+
 /* ---- shard summaries for the multi-GPU gather ---------------------------------- */
 /* Pack bit 0 of each result byte into a bitmap (item i -> bit i%8 of byte i/8), device pointers.  */
 int pbh_pack_verdicts_dev(pbh_ctx* ctx, size_t n, const uint8_t* result, uint8_t* bitmap);

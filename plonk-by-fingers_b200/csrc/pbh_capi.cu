@@ -1307,6 +1307,61 @@ int pbh_pairing_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch
   });
 }
 
+int pbh_gt_mul_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return planes_impl(ctx, n, in, in_pitch, 4, out, out_pitch, 2, on_device, [&](int grid, const uint8_t* di, size_t ip, uint8_t* dout, size_t op) {
+    gt_kernel<0><<<grid, kBlock, 0, ctx->compute>>>(ctx->d_tables, n, di, ip, dout, op);
+  });
+}
+int pbh_gt_pow600_batch(pbh_ctx* ctx, size_t n, const uint8_t* in, size_t in_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  return planes_impl(ctx, n, in, in_pitch, 2, out, out_pitch, 2, on_device, [&](int grid, const uint8_t* di, size_t ip, uint8_t* dout, size_t op) {
+    gt_kernel<1><<<grid, kBlock, 0, ctx->compute>>>(ctx->d_tables, n, di, ip, dout, op);
+  });
+}
+
+int pbh_poly_divrem_batch(pbh_ctx* ctx, size_t n, uint32_t ln, uint32_t ld, const uint8_t* num, size_t num_pitch, const uint8_t* den,
+                          size_t den_pitch, uint8_t* q, size_t q_pitch, uint8_t* r, size_t r_pitch, uint8_t* status, int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!num || !den || !q || !r || !status || num_pitch < n || den_pitch < n || q_pitch < n || r_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  if (ln < 1 || ln > 32 || ld < 1 || ld > 16) return fail(ctx, PBH_ERR_UNSUPPORTED, "1 <= ln <= 32, 1 <= ld <= 16");
+  const uint8_t *d_num = num, *d_den = den; uint8_t *d_q = q, *d_r = r, *d_st = status; size_t np = num_pitch, dp = den_pitch, qp = q_pitch, rp = r_pitch;
+  if (!on_device) {
+    d_num = stg.in(num, num_pitch, n, ln, ce); CUDA_TRY(ctx, ce);
+    d_den = stg.in(den, den_pitch, n, ld, ce); CUDA_TRY(ctx, ce);
+    d_q = stg.in<uint8_t>(nullptr, 0, n, ln, ce); CUDA_TRY(ctx, ce);
+    d_r = stg.in<uint8_t>(nullptr, 0, n, ld, ce); CUDA_TRY(ctx, ce);
+    d_st = stg.in<uint8_t>(nullptr, 0, n, 1, ce); CUDA_TRY(ctx, ce);
+    np = dp = qp = rp = n;
+  }
+  poly_divrem_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(ctx->d_tables, n, ln, ld, d_num, np, d_den, dp, d_q, qp, d_r, rp, d_st);
+  SWEEP_FINISH(ctx);
+  if (!on_device) {
+    CUDA_TRY(ctx, stg.out(q, q_pitch, d_q, n, ln));
+    CUDA_TRY(ctx, stg.out(r, r_pitch, d_r, n, ld));
+    CUDA_TRY(ctx, stg.out(status, n, d_st, n, 1));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute));
+  }
+  return PBH_OK;
+}
+
+int pbh_poly_addsub_ragged_batch(pbh_ctx* ctx, size_t n, uint32_t la, uint32_t lb, int subtract, const uint8_t* a, size_t a_pitch,
+                                 const uint8_t* b, size_t b_pitch, uint8_t* out, size_t out_pitch, int on_device) {
+  SWEEP_PROLOGUE(ctx, n);
+  if (!a || !b || !out || a_pitch < n || b_pitch < n || out_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "bad pointer or pitch");
+  if (la < 1 || la > 64 || lb < 1 || lb > 64) return fail(ctx, PBH_ERR_UNSUPPORTED, "1 <= la, lb <= 64");
+  const uint32_t lo = std::max(la, lb);
+  const uint8_t *d_a = a, *d_b = b; uint8_t* d_out = out; size_t ap = a_pitch, bp = b_pitch, op = out_pitch;
+  if (!on_device) {
+    d_a = stg.in(a, a_pitch, n, la, ce); CUDA_TRY(ctx, ce);
+    d_b = stg.in(b, b_pitch, n, lb, ce); CUDA_TRY(ctx, ce);
+    d_out = stg.in<uint8_t>(nullptr, 0, n, lo, ce); CUDA_TRY(ctx, ce);
+    ap = bp = op = n;
+  }
+  poly_addsub_ragged_kernel<<<grid_for(ctx, n, 8), kBlock, 0, ctx->compute>>>(n, la, lb, subtract, d_a, ap, d_b, bp, d_out, op);
+  SWEEP_FINISH(ctx);
+  if (!on_device) { CUDA_TRY(ctx, stg.out(out, out_pitch, d_out, n, lo)); CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute)); }
+  return PBH_OK;
+}
+
 // ---- shard summaries, synthetic inputs, measurement --------------------------------------------------------
 int pbh_pack_verdicts_dev(pbh_ctx* ctx, size_t n, const uint8_t* result, uint8_t* bitmap) {
   CTX_CHECK(ctx);

@@ -1083,6 +1083,79 @@ __global__ void __launch_bounds__(kBlock) pairing_kernel(const Tables* __restric
   }
 }
 
+// GTP * GTP (src/pbh/gt.rs:61-69; OP 0: planes a1 b1 a2 b2 -> a b) and GTP::pow(600) (src/pbh/gt.rs:33-59, the final
+// exponentiation of src/pbh/pairing.rs:17; OP 1: planes a b -> a b) on the exact FP32 arithmetic of pbh_g1f.cuh
+template <int OP>
+__global__ void __launch_bounds__(kBlock) gt_kernel(const Tables* __restrict__ gT, size_t n, const uint8_t* __restrict__ in, size_t in_pitch,
+                                                     uint8_t* __restrict__ out, size_t out_pitch) {
+  __shared__ Tables sT;
+  stage_tables(sT, gT);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    F32* tag = nullptr;
+    GTF<F32> p, r;
+    p.a = f_from_u32(in[i] % 101u, tag); p.b = f_from_u32(in[in_pitch + i] % 101u, tag);
+    if (OP == 0) {
+      GTF<F32> q;
+      q.a = f_from_u32(in[2 * in_pitch + i] % 101u, tag); q.b = f_from_u32(in[3 * in_pitch + i] % 101u, tag);
+      r = gtf_mul(p, q);
+    } else {
+      r = gtf_final_exp(p, sT.inv101c);
+    }
+    out[i] = (uint8_t)f_canon101(r.a); out[out_pitch + i] = (uint8_t)f_canon101(r.b);
+  }
+}
+
+// Poly / Poly -> (q, r) for ANY divisor (src/poly.rs:230-247), one item per thread: `ln` numerator planes, `ld` divisor
+// planes (zero padded; the normalised lengths are implied by the values), ln quotient planes and ld remainder planes out.
+// The reference inverts the divisor's leading coefficient at every step and panics on the zero polynomial
+// (`lead_d.inv().unwrap()`): status 1, outputs zero.  ln <= 32, ld <= 16.
+__global__ void __launch_bounds__(kBlock) poly_divrem_kernel(const Tables* __restrict__ gT, size_t n, uint32_t ln, uint32_t ld,
+                                                              const uint8_t* __restrict__ num, size_t num_pitch, const uint8_t* __restrict__ den,
+                                                              size_t den_pitch, uint8_t* __restrict__ q, size_t q_pitch, uint8_t* __restrict__ r,
+                                                              size_t r_pitch, uint8_t* __restrict__ status) {
+  __shared__ uint8_t s_inv[32];
+  if (threadIdx.x < 32) s_inv[threadIdx.x] = gT->inv17[threadIdx.x];
+  __syncthreads();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t rem[32], d[16], quo[32];
+    uint32_t dlen = 0;                                           // normalised length of the divisor (0: the zero polynomial)
+    bool num_zero = true;
+    for (uint32_t k = 0; k < 32; k++) { rem[k] = k < ln ? mod17(num[(size_t)k * num_pitch + i]) : 0u; quo[k] = 0u; num_zero = num_zero && rem[k] == 0u; }
+    for (uint32_t k = 0; k < 16; k++) { d[k] = k < ld ? mod17(den[(size_t)k * den_pitch + i]) : 0u; if (d[k]) dlen = k + 1; }
+    // `while !r.is_zero() && r.degree() >= rhs.degree()`: a zero numerator never reaches the inversion, so 0 / 0 = (0, 0)
+    const bool panic = dlen == 0 && !num_zero;
+    if (dlen != 0) {
+      const uint32_t linv = s_inv[d[dlen - 1]];
+      for (int top = (int)ln - 1; top >= (int)dlen - 1; top--) {   // r.degree() >= rhs.degree()
+        const uint32_t c = mul17(rem[top], linv);
+        if (c == 0u) continue;
+        quo[top - (dlen - 1)] = c;
+        for (uint32_t j = 0; j < dlen; j++) rem[top - j] = mod17(rem[top - j] + 17u * 16u - c * d[dlen - 1 - j]);
+      }
+    }
+    for (uint32_t k = 0; k < ln; k++) q[(size_t)k * q_pitch + i] = (uint8_t)(panic ? 0u : quo[k]);
+    for (uint32_t k = 0; k < ld; k++) r[(size_t)k * r_pitch + i] = (uint8_t)(panic ? 0u : rem[k]);
+    status[i] = panic ? 1 : 0;
+  }
+}
+
+// `a += b` / `a -= b` for operands of DIFFERENT lengths exactly as the reference does it (src/poly.rs:165-176, 192-203):
+// la and lb planes, zero padded; with len(a) the normalised length of a (the zero polynomial keeps one coefficient),
+// out[n] = a[n] +- b[n] below len(a) and b[n] AS IT IS at or beyond it - for the subtraction too, which is quirk Q1.
+__global__ void __launch_bounds__(kBlock) poly_addsub_ragged_kernel(size_t n, uint32_t la, uint32_t lb, int subtract, const uint8_t* __restrict__ a,
+                                                                     size_t a_pitch, const uint8_t* __restrict__ b, size_t b_pitch,
+                                                                     uint8_t* __restrict__ out, size_t out_pitch) {
+  const uint32_t lo = la > lb ? la : lb;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t alen = 1;
+    for (uint32_t k = 0; k < la; k++) if (mod17(a[(size_t)k * a_pitch + i])) alen = k + 1;
+    for (uint32_t k = 0; k < lo; k++) {
+      const uint32_t x = k < la ? mod17(a[(size_t)k * a_pitch + i]) : 0u, y = k < lb ? mod17(b[(size_t)k * b_pitch + i]) : 0u;
+      out[(size_t)k * out_pitch + i] = (uint8_t)(k < alen ? (subtract ? sub17(x, y) : add17(x, y)) : y);
+    }
+  }
+}
+
 // ---- record <-> plane transposes (include/pbh_b200.h "record wire format") ------------------------------------------
 // One thread per 32-byte record: two 128-bit accesses on the record side (a warp touches 1 KB contiguously), byte-wide
 // coalesced accesses on the plane side.

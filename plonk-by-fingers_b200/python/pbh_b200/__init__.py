@@ -48,7 +48,8 @@ pbh_kzg_commit_batch pbh_pairing_batch pbh_pack_verdicts_dev pbh_digest_dev pbh_
 pbh_measure_int32_peak pbh_mul_ntt_batch pbh_poly_scale_batch pbh_poly_eval_batch pbh_poly_div_linear_batch pbh_ctx_get_fs_seed pbh_prove_fs_batch pbh_prove_fs_batch_dev pbh_verify_fs_batch pbh_verify_fs_batch_dev
 pbh_prove_batch_async pbh_verify_batch_async pbh_lane_sync pbh_host_alloc pbh_host_free pbh_ctx_numa_node
 pbh_coset_ntt4_batch pbh_coset_intt4_batch pbh_multi_create pbh_multi_destroy pbh_multi_device_count pbh_multi_ctx pbh_multi_last_error
-pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_verify_sharded""".split()
+pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_verify_sharded
+pbh_gt_mul_batch pbh_gt_pow600_batch pbh_poly_divrem_batch pbh_poly_addsub_ragged_batch""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -524,6 +525,30 @@ class Context:
     def g1_add_batch(self, arr): return self._sweep(self.lib.pbh_g1_add_batch, arr, 6, 3)
     def kzg_commit_batch(self, arr): return self._sweep(self.lib.pbh_kzg_commit_batch, arr, 7, 3)
     def pairing_batch(self, arr): return self._sweep(self.lib.pbh_pairing_batch, arr, 5, 2)
+    def gt_mul_batch(self, arr): return self._sweep(self.lib.pbh_gt_mul_batch, arr, 4, 2)
+    def gt_pow600_batch(self, arr): return self._sweep(self.lib.pbh_gt_pow600_batch, arr, 2, 2)
+
+    def poly_divrem_batch(self, num, den):
+        """num (ln, n), den (ld, n) host arrays -> q (ln, n), r (ld, n), status (n,): src/poly.rs:230-247 for any divisor."""
+        N = _Planes(num, np.shape(num)[0], name="num"); D = _Planes(den, np.shape(den)[0], N.n, "den")
+        ln, ld = N.arr.shape[0], D.arr.shape[0]
+        q = np.empty((ln, N.n), np.uint8); r = np.empty((ld, N.n), np.uint8); st = np.empty((N.n,), np.uint8)
+        Q = _Planes(q, ln, N.n, "q", out=True); R = _Planes(r, ld, N.n, "r", out=True)
+        rc = self.lib.pbh_poly_divrem_batch(self.h, C.c_size_t(N.n), C.c_uint32(ln), C.c_uint32(ld), C.c_void_p(N.ptr), C.c_size_t(N.pitch),
+                                            C.c_void_p(D.ptr), C.c_size_t(D.pitch), C.c_void_p(Q.ptr), C.c_size_t(Q.pitch), C.c_void_p(R.ptr),
+                                            C.c_size_t(R.pitch), C.c_void_p(st.ctypes.data), 0)
+        self._check(rc, "pbh_poly_divrem_batch")
+        return q, r, st
+
+    def poly_addsub_ragged_batch(self, a, b, subtract=False):
+        """a (la, n), b (lb, n) host arrays -> (max(la, lb), n): the reference's += / -= for different lengths (Q1 included)."""
+        A = _Planes(a, np.shape(a)[0], name="a"); B = _Planes(b, np.shape(b)[0], A.n, "b")
+        la, lb = A.arr.shape[0], B.arr.shape[0]
+        out = np.empty((max(la, lb), A.n), np.uint8); O = _Planes(out, max(la, lb), A.n, "out", out=True)
+        rc = self.lib.pbh_poly_addsub_ragged_batch(self.h, C.c_size_t(A.n), C.c_uint32(la), C.c_uint32(lb), int(subtract), C.c_void_p(A.ptr),
+                                                   C.c_size_t(A.pitch), C.c_void_p(B.ptr), C.c_size_t(B.pitch), C.c_void_p(O.ptr), C.c_size_t(O.pitch), 0)
+        self._check(rc, "pbh_poly_addsub_ragged_batch")
+        return out
 
     def poly_mul_batch(self, a, b):
         A = _Planes(a, np.shape(a)[0] if not _is_torch(a) else a.shape[0], name="a")

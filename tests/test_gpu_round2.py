@@ -271,3 +271,54 @@ def test_multi_device_context(gpu_ctx, oracle):
                 assert sum(int(x) for x in out["digests"]) % 2**64 == dg and out["ms"] > 0
     with pytest.raises(pbh_b200.PbhError):
         pbh_b200.MultiContext([torch.cuda.device_count() + 3])
+
+
+def test_gt_sweeps_exhaustive(gpu_ctx, oracle):
+    """GTP::pow(600) on ALL 101^2 elements of F_101^2 and GTP * GTP on a 101^2 x 40 sample, on the GPU (SURVEY.md section 4;
+    src/pbh/gt.rs:33-69 and its vectors :88-97)."""
+    ctx = gpu_ctx["arith"]
+    allgt = np.ascontiguousarray(np.array([(a, b) for a in range(101) for b in range(101)], dtype=np.uint8).T)
+    got = ctx.gt_pow600_batch(allgt)
+    for i in range(allgt.shape[1]):
+        assert tuple(int(x) for x in got[:, i]) == oracle.gt_pow((int(allgt[0, i]), int(allgt[1, i])), 600), allgt[:, i]
+    assert tuple(got[:, 68 * 101 + 47]) == (97, 89)                                  # (68+47u)^600 = 97+89u   src/pbh/gt.rs:96
+    rng = np.random.default_rng(3)
+    pairs = rng.integers(0, 101, size=(4, 4000), dtype=np.uint8)
+    pairs[:, 0] = (26, 97, 93, 76)                                                   # (26+97u)(93+76u) = 97+89u  src/pbh/gt.rs:90
+    prod = ctx.gt_mul_batch(pairs)
+    assert tuple(prod[:, 0]) == (97, 89)
+    for i in range(pairs.shape[1]):
+        assert tuple(int(x) for x in prod[:, i]) == oracle.gt_mul((int(pairs[0, i]), int(pairs[1, i])), (int(pairs[2, i]), int(pairs[3, i])))
+
+
+def test_general_division_and_ragged_subtraction(gpu_ctx, oracle):
+    """Poly / Poly for arbitrary divisors (src/poly.rs:230-247; the vectors of src/poly.rs:436-449 as q d + r == n) and the
+    reference's += / -= on operands of different lengths (src/poly.rs:165-203), whose subtraction pushes the longer right-hand
+    tail UN-NEGATED (Q1): against the oracle's restatement item by item, zero and short operands included."""
+    ctx = gpu_ctx["table"]
+    rng = np.random.default_rng(21)
+    strip = lambda v: (lambda l: l[:max(1, max([k + 1 for k, x in enumerate(l) if x] or [1]))])([int(x) for x in v])
+    for ln, ld in ((6, 3), (22, 5), (4, 7), (9, 1), (32, 16)):
+        n = 1500
+        num = rng.integers(0, 17, size=(ln, n), dtype=np.uint8); den = rng.integers(0, 17, size=(ld, n), dtype=np.uint8)
+        den[:, :40] = 0                                    # the zero polynomial: the reference panics
+        den[ld // 2:, 40:300] = 0; num[ln // 2:, 200:500] = 0; num[:, 500:520] = 0
+        q, r, st = ctx.poly_divrem_batch(num, den)
+        for i in range(n):
+            try:
+                qo, ro = oracle.poly_op(17, "div", strip(num[:, i]), strip(den[:, i]))
+                assert st[i] == 0 and strip(q[:, i]) == qo and strip(r[:, i]) == ro, (ln, ld, i)
+            except ArithmeticError:
+                assert st[i] == 1 and not q[:, i].any() and not r[:, i].any(), (ln, ld, i)
+    for la, lb in ((4, 7), (7, 4), (6, 6), (1, 22), (22, 1)):
+        n = 1200
+        a = rng.integers(0, 17, size=(la, n), dtype=np.uint8); b = rng.integers(0, 17, size=(lb, n), dtype=np.uint8)
+        a[la // 2:, :400] = 0; a[:, 400:450] = 0; b[lb // 2:, 300:700] = 0
+        for subtract in (False, True):
+            out = ctx.poly_addsub_ragged_batch(a, b, subtract=subtract)
+            for i in range(n):
+                exp = oracle.poly_op(17, "sub" if subtract else "add", strip(a[:, i]), strip(b[:, i]))
+                assert strip(out[:, i]) == exp, (la, lb, subtract, i)
+    # Q1 by hand: [1] -= [2, 3] gives [16, 3], not [16, 14]
+    out = ctx.poly_addsub_ragged_batch(np.array([[1]], np.uint8), np.array([[2], [3]], np.uint8), subtract=True)
+    assert out[:, 0].tolist() == [16, 3]

@@ -220,11 +220,19 @@ def main():
     ap.add_argument("--config4-log2", type=int, default=28)
     ap.add_argument("--sweep-log2", type=str, default="24,28")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying one CUDA graph per K-step region")
+    ap.add_argument("--no-overlap-prove", dest="overlap_prove", action="store_false",
+                    help="launch every prover from one stream (default: odd steps launch from a second prover stream, so prove(k+1) fills the SMs prove(k) leaves)")
     ap.add_argument("--no-overlap-verify", dest="overlap_verify", action="store_false",
                     help="keep verify(k) and prove(k+1) on one stream inside the graph (default: verify(k) runs on a second stream beside prove(k+1))")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+
+    # Only the JSON line may reach stdout: libraries that print there (NCCL's version banner under NCCL_DEBUG, for one)
+    # are sent to stderr for the whole run; the line itself is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -271,12 +279,18 @@ def main():
     torch.cuda.synchronize()
     comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
     KERNELS_PER_STEP = 2   # prover (+ fused proof digest), verifier (+ fused verdict bitmap)
-    ctx_v = vstream = None
+    ctx_v = vstream = ctx_p1 = pstream1 = None
     if args.overlap_verify:
         # the verifier of step k runs on a second context (its own stream) beside the prover of step k + 1: the two touch
         # different ring slots, and the tail of one kernel fills the SMs the other has not reached yet
         ctx_v = pbh_b200.Context(device=local, algo=args.algo)
         vstream = ctx_v.torch_stream()
+        if args.overlap_prove and ring >= 2:
+            # the provers of consecutive steps are independent too (different ring slots): odd steps launch from a third
+            # context's stream, so the persistent blocks of prove(k+1) take over each SM as the blocks of prove(k) leave it
+            # instead of waiting for the whole grid to drain
+            ctx_p1 = pbh_b200.Context(device=local, algo=args.algo)
+            pstream1 = ctx_p1.torch_stream()
 
     def enqueue_region(steps):
         """Enqueue exactly `steps` steps on `stream` (+ `vstream`, + the cycle all-gathers on `comm_stream`), joined back into
@@ -290,18 +304,28 @@ def main():
                 stream.wait_event(gather_done[cyc - 2])       # the all-gather that read this summary set has finished
                 if vstream is not None:
                     vstream.wait_event(gather_done[cyc - 2])
+            if pstream1 is not None:
+                pstream1.wait_stream(stream)                  # everything `stream` waited for (previous cycle, gathers)
             for slot in range(min(ring, steps - cyc * ring)):
                 w, rd, c, u, first = ins[slot]
                 o = outs[slot]
-                ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
+                if pstream1 is not None and slot % 2 == 1:
+                    with torch.cuda.stream(pstream1):
+                        ctx_p1.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
+                    pst = pstream1
+                else:
+                    ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
+                    pst = stream
                 if vstream is None:
                     ctx.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
                 else:
                     proved = torch.cuda.Event()
-                    proved.record(stream)
+                    proved.record(pst)
                     vstream.wait_event(proved)
                     with torch.cuda.stream(vstream):
                         ctx_v.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
+            if pstream1 is not None:
+                stream.wait_stream(pstream1)
             if vstream is not None:
                 stream.wait_stream(vstream)
             if world > 1:
@@ -335,7 +359,8 @@ def main():
             region_graph = g
             launch_mode = (f"one CUDA graph per {K}-step region: {2 * K} kernels" +
                            (f" + {(K + ring - 1) // ring} NCCL all-gathers (one per {ring}-step cycle, overlapping the next cycle)" if world > 1 else "") +
-                           ("; verify(k) on a second stream beside prove(k+1)" if vstream is not None else ""))
+                           ("; verify(k) on a second stream beside prove(k+1)" if vstream is not None else "") +
+                           ("; provers alternate between two streams" if pstream1 is not None else ""))
         except Exception as e:   # pragma: no cover - capture not supported
             region_graph, launch_mode = None, f"direct launches (graph capture failed: {type(e).__name__}: {e})"
             torch.cuda.synchronize()
@@ -540,12 +565,41 @@ def main():
             s_ = sets[0]
             ctx.prove_verify_batch(s_["w"], s_["r"], s_["c"], s_["u"], proof=s_["proof"], status=s_["status"], result=s_["result"])
 
-        for fn in (lanes_step, pinned_step, pageable_step, fused_step):
+        # packed wire format (include/pbh_b200.h): 16-byte prover inputs, 12-byte proofs, 4-byte challenge words - 32 bytes up
+        # and 13 bytes down per proof + verification instead of 59 and 29
+        packed_in0 = pbh_b200.pack_witness(*host_in)              # host-side format conversion, outside the timed region
+        pk_sets = []
+        for _ in range(2):
+            d_ = dict(pin=ctx.host_alloc_as(n, pbh_b200.PACKED_WITNESS), out=ctx.host_alloc_as(n, pbh_b200.PACKED_PROOF),
+                      cu=ctx.host_alloc_as(n, "<u4"), res=ctx.host_alloc_as(n, np.uint8))
+            d_["pin"][...] = packed_in0
+            d_["cu"][...] = pbh_b200.pack_chal_u(host_in[2], host_in[3])
+            pk_sets.append(d_)
+
+        def packed_lanes_step(i):
+            s_ = pk_sets[i % 2]
+            ctx.lane_sync(i % 2)
+            ctx.prove_packed_async(i % 2, s_["pin"], s_["out"])
+            ctx.verify_packed_async(i % 2, s_["out"], s_["cu"], s_["res"])
+
+        def packed_fused_step(i):
+            s_ = pk_sets[0]
+            ctx.prove_verify_packed(s_["pin"], out=s_["out"], result=s_["res"])
+
+        for fn in (lanes_step, pinned_step, pageable_step, fused_step, packed_lanes_step, packed_fused_step):
             for i in range(3):
                 fn(i)
             ctx.sync()
         for s_ in sets:
             s_["proof"][...] = 0; s_["status"][...] = 255; s_["result"][...] = 255
+        for s_ in pk_sets:
+            s_["out"].view(np.uint8)[...] = 0xEE; s_["res"][...] = 0xEE
+        dt_packed = timed(packed_lanes_step, ksteps)
+        ref_packed = pbh_b200.pack_proofs(outs[0]["proof"].cpu().numpy(), outs[0]["status"].cpu().numpy())
+        ref_result0 = outs[0]["result"].cpu().numpy()
+        packed_equal = all(np.array_equal(s_["out"], ref_packed) and np.array_equal(s_["res"], ref_result0) for s_ in pk_sets)
+        dt_packed_fused = timed(packed_fused_step, ksteps)
+        packed_equal = packed_equal and np.array_equal(pk_sets[0]["out"], ref_packed) and np.array_equal(pk_sets[0]["res"], ref_result0)
         dt_lanes = timed(lanes_step, ksteps)             # the library's default PBH_OPT_LANE_MODE
         lane_modes = {}
         for mode, what in ((0, "kernels read and write the host buffers in place"), (1, "copy-engine upload, in-place stores"),
@@ -566,22 +620,30 @@ def main():
         e2e_equal = e2e_equal and np.array_equal(pg["proof"], ref_proof) and np.array_equal(pg["result"], ref_result)
         dt_fused = timed(fused_step, ksteps)
         per = lambda dt, st: {"value": n * world * st / dt, "ms_per_step": 1e3 * dt / st}
-        e2e = {"value": n * world * ksteps / dt_lanes, "unit": UNIT, "h2d_bytes_per_step": n * (26 + 33) * world,
-               "d2h_bytes_per_step": n * (28 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt_lanes / ksteps,
-               "api": "pbh_prove_batch_async + pbh_verify_batch_async on two lanes (two batches in flight), pbh_lane_sync before a lane's buffers are reused",
-               "host_memory": "page-locked (pbh_host_alloc); default PBH_OPT_LANE_MODE 3: whole-batch copy-engine transfers both ways on the lane's stream",
+        e2e = {"value": n * world * ksteps / dt_packed, "unit": UNIT, "h2d_bytes_per_step": n * (16 + 12 + 4) * world,
+               "d2h_bytes_per_step": n * (12 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt_packed / ksteps,
+               "api": "pbh_prove_packed_async + pbh_verify_packed_async on two lanes (two batches in flight), pbh_lane_sync before a lane's buffers are reused; "
+                      "the two reference calls, Plonk::prove then Plonk::verify, on the packed wire format",
+               "wire_format": "packed records (include/pbh_b200.h): prove 16 B in / 12 B out per item, verify 12 + 4 B in / 1 B out; the proof crosses PCIe "
+                              "twice (down from prove, up into verify) as with any two-call use; unpacking and packing run on the GPU inside the timed region",
+               "host_memory": "page-locked (pbh_host_alloc), whole-batch copy-engine transfers both ways on the lane's stream",
                "numa_node_of_device": ctx.numa_node,
                "timing": "host wall clock around the C-ABI calls up to the final pbh_ctx_sync, max over ranks",
-               "bytes_equal_device_path": bool(e2e_equal),
+               "bytes_equal_device_path": bool(e2e_equal and packed_equal),
+               "packed_equals_pack_of_device_path": bool(packed_equal),
+               "byte_plane_lanes": dict(per(dt_lanes, ksteps), h2d_bytes_per_step=n * (26 + 33) * world, d2h_bytes_per_step=n * (28 + 1) * world,
+                                        api="pbh_prove_batch_async + pbh_verify_batch_async on two lanes, one byte per field element (default PBH_OPT_LANE_MODE 3)"),
+               "packed_fused_call": dict(per(dt_packed_fused, ksteps), h2d_bytes_per_step=n * 16 * world, d2h_bytes_per_step=n * 13 * world,
+                                         api="pbh_prove_verify_packed (extension: the proof does not cross PCIe twice)"),
                "lane_modes": lane_modes,
                "two_sync_calls_pinned": dict(per(dt_pinned, ksteps), api="pbh_prove_batch then pbh_verify_batch, page-locked buffers"),
                "two_sync_calls_pageable": dict(per(dt_pageable, max(3, ksteps // 2)), api="pbh_prove_batch then pbh_verify_batch, pageable numpy buffers (staged chunks)"),
                "fused_call": dict(per(dt_fused, ksteps), h2d_bytes_per_step=n * 27 * world, d2h_bytes_per_step=n * 29 * world,
                                   api="pbh_prove_verify_batch (extension: the proof does not cross PCIe twice)")}
-        for s_ in sets:
+        for s_ in sets + pk_sets:
             for a in s_.values():
                 ctx.host_free(a)
-        del sets, pg
+        del sets, pg, pk_sets
 
     # ---- BASELINE.json configs[4]: 2^28 witnesses in total, sharded over the N ranks (strong scaling), ONE all-gather of
     # the verdict bitmaps + digests at the end of each pass
@@ -801,7 +863,8 @@ def main():
                   "oracle_full_batch": oracle_full, "generator_prefix_equals_oracle": generator_sample_ok,
                   "gathered_summaries_ok": gather_ok, "sharded_equals_single": sharded_equals_single},
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     finish()
 
 

@@ -60,6 +60,7 @@ typedef enum pbh_error {
 #define PBH_ST_T_SLICE 4       /* src/plonk.rs:376  t_x.coeffs()[12..18]           (Q5)             */
 #define PBH_ST_SRS_OOB 5       /* src/plonk.rs:56   g1s[n] out of bounds           (Q2)             */
 #define PBH_ST_BAD_ENCODING 32 /* input byte outside the field (not representable in the reference) */
+#define PBH_ST_UNREPRESENTABLE 33 /* only from the packed-format helpers: this proof has no packed form (see below) */
 
 /* ---- per-item verifier result byte ------------------------------------------------------------ */
 #define PBH_VR_ACCEPT 0x01        /* verify() == true                      src/plonk.rs:649         */
@@ -280,6 +281,56 @@ int pbh_proof_records_to_planes_dev(pbh_ctx* ctx, size_t n, const pbh_proof_reco
                                     uint8_t* status);
 int pbh_proof_planes_to_records_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status,
                                     pbh_proof_record* rec);
+
+/* ---- packed wire format: the PCIe-lean form of the same batches -----------------------------------------------------------
+ * Byte planes cost 59 bytes up and 29 bytes down per proof + verification, and for host-resident batches the host link, not
+ * the GPU, is the bound.  Packed records carry the same values in radix form, 32 bytes up and 13 bytes down:
+ *   pbh_packed_witness  16 bytes: the 27 values wit[0..12) rand[0..9) chal[0..5) u, each < 17, as base-17 digits, least
+ *                       significant first: values 0..6 in w[0], 7..13 in w[1], 14..20 in w[2], 21..26 in w[3].
+ *   pbh_packed_proof    12 bytes.  points (lo | hi << 32): nine base-102 digits, least significant first, one POINT CODE per
+ *                       commitment in proof order.  Code 0 is the identity (0, 0, infinite); code c >= 1 is the c-th finite
+ *                       point of y^2 = x^3 + 3 over F_101 in increasing (x, y) order (the curve has exactly 101 of them, so every
+ *                       point a prover emits has a code; (1, 2), the generator of src/pbh/g1.rs:91-96, is code 1).  evals_status:
+ *                       bits 0..28 the seven evaluations as base-17 digits, bits 29..31 the STATUS CODE: 0..5 = PBH_ST_OK ..
+ *                       PBH_ST_SRS_OOB, 7 = PBH_ST_BAD_ENCODING, 6 = PBH_ST_UNREPRESENTABLE (set only when packing a proof the
+ *                       format cannot express: a point off the curve, a flagged identity with coordinates, an evaluation >= 17).
+ *                       Both payload words are zero whenever the status code is not 0.
+ *   chal_u              4 bytes per verification: alpha beta gamma z v u as six base-17 digits.
+ * Semantics are those of the byte-plane entry points on the decoded values, bit for bit: pbh_prove_packed(in) = pack(
+ * pbh_prove_batch(unpack(in))), pbh_verify_packed(proofs, chal_u) = pbh_verify_batch(unpack(proofs), unpack(chal_u)).  A word
+ * outside the format decodes to a byte outside the field (its top digit saturates at 255), hence PBH_ST_BAD_ENCODING /
+ * PBH_VR_BAD_ENCODING / PBH_VR_NOT_IN_FIELD as for byte planes; a packed proof whose status code is not 0 decodes to the all-zero
+ * proof that pbh_prove_batch leaves for such an item (the verifier answers PBH_VR_NOT_ON_CURVE), as does a ninth point digit
+ * >= 102.  Off-curve and malformed proofs - the verifier's adversarial inputs - have no packed form: use the byte planes. */
+typedef struct pbh_packed_witness { uint32_t w[4]; } pbh_packed_witness;
+typedef struct pbh_packed_proof { uint32_t points_lo, points_hi, evals_status; } pbh_packed_proof;
+/* Plonk::prove / Plonk::verify over packed records, HOST pointers (any memory; page-locked memory overlaps best). */
+int pbh_prove_packed(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out);
+int pbh_verify_packed(pbh_ctx* ctx, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result);
+/* The same on a lane (see "lanes" above): page-locked buffers are moved whole by the copy engines on the lane's stream and the
+ * call returns at once; with pageable memory the call waits for the context's earlier work and runs synchronously. */
+int pbh_prove_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out);
+int pbh_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result);
+/* Extension: prove, then verify the fresh proofs with the same record's challenges and u; the proof never re-crosses PCIe. */
+int pbh_prove_verify_packed(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out, uint8_t* result);
+/* Device-side conversions between packed records and byte planes (device pointers; null plane pointers are skipped). */
+int pbh_unpack_witness_dev(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, uint8_t* wit, size_t wit_pitch, uint8_t* rand,
+                           size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u);
+int pbh_pack_proof_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status, pbh_packed_proof* out);
+int pbh_unpack_proof_dev(pbh_ctx* ctx, size_t n, const pbh_packed_proof* in, const uint32_t* chal_u, uint8_t* proof, size_t proof_pitch,
+                         uint8_t* status, uint8_t* chal, size_t chal_pitch, uint8_t* u);
+/* Host-side format conversion (plain CPU loops over host memory; no context, no device, nothing is proved or verified): what
+ * a host program uses to build packed records from its own values and to read proofs back.  pack functions return
+ * PBH_ERR_BAD_ARGUMENT when a value is >= 17 (witness, chal_u); pbh_pack_proofs_host marks inexpressible proofs with status
+ * code 6 instead.  Null plane pointers are skipped by the unpack functions; u / chal may be null for pbh_pack_witness_host
+ * (packed as zero). */
+int pbh_pack_witness_host(size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rand, size_t rand_pitch, const uint8_t* chal,
+                          size_t chal_pitch, const uint8_t* u, pbh_packed_witness* out);
+int pbh_unpack_witness_host(size_t n, const pbh_packed_witness* in, uint8_t* wit, size_t wit_pitch, uint8_t* rand, size_t rand_pitch,
+                            uint8_t* chal, size_t chal_pitch, uint8_t* u);
+int pbh_pack_chal_u_host(size_t n, const uint8_t* chal, size_t chal_pitch, const uint8_t* u, uint32_t* out);
+int pbh_pack_proofs_host(size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status, pbh_packed_proof* out);
+int pbh_unpack_proofs_host(size_t n, const pbh_packed_proof* in, uint8_t* proof, size_t proof_pitch, uint8_t* status);
 
 /* ---- sweep kernels (the per-kernel configs of BASELINE.json), HOST or DEVICE pointers --------- */
 /* `on_device` != 0: pointers are device pointers, kernels are only enqueued.                      */

@@ -458,3 +458,130 @@ def encode_proof(d):
     for k, name in enumerate(EVAL_NAMES):
         col[20 + k] = d[name]
     return col
+
+
+# ---- packed wire format (include/pbh_b200.h "packed wire format"): an independent restatement of the specification in numpy /
+# Python integers, written from the header's text, against which the product's codec (device kernels and host helpers) is
+# checked.  The reference has no serialisation of its own (src/plonk.rs:61), so this format is "parity unpinned by the
+# reference": what IS pinned is that packed calls equal the byte-plane calls on the decoded values.
+def packed_point_codes():
+    """code -> (x, y) for the 101 finite points of y^2 = x^3 + 3 over F_101 in increasing (x, y) order; code 0 is the identity."""
+    pts = [(0, 0)]
+    for x in range(101):
+        for y in range(101):
+            if (y * y - x * x * x - 3) % 101 == 0:
+                pts.append((x, y))
+    assert len(pts) == 102
+    return pts
+
+
+def _digits(word, base, count):
+    """`count` digits of `word`, least significant first; the last one takes whatever is left and saturates at 255."""
+    out = []
+    for _ in range(count - 1):
+        out.append(word % base)
+        word //= base
+    out.append(min(word, 255))
+    return out
+
+
+def packed_pack_witness(wit, rand, chal, u):
+    vals = np.concatenate([wit, rand, chal, np.asarray(u).reshape(1, -1)], axis=0).astype(np.uint64)      # (27, n)
+    assert vals.shape[0] == 27 and int(vals.max(initial=0)) < 17
+    w = np.zeros((vals.shape[1], 4), dtype=np.uint64)
+    for j, (lo, hi) in enumerate(((0, 7), (7, 14), (14, 21), (21, 27))):
+        for k in range(hi - 1, lo - 1, -1):
+            w[:, j] = w[:, j] * 17 + vals[k]
+    return w.astype("<u4")
+
+
+def packed_unpack_witness(words):
+    """(n, 4) uint32 -> (wit, rand, chal, u)"""
+    words = np.asarray(words).reshape(-1, 4)
+    n = words.shape[0]
+    vals = np.zeros((27, n), dtype=np.uint8)
+    for i in range(n):
+        d = []
+        for j, cnt in enumerate((7, 7, 7, 6)):
+            d += _digits(int(words[i, j]), 17, cnt)
+        vals[:, i] = d
+    return vals[:12].copy(), vals[12:21].copy(), vals[21:26].copy(), vals[26].copy()
+
+
+def packed_pack_chal_u(chal, u):
+    vals = np.concatenate([chal, np.asarray(u).reshape(1, -1)], axis=0).astype(np.uint64)
+    w = np.zeros(vals.shape[1], dtype=np.uint64)
+    for k in range(5, -1, -1):
+        w = w * 17 + vals[k]
+    return w.astype("<u4")
+
+
+def packed_unpack_chal_u(words):
+    words = np.asarray(words).reshape(-1)
+    vals = np.array([_digits(int(x), 17, 6) for x in words], dtype=np.uint8).T.reshape(6, -1)
+    return vals[:5].copy(), vals[5].copy()
+
+
+_STATUS_CODE = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 32: 7}
+_CODE_STATUS = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4, 5: 5, 6: 33, 7: 32}
+
+
+def packed_pack_proofs(proof, status=None):
+    """(27, n) planes (+ status) -> (n, 3) uint32 (points_lo, points_hi, evals_status)."""
+    pts = packed_point_codes()
+    code_of = {p: c for c, p in enumerate(pts) if c > 0}
+    n = proof.shape[1]
+    out = np.zeros((n, 3), dtype="<u4")
+    for i in range(n):
+        col = [int(b) for b in proof[:, i]]
+        ok = (col[19] & 0xFE) == 0
+        codes = []
+        for k in range(9):
+            x, y = col[2 * k], col[2 * k + 1]
+            inf = (col[18] >> k) & 1 if k < 8 else col[19] & 1
+            if inf:
+                ok = ok and x == 0 and y == 0
+                codes.append(0)
+            else:
+                ok = ok and (x, y) in code_of
+                codes.append(code_of.get((x, y), 0))
+        evals = col[20:27]
+        ok = ok and all(e < 17 for e in evals)
+        sc = _STATUS_CODE.get(int(status[i]) if status is not None else 0, 6)
+        if sc == 0 and not ok:
+            sc = 6
+        P = E = 0
+        if sc == 0:
+            for c in reversed(codes):
+                P = P * 102 + c
+            for e in reversed(evals):
+                E = E * 17 + e
+        out[i] = (P & 0xFFFFFFFF, P >> 32, E | (sc << 29))
+    return out
+
+
+def packed_unpack_proofs(words):
+    """(n, 3) uint32 -> ((27, n) proof planes, status)"""
+    pts = packed_point_codes()
+    words = np.asarray(words).reshape(-1, 3)
+    n = words.shape[0]
+    proof = np.zeros((27, n), dtype=np.uint8)
+    status = np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        lo, hi, es = (int(x) for x in words[i])
+        sc = es >> 29
+        status[i] = _CODE_STATUS[sc]
+        if sc != 0:
+            continue
+        P = lo | (hi << 32)
+        flags = 0
+        for k in range(9):
+            d = P % 102 if k < 8 else P
+            P //= 102
+            if d == 0:
+                flags |= 1 << k
+            x, y = pts[d] if d < 102 else (0, 0)
+            proof[2 * k, i], proof[2 * k + 1, i] = x, y
+        proof[18, i], proof[19, i] = flags & 0xFF, flags >> 8
+        proof[20:27, i] = _digits(es & ((1 << 29) - 1), 17, 7)
+    return proof, status

@@ -17,6 +17,7 @@
 #include <string>
 
 #include "pbh_kernels.cuh"
+#include "pbh_packed.cuh"
 #include "pbh_setup.hpp"
 
 using namespace pbh;
@@ -72,6 +73,7 @@ struct pbh_ctx {
 #define CTX_CHECK(ctx)                                     \
   do {                                                     \
     if (!(ctx)) { set_global_error("null context"); return PBH_ERR_BAD_ARGUMENT; } \
+    (void)cudaGetLastError(); /* a stale, non-sticky error of an earlier call (say, a refused device ordinal) is not this call's */ \
   } while (0)
 
 #define CUDA_TRY(ctx, expr)                                                                      \
@@ -626,6 +628,8 @@ static_assert(34 + 4 <= kStagePlanes, "pbh_verify_batch: 27 + 5 + 1 + 1 + 4 plan
 static_assert(55 + 1 <= kStagePlanes, "pbh_prove_verify_batch: 54 + u + result");
 static_assert(49 + 6 <= kStagePlanes && 34 + 4 <= kStagePlanes, "Fiat-Shamir bodies");
 static_assert(96 + sizeof(pbh_proof_record) <= kStagePlanes && 64 + sizeof(pbh_witness_record) <= 96, "record bodies: planes below row 64, records above");
+static_assert(64 + sizeof(pbh_packed_witness) <= 80 && 80 + sizeof(pbh_packed_proof) <= 96 && 96 + sizeof(pbh_packed_proof) + 4 <= kStagePlanes,
+              "packed bodies: planes below row 64, packed input 64..79, packed output 80..91, verifier input 96..111");
 
 // ---- asynchronous host-pointer calls (include/pbh_b200.h "lanes") ------------------------------------------------------
 // A lane is one of the context's slot streams.  Page-locked, mapped buffers run in place on the lane's stream and the call
@@ -1008,6 +1012,232 @@ int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, c
     CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
     return PBH_OK;
   });
+}
+
+// ---- packed wire format (include/pbh_b200.h "packed wire format", csrc/pbh_packed.cuh) ------------------------------------
+static_assert(sizeof(pbh_packed_witness) == 16 && sizeof(pbh_packed_proof) == 12, "packed records are 16 and 12 bytes");
+static int launch_unpack_witness(pbh_ctx* ctx, cudaStream_t st, size_t n, const pbh_packed_witness* in, uint8_t* wit, size_t wit_pitch,
+                                 uint8_t* rnd, size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u) {
+  unpack_witness_kernel<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, in, wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, u);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+static int launch_pack_proof(pbh_ctx* ctx, cudaStream_t st, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status,
+                             pbh_packed_proof* out) {
+  pack_proof_kernel<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, proof, proof_pitch, status, out);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+static int launch_unpack_proof(pbh_ctx* ctx, cudaStream_t st, size_t n, const pbh_packed_proof* in, const uint32_t* chal_u, uint8_t* proof,
+                               size_t proof_pitch, uint8_t* status, uint8_t* chal, size_t chal_pitch, uint8_t* u) {
+  unpack_proof_kernel<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, in, chal_u, proof, proof_pitch, status, chal, chal_pitch, u);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+
+int pbh_unpack_witness_dev(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, uint8_t* wit, size_t wit_pitch, uint8_t* rnd,
+                           size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!in || ((uintptr_t)in % 16) != 0) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "packed witnesses must be 16-byte aligned");
+  if ((wit && wit_pitch < n) || (rnd && rand_pitch < n) || (chal && chal_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return launch_unpack_witness(ctx, ctx->compute, n, in, wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, u);
+}
+int pbh_pack_proof_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status, pbh_packed_proof* out) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proof || !out || ((uintptr_t)out % 4) != 0) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer or packed proofs not 4-byte aligned");
+  if (proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return launch_pack_proof(ctx, ctx->compute, n, proof, proof_pitch, status, out);
+}
+int pbh_unpack_proof_dev(pbh_ctx* ctx, size_t n, const pbh_packed_proof* in, const uint32_t* chal_u, uint8_t* proof, size_t proof_pitch,
+                         uint8_t* status, uint8_t* chal, size_t chal_pitch, uint8_t* u) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if ((!in && !chal_u) || ((uintptr_t)in % 4) != 0 || ((uintptr_t)chal_u % 4) != 0)
+    return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointers or packed words not 4-byte aligned");
+  if ((in && !proof) || (proof && proof_pitch < n) || (chal && chal_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "proof planes missing or pitch < n");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return launch_unpack_proof(ctx, ctx->compute, n, in, chal_u, proof, proof_pitch, status, chal, chal_pitch, u);
+}
+
+// One chunk (or one whole lane batch) of the packed prover / verifier on stream st, staged in `base` (rows of C bytes):
+// planes below row 64 as in the byte-plane bodies, packed prover input in rows 64..79, packed proofs out in 80..91, the
+// verifier's packed proofs in 96..107 and its challenge words in 108..111.
+static int packed_prove_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size_t C, size_t m, const pbh_packed_witness* in,
+                             pbh_packed_proof* out, uint8_t* result_host) {
+  uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C,
+          *d_u = base + 54 * C, *d_res = base + 55 * C;
+  pbh_packed_witness* d_in = reinterpret_cast<pbh_packed_witness*>(base + 64 * C);
+  pbh_packed_proof* d_out = reinterpret_cast<pbh_packed_proof*>(base + 80 * C);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, m * sizeof(pbh_packed_witness), cudaMemcpyHostToDevice, st));
+  int rc = launch_unpack_witness(ctx, st, m, d_in, d_wit, C, d_rnd, C, d_chal, C, result_host ? d_u : nullptr);
+  if (rc) return rc;
+  ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
+  rc = launch_prove(ctx, st, A);
+  if (rc) return rc;
+  if (result_host) {
+    VerifyArgs V{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
+    rc = launch_verify(ctx, st, V);
+    if (rc) return rc;
+  }
+  rc = launch_pack_proof(ctx, st, m, d_proof, C, d_status, d_out);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, m * sizeof(pbh_packed_proof), cudaMemcpyDeviceToHost, st));
+  if (result_host) CUDA_TRY(ctx, cudaMemcpyAsync(result_host, d_res, m, cudaMemcpyDeviceToHost, st));
+  return PBH_OK;
+}
+static int packed_verify_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size_t C, size_t m, const pbh_packed_proof* proofs,
+                              const uint32_t* chal_u, uint8_t* result) {
+  uint8_t *d_proof = base + 26 * C, *d_chal = base + 54 * C, *d_u = base + 59 * C, *d_res = base + 60 * C;
+  pbh_packed_proof* d_prf = reinterpret_cast<pbh_packed_proof*>(base + 96 * C);
+  uint32_t* d_cu = reinterpret_cast<uint32_t*>(base + 108 * C);
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_prf, proofs, m * sizeof(pbh_packed_proof), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(ctx, cudaMemcpyAsync(d_cu, chal_u, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  int rc = launch_unpack_proof(ctx, st, m, d_prf, d_cu, d_proof, C, nullptr, d_chal, C, d_u);
+  if (rc) return rc;
+  VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
+  rc = launch_verify(ctx, st, A);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(result, d_res, m, cudaMemcpyDeviceToHost, st));
+  return PBH_OK;
+}
+
+int pbh_prove_packed(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!in || !out) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
+    return packed_prove_body(ctx, st, base, C, m, in + lo, out + lo, nullptr);
+  });
+}
+int pbh_prove_verify_packed(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out, uint8_t* result) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!in || !out || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
+    return packed_prove_body(ctx, st, base, C, m, in + lo, out + lo, result + lo);
+  });
+}
+int pbh_verify_packed(pbh_ctx* ctx, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result) {
+  CTX_CHECK(ctx);
+  if (n == 0) return PBH_OK;
+  if (!proofs || !chal_u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
+    return packed_verify_body(ctx, st, base, C, m, proofs + lo, chal_u + lo, result + lo);
+  });
+}
+int pbh_prove_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out) {
+  CTX_CHECK(ctx);
+  cudaStream_t st;
+  int rc = lane_stream(ctx, lane, &st);
+  if (rc) return rc;
+  if (n == 0) return PBH_OK;
+  if (!in || !out) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n <= kLaneMaxItems && host_pinned(reinterpret_cast<const uint8_t*>(in)) && host_pinned(reinterpret_cast<const uint8_t*>(out))) {
+    const size_t C = (n + kTile - 1) / kTile * kTile;
+    rc = ensure_lane(ctx, lane, kStagePlanes * C);
+    if (rc) return rc;
+    return packed_prove_body(ctx, st, ctx->lane_buf[lane], C, n, in, out, nullptr);
+  }
+  rc = pbh_ctx_sync(ctx);
+  if (rc) return rc;
+  return pbh_prove_packed(ctx, n, in, out);
+}
+int pbh_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result) {
+  CTX_CHECK(ctx);
+  cudaStream_t st;
+  int rc = lane_stream(ctx, lane, &st);
+  if (rc) return rc;
+  if (n == 0) return PBH_OK;
+  if (!proofs || !chal_u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n <= kLaneMaxItems && host_pinned(reinterpret_cast<const uint8_t*>(proofs)) && host_pinned(reinterpret_cast<const uint8_t*>(chal_u)) &&
+      host_pinned(result)) {
+    const size_t C = (n + kTile - 1) / kTile * kTile;
+    rc = ensure_lane(ctx, lane, kStagePlanes * C);
+    if (rc) return rc;
+    return packed_verify_body(ctx, st, ctx->lane_buf[lane], C, n, proofs, chal_u, result);
+  }
+  rc = pbh_ctx_sync(ctx);
+  if (rc) return rc;
+  return pbh_verify_packed(ctx, n, proofs, chal_u, result);
+}
+
+// host-side format conversion: the codec of pbh_packed.cuh on the CPU (no context, no device)
+int pbh_pack_witness_host(size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch, const uint8_t* chal,
+                          size_t chal_pitch, const uint8_t* u, pbh_packed_witness* out) {
+  if (n == 0) return PBH_OK;
+  if (!wit || !rnd || !out || wit_pitch < n || rand_pitch < n || (chal && chal_pitch < n)) return PBH_ERR_BAD_ARGUMENT;
+  bool ok = true;
+  for (size_t i = 0; i < n; i++) {
+    uint8_t v[27];
+    for (int k = 0; k < 12; k++) v[k] = wit[k * wit_pitch + i];
+    for (int k = 0; k < 9; k++) v[12 + k] = rnd[k * rand_pitch + i];
+    for (int k = 0; k < 5; k++) v[21 + k] = chal ? chal[k * chal_pitch + i] : 0;
+    v[26] = u ? u[i] : 0;
+    ok = pack_witness_item(v, out[i].w) && ok;
+  }
+  return ok ? PBH_OK : PBH_ERR_BAD_ARGUMENT;
+}
+int pbh_unpack_witness_host(size_t n, const pbh_packed_witness* in, uint8_t* wit, size_t wit_pitch, uint8_t* rnd, size_t rand_pitch,
+                            uint8_t* chal, size_t chal_pitch, uint8_t* u) {
+  if (n == 0) return PBH_OK;
+  if (!in || (wit && wit_pitch < n) || (rnd && rand_pitch < n) || (chal && chal_pitch < n)) return PBH_ERR_BAD_ARGUMENT;
+  for (size_t i = 0; i < n; i++) {
+    uint8_t v[27];
+    unpack_witness_item(in[i].w, v);
+    if (wit) for (int k = 0; k < 12; k++) wit[k * wit_pitch + i] = v[k];
+    if (rnd) for (int k = 0; k < 9; k++) rnd[k * rand_pitch + i] = v[12 + k];
+    if (chal) for (int k = 0; k < 5; k++) chal[k * chal_pitch + i] = v[21 + k];
+    if (u) u[i] = v[26];
+  }
+  return PBH_OK;
+}
+int pbh_pack_chal_u_host(size_t n, const uint8_t* chal, size_t chal_pitch, const uint8_t* u, uint32_t* out) {
+  if (n == 0) return PBH_OK;
+  if (!chal || !u || !out || chal_pitch < n) return PBH_ERR_BAD_ARGUMENT;
+  bool ok = true;
+  for (size_t i = 0; i < n; i++) {
+    uint8_t v[6];
+    for (int k = 0; k < 5; k++) v[k] = chal[k * chal_pitch + i];
+    v[5] = u[i];
+    ok = pack_chal_u(v, &out[i]) && ok;
+  }
+  return ok ? PBH_OK : PBH_ERR_BAD_ARGUMENT;
+}
+int pbh_pack_proofs_host(size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status, pbh_packed_proof* out) {
+  if (n == 0) return PBH_OK;
+  if (!proof || !out || proof_pitch < n) return PBH_ERR_BAD_ARGUMENT;
+  for (size_t i = 0; i < n; i++) {
+    uint8_t p[27];
+    for (int k = 0; k < 27; k++) p[k] = proof[k * proof_pitch + i];
+    uint32_t w[3];
+    pack_proof_item(kPackedTablesHost, p, status ? status[i] : (uint8_t)0, w);
+    out[i].points_lo = w[0]; out[i].points_hi = w[1]; out[i].evals_status = w[2];
+  }
+  return PBH_OK;
+}
+int pbh_unpack_proofs_host(size_t n, const pbh_packed_proof* in, uint8_t* proof, size_t proof_pitch, uint8_t* status) {
+  if (n == 0) return PBH_OK;
+  if (!in || (proof && proof_pitch < n)) return PBH_ERR_BAD_ARGUMENT;
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t w[3] = {in[i].points_lo, in[i].points_hi, in[i].evals_status};
+    uint8_t p[27], st;
+    unpack_proof_item(kPackedTablesHost, w, p, &st);
+    if (proof) for (int k = 0; k < 27; k++) proof[k * proof_pitch + i] = p[k];
+    if (status) status[i] = st;
+  }
+  return PBH_OK;
 }
 
 // ---- sweep entry points ---------------------------------------------------------------------------------

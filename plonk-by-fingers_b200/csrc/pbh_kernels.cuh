@@ -215,13 +215,6 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
   __shared__ ProveTmaSmem S;
   unsigned long long digest_acc = 0;
   const int tid = threadIdx.x;
-  stage_tables(S.T, gT);
-  if (tid == 0) {
-    tma::mbar_init(&S.full[0], 1);
-    tma::mbar_init(&S.full[1], 1);
-    tma::fence_mbar_init();
-  }
-  __syncthreads();
   const size_t tiles = (n + kTile - 1) / kTile;
   auto issue = [&](size_t tile, int stage) {
     tma::mbar_arrive_expect_tx(&S.full[stage], 26 * kTile);
@@ -230,18 +223,22 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     tma::load_2d(&S.in[stage][12][0], &M.rnd, &S.full[stage], c0, 0);
     tma::load_2d(&S.in[stage][21][0], &M.chal, &S.full[stage], c0, 0);
   };
-  // Tiles are handed out by an atomic counter (zeroed by the host before the launch), one iteration ahead of their use
-  // so that the TMA prefetch overlaps the current tile: blocks that start late, e.g. because a collective's CTAs hold an
-  // SM, simply take fewer tiles, and there is no wave-quantisation tail.
-  // The index is fetched two iterations ahead (`pending`), so the atomic's round trip is never waited for.
+  // A block's FIRST tile is its block index, so its loads leave before anything else happens in the block (no atomic
+  // round trip in front of them; the tables are staged while they fly).  Every later tile is handed out by an atomic
+  // counter (zero when the launch starts), offset by the grid size and fetched one iteration ahead of its use so that
+  // the TMA prefetch overlaps the current tile and the atomic's round trip is never waited for: blocks that are slow,
+  // e.g. because a collective's CTAs share their SM, simply take fewer tiles, and there is no wave-quantisation tail.
   uint32_t pending = 0;
   if (tid == 0) {
-    const uint32_t t0 = atomicAdd(tile_counter, 1u);
-    pending = atomicAdd(tile_counter, 1u);
+    tma::mbar_init(&S.full[0], 1);
+    tma::mbar_init(&S.full[1], 1);
+    tma::fence_mbar_init();
+    const uint32_t t0 = blockIdx.x;
     S.tile_of_stage[0] = t0;
     if (t0 < tiles) issue(t0, 0);
+    pending = atomicAdd(tile_counter, 1u) + gridDim.x;
   }
-  __syncthreads();
+  stage_tables(S.T, gT);   // ends with the block barrier that publishes the mbarriers and tile_of_stage[0]
   uint32_t phase0 = 0, phase1 = 0;
   for (int stage = 0;; stage ^= 1) {
     const size_t tile = S.tile_of_stage[stage];
@@ -251,7 +248,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
       S.tile_of_stage[stage ^ 1] = nt;
       if (nt < tiles) {
         issue(nt, stage ^ 1);
-        pending = atomicAdd(tile_counter, 1u);                // consumed in the next iteration
+        pending = atomicAdd(tile_counter, 1u) + gridDim.x;    // consumed in the next iteration
       }
     }
     if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }
@@ -431,13 +428,6 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
                                                                          unsigned int* __restrict__ tile_counter) {
   __shared__ VerifyTmaSmem S;
   const int tid = threadIdx.x;
-  stage_tables(S.T, gT);
-  if (tid == 0) {
-    tma::mbar_init(&S.full[0], 1);
-    tma::mbar_init(&S.full[1], 1);
-    tma::fence_mbar_init();
-  }
-  __syncthreads();
   const size_t tiles = (A.n + kTile - 1) / kTile;
   auto issue = [&](size_t tile, int stage) {
     tma::mbar_arrive_expect_tx(&S.full[stage], 33 * kTile);
@@ -447,13 +437,16 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
     tma::load_2d(&S.in[stage][32][0], &M.u, &S.full[stage], c0, 0);
   };
   uint32_t pending = 0;
-  if (tid == 0) {                                             // dynamic tile scheduler, see prove_f32_tma_kernel
-    const uint32_t t0 = atomicAdd(tile_counter, 1u);
-    pending = atomicAdd(tile_counter, 1u);
+  if (tid == 0) {                                             // static first tile, then the dynamic scheduler: see prove_f32_tma_kernel
+    tma::mbar_init(&S.full[0], 1);
+    tma::mbar_init(&S.full[1], 1);
+    tma::fence_mbar_init();
+    const uint32_t t0 = blockIdx.x;
     S.tile_of_stage[0] = t0;
     if (t0 < tiles) issue(t0, 0);
+    pending = atomicAdd(tile_counter, 1u) + gridDim.x;
   }
-  __syncthreads();
+  stage_tables(S.T, gT);
   uint32_t phase0 = 0, phase1 = 0;
   for (int stage = 0;; stage ^= 1) {
     const size_t tile = S.tile_of_stage[stage];
@@ -463,7 +456,7 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
       S.tile_of_stage[stage ^ 1] = nt;
       if (nt < tiles) {
         issue(nt, stage ^ 1);
-        pending = atomicAdd(tile_counter, 1u);
+        pending = atomicAdd(tile_counter, 1u) + gridDim.x;
       }
     }
     if (stage == 0) { tma::mbar_wait(&S.full[0], phase0); phase0 ^= 1; } else { tma::mbar_wait(&S.full[1], phase1); phase1 ^= 1; }

@@ -87,6 +87,7 @@ constexpr size_t kAlign = 256;   // shard boundaries: whole tiles, so every shar
 size_t shard_items(size_t n, size_t n_dev) { return ((n + n_dev - 1) / n_dev + kAlign - 1) / kAlign * kAlign; }
 
 void free_shard_buffers(Shard& s) {
+  if (!s.ctx) return;   // a shard whose context was never created (refused device ordinal) owns nothing
   cudaSetDevice(s.device);
   if (s.buf) cudaFree(s.buf);
   if (s.summary) cudaFree(s.summary);

@@ -49,7 +49,10 @@ pbh_measure_int32_peak pbh_mul_ntt_batch pbh_poly_scale_batch pbh_poly_eval_batc
 pbh_prove_batch_async pbh_verify_batch_async pbh_lane_sync pbh_host_alloc pbh_host_free pbh_ctx_numa_node
 pbh_coset_ntt4_batch pbh_coset_intt4_batch pbh_multi_create pbh_multi_destroy pbh_multi_device_count pbh_multi_ctx pbh_multi_last_error
 pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_verify_sharded
-pbh_gt_mul_batch pbh_gt_pow600_batch pbh_poly_divrem_batch pbh_poly_addsub_ragged_batch""".split()
+pbh_gt_mul_batch pbh_gt_pow600_batch pbh_poly_divrem_batch pbh_poly_addsub_ragged_batch
+pbh_prove_packed pbh_verify_packed pbh_prove_packed_async pbh_verify_packed_async pbh_prove_verify_packed pbh_unpack_witness_dev
+pbh_pack_proof_dev pbh_unpack_proof_dev pbh_pack_witness_host pbh_unpack_witness_host pbh_pack_chal_u_host pbh_pack_proofs_host
+pbh_unpack_proofs_host""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -102,6 +105,84 @@ class Circuit(C.Structure):
     """pbh_circuit of include/pbh_b200.h == Constrains of src/constraints.rs:109-118 for 4 gates."""
     _fields_ = [(name, C.c_uint8 * 4) for name in (
         "q_l", "q_r", "q_o", "q_m", "q_c", "c_a_wire", "c_a_index", "c_b_wire", "c_b_index", "c_c_wire", "c_c_index")]
+
+# packed records of include/pbh_b200.h ("packed wire format"): 16-byte prover inputs, 12-byte proofs, 4-byte challenge words
+PACKED_WITNESS = np.dtype([("w", "<u4", (4,))])
+PACKED_PROOF = np.dtype([("points_lo", "<u4"), ("points_hi", "<u4"), ("evals_status", "<u4")])
+ST_UNREPRESENTABLE = 33
+
+
+def _host_u8(a, planes, name):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.shape[0] != planes:
+        raise PbhError(f"{name}: expected {planes} planes, got {a.shape[0]}")
+    return a
+
+
+def pack_witness(wit, rand, chal=None, u=None):
+    """Byte planes (host) -> PACKED_WITNESS array (pbh_pack_witness_host: a CPU format conversion, no device involved)."""
+    lib = load_library()
+    W = _host_u8(wit, 12, "wit"); n = W.shape[1]
+    R = _host_u8(rand, 9, "rand")
+    Ch = _host_u8(chal, 5, "chal") if chal is not None else None
+    U = np.ascontiguousarray(u, dtype=np.uint8).reshape(-1) if u is not None else None
+    out = np.zeros(n, dtype=PACKED_WITNESS)
+    rc = lib.pbh_pack_witness_host(C.c_size_t(n), C.c_void_p(W.ctypes.data), C.c_size_t(n), C.c_void_p(R.ctypes.data), C.c_size_t(n),
+                                   C.c_void_p(Ch.ctypes.data if Ch is not None else None), C.c_size_t(n),
+                                   C.c_void_p(U.ctypes.data if U is not None else None), C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise PbhError(f"pbh_pack_witness_host: {ERR.get(rc, rc)} (a value >= 17 has no packed form)")
+    return out
+
+
+def unpack_witness(packed):
+    """PACKED_WITNESS array -> (wit, rand, chal, u) byte planes."""
+    lib = load_library()
+    pk = np.ascontiguousarray(packed, dtype=PACKED_WITNESS); n = pk.shape[0]
+    wit, rand, chal, u = (np.zeros((k, n), np.uint8) for k in (12, 9, 5, 1))
+    rc = lib.pbh_unpack_witness_host(C.c_size_t(n), C.c_void_p(pk.ctypes.data), C.c_void_p(wit.ctypes.data), C.c_size_t(n),
+                                     C.c_void_p(rand.ctypes.data), C.c_size_t(n), C.c_void_p(chal.ctypes.data), C.c_size_t(n),
+                                     C.c_void_p(u.ctypes.data))
+    if rc != 0:
+        raise PbhError(f"pbh_unpack_witness_host: {ERR.get(rc, rc)}")
+    return wit, rand, chal, u[0]
+
+
+def pack_chal_u(chal, u):
+    lib = load_library()
+    Ch = _host_u8(chal, 5, "chal"); n = Ch.shape[1]
+    U = np.ascontiguousarray(u, dtype=np.uint8).reshape(-1)
+    out = np.zeros(n, dtype="<u4")
+    rc = lib.pbh_pack_chal_u_host(C.c_size_t(n), C.c_void_p(Ch.ctypes.data), C.c_size_t(n), C.c_void_p(U.ctypes.data), C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise PbhError(f"pbh_pack_chal_u_host: {ERR.get(rc, rc)} (a value >= 17 has no packed form)")
+    return out
+
+
+def pack_proofs(proof, status=None):
+    """(27, n) proof planes (+ status) -> PACKED_PROOF array; inexpressible proofs get status code 6 (ST_UNREPRESENTABLE)."""
+    lib = load_library()
+    P = _host_u8(proof, 27, "proof"); n = P.shape[1]
+    S = np.ascontiguousarray(status, dtype=np.uint8).reshape(-1) if status is not None else None
+    out = np.zeros(n, dtype=PACKED_PROOF)
+    rc = lib.pbh_pack_proofs_host(C.c_size_t(n), C.c_void_p(P.ctypes.data), C.c_size_t(n), C.c_void_p(S.ctypes.data if S is not None else None),
+                                  C.c_void_p(out.ctypes.data))
+    if rc != 0:
+        raise PbhError(f"pbh_pack_proofs_host: {ERR.get(rc, rc)}")
+    return out
+
+
+def unpack_proofs(packed):
+    """PACKED_PROOF array -> ((27, n) proof planes, status)."""
+    lib = load_library()
+    pk = np.ascontiguousarray(packed, dtype=PACKED_PROOF); n = pk.shape[0]
+    proof = np.zeros((27, n), np.uint8); status = np.zeros(n, np.uint8)
+    rc = lib.pbh_unpack_proofs_host(C.c_size_t(n), C.c_void_p(pk.ctypes.data), C.c_void_p(proof.ctypes.data), C.c_size_t(n), C.c_void_p(status.ctypes.data))
+    if rc != 0:
+        raise PbhError(f"pbh_unpack_proofs_host: {ERR.get(rc, rc)}")
+    return proof, status
 
 
 _LIB = None
@@ -489,6 +570,101 @@ class Context:
                                          C.c_void_p(res.ctypes.data))
         self._check(rc, "pbh_verify_records")
         return res
+
+    # ---- packed wire format (16-byte prover inputs, 12-byte proofs, 4-byte challenge words) ----
+    @staticmethod
+    def _packed(a, dtype, name, out=False):
+        a = np.asarray(a)
+        if a.dtype != dtype or a.ndim != 1 or not a.flags.c_contiguous or (out and not a.flags.writeable):
+            raise PbhError(f"{name}: expected a contiguous 1-D array of {dtype}")
+        return a
+
+    def prove_packed(self, packed_in, out=None):
+        """PACKED_WITNESS array (host) -> PACKED_PROOF array: pack(pbh_prove_batch(unpack(in)))."""
+        pin = self._packed(packed_in, PACKED_WITNESS, "packed_in"); n = pin.shape[0]
+        out = np.zeros(n, dtype=PACKED_PROOF) if out is None else self._packed(out, PACKED_PROOF, "out", True)
+        self._check(self.lib.pbh_prove_packed(self.h, C.c_size_t(n), C.c_void_p(pin.ctypes.data), C.c_void_p(out.ctypes.data)), "pbh_prove_packed")
+        return out
+
+    def verify_packed(self, proofs, chal_u, result=None):
+        prf = self._packed(proofs, PACKED_PROOF, "proofs"); n = prf.shape[0]
+        cu = self._packed(chal_u, np.dtype("<u4"), "chal_u")
+        if cu.shape[0] != n:
+            raise PbhError("proofs and chal_u must have the same length")
+        res = np.zeros(n, dtype=np.uint8) if result is None else self._packed(result, np.dtype(np.uint8), "result", True)
+        self._check(self.lib.pbh_verify_packed(self.h, C.c_size_t(n), C.c_void_p(prf.ctypes.data), C.c_void_p(cu.ctypes.data),
+                                               C.c_void_p(res.ctypes.data)), "pbh_verify_packed")
+        return res
+
+    def prove_verify_packed(self, packed_in, out=None, result=None):
+        pin = self._packed(packed_in, PACKED_WITNESS, "packed_in"); n = pin.shape[0]
+        out = np.zeros(n, dtype=PACKED_PROOF) if out is None else self._packed(out, PACKED_PROOF, "out", True)
+        res = np.zeros(n, dtype=np.uint8) if result is None else self._packed(result, np.dtype(np.uint8), "result", True)
+        self._check(self.lib.pbh_prove_verify_packed(self.h, C.c_size_t(n), C.c_void_p(pin.ctypes.data), C.c_void_p(out.ctypes.data),
+                                                     C.c_void_p(res.ctypes.data)), "pbh_prove_verify_packed")
+        return out, res
+
+    def prove_packed_async(self, lane, packed_in, out):
+        """Enqueue pbh_prove_packed on `lane`; the arrays must stay alive and untouched until lane_sync(lane)."""
+        pin = self._packed(packed_in, PACKED_WITNESS, "packed_in"); o = self._packed(out, PACKED_PROOF, "out", True)
+        if o.shape[0] != pin.shape[0]:
+            raise PbhError("packed_in and out must have the same length")
+        self._check(self.lib.pbh_prove_packed_async(self.h, int(lane), C.c_size_t(pin.shape[0]), C.c_void_p(pin.ctypes.data),
+                                                    C.c_void_p(o.ctypes.data)), "pbh_prove_packed_async")
+
+    def verify_packed_async(self, lane, proofs, chal_u, result):
+        prf = self._packed(proofs, PACKED_PROOF, "proofs"); cu = self._packed(chal_u, np.dtype("<u4"), "chal_u")
+        res = self._packed(result, np.dtype(np.uint8), "result", True)
+        if cu.shape[0] != prf.shape[0] or res.shape[0] != prf.shape[0]:
+            raise PbhError("proofs, chal_u and result must have the same length")
+        self._check(self.lib.pbh_verify_packed_async(self.h, int(lane), C.c_size_t(prf.shape[0]), C.c_void_p(prf.ctypes.data),
+                                                     C.c_void_p(cu.ctypes.data), C.c_void_p(res.ctypes.data)), "pbh_verify_packed_async")
+
+    def host_alloc_as(self, n, dtype):
+        """host_alloc viewed as n records of `dtype` (page-locked memory for the packed lane calls)."""
+        dtype = np.dtype(dtype)
+        raw = self.host_alloc(max(1, int(n)) * dtype.itemsize)
+        arr = raw[:int(n) * dtype.itemsize].view(dtype)
+        self._host_ptrs[arr.ctypes.data] = self._host_ptrs[raw.ctypes.data]
+        return arr
+
+    def unpack_witness_dev(self, packed_dev, n):
+        """Device conversion: torch uint8 tensor holding n PACKED_WITNESS records -> (wit, rand, chal, u) device planes."""
+        import torch
+        wit, rand, chal = (torch.empty((k, n), dtype=torch.uint8, device=packed_dev.device) for k in (12, 9, 5))
+        u = torch.empty((n,), dtype=torch.uint8, device=packed_dev.device)
+        cur = self._dev_begin()
+        rc = self.lib.pbh_unpack_witness_dev(self.h, C.c_size_t(n), C.c_void_p(packed_dev.data_ptr()), C.c_void_p(wit.data_ptr()), C.c_size_t(n),
+                                             C.c_void_p(rand.data_ptr()), C.c_size_t(n), C.c_void_p(chal.data_ptr()), C.c_size_t(n), C.c_void_p(u.data_ptr()))
+        self._dev_end(cur)
+        self._check(rc, "pbh_unpack_witness_dev")
+        return wit, rand, chal, u
+
+    def pack_proof_dev(self, proof, status):
+        """Device conversion: (27, n) proof planes + status -> torch uint8 tensor of n 12-byte PACKED_PROOF records."""
+        import torch
+        P = _Planes(proof, 27, name="proof"); n = P.n
+        out = torch.empty((n * 12,), dtype=torch.uint8, device=proof.device)
+        cur = self._dev_begin()
+        rc = self.lib.pbh_pack_proof_dev(self.h, C.c_size_t(n), C.c_void_p(P.ptr), C.c_size_t(P.pitch),
+                                         C.c_void_p(status.data_ptr() if status is not None else None), C.c_void_p(out.data_ptr()))
+        self._dev_end(cur)
+        self._check(rc, "pbh_pack_proof_dev")
+        return out
+
+    def unpack_proof_dev(self, packed_dev, chal_u_dev, n):
+        """Device conversion: packed proofs (+ challenge words) -> (proof planes, status, chal planes, u)."""
+        import torch
+        dev = packed_dev.device
+        proof = torch.empty((27, n), dtype=torch.uint8, device=dev); status = torch.empty((n,), dtype=torch.uint8, device=dev)
+        chal = torch.empty((5, n), dtype=torch.uint8, device=dev); u = torch.empty((n,), dtype=torch.uint8, device=dev)
+        cur = self._dev_begin()
+        rc = self.lib.pbh_unpack_proof_dev(self.h, C.c_size_t(n), C.c_void_p(packed_dev.data_ptr()),
+                                           C.c_void_p(chal_u_dev.data_ptr() if chal_u_dev is not None else None), C.c_void_p(proof.data_ptr()),
+                                           C.c_size_t(n), C.c_void_p(status.data_ptr()), C.c_void_p(chal.data_ptr()), C.c_size_t(n), C.c_void_p(u.data_ptr()))
+        self._dev_end(cur)
+        self._check(rc, "pbh_unpack_proof_dev")
+        return proof, status, chal, u
 
     # ---- sweep kernels ----
     def _sweep(self, fn, arr, pin, pout, *pre):

@@ -31,6 +31,7 @@ pub const PBH_ST_T_REMAINDER: u8 = 3;
 pub const PBH_ST_T_SLICE: u8 = 4;
 pub const PBH_ST_SRS_OOB: u8 = 5;
 pub const PBH_ST_BAD_ENCODING: u8 = 32;
+pub const PBH_ST_UNREPRESENTABLE: u8 = 33;
 // per-item verifier result
 pub const PBH_VR_ACCEPT: u8 = 0x01;
 pub const PBH_VR_REJECT_PAIRING: u8 = 0x00;
@@ -82,6 +83,21 @@ extern "C" {
     pub fn pbh_prove_records(ctx: *mut pbh_ctx, n: usize, input: *const WitnessRecord, out: *mut ProofRecord) -> c_int;
     pub fn pbh_verify_records(ctx: *mut pbh_ctx, n: usize, proofs: *const ProofRecord, params: *const WitnessRecord,
                               result: *mut u8) -> c_int;
+    // packed wire format: 16-byte prover inputs, 12-byte proofs, 4-byte challenge words (32 B up / 13 B down per proof + verification)
+    pub fn pbh_prove_packed(ctx: *mut pbh_ctx, n: usize, input: *const PackedWitness, out: *mut PackedProof) -> c_int;
+    pub fn pbh_verify_packed(ctx: *mut pbh_ctx, n: usize, proofs: *const PackedProof, chal_u: *const u32, result: *mut u8) -> c_int;
+    pub fn pbh_prove_packed_async(ctx: *mut pbh_ctx, lane: c_int, n: usize, input: *const PackedWitness, out: *mut PackedProof) -> c_int;
+    pub fn pbh_verify_packed_async(ctx: *mut pbh_ctx, lane: c_int, n: usize, proofs: *const PackedProof, chal_u: *const u32,
+                                   result: *mut u8) -> c_int;
+    pub fn pbh_prove_verify_packed(ctx: *mut pbh_ctx, n: usize, input: *const PackedWitness, out: *mut PackedProof, result: *mut u8) -> c_int;
+    // host-side format conversion (CPU loops, no device): build packed records from byte planes and read proofs back
+    pub fn pbh_pack_witness_host(n: usize, wit: *const u8, wit_pitch: usize, rand: *const u8, rand_pitch: usize, chal: *const u8,
+                                 chal_pitch: usize, u: *const u8, out: *mut PackedWitness) -> c_int;
+    pub fn pbh_unpack_witness_host(n: usize, input: *const PackedWitness, wit: *mut u8, wit_pitch: usize, rand: *mut u8, rand_pitch: usize,
+                                   chal: *mut u8, chal_pitch: usize, u: *mut u8) -> c_int;
+    pub fn pbh_pack_chal_u_host(n: usize, chal: *const u8, chal_pitch: usize, u: *const u8, out: *mut u32) -> c_int;
+    pub fn pbh_pack_proofs_host(n: usize, proof: *const u8, proof_pitch: usize, status: *const u8, out: *mut PackedProof) -> c_int;
+    pub fn pbh_unpack_proofs_host(n: usize, input: *const PackedProof, proof: *mut u8, proof_pitch: usize, status: *mut u8) -> c_int;
     // batched equivalents of the crate's value-type operations (a selection; the header has them all)
     pub fn pbh_kzg_commit_batch(ctx: *mut pbh_ctx, n: usize, coeffs: *const u8, in_pitch: usize, out: *mut u8, out_pitch: usize,
                                 on_device: c_int) -> c_int;                       // SRS::eval_at_s
@@ -116,3 +132,9 @@ pub struct WitnessRecord { pub wit: [u8; 12], pub rand: [u8; 9], pub chal: [u8; 
 #[repr(C)]
 #[derive(Clone, Copy, Default)]
 pub struct ProofRecord { pub xy: [u8; 18], pub inf_lo: u8, pub inf_hi: u8, pub evals: [u8; 7], pub status: u8, pub reserved: [u8; 4] }
+#[repr(C)]
+#[derive(Clone, Copy, Default, PartialEq, Eq, Debug)]
+pub struct PackedWitness { pub w: [u32; 4] }
+#[repr(C)]
+#[derive(Clone, Copy, Default, PartialEq, Eq, Debug)]
+pub struct PackedProof { pub points_lo: u32, pub points_hi: u32, pub evals_status: u32 }

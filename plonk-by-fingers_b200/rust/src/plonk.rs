@@ -220,6 +220,23 @@ impl<P: PlonkTypes + B200Wire> Plonk<P> {
         result
     }
 
+    /// Addition: the same two calls over PACKED records (include/pbh_b200.h "packed wire format": 16-byte inputs, 12-byte
+    /// proofs, 4-byte challenge words), the form that crosses PCIe with 32 bytes up and 13 bytes down per proof +
+    /// verification.  `PackedWitness::pack` / `PackedProof::unpack` below convert to and from byte planes on the host.
+    pub fn prove_packed(&self, c: &Constrains<P::HF>, input: &[PackedWitness]) -> Vec<PackedProof> {
+        let mut out = vec![PackedProof::default(); input.len()];
+        let rc = self.with_ctx(c, |h| unsafe { pbh_prove_packed(h, input.len(), input.as_ptr(), out.as_mut_ptr()) });
+        assert_eq!(rc, PBH_OK);
+        out
+    }
+    pub fn verify_packed(&self, c: &Constrains<P::HF>, proofs: &[PackedProof], chal_u: &[u32]) -> Vec<u8> {
+        assert_eq!(proofs.len(), chal_u.len());
+        let mut result = vec![0u8; proofs.len()];
+        let rc = self.with_ctx(c, |h| unsafe { pbh_verify_packed(h, proofs.len(), proofs.as_ptr(), chal_u.as_ptr(), result.as_mut_ptr()) });
+        assert_eq!(rc, PBH_OK);
+        result
+    }
+
     /// src/plonk.rs:191-466: a batch of one; panics where (and with what) the reference panics.
     pub fn prove(
         &self,
@@ -275,5 +292,25 @@ impl<P: PlonkTypes + B200Wire> Plonk<P> {
         let r = self.verify_batch(constraints, &p, &chal, &[b(&rand[0])], 1)[0];
         if r == PBH_VR_PANIC_ZH0 { panic!("called `Option::unwrap()` on a `None` value") }      // src/plonk.rs:579
         r & 1 == 1
+    }
+}
+
+impl PackedWitness {
+    /// byte planes (12 x n, 9 x n, 5 x n, n) -> packed records; `None` when a value is >= 17 (it has no packed form)
+    pub fn pack(wit: &[u8], rand: &[u8], chal: &[u8], u: &[u8], n: usize) -> Option<Vec<PackedWitness>> {
+        assert!(wit.len() >= 12 * n && rand.len() >= 9 * n && chal.len() >= 5 * n && u.len() >= n);
+        let mut out = vec![PackedWitness::default(); n];
+        let rc = unsafe { pbh_pack_witness_host(n, wit.as_ptr(), n, rand.as_ptr(), n, chal.as_ptr(), n, u.as_ptr(), out.as_mut_ptr()) };
+        if rc == PBH_OK { Some(out) } else { None }
+    }
+}
+impl PackedProof {
+    /// packed proofs -> (proof planes 27 x n, status n)
+    pub fn unpack(packed: &[PackedProof]) -> (Vec<u8>, Vec<u8>) {
+        let n = packed.len();
+        let (mut proof, mut status) = (vec![0u8; 27 * n], vec![0u8; n]);
+        let rc = unsafe { pbh_unpack_proofs_host(n, packed.as_ptr(), proof.as_mut_ptr(), n, status.as_mut_ptr()) };
+        assert_eq!(rc, PBH_OK);
+        (proof, status)
     }
 }

@@ -219,6 +219,11 @@ def main():
     ap.add_argument("--no-config4", action="store_true", help="skip the 256 M-witness sharded run of BASELINE.json configs[4]")
     ap.add_argument("--config4-log2", type=int, default=28)
     ap.add_argument("--sweep-log2", type=str, default="24,28")
+    ap.add_argument("--gather", default="window", choices=["window", "nccl"],
+                    help="N > 1: how the shard summaries reach every rank: 'window' = stored into the peers' windows over NVLink by the "
+                         "prover / verifier kernels themselves (pbh_window_*), 'nccl' = one NCCL all-gather per ring cycle")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="DIAGNOSTIC ONLY: leave the all-gathers out of the timed region (the line is marked invalid); shows what the collective costs")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels directly instead of replaying one CUDA graph per K-step region")
     ap.add_argument("--no-overlap-prove", dest="overlap_prove", action="store_false",
                     help="launch every prover from one stream (default: odd steps launch from a second prover stream, so prove(k+1) fills the SMs prove(k) leaves)")
@@ -263,8 +268,35 @@ def main():
     # Summaries (verdict bitmap, then the 64-bit proof digest) of a whole ring cycle are contiguous so that ONE all-gather
     # can carry them; two sets, so that cycle c+1's kernels write set (c+1)%2 while set c%2 is still being gathered.
     row = nb + 8
-    summary_all = [torch.zeros(ring * row, dtype=torch.uint8, device=dev) for _ in range(2)]
-    gathered_all = [torch.empty(world * ring * row, dtype=torch.uint8, device=dev) if world > 1 else None for _ in range(2)]
+    # How the N ranks exchange the summaries.  "window" (default): every rank owns a peer window (pbh_window_*) whose row r is rank
+    # r's region; the prover and verifier kernels store their digest / bitmap into the own row AND, over NVLink, into the same
+    # row of every peer's window, so the all-gather is complete when the kernels are and the timed region holds no collective.
+    # "nccl": one all_gather_into_tensor per ring cycle on a side stream.
+    collective = None
+    window = None
+    if world > 1:
+        collective = args.gather
+        if collective == "window":
+            try:
+                bpr = (2 * ring * row + 15) // 16 * 16
+                window, handle = ctx.window_create(bpr, rank, world)
+                hs = torch.zeros((world, 64), dtype=torch.uint8, device=dev)
+                dist.all_gather_into_tensor(hs, torch.from_numpy(handle).to(dev))
+                ctx.window_attach(hs.cpu().numpy())
+            except Exception as e:   # no peer access between these devices: the NCCL path is the fallback FOR THE COLLECTIVE only
+                print(f"[rank {rank}] peer window unavailable ({type(e).__name__}: {e}); using the NCCL all-gather", file=sys.stderr)
+                window = None
+            flag = torch.tensor([1 if window is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                window, collective = None, "nccl"
+    if window is not None:
+        win_sets = window[:, :2 * ring * row].view(world, 2, ring * row)
+        summary_all = [win_sets[rank, b] for b in range(2)]
+        gathered_all = [None, None]
+    else:
+        summary_all = [torch.zeros(ring * row, dtype=torch.uint8, device=dev) for _ in range(2)]
+        gathered_all = [torch.empty(world * ring * row, dtype=torch.uint8, device=dev) if world > 1 else None for _ in range(2)]
     for r in range(ring):
         first = (r * world + rank) * n
         w, rd, c, u = ctx.generate_inputs(n, first_index=first, seed=SEED, dist=pbh_b200.DIST_FULLPATH)
@@ -291,6 +323,10 @@ def main():
             # instead of waiting for the whole grid to drain
             ctx_p1 = pbh_b200.Context(device=local, algo=args.algo)
             pstream1 = ctx_p1.torch_stream()
+    if window is not None:
+        for other in (ctx_v, ctx_p1):
+            if other is not None:
+                ctx.window_share(other)
 
     def enqueue_region(steps):
         """Enqueue exactly `steps` steps on `stream` (+ `vstream`, + the cycle all-gathers on `comm_stream`), joined back into
@@ -300,7 +336,7 @@ def main():
         cycles = (steps + ring - 1) // ring
         for cyc in range(cycles):
             b = cyc % 2
-            if world > 1 and cyc >= 2:
+            if world > 1 and cyc >= 2 and not args.no_gather and window is None:
                 stream.wait_event(gather_done[cyc - 2])       # the all-gather that read this summary set has finished
                 if vstream is not None:
                     vstream.wait_event(gather_done[cyc - 2])
@@ -328,7 +364,7 @@ def main():
                 stream.wait_stream(pstream1)
             if vstream is not None:
                 stream.wait_stream(vstream)
-            if world > 1:
+            if world > 1 and not args.no_gather and window is None:
                 ev_ = torch.cuda.Event()
                 ev_.record(stream)
                 comm_stream.wait_event(ev_)
@@ -336,7 +372,7 @@ def main():
                     dist.all_gather_into_tensor(gathered_all[b], summary_all[b])   # the only collective
                     gather_done[cyc] = torch.cuda.Event()
                     gather_done[cyc].record(comm_stream)
-        if world > 1:
+        if world > 1 and window is None and not args.no_gather:
             stream.wait_stream(comm_stream)
         return cycles
 
@@ -358,7 +394,8 @@ def main():
                 enqueue_region(K)
             region_graph = g
             launch_mode = (f"one CUDA graph per {K}-step region: {2 * K} kernels" +
-                           (f" + {(K + ring - 1) // ring} NCCL all-gathers (one per {ring}-step cycle, overlapping the next cycle)" if world > 1 else "") +
+                           (f" + {(K + ring - 1) // ring} NCCL all-gathers (one per {ring}-step cycle, overlapping the next cycle)" if world > 1 and window is None else "") +
+                           ("; summaries stored into the peers' windows by the kernels (no collective)" if window is not None else "") +
                            ("; verify(k) on a second stream beside prove(k+1)" if vstream is not None else "") +
                            ("; provers alternate between two streams" if pstream1 is not None else ""))
         except Exception as e:   # pragma: no cover - capture not supported
@@ -404,8 +441,12 @@ def main():
             t_end.record(stream)
         barrier()
         rep_ms.append(t_begin.elapsed_time(t_end))
+    per_rank_ms = None
     if world > 1:
         t = torch.tensor(rep_ms, dtype=torch.float64, device=dev)
+        allt = torch.empty((world, len(rep_ms)), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, t)
+        per_rank_ms = [statistics.median(r_) for r_ in allt.tolist()]        # each rank's own median: shows a slow device
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         rep_ms = [float(x) for x in t.tolist()]
     ms_total = statistics.median(rep_ms)
@@ -455,9 +496,14 @@ def main():
     # [0, N n): rank 0 recomputes all of it alone and requires gathered bitmap == its bitmap and the sum of the gathered
     # digests == its digest.  Every rank also finds its own summary at its place in the gathered buffer.
     gather_ok = sharded_equals_single = single_ref = None
-    if world > 1:
+    if world > 1 and not args.no_gather:
         torch.cuda.synchronize()
-        g_ = gathered_all[last_set].view(world, ring, row)
+        if window is not None:
+            dist.barrier()                                   # every rank's kernels (and with them its stores into this window) are done
+            torch.cuda.synchronize()
+            g_ = win_sets[:, last_set].reshape(world, ring, row)
+        else:
+            g_ = gathered_all[last_set].view(world, ring, row)
         gather_ok = bool(torch.equal(g_[rank].reshape(-1), summary_all[last_set]))
         flag = torch.tensor([1 if gather_ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
@@ -829,8 +875,11 @@ def main():
         "config": {"workload": WORKLOAD, "items_per_gpu_per_step": n, "algo": args.algo, "distribution": "D_fullpath seed 0xB200",
                    "l2": f"ring of {ring} distinct input/output batches ({ring * n * 88 / 1e6:.0f} MB) cycled, larger than the 126 MB L2",
                    "parallelism": f"shard x{world}, all-gather of verdict bitmaps + digests" if world > 1 else "single GPU",
+                   "collective": ({"window": "peer windows: the verifier / prover kernels store bitmap / digest into every peer's buffer over NVLink (pbh_window_*); "
+                                             "no collective call in the timed region; the NCCL all-gather is timed in config4_256m_sharded",
+                                   "nccl": "NCCL all_gather_into_tensor, one per ring cycle, on a side stream"}[collective] if world > 1 else None),
                    "timing": f"median of {reps} repetitions of the exactly-{K}-step region (CUDA events on the launching stream, max over ranks per repetition)"},
-        "timed_region_ms": {"median": ms_total, "all_repetitions": rep_ms},
+        "timed_region_ms": {"median": ms_total, "all_repetitions": rep_ms, "median_of_each_rank": per_rank_ms},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": launches,
@@ -863,6 +912,8 @@ def main():
                   "oracle_full_batch": oracle_full, "generator_prefix_equals_oracle": generator_sample_ok,
                   "gathered_summaries_ok": gather_ok, "sharded_equals_single": sharded_equals_single},
     }
+    if args.no_gather:
+        line["INVALID"] = "--no-gather: diagnostic run without the exchange of the summaries"
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     finish()

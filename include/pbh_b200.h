@@ -436,6 +436,29 @@ int pbh_prove_digest_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_
 int pbh_verify_bitmap_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
                                 size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* bitmap);
 
+/* ---- peer windows: the gather of the shard summaries as plain stores over NVLink ----------------------------------------
+ * The only exchange of the sharded path is that every device ends up with every shard's verdict bitmap and proof digest
+ * (SURVEY.md 8e).  A collective after the kernels costs a rendezvous per call; a peer window removes it: every rank owns a
+ * device buffer of world x bytes_per_rank bytes, rank r's region being bytes [r * bytes_per_rank, (r + 1) * bytes_per_rank)
+ * of EVERY rank's buffer.  When the `digest` of pbh_prove_digest_batch_dev or the `bitmap` of pbh_verify_bitmap_batch_dev
+ * points into the calling rank's own region, the kernel that produces the summary also stores it at the same offset of every
+ * peer's buffer - the verifier per 256-item tile (one 32-byte store per peer), the prover's last block its 8-byte digest -
+ * through peer-mapped device memory (NVLink / NVSwitch), so the all-gather has happened when the kernels have finished and
+ * costs neither a launch nor a rendezvous.  A consumer on another rank must be ordered after the producing rank's stream
+ * (a barrier at the end of a pass).  world <= 8; bytes_per_rank a multiple of 16.
+ *   pbh_window_create      allocates (zeroed) this rank's buffer; base_out = its device address; handle_out (nullable) = a
+ *                          CUDA IPC handle other PROCESSES open with pbh_window_attach (one process per GPU, torchrun)
+ *   pbh_window_attach      handles: world x PBH_IPC_HANDLE_BYTES bytes, entry r from rank r (the own entry is ignored)
+ *   pbh_window_attach_ptrs the same for peers of THIS process: their buffers' device addresses (peer access is enabled)
+ *   pbh_window_share       lets another context of the same device (its own stream) write through an attached window
+ *   pbh_window_destroy     detaches and frees; also done by pbh_ctx_destroy */
+#define PBH_IPC_HANDLE_BYTES 64
+int pbh_window_create(pbh_ctx* ctx, size_t bytes_per_rank, int rank, int world, void** base_out, uint8_t handle_out[PBH_IPC_HANDLE_BYTES]);
+int pbh_window_attach(pbh_ctx* ctx, const uint8_t* handles);
+int pbh_window_attach_ptrs(pbh_ctx* ctx, void* const* bases);
+int pbh_window_share(pbh_ctx* owner, pbh_ctx* other);
+int pbh_window_destroy(pbh_ctx* ctx);
+
 /* ---- multi-device: several GPUs driven from ONE process -------------------------------------------
  * pbh_multi_create does pbh_ctx_create on each of the n_dev devices (devices == NULL: 0 .. n_dev-1), with one stream per
  * device, and - when n_dev > 1 - builds one NCCL communicator over them (ncclCommInitAll; libnccl.so.2 is loaded at run

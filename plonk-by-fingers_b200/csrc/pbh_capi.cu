@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cstdio>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <string>
@@ -67,6 +68,13 @@ struct pbh_ctx {
   int grid_scale = 2;                      // persistent-grid blocks per SM are grid_scale/2 of the kernel's residency (1: half grids, async lanes)
   int numa_node = -1;                      // NUMA node of the device's PCIe root (sysfs), -1 when the platform does not say
   std::map<void*, std::pair<size_t, bool>> host_allocs;   // pbh_host_alloc: pointer -> (bytes, mmap'ed + registered)
+  // peer window (pbh_window_*): this rank's copy of the world x bytes_per_rank window and the peers' copies
+  uint8_t* win_base = nullptr;
+  size_t win_bytes_per_rank = 0;
+  int win_rank = 0, win_world = 0;
+  bool win_owner = false, win_attached = false;
+  uint8_t* win_peer[8] = {};
+  bool win_peer_ipc[8] = {};
   std::string last_error;
 };
 
@@ -86,6 +94,7 @@ struct pbh_ctx {
   } while (0)
 
 static int device_numa_node(int device);
+static void window_release(pbh_ctx* ctx);
 
 static int fail(pbh_ctx* ctx, int code, const char* msg) {
   if (ctx) ctx->last_error = msg; else set_global_error(msg);
@@ -184,6 +193,7 @@ void pbh_ctx_destroy(pbh_ctx* ctx) {
   if (ctx->d_tables) cudaFree(ctx->d_tables);
   if (ctx->d_pairs) cudaFree(ctx->d_pairs);
   if (ctx->d_wtab) cudaFree(ctx->d_wtab);
+  window_release(ctx);
   if (ctx->d_tile_counters) cudaFree(ctx->d_tile_counters);
   delete ctx;
 }
@@ -307,6 +317,29 @@ static int launch_digest(pbh_ctx* ctx, cudaStream_t st, size_t n, uint64_t first
   return PBH_OK;
 }
 
+// The peers of a summary pointer: non-empty when the context has an attached peer window and [p, p + bytes) lies inside this
+// rank's region of it.
+static PeerWindow peer_window_for(const pbh_ctx* ctx, const void* p, size_t bytes) {
+  PeerWindow pw{};
+  if (!ctx->win_attached || !p) return pw;
+  const uint8_t* lo = ctx->win_base + (size_t)ctx->win_rank * ctx->win_bytes_per_rank;
+  const uint8_t* q = static_cast<const uint8_t*>(p);
+  if (q < lo || q + bytes > lo + ctx->win_bytes_per_rank) return pw;
+  for (int r = 0; r < ctx->win_world; r++) {
+    if (r == ctx->win_rank || !ctx->win_peer[r]) continue;
+    pw.delta[pw.n++] = (long long)(ctx->win_peer[r] - ctx->win_base);
+  }
+  return pw;
+}
+static int launch_publish(pbh_ctx* ctx, cudaStream_t st, const void* src, size_t bytes, const PeerWindow& pw) {
+  if (pw.n == 0 || bytes == 0) return PBH_OK;
+  window_publish_kernel<<<(int)std::max<size_t>(1, std::min<size_t>((bytes + kBlock - 1) / kBlock, 64)), kBlock, 0, st>>>(
+      static_cast<const uint8_t*>(src), bytes, pw);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return PBH_OK;
+}
+
 // digest (nullable): device uint64, already zeroed on `st`; receives the digest of the 27 proof planes
 static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint64_t first_index = 0, uint64_t* digest = nullptr) {
   if (A.n == 0) return PBH_OK;
@@ -319,16 +352,17 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint6
       unsigned int* tc = fresh_tile_counter(ctx, st);
       if (!tc) return fail(ctx, PBH_ERR_UNSUPPORTED, "too many launches captured into CUDA graphs from this context");
       unsigned long long* dg = (unsigned long long*)digest;
+      const PeerWindow pw = peer_window_for(ctx, digest, sizeof(uint64_t));
       // the compile-time instantiation for the reference's own circuit + SRS(2, 6) when the context's constants match it
       const bool special = ctx->pbh_circuit && ctx->specialise;
       if (ctx->algo == PBH_ALGO_TABLE && special)
-        prove_f32_tma_kernel<ALGO_TABLE, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
+        prove_f32_tma_kernel<ALGO_TABLE, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc, pw);
       else if (ctx->algo == PBH_ALGO_TABLE)
-        prove_f32_tma_kernel<ALGO_TABLE, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
+        prove_f32_tma_kernel<ALGO_TABLE, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc, pw);
       else if (special)
-        prove_f32_tma_kernel<ALGO_ARITH, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
+        prove_f32_tma_kernel<ALGO_ARITH, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc, pw);
       else
-        prove_f32_tma_kernel<ALGO_ARITH, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc);
+        prove_f32_tma_kernel<ALGO_ARITH, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->d_tables, A.proof, A.proof_pitch, A.status, A.n, first_index, dg, tc, pw);
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
       return PBH_OK;
@@ -351,12 +385,17 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint6
   else prove_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
-  if (digest) return launch_digest(ctx, st, A.n, first_index, 27, A.proof, A.proof_pitch, digest);   // not fused on this path
+  if (digest) {   // not fused on this path
+    int rc = launch_digest(ctx, st, A.n, first_index, 27, A.proof, A.proof_pitch, digest);
+    if (rc) return rc;
+    return launch_publish(ctx, st, digest, sizeof(uint64_t), peer_window_for(ctx, digest, sizeof(uint64_t)));
+  }
   return PBH_OK;
 }
 static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) {
   if (A_in.n == 0) return PBH_OK;
   VerifyArgs A = A_in;
+  const PeerWindow pw = peer_window_for(ctx, A_in.bitmap, (A_in.n + 7) / 8);
   uint8_t* bitmap_later = nullptr;
   if (A.bitmap && (((uintptr_t)A.bitmap % 4) != 0)) { bitmap_later = A.bitmap; A.bitmap = nullptr; }
   if (ctx->use_tma) {
@@ -368,10 +407,10 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
       if (!tc) return fail(ctx, PBH_ERR_UNSUPPORTED, "too many launches captured into CUDA graphs from this context");
       if (ctx->algo == PBH_ALGO_TABLE) {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2 * ctx->grid_scale);
-        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A, tc);
+        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A, tc, A.bitmap ? pw : PeerWindow{});
       } else {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * (ctx->grid_scale == 2 ? 3 : 2));
-        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A, tc);
+        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A, tc, A.bitmap ? pw : PeerWindow{});
       }
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());
@@ -379,6 +418,7 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
         pack_verdicts_kernel<<<grid_for(ctx, (A.n + 7) / 8, 8), kBlock, 0, st>>>(A.n, A.result, bitmap_later);
         ctx->launches++;
         CUDA_TRY(ctx, cudaGetLastError());
+        return launch_publish(ctx, st, bitmap_later, (A.n + 7) / 8, pw);
       }
       return PBH_OK;
     }
@@ -393,8 +433,106 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
     pack_verdicts_kernel<<<grid_for(ctx, (A.n + 7) / 8, 8), kBlock, 0, st>>>(A.n, A.result, bitmap_later);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
+    return launch_publish(ctx, st, bitmap_later, (A.n + 7) / 8, pw);
   }
   return PBH_OK;
+}
+
+// ---- peer windows (include/pbh_b200.h) -----------------------------------------------------------------------------------
+static void window_release(pbh_ctx* ctx) {
+  for (int r = 0; r < 8; r++) {
+    if (ctx->win_peer[r] && ctx->win_peer_ipc[r] && ctx->win_owner) cudaIpcCloseMemHandle(ctx->win_peer[r]);
+    ctx->win_peer[r] = nullptr;
+    ctx->win_peer_ipc[r] = false;
+  }
+  if (ctx->win_base && ctx->win_owner) cudaFree(ctx->win_base);
+  ctx->win_base = nullptr;
+  ctx->win_bytes_per_rank = 0;
+  ctx->win_owner = ctx->win_attached = false;
+  (void)cudaGetLastError();
+}
+int pbh_window_create(pbh_ctx* ctx, size_t bytes_per_rank, int rank, int world, void** base_out, uint8_t handle_out[PBH_IPC_HANDLE_BYTES]) {
+  CTX_CHECK(ctx);
+  static_assert(sizeof(cudaIpcMemHandle_t) == PBH_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!base_out || bytes_per_rank == 0 || (bytes_per_rank % 16) != 0 || world < 1 || world > 8 || rank < 0 || rank >= world)
+    return fail(ctx, PBH_ERR_BAD_ARGUMENT, "window: 1 <= world <= 8, 0 <= rank < world, bytes_per_rank a positive multiple of 16");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute));
+  window_release(ctx);
+  CUDA_TRY(ctx, cudaMalloc(&ctx->win_base, bytes_per_rank * (size_t)world));
+  CUDA_TRY(ctx, cudaMemset(ctx->win_base, 0, bytes_per_rank * (size_t)world));
+  ctx->win_bytes_per_rank = bytes_per_rank;
+  ctx->win_rank = rank;
+  ctx->win_world = world;
+  ctx->win_owner = true;
+  if (handle_out) {
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&h, ctx->win_base));
+    std::memcpy(handle_out, &h, sizeof h);
+  }
+  *base_out = ctx->win_base;
+  return PBH_OK;
+}
+int pbh_window_attach(pbh_ctx* ctx, const uint8_t* handles) {
+  CTX_CHECK(ctx);
+  if (!handles || !ctx->win_base || !ctx->win_owner) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "window: create it first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->win_world; r++) {
+    if (r == ctx->win_rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + (size_t)r * PBH_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    CUDA_TRY(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->win_peer[r] = static_cast<uint8_t*>(p);
+    ctx->win_peer_ipc[r] = true;
+  }
+  ctx->win_attached = true;
+  return PBH_OK;
+}
+int pbh_window_attach_ptrs(pbh_ctx* ctx, void* const* bases) {
+  CTX_CHECK(ctx);
+  if (!bases || !ctx->win_base || !ctx->win_owner) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "window: create it first");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  for (int r = 0; r < ctx->win_world; r++) {
+    if (r == ctx->win_rank) continue;
+    if (!bases[r]) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "window: null peer base");
+    cudaPointerAttributes a{};
+    CUDA_TRY(ctx, cudaPointerGetAttributes(&a, bases[r]));
+    if (a.type != cudaMemoryTypeDevice) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "window: peer base is not device memory");
+    if (a.device != ctx->device) {
+      int can = 0;
+      CUDA_TRY(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, a.device));
+      if (!can) return fail(ctx, PBH_ERR_UNSUPPORTED, "window: no peer access to that device");
+      cudaError_t e = cudaDeviceEnablePeerAccess(a.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(ctx, e);
+      (void)cudaGetLastError();
+    }
+    ctx->win_peer[r] = static_cast<uint8_t*>(bases[r]);
+    ctx->win_peer_ipc[r] = false;
+  }
+  ctx->win_attached = true;
+  return PBH_OK;
+}
+int pbh_window_share(pbh_ctx* owner, pbh_ctx* other) {
+  CTX_CHECK(owner);
+  CTX_CHECK(other);
+  if (owner == other || !owner->win_attached || owner->device != other->device) return fail(owner, PBH_ERR_BAD_ARGUMENT, "window: share an attached window with another context of the same device");
+  window_release(other);
+  other->win_base = owner->win_base;
+  other->win_bytes_per_rank = owner->win_bytes_per_rank;
+  other->win_rank = owner->win_rank;
+  other->win_world = owner->win_world;
+  for (int r = 0; r < 8; r++) other->win_peer[r] = owner->win_peer[r];
+  other->win_owner = false;
+  other->win_attached = true;
+  return PBH_OK;
+}
+int pbh_window_destroy(pbh_ctx* ctx) {
+  CTX_CHECK(ctx);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = pbh_ctx_sync(ctx);
+  window_release(ctx);
+  return rc;
 }
 
 int pbh_prove_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch, const uint8_t* rnd, size_t rand_pitch,

@@ -53,16 +53,29 @@ __device__ __forceinline__ void digest_flush(unsigned long long acc, unsigned lo
 // Dynamic tile scheduler state: c[0] = next tile, c[1] = blocks finished.  The pair is launch-local (the host hands every
 // launch its own, pbh_capi.cu: fresh_tile_counter) and zero when the launch starts: the last block to leave resets it, so
 // a launch recorded into a CUDA graph finds it zero again at every replay and no memset node is needed.
-__device__ __forceinline__ void tile_scheduler_leave(unsigned int* c) {
+// Returns true in thread 0 of the LAST block to leave (every other block's writes that preceded its own leave are then visible
+// to that thread).
+__device__ __forceinline__ bool tile_scheduler_leave(unsigned int* c) {
+  bool last = false;
   if (threadIdx.x == 0) {
     __threadfence();
     if (atomicAdd(&c[1], 1u) == gridDim.x - 1) {
       c[0] = 0u;
       c[1] = 0u;
       __threadfence();
+      last = true;
     }
   }
+  return last;
 }
+
+// Peer window (include/pbh_b200.h "peer windows"): the shard summaries a kernel writes (the verifier's verdict bitmap, the
+// prover's proof digest) are ALSO stored, by the same kernel, at the same offset of every peer's window - plain stores over
+// NVLink into peer memory - so that after the kernel every device holds this shard's summary and no collective is needed.
+struct PeerWindow {
+  uint32_t n;            // number of peers (0: not replicated)
+  long long delta[7];    // peer address = local address + delta[p]
+};
 
 struct ProveArgs {
   const uint8_t* wit; size_t wit_pitch;
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
                                                                   const Tables* __restrict__ gT, uint8_t* __restrict__ proof_out,
                                                                   size_t proof_pitch, uint8_t* __restrict__ status_out, size_t n,
                                                                   uint64_t first_index, unsigned long long* __restrict__ digest_out,
-                                                                  unsigned int* __restrict__ tile_counter) {
+                                                                  unsigned int* __restrict__ tile_counter, const PeerWindow PW) {
   __shared__ ProveTmaSmem S;
   unsigned long long digest_acc = 0;
   const int tid = threadIdx.x;
@@ -333,7 +346,17 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
   }
   if (tid == 0) tma::store_wait_all();
   if (digest_out != nullptr) digest_flush(digest_acc, digest_out);   // one atomic per warp per launch
-  tile_scheduler_leave(tile_counter);
+  const bool replicate = PW.n != 0 && digest_out != nullptr;
+  if (replicate) __syncthreads();                                    // every warp's digest atomic precedes thread 0's fence in leave
+  const bool last = tile_scheduler_leave(tile_counter);
+  if (replicate && last) {
+    // the launch's digest is complete: the last block pushes it to the same offset of every peer's window
+    __threadfence();
+    const unsigned long long d = *reinterpret_cast<volatile unsigned long long*>(digest_out);
+#pragma unroll
+    for (uint32_t p = 0; p < 7; p++)     // fixed trip count: delta[] stays in the parameter bank (no local copy)
+      if (p < PW.n) *reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(digest_out) + PW.delta[p]) = d;
+  }
 }
 
 struct VerifyArgs {
@@ -419,13 +442,14 @@ struct VerifyTmaSmem {
   alignas(128) uint8_t in[2][34][kTile];    // planes 0..26 proof, 27..31 challenges, 32 u (33 unused: keeps stages 128-byte aligned)
   alignas(8) uint64_t full[2];
   uint32_t tile_of_stage[2];
+  alignas(32) uint32_t ballot[2][8];        // the tile's eight verdict words, kept for the peer-window stores
   Tables T;
 };
 template <int ALGO, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __grid_constant__ VerifyTmaMaps M, const Consts K,
                                                                          const ConstsF KF, const bool fp32,
                                                                          const Tables* __restrict__ gT, const VerifyArgs A,
-                                                                         unsigned int* __restrict__ tile_counter) {
+                                                                         unsigned int* __restrict__ tile_counter, const PeerWindow PW) {
   __shared__ VerifyTmaSmem S;
   const int tid = threadIdx.x;
   const size_t tiles = (A.n + kTile - 1) / kTile;
@@ -491,8 +515,27 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
           for (size_t b = 0; b < (A.n - w0 + 7) / 8; b++) A.bitmap[w0 / 8 + b] = (uint8_t)(bits >> (8 * b));
         }
       }
+      if (PW.n != 0 && (tid & 31) == 0) S.ballot[stage][tid >> 5] = bits;
     }
     __syncthreads();   // every thread has read in[stage]; it may be refilled by the prefetch of the iteration after next
+    if (PW.n != 0 && A.bitmap != nullptr && tid < 8) {
+      // the tile's 32 bitmap bytes go to every peer as one 32-byte store of eight lanes (ballot[stage] is rewritten two
+      // iterations from now, behind another block barrier)
+      const size_t w0 = tile * kTile + (size_t)tid * 32;
+      if (w0 < A.n) {
+        const uint32_t word = S.ballot[stage][tid];
+#pragma unroll
+        for (uint32_t p = 0; p < 7; p++) {
+          if (p >= PW.n) continue;
+          uint8_t* dst = A.bitmap + w0 / 8 + PW.delta[p];
+          if (w0 + 32 <= A.n) {
+            *reinterpret_cast<uint32_t*>(dst) = word;
+          } else {
+            for (size_t b = 0; b < (A.n - w0 + 7) / 8; b++) dst[b] = (uint8_t)(word >> (8 * b));
+          }
+        }
+      }
+    }
   }
   tile_scheduler_leave(tile_counter);
 }
@@ -1206,6 +1249,17 @@ __global__ void __launch_bounds__(kBlock) proof_planes_to_records_kernel(size_t 
     uint4* p = reinterpret_cast<uint4*>(rec) + 2 * i;
     p[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
     p[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+  }
+}
+
+// Peer-window publication for the paths whose summaries come from a separate kernel (unaligned batches): copies `bytes`
+// bytes at `src` to the same offset of every peer's window.
+__global__ void __launch_bounds__(kBlock) window_publish_kernel(const uint8_t* __restrict__ src, size_t bytes, const PeerWindow PW) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < bytes; i += (size_t)gridDim.x * blockDim.x) {
+    const uint8_t v = src[i];
+#pragma unroll
+    for (uint32_t p = 0; p < 7; p++)
+      if (p < PW.n) const_cast<uint8_t*>(src)[(long long)i + PW.delta[p]] = v;
   }
 }
 

@@ -52,7 +52,7 @@ pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_
 pbh_gt_mul_batch pbh_gt_pow600_batch pbh_poly_divrem_batch pbh_poly_addsub_ragged_batch
 pbh_prove_packed pbh_verify_packed pbh_prove_packed_async pbh_verify_packed_async pbh_prove_verify_packed pbh_unpack_witness_dev
 pbh_pack_proof_dev pbh_unpack_proof_dev pbh_pack_witness_host pbh_unpack_witness_host pbh_pack_chal_u_host pbh_pack_proofs_host
-pbh_unpack_proofs_host""".split()
+pbh_unpack_proofs_host pbh_window_create pbh_window_attach pbh_window_attach_ptrs pbh_window_share pbh_window_destroy""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -570,6 +570,40 @@ class Context:
                                          C.c_void_p(res.ctypes.data))
         self._check(rc, "pbh_verify_records")
         return res
+
+    # ---- peer windows: the shard summaries stored into every peer's buffer by the kernels that produce them ----
+    def window_create(self, bytes_per_rank, rank, world):
+        """-> (torch uint8 tensor of shape (world, bytes_per_rank) over this rank's window, 64-byte IPC handle as numpy uint8).
+        Rank r's region is row r of EVERY rank's tensor; summaries written into the own row (the `digest` of
+        prove_digest_batch, the `bitmap` of verify_bitmap_batch) appear in the same place of every attached peer."""
+        import torch
+        base = C.c_void_p()
+        handle = np.zeros(64, dtype=np.uint8)
+        self._check(self.lib.pbh_window_create(self.h, C.c_size_t(bytes_per_rank), int(rank), int(world), C.byref(base),
+                                               C.c_void_p(handle.ctypes.data)), "pbh_window_create")
+
+        class _Dev:   # CUDA array interface over library-owned device memory (lives until window_destroy / close)
+            __cuda_array_interface__ = {"shape": (int(world) * int(bytes_per_rank),), "typestr": "|u1", "data": (int(base.value), False), "version": 3}
+        with torch.cuda.device(self.device):
+            t = torch.as_tensor(_Dev(), device=torch.device("cuda", self.device))
+        self._window_base = int(base.value)
+        return t.view(int(world), int(bytes_per_rank)), handle
+
+    def window_attach(self, handles):
+        """handles: (world, 64) uint8 array, row r = rank r's IPC handle (other processes)."""
+        hs = np.ascontiguousarray(handles, dtype=np.uint8)
+        self._check(self.lib.pbh_window_attach(self.h, C.c_void_p(hs.ctypes.data)), "pbh_window_attach")
+
+    def window_attach_ptrs(self, bases):
+        """bases: one device address per rank (peers of this process; the own entry is ignored)."""
+        arr = (C.c_void_p * len(bases))(*[C.c_void_p(int(b)) for b in bases])
+        self._check(self.lib.pbh_window_attach_ptrs(self.h, arr), "pbh_window_attach_ptrs")
+
+    def window_share(self, other):
+        self._check(self.lib.pbh_window_share(self.h, other.h), "pbh_window_share")
+
+    def window_destroy(self):
+        self._check(self.lib.pbh_window_destroy(self.h), "pbh_window_destroy")
 
     # ---- packed wire format (16-byte prover inputs, 12-byte proofs, 4-byte challenge words) ----
     @staticmethod

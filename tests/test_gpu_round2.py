@@ -322,3 +322,68 @@ def test_general_division_and_ragged_subtraction(gpu_ctx, oracle):
     # Q1 by hand: [1] -= [2, 3] gives [16, 3], not [16, 14]
     out = ctx.poly_addsub_ragged_batch(np.array([[1]], np.uint8), np.array([[2], [3]], np.uint8), subtract=True)
     assert out[:, 0].tolist() == [16, 3]
+
+
+def test_peer_window_replicates_the_summaries(gpu_ctx, oracle):
+    """pbh_window_* (include/pbh_b200.h "peer windows"): two ranks of ONE process on cuda:0 (pbh_window_attach_ptrs), each with a
+    window of world x bytes_per_rank; the bitmap the verifier writes into its own row and the digest the prover's last block
+    writes there must appear at the same offset of the peer's window - on the fused TMA path and on the unaligned fallback -
+    and equal what pack_verdicts / digest compute from the result and proof bytes.  Pointers outside the own row are not
+    replicated."""
+    import torch
+    import pbh_b200
+    world = 2
+    n = 256 * 37 + 64                       # ragged last tile
+    nb = (n + 7) // 8
+    row = (nb + 8 + 15) // 16 * 16
+    bpr = 4 * row
+    ranks = [pbh_b200.Context(device=0, algo="table") for _ in range(world)]
+    helper = pbh_b200.Context(device=0, algo="table")      # a second stream of rank 0 (pbh_window_share)
+    try:
+        wins = []
+        for r, c in enumerate(ranks):
+            w, _h = c.window_create(bpr, r, world)
+            wins.append(w)
+        for c in ranks:
+            c.window_attach_ptrs([c2._window_base for c2 in ranks])
+        ranks[0].window_share(helper)
+        ref = gpu_ctx["table"]
+        for r, c in enumerate(ranks):
+            first = r * n
+            w, rd, ch, u = ref.generate_inputs(n, first_index=first, seed=99, dist=pbh_b200.DIST_FULLPATH)
+            ref.sync()
+            proof = torch.empty((27, n), dtype=torch.uint8, device="cuda"); status = torch.empty((n,), dtype=torch.uint8, device="cuda")
+            result = torch.empty((n,), dtype=torch.uint8, device="cuda")
+            for slot, aligned in ((0, True), (1, False)):
+                mine = wins[r][r, slot * row:(slot + 1) * row]
+                bitmap, digest = mine[:nb], mine[nb:nb + 8].view(torch.int64)
+                if aligned:
+                    prover = helper if r == 0 else c
+                    prover.prove_digest_batch(w, rd, ch, proof, status, digest, first_index=first)
+                    prover.sync()
+                    c.verify_bitmap_batch(proof, ch, u, result, bitmap)
+                else:                       # planes at an odd offset: the plain-load kernels + separate digest / pack kernels + publish
+                    wo = torch.empty((12, n + 16), dtype=torch.uint8, device="cuda")[:, 1:n + 1]; wo.copy_(w)
+                    po = torch.empty((27, n + 16), dtype=torch.uint8, device="cuda")[:, 3:n + 3]
+                    c.prove_digest_batch(wo, rd, ch, po, status, digest, first_index=first)
+                    c.verify_bitmap_batch(po, ch, u, result, bitmap)
+                    c.sync()
+                    assert torch.equal(po, proof)
+                c.sync()
+                want_bm = ref.pack_verdicts(result); want_dg = ref.digest(proof, first_index=first)
+                ref.sync()
+                for holder in range(world):          # the own window and the peer's
+                    got = wins[holder][r, slot * row:(slot + 1) * row]
+                    assert torch.equal(got[:nb], want_bm), (r, slot, holder)
+                    assert int(got[nb:nb + 8].view(torch.int64).item()) == int(want_dg.item()), (r, slot, holder)
+            # a summary outside the own row (here: the peer's row of the own window) is written locally only
+            other = wins[r][1 - r, 2 * row:3 * row]
+            before = wins[1 - r][1 - r, 2 * row:3 * row].clone()
+            c.verify_bitmap_batch(proof, ch, u, result, other[:nb])
+            c.sync()
+            assert torch.equal(other[:nb], want_bm) and torch.equal(wins[1 - r][1 - r, 2 * row:3 * row], before)
+        with pytest.raises(pbh_b200.PbhError):
+            ranks[0].window_create(24, 0, 2)            # not a multiple of 16
+    finally:
+        for c in ranks + [helper]:
+            c.close()

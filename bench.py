@@ -52,6 +52,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self.power_w = []
         self._stop_evt = threading.Event()
         try:
             import pynvml
@@ -76,6 +77,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 try:
+                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
@@ -90,8 +95,10 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
+        pw = sorted(self.power_w)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "sm_mhz_min": (s[0] if s else None), "power_w_median": (pw[len(pw) // 2] if pw else None),
+                "power_w_max": (pw[-1] if pw else None)}
 
 
 _CPU_INPUTS = {}
@@ -475,6 +482,13 @@ def main():
     verify_bitmap_ms = time_kernel(lambda s_: ctx.verify_bitmap_batch(outs[s_]["proof"], ins[s_][2], ins[s_][3], outs[s_]["result"],
                                                                       outs[s_]["bitmap"]), kreps)
     clocks = sampler.stop()
+    if world > 1:
+        # every rank samples its own device: a box that slows all its GPUs down when they run together shows up here
+        mine = torch.tensor([float(clocks.get("sm_mhz") or 0), float(clocks.get("sm_mhz_min") or 0), float(clocks.get("power_w_median") or 0),
+                             float(len(clocks.get("reasons") or []))], dtype=torch.float64, device=dev)
+        allc = torch.empty((world, 4), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allc, mine)
+        clocks["per_rank"] = [{"sm_mhz": r_[0], "sm_mhz_min": r_[1], "power_w_median": r_[2], "throttle_reasons": int(r_[3])} for r_ in allc.tolist()]
     # the same kernels with per-item curve arithmetic (PBH_ALGO_ARITH: fixed-base MSM commitments, Straus MSM, Miller loops,
     # final exponentiations): reported beside the default group-table algorithm, both bit-exact
     arith = None
@@ -769,7 +783,13 @@ def main():
              "imad_thread_ops_per_s": int32.get("imad_thread_ops_per_s"),      # IMAD issues on the heavy FMA pipe only
              "alu_thread_ops_per_s": int32.get("shf_thread_ops_per_s")}        # SHF = one ALU-pipe instruction per chain step
     instr = instr_table()
-    kernels_rf = [roofline_entry("prove_f32_tma_kernel<TABLE>" if args.algo == "table" else "prove_f32_tma_kernel<ARITH>",
+    # the two kernels of the timed step first (prover with its fused digest, verifier with its fused bitmap), then the same
+    # kernels without the fused summaries
+    kernels_rf = [roofline_entry(("prove_f32_tma_kernel<TABLE>" if args.algo == "table" else "prove_f32_tma_kernel<ARITH>") + " + fused digest (the step's prover)",
+                                 "prove_table_digest" if args.algo == "table" else "prove_arith", prove_digest_ms, n, 54, peaks, instr),
+                  roofline_entry(("verify_tma_kernel<TABLE>" if args.algo == "table" else "verify_tma_kernel<ARITH>") + " + fused bitmap (the step's verifier)",
+                                 "verify_table_bitmap" if args.algo == "table" else "verify_arith", verify_bitmap_ms, n, 34, peaks, instr),
+                  roofline_entry("prove_f32_tma_kernel<TABLE>" if args.algo == "table" else "prove_f32_tma_kernel<ARITH>",
                                  "prove_table" if args.algo == "table" else "prove_arith", prove_ms, n, 54, peaks, instr),
                   roofline_entry("verify_tma_kernel<TABLE>" if args.algo == "table" else "verify_tma_kernel<ARITH>",
                                  "verify_table" if args.algo == "table" else "verify_arith", verify_ms, n, 34, peaks, instr)]

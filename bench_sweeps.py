@@ -110,6 +110,26 @@ def run_sweeps(ctx, log2n, reps=20, hbm_peak=6558.1, peaks=None):
     p11 = rnd(11, 17)
     report("poly_div_linear_10", 21, lambda: ctx.poly_div_linear_batch(p11), "the w_z quotient shape of src/plonk.rs:437")
     del p11
+    if hasattr(ctx, "unpack_witness_dev"):
+        # packed wire format conversions (include/pbh_b200.h): valid random records built on the device
+        words = torch.stack([torch.randint(0, 17 ** 7, (n,), dtype=torch.int64, device=dev, generator=g) for _ in range(3)] +
+                            [torch.randint(0, 17 ** 6, (n,), dtype=torch.int64, device=dev, generator=g)], dim=1).to(torch.int32)
+        pin = words.contiguous().view(torch.uint8).reshape(-1)
+        del words
+        report("unpack_witness", 43, lambda: ctx.unpack_witness_dev(pin, n), "16-byte packed prover input -> 27 byte planes")
+        cu = pin.view(torch.int32).reshape(n, 4)[:, 3].contiguous().view(torch.uint8).reshape(-1)
+        del pin
+        pts9 = torch.randint(0, 102 ** 9, (n,), dtype=torch.int64, device=dev, generator=g)
+        ev = torch.randint(0, 17 ** 7, (n,), dtype=torch.int64, device=dev, generator=g)
+        rec = torch.stack([pts9 & 0xFFFFFFFF, pts9 >> 32, ev], dim=1).to(torch.int32)
+        del pts9, ev
+        packed = rec.contiguous().view(torch.uint8).reshape(-1)
+        del rec
+        report("unpack_proof", 50, lambda: ctx.unpack_proof_dev(packed, cu, n), "12-byte packed proof + 4-byte challenge word -> 27 + 1 + 5 + 1 byte planes")
+        planes, status, _c, _u = ctx.unpack_proof_dev(packed, cu, n)
+        del packed, cu, _c, _u
+        report("pack_proof", 40, lambda: ctx.pack_proof_dev(planes, status), "27 proof planes + status -> 12-byte packed proof")
+        del planes, status
     return out
 
 

@@ -480,6 +480,9 @@ int pbh_multi_prove_batch(pbh_multi* m, size_t n, const uint8_t* wit, size_t wit
                           const uint8_t* chal, size_t chal_pitch, uint8_t* proof, size_t proof_pitch, uint8_t* status);
 int pbh_multi_verify_batch(pbh_multi* m, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* chal,
                            size_t chal_pitch, const uint8_t* u, uint8_t* result, uint8_t* gt, size_t gt_pitch);
+/* The same over packed records (pbh_prove_packed / pbh_verify_packed per shard). */
+int pbh_multi_prove_packed(pbh_multi* m, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out);
+int pbh_multi_verify_packed(pbh_multi* m, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result);
 /* The sharded end-to-end pass of BASELINE.json configs[4] in one call.  The synthetic items with global indices
  * [first_index, first_index + n_total) (pbh_generate_inputs_dev) are generated, proved and verified shard by shard on the
  * devices, the digest fused into the prover and the verdict bitmap into the verifier; then ONE ncclAllGather exchanges the

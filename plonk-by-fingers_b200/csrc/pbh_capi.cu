@@ -1156,21 +1156,26 @@ int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, c
 static_assert(sizeof(pbh_packed_witness) == 16 && sizeof(pbh_packed_proof) == 12, "packed records are 16 and 12 bytes");
 static int launch_unpack_witness(pbh_ctx* ctx, cudaStream_t st, size_t n, const pbh_packed_witness* in, uint8_t* wit, size_t wit_pitch,
                                  uint8_t* rnd, size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u) {
-  unpack_witness_kernel<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, in, wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, u);
+  auto al4 = [](const void* p, size_t pitch) { return !p || (((uintptr_t)p | pitch) % 4) == 0; };
+  const bool vec = al4(wit, wit_pitch) && al4(rnd, rand_pitch) && al4(chal, chal_pitch) && al4(u, 0);
+  unpack_witness_kernel<<<grid_for(ctx, (n + 3) / 4, 8), kBlock, 0, st>>>(n, in, wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, u, vec);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return PBH_OK;
 }
 static int launch_pack_proof(pbh_ctx* ctx, cudaStream_t st, size_t n, const uint8_t* proof, size_t proof_pitch, const uint8_t* status,
                              pbh_packed_proof* out) {
-  pack_proof_kernel<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, proof, proof_pitch, status, out);
+  const bool vec = (((uintptr_t)proof | proof_pitch) % 4) == 0 && ((uintptr_t)status % 4) == 0 && ((uintptr_t)out % 16) == 0;
+  pack_proof_kernel<<<grid_for(ctx, (n + 3) / 4, 8), kBlock, 0, st>>>(n, proof, proof_pitch, status, out, vec);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return PBH_OK;
 }
 static int launch_unpack_proof(pbh_ctx* ctx, cudaStream_t st, size_t n, const pbh_packed_proof* in, const uint32_t* chal_u, uint8_t* proof,
                                size_t proof_pitch, uint8_t* status, uint8_t* chal, size_t chal_pitch, uint8_t* u) {
-  unpack_proof_kernel<<<grid_for(ctx, n, 8), kBlock, 0, st>>>(n, in, chal_u, proof, proof_pitch, status, chal, chal_pitch, u);
+  auto al4 = [](const void* p, size_t pitch) { return !p || (((uintptr_t)p | pitch) % 4) == 0; };
+  const bool vec = al4(proof, proof_pitch) && al4(status, 0) && al4(chal, chal_pitch) && al4(u, 0) && ((uintptr_t)in % 16) == 0;
+  unpack_proof_kernel<<<grid_for(ctx, (n + 3) / 4, 8), kBlock, 0, st>>>(n, in, chal_u, proof, proof_pitch, status, chal, chal_pitch, u, vec);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return PBH_OK;

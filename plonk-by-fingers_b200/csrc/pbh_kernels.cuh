@@ -216,6 +216,7 @@ struct ProveTmaSmem {
   alignas(128) uint8_t out[2][27][kTile];
   alignas(8) uint64_t full[2];
   uint32_t tile_of_stage[2];                // dynamic tile scheduler: tile index staged in each buffer
+  alignas(8) unsigned long long digest_part[kTile / 32];   // per-warp digest sums, folded into ONE atomic per block
   Tables T;
 };
 
@@ -345,10 +346,21 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
     }
   }
   if (tid == 0) tma::store_wait_all();
-  if (digest_out != nullptr) digest_flush(digest_acc, digest_out);   // one atomic per warp per launch
+  if (digest_out != nullptr) {
+    // ONE atomic per block: 2368 same-address atomics (one per warp) at the end of a 2^20-item launch serialise in L2 for
+    // microseconds; 296 do not
+    for (int o = 16; o > 0; o >>= 1) digest_acc += __shfl_down_sync(0xFFFFFFFFu, digest_acc, o);
+    if ((tid & 31) == 0) S.digest_part[tid >> 5] = digest_acc;
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long sum = 0;
+#pragma unroll
+      for (int k = 0; k < kTile / 32; k++) sum += S.digest_part[k];
+      atomicAdd(digest_out, sum);
+    }
+  }
   const bool replicate = PW.n != 0 && digest_out != nullptr;
-  if (replicate) __syncthreads();                                    // every warp's digest atomic precedes thread 0's fence in leave
-  const bool last = tile_scheduler_leave(tile_counter);
+  const bool last = tile_scheduler_leave(tile_counter);              // thread 0: its digest atomic precedes the fence in leave
   if (replicate && last) {
     // the launch's digest is complete: the last block pushes it to the same offset of every peer's window
     __threadfence();

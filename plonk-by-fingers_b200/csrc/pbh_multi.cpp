@@ -191,6 +191,20 @@ int pbh_multi_verify_batch(pbh_multi* m, size_t n, const uint8_t* proof, size_t 
   });
 }
 
+int pbh_multi_prove_packed(pbh_multi* m, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out) {
+  if (!m) return PBH_ERR_BAD_ARGUMENT;
+  if (n == 0) return PBH_OK;
+  if (!in || !out) return mfail(m, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  return for_each_shard(m, n, [&](pbh_ctx* ctx, size_t lo, size_t cnt) { return pbh_prove_packed(ctx, cnt, in + lo, out + lo); });
+}
+
+int pbh_multi_verify_packed(pbh_multi* m, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result) {
+  if (!m) return PBH_ERR_BAD_ARGUMENT;
+  if (n == 0) return PBH_OK;
+  if (!proofs || !chal_u || !result) return mfail(m, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  return for_each_shard(m, n, [&](pbh_ctx* ctx, size_t lo, size_t cnt) { return pbh_verify_packed(ctx, cnt, proofs + lo, chal_u + lo, result + lo); });
+}
+
 int pbh_multi_prove_verify_sharded(pbh_multi* m, uint64_t n_total, uint64_t first_index, uint64_t seed, int dist, uint8_t* bitmap_out,
                                    uint64_t* digests_out, uint64_t* total_digest_out, uint64_t* accepted_out, float* ms_out) {
   if (!m) return PBH_ERR_BAD_ARGUMENT;

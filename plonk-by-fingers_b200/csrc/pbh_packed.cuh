@@ -56,6 +56,7 @@ static_assert(kPackedTablesHost.pt_x[kPackedTablesHost.first[1]] == 1 && kPacked
 
 constexpr uint32_t kPow17_5 = 1419857u, kPow17_6 = 24137569u, kPow17_7 = 410338673u;
 constexpr uint32_t kStatusShift = 29, kEvalMask = (1u << 29) - 1;
+constexpr uint32_t kPow102_4 = 108243216u;   // 102^4
 
 PBH_PK_HD uint32_t div17(uint32_t x) {
 #if defined(__CUDA_ARCH__)
@@ -121,7 +122,7 @@ PBH_PK_HD uint8_t code_to_status(uint32_t c) { return c <= 5 ? (uint8_t)c : c ==
 // bits) gets status code 6; whenever the status code is not 0 the two payload words are zero.
 PBH_PK_HD void pack_proof_item(const PackedTables& T, const uint8_t p[27], uint8_t status, uint32_t out[3]) {
   bool ok = (p[PBH_PROOF_INF_PLANE + 1] & 0xFEu) == 0;
-  uint64_t P = 0;
+  uint32_t code_of[9];
 #pragma unroll
   for (int k = 8; k >= 0; k--) {
     const uint32_t x = p[2 * k], y = p[2 * k + 1];
@@ -136,8 +137,12 @@ PBH_PK_HD void pack_proof_item(const PackedTables& T, const uint8_t p[27], uint8
       ok = ok && y0 != 0xFF && (lo || hi);
       code = T.first[xs] + (hi ? 1u : 0u);
     }
-    P = P * 102u + code;
+    code_of[k] = code;
   }
+  // digits 0..3 and 4..7 by 32-bit Horner, then P = a + 102^4 (b + 102^4 c)
+  const uint32_t a = ((code_of[3] * 102u + code_of[2]) * 102u + code_of[1]) * 102u + code_of[0];
+  const uint32_t b = ((code_of[7] * 102u + code_of[6]) * 102u + code_of[5]) * 102u + code_of[4];
+  uint64_t P = ((uint64_t)code_of[8] * kPow102_4 + b) * kPow102_4 + a;
   uint32_t E = 0;
 #pragma unroll
   for (int k = 6; k >= 0; k--) {
@@ -161,12 +166,20 @@ PBH_PK_HD void unpack_proof_item(const PackedTables& T, const uint32_t in[3], ui
 #pragma unroll
   for (int k = 0; k < 27; k++) p[k] = 0;
   if (sc != 0) return;
-  uint64_t P = (uint64_t)in[0] | ((uint64_t)in[1] << 32);
+  // P = a + 102^4 (b + 102^4 c): two 64-bit divisions by 102^4, then 32-bit digit extraction (a, b < 102^4 < 2^27);
+  // c = floor(P / 102^8) is the ninth digit, whatever its size
+  const uint64_t P = (uint64_t)in[0] | ((uint64_t)in[1] << 32);
+  const uint64_t q1 = P / kPow102_4;
+  uint32_t a = (uint32_t)(P - q1 * kPow102_4);
+  const uint64_t q2 = q1 / kPow102_4;
+  uint32_t b = (uint32_t)(q1 - q2 * kPow102_4);
   uint32_t flags = 0;
 #pragma unroll
   for (int k = 0; k < 9; k++) {
     uint32_t d;
-    if (k < 8) { const uint64_t q = P / 102u; d = (uint32_t)(P - q * 102u); P = q; } else { d = P >= 102u ? 102u : (uint32_t)P; }
+    if (k < 4) { const uint32_t q = a / 102u; d = a - q * 102u; a = q; }
+    else if (k < 8) { const uint32_t q = b / 102u; d = b - q * 102u; b = q; }
+    else d = q2 >= 102u ? 102u : (uint32_t)q2;
     if (d == 0) flags |= 1u << k;
     const uint32_t c = d < 102 ? d : 0;
     p[2 * k] = T.pt_x[c];
@@ -188,75 +201,156 @@ __device__ __forceinline__ void stage_packed_tables(PackedTables* sT) {
   __syncthreads();
 }
 
-// One thread per item: one 128-bit load of the packed input, byte-wide coalesced stores into the planes (a warp writes one
-// 32-byte sector per plane).  Null plane pointers are skipped.
+// FOUR consecutive items per thread: the packed side moves as 128-bit words, the plane side as one 32-bit word per plane
+// (byte lane j = item 4q + j; a warp writes 128 contiguous bytes per plane).  `vec` = every plane base and pitch is a multiple
+// of 4 (the host decides); otherwise, and for the ragged last group, the bytes are stored one by one.  Null plane pointers are
+// skipped.
+__device__ __forceinline__ void store_plane_group(uint8_t* plane, size_t i0, size_t n, uint32_t word, bool vec) {
+  if (vec && i0 + 4 <= n) {
+    *reinterpret_cast<uint32_t*>(plane + i0) = word;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (i0 + j < n) plane[i0 + j] = (uint8_t)(word >> (8 * j));
+  }
+}
+__device__ __forceinline__ uint32_t load_plane_group(const uint8_t* plane, size_t i0, size_t n, bool vec) {
+  if (vec && i0 + 4 <= n) return *reinterpret_cast<const uint32_t*>(plane + i0);
+  uint32_t word = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++)
+    if (i0 + j < n) word |= (uint32_t)plane[i0 + j] << (8 * j);
+  return word;
+}
+
 __global__ void __launch_bounds__(256) unpack_witness_kernel(size_t n, const pbh_packed_witness* __restrict__ in,
                                                              uint8_t* __restrict__ wit, size_t wit_pitch, uint8_t* __restrict__ rnd,
                                                              size_t rand_pitch, uint8_t* __restrict__ chal, size_t chal_pitch,
-                                                             uint8_t* __restrict__ u) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const uint4 q = reinterpret_cast<const uint4*>(in)[i];
-    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-    uint8_t v[27];
-    unpack_witness_item(w, v);
+                                                             uint8_t* __restrict__ u, const bool vec) {
+  const size_t groups = (n + 3) / 4;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t i0 = 4 * g;
+    uint32_t acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; k++) acc[k] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (i0 + j < n) {
+        const uint4 q = reinterpret_cast<const uint4*>(in)[i0 + j];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        uint8_t v[27];
+        unpack_witness_item(w, v);
+#pragma unroll
+        for (int k = 0; k < 27; k++) acc[k] |= (uint32_t)v[k] << (8 * j);
+      }
+    }
     if (wit) {
 #pragma unroll
-      for (int k = 0; k < 12; k++) wit[(size_t)k * wit_pitch + i] = v[k];
+      for (int k = 0; k < 12; k++) store_plane_group(wit + (size_t)k * wit_pitch, i0, n, acc[k], vec);
     }
     if (rnd) {
 #pragma unroll
-      for (int k = 0; k < 9; k++) rnd[(size_t)k * rand_pitch + i] = v[12 + k];
+      for (int k = 0; k < 9; k++) store_plane_group(rnd + (size_t)k * rand_pitch, i0, n, acc[12 + k], vec);
     }
     if (chal) {
 #pragma unroll
-      for (int k = 0; k < 5; k++) chal[(size_t)k * chal_pitch + i] = v[21 + k];
+      for (int k = 0; k < 5; k++) store_plane_group(chal + (size_t)k * chal_pitch, i0, n, acc[21 + k], vec);
     }
-    if (u) u[i] = v[26];
+    if (u) store_plane_group(u, i0, n, acc[26], vec);
   }
 }
 
-// proof planes + status -> 12-byte packed proofs (three 32-bit stores per item; a warp writes 384 contiguous bytes)
+// proof planes + status -> 12-byte packed proofs: four items = 48 contiguous bytes = three 128-bit stores (`vec` also requires
+// `out` to be 16-byte aligned)
 __global__ void __launch_bounds__(256) pack_proof_kernel(size_t n, const uint8_t* __restrict__ proof, size_t proof_pitch,
-                                                         const uint8_t* __restrict__ status, pbh_packed_proof* __restrict__ out) {
+                                                         const uint8_t* __restrict__ status, pbh_packed_proof* __restrict__ out, const bool vec) {
   __shared__ PackedTables sT;
   stage_packed_tables(&sT);
   uint32_t* o = reinterpret_cast<uint32_t*>(out);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    uint8_t p[27];
+  const size_t groups = (n + 3) / 4;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t i0 = 4 * g;
+    uint32_t pl[27];
 #pragma unroll
-    for (int k = 0; k < 27; k++) p[k] = proof[(size_t)k * proof_pitch + i];
-    uint32_t w[3];
-    pack_proof_item(sT, p, status ? status[i] : (uint8_t)0, w);
-    o[3 * i] = w[0];
-    o[3 * i + 1] = w[1];
-    o[3 * i + 2] = w[2];
+    for (int k = 0; k < 27; k++) pl[k] = load_plane_group(proof + (size_t)k * proof_pitch, i0, n, vec);
+    const uint32_t st = status ? load_plane_group(status, i0, n, vec) : 0u;
+    uint32_t w[12];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint8_t p[27];
+#pragma unroll
+      for (int k = 0; k < 27; k++) p[k] = (uint8_t)(pl[k] >> (8 * j));
+      pack_proof_item(sT, p, (uint8_t)(st >> (8 * j)), &w[3 * j]);
+    }
+    if (vec && i0 + 4 <= n) {
+      uint4* dst = reinterpret_cast<uint4*>(o + 3 * i0);
+      dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (i0 + j < n) { o[3 * (i0 + j)] = w[3 * j]; o[3 * (i0 + j) + 1] = w[3 * j + 1]; o[3 * (i0 + j) + 2] = w[3 * j + 2]; }
+    }
   }
 }
 
 // packed proofs (+ the challenges-and-u words) -> the verifier's planes.  Null pointers are skipped.
 __global__ void __launch_bounds__(256) unpack_proof_kernel(size_t n, const pbh_packed_proof* __restrict__ in, const uint32_t* __restrict__ chal_u,
                                                            uint8_t* __restrict__ proof, size_t proof_pitch, uint8_t* __restrict__ status,
-                                                           uint8_t* __restrict__ chal, size_t chal_pitch, uint8_t* __restrict__ u) {
+                                                           uint8_t* __restrict__ chal, size_t chal_pitch, uint8_t* __restrict__ u, const bool vec) {
   __shared__ PackedTables sT;
   stage_packed_tables(&sT);
   const uint32_t* src = reinterpret_cast<const uint32_t*>(in);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+  const size_t groups = (n + 3) / 4;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+    const size_t i0 = 4 * g;
     if (in && proof) {
-      const uint32_t w[3] = {src[3 * i], src[3 * i + 1], src[3 * i + 2]};
-      uint8_t p[27], st;
-      unpack_proof_item(sT, w, p, &st);
+      uint32_t w[12];
+      if (vec && i0 + 4 <= n) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + 3 * i0);
+        const uint4 a = s4[0], b = s4[1], c = s4[2];
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w; w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+      } else {
 #pragma unroll
-      for (int k = 0; k < 27; k++) proof[(size_t)k * proof_pitch + i] = p[k];
-      if (status) status[i] = st;
+        for (int j = 0; j < 4; j++) {
+          const bool in_range = i0 + j < n;
+          w[3 * j] = in_range ? src[3 * (i0 + j)] : 0u;
+          w[3 * j + 1] = in_range ? src[3 * (i0 + j) + 1] : 0u;
+          w[3 * j + 2] = in_range ? src[3 * (i0 + j) + 2] : 0u;
+        }
+      }
+      uint32_t acc[27], st_acc = 0;
+#pragma unroll
+      for (int k = 0; k < 27; k++) acc[k] = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint8_t p[27], st;
+        unpack_proof_item(sT, &w[3 * j], p, &st);
+#pragma unroll
+        for (int k = 0; k < 27; k++) acc[k] |= (uint32_t)p[k] << (8 * j);
+        st_acc |= (uint32_t)st << (8 * j);
+      }
+#pragma unroll
+      for (int k = 0; k < 27; k++) store_plane_group(proof + (size_t)k * proof_pitch, i0, n, acc[k], vec);
+      if (status) store_plane_group(status, i0, n, st_acc, vec);
     }
     if (chal_u) {
-      uint8_t v[6];
-      unpack_chal_u(chal_u[i], v);
+      uint32_t acc[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (i0 + j < n) {
+          uint8_t v[6];
+          unpack_chal_u(chal_u[i0 + j], v);
+#pragma unroll
+          for (int k = 0; k < 6; k++) acc[k] |= (uint32_t)v[k] << (8 * j);
+        }
+      }
       if (chal) {
 #pragma unroll
-        for (int k = 0; k < 5; k++) chal[(size_t)k * chal_pitch + i] = v[k];
+        for (int k = 0; k < 5; k++) store_plane_group(chal + (size_t)k * chal_pitch, i0, n, acc[k], vec);
       }
-      if (u) u[i] = v[5];
+      if (u) store_plane_group(u, i0, n, acc[5], vec);
     }
   }
 }

@@ -52,7 +52,7 @@ pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_
 pbh_gt_mul_batch pbh_gt_pow600_batch pbh_poly_divrem_batch pbh_poly_addsub_ragged_batch
 pbh_prove_packed pbh_verify_packed pbh_prove_packed_async pbh_verify_packed_async pbh_prove_verify_packed pbh_unpack_witness_dev
 pbh_pack_proof_dev pbh_unpack_proof_dev pbh_pack_witness_host pbh_unpack_witness_host pbh_pack_chal_u_host pbh_pack_proofs_host
-pbh_unpack_proofs_host pbh_window_create pbh_window_attach pbh_window_attach_ptrs pbh_window_share pbh_window_destroy""".split()
+pbh_unpack_proofs_host pbh_window_create pbh_window_attach pbh_window_attach_ptrs pbh_window_share pbh_window_destroy pbh_multi_prove_packed pbh_multi_verify_packed""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -951,6 +951,19 @@ class MultiContext:
                                              C.c_void_p(U.ptr), C.c_void_p(Rs.ptr), C.c_void_p(G.ptr if G else None), C.c_size_t(G.pitch if G else 0))
         self._check(rc, "pbh_multi_verify_batch")
         return (result, gt) if want_gt else result
+
+    def prove_packed(self, packed_in):
+        pin = Context._packed(packed_in, PACKED_WITNESS, "packed_in"); n = pin.shape[0]
+        out = np.zeros(n, dtype=PACKED_PROOF)
+        self._check(self.lib.pbh_multi_prove_packed(self.h, C.c_size_t(n), C.c_void_p(pin.ctypes.data), C.c_void_p(out.ctypes.data)), "pbh_multi_prove_packed")
+        return out
+
+    def verify_packed(self, proofs, chal_u):
+        prf = Context._packed(proofs, PACKED_PROOF, "proofs"); cu = Context._packed(chal_u, np.dtype("<u4"), "chal_u")
+        res = np.zeros(prf.shape[0], dtype=np.uint8)
+        self._check(self.lib.pbh_multi_verify_packed(self.h, C.c_size_t(prf.shape[0]), C.c_void_p(prf.ctypes.data), C.c_void_p(cu.ctypes.data),
+                                                     C.c_void_p(res.ctypes.data)), "pbh_multi_verify_packed")
+        return res
 
     def prove_verify_sharded(self, n_total, first_index=0, seed=0xB200, dist=DIST_FULLPATH):
         """-> dict(bitmap uint8[ceil(n/8)], digests uint64[n_dev], total_digest int, accepted int, ms float)."""

@@ -121,6 +121,15 @@ extern "C" {
                                  chal: *const u8, chal_pitch: usize, proof: *mut u8, proof_pitch: usize, status: *mut u8) -> c_int;
     pub fn pbh_multi_verify_batch(m: *mut pbh_multi, n: usize, proof: *const u8, proof_pitch: usize, chal: *const u8,
                                   chal_pitch: usize, u: *const u8, result: *mut u8, gt: *mut u8, gt_pitch: usize) -> c_int;
+    pub fn pbh_multi_prove_packed(m: *mut pbh_multi, n: usize, input: *const PackedWitness, out: *mut PackedProof) -> c_int;
+    pub fn pbh_multi_verify_packed(m: *mut pbh_multi, n: usize, proofs: *const PackedProof, chal_u: *const u32, result: *mut u8) -> c_int;
+    // peer windows: the shard summaries stored into every peer's buffer by the kernels that produce them
+    pub fn pbh_window_create(ctx: *mut pbh_ctx, bytes_per_rank: usize, rank: c_int, world: c_int, base_out: *mut *mut c_void,
+                             handle_out: *mut u8) -> c_int;
+    pub fn pbh_window_attach(ctx: *mut pbh_ctx, handles: *const u8) -> c_int;
+    pub fn pbh_window_attach_ptrs(ctx: *mut pbh_ctx, bases: *const *mut c_void) -> c_int;
+    pub fn pbh_window_share(owner: *mut pbh_ctx, other: *mut pbh_ctx) -> c_int;
+    pub fn pbh_window_destroy(ctx: *mut pbh_ctx) -> c_int;
     pub fn pbh_multi_prove_verify_sharded(m: *mut pbh_multi, n_total: u64, first_index: u64, seed: u64, dist: c_int,
                                           bitmap_out: *mut u8, digests_out: *mut u64, total_digest_out: *mut u64,
                                           accepted_out: *mut u64, ms_out: *mut c_float) -> c_int;

@@ -258,6 +258,10 @@ def test_multi_device_context(gpu_ctx, oracle):
             v, g = mc.verify_batch(p, c, u, want_gt=True)
             vo, go = oracle.verify_batch(po, c, u, threads=8)
             assert np.array_equal(v, vo) and np.array_equal(g, go)
+            pk = mc.prove_packed(pbh_b200.pack_witness(w, r, c, u))           # the same shards over packed records
+            want = oracle.packed_pack_proofs(po, so)
+            assert np.array_equal(np.stack([pk["points_lo"], pk["points_hi"], pk["evals_status"]], axis=1), want)
+            assert np.array_equal(mc.verify_packed(pk, pbh_b200.pack_chal_u(c, u)), vo)
             for n_total, first in ((300000 + 40, 0), (4096, 123456 * 8), (77, 8)):
                 out = mc.prove_verify_sharded(n_total, first_index=first, seed=0xB200)
                 gw, gr, gc, gu = ctx.generate_inputs(n_total, first_index=first, seed=0xB200, dist=1)

@@ -76,10 +76,11 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-                try:
-                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
-                except Exception:
-                    pass
+                if len(self.samples) % 4 == 2:      # NVML queries take milliseconds each: power only every fourth round
+                    try:
+                        self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+                    except Exception:
+                        pass
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
@@ -636,6 +637,12 @@ def main():
             d_["cu"][...] = pbh_b200.pack_chal_u(host_in[2], host_in[3])
             pk_sets.append(d_)
 
+        pgk = dict(pin=np.array(packed_in0), cu=pbh_b200.pack_chal_u(host_in[2], host_in[3]), out=np.zeros(n, pbh_b200.PACKED_PROOF), res=np.zeros(n, np.uint8))
+
+        def pageable_packed_step(i):
+            ctx.prove_packed(pgk["pin"], out=pgk["out"])
+            ctx.verify_packed(pgk["out"], pgk["cu"], result=pgk["res"])
+
         def packed_lanes_step(i):
             s_ = pk_sets[i % 2]
             ctx.lane_sync(i % 2)
@@ -646,7 +653,7 @@ def main():
             s_ = pk_sets[0]
             ctx.prove_verify_packed(s_["pin"], out=s_["out"], result=s_["res"])
 
-        for fn in (lanes_step, pinned_step, pageable_step, fused_step, packed_lanes_step, packed_fused_step):
+        for fn in (lanes_step, pinned_step, pageable_step, fused_step, packed_lanes_step, packed_fused_step, pageable_packed_step):
             for i in range(3):
                 fn(i)
             ctx.sync()
@@ -677,6 +684,12 @@ def main():
                         np.array_equal(s_["result"], ref_result) for s_ in sets)
         dt_pinned = timed(pinned_step, ksteps)
         dt_pageable = timed(pageable_step, max(3, ksteps // 2))
+        dt_pageable_packed = timed(pageable_packed_step, max(3, ksteps // 2))
+        packed_equal = packed_equal and np.array_equal(pgk["out"], ref_packed) and np.array_equal(pgk["res"], ref_result0)
+        ctx.set_option(pbh_b200.OPT_HOST_STAGE, 0)
+        pageable_step(0)
+        dt_pageable_driver = timed(pageable_step, 3)
+        ctx.set_option(pbh_b200.OPT_HOST_STAGE, 1)
         e2e_equal = e2e_equal and np.array_equal(pg["proof"], ref_proof) and np.array_equal(pg["result"], ref_result)
         dt_fused = timed(fused_step, ksteps)
         per = lambda dt, st: {"value": n * world * st / dt, "ms_per_step": 1e3 * dt / st}
@@ -697,13 +710,16 @@ def main():
                                          api="pbh_prove_verify_packed (extension: the proof does not cross PCIe twice)"),
                "lane_modes": lane_modes,
                "two_sync_calls_pinned": dict(per(dt_pinned, ksteps), api="pbh_prove_batch then pbh_verify_batch, page-locked buffers"),
-               "two_sync_calls_pageable": dict(per(dt_pageable, max(3, ksteps // 2)), api="pbh_prove_batch then pbh_verify_batch, pageable numpy buffers (staged chunks)"),
+               "two_sync_calls_pageable": dict(per(dt_pageable, max(3, ksteps // 2)), api="pbh_prove_batch then pbh_verify_batch, pageable numpy buffers (what a plain Vec<u8> is): "
+                                               "staged chunks through page-locked mirrors filled by the library's copy threads (PBH_OPT_HOST_STAGE 1)",
+                                               driver_staging=dict(per(dt_pageable_driver, 3), api="the same with PBH_OPT_HOST_STAGE 0: the driver stages the pageable copies")),
+               "two_sync_calls_pageable_packed": dict(per(dt_pageable_packed, max(3, ksteps // 2)), api="pbh_prove_packed then pbh_verify_packed, pageable numpy buffers"),
                "fused_call": dict(per(dt_fused, ksteps), h2d_bytes_per_step=n * 27 * world, d2h_bytes_per_step=n * 29 * world,
                                   api="pbh_prove_verify_batch (extension: the proof does not cross PCIe twice)")}
         for s_ in sets + pk_sets:
             for a in s_.values():
                 ctx.host_free(a)
-        del sets, pg, pk_sets
+        del sets, pg, pk_sets, pgk
 
     # ---- BASELINE.json configs[4]: 2^28 witnesses in total, sharded over the N ranks (strong scaling), ONE all-gather of
     # the verdict bitmaps + digests at the end of each pass

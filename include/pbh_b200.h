@@ -151,6 +151,11 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
  * 0 = in place both ways, 1 = copy-engine upload + in-place stores, 3 = copy engine both ways (default: measured 1.28 ms per
  * 2^20 prove + verify pairs on PCIe Gen5 x16, i.e. the upload link at 48 GB/s, against 1.33 ms for mode 1 and 1.48 ms for 0).  Buffers that are page-locked but not mapped always go through the copy engine. */
 #define PBH_OPT_LANE_MODE 8
+/* PBH_OPT_HOST_STAGE: PAGEABLE caller memory (a plain Vec<u8> / malloc) in the synchronous host-pointer calls is staged by the
+ * library itself - a small pool of host threads copies row segments between the caller's memory and page-locked mirrors of
+ * the staging buffers, which the copy engines then move asynchronously - (1, default) or left to the driver's own staging
+ * of pageable copies, which runs on the calling thread at about 12 GB/s (0).  Page-locked memory never takes this path. */
+#define PBH_OPT_HOST_STAGE 9
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */

@@ -10,6 +10,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <thread>
+#include <vector>
 #include <cctype>
 #include <cstdio>
 #include <cstring>
@@ -34,6 +37,63 @@ void set_global_error(const std::string& e) { std::lock_guard<std::mutex> l(g_er
 static constexpr size_t kChunkMax = (size_t)1 << 20;   // upper bound of the staged chunk (staging buffers are sized for it lazily)
 static constexpr int kSlots = 4;
 static constexpr uint32_t kCounterRing = 4096, kCounterGraphPool = 32768;   // tile-counter pairs (8 bytes each)
+
+// ---- pageable host buffers ----------------------------------------------------------------------------------------------
+// A copy between PAGEABLE host memory and the device is staged by the driver through its own page-locked buffer, on the
+// calling thread, at ~12 GB/s - a fifth of the link.  The staged entry points therefore do the staging themselves: every
+// staging slot has a page-locked MIRROR of its device buffer; inputs are copied into the mirror by a small pool of host
+// threads (row segments in parallel) and travel from there with an asynchronous copy, outputs land in the mirror and are
+// copied out to the caller's memory by the same pool once the slot's stream has drained (before the slot is reused, and at
+// the end of the call).  Page-locked caller memory bypasses all of this.
+struct CopyTask { uint8_t* dst; const uint8_t* src; size_t bytes; };
+class CopyPool {
+ public:
+  explicit CopyPool(int workers) {
+    for (int i = 0; i < workers; i++) threads_.emplace_back([this] { loop(); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (std::thread& t : threads_) t.join();
+  }
+  // runs every task (the caller works too) and returns when all are done
+  void run(std::vector<CopyTask>& tasks) {
+    if (tasks.empty()) return;
+    std::unique_lock<std::mutex> l(m_);
+    tasks_.swap(tasks);
+    next_ = 0;
+    pending_ = tasks_.size();
+    cv_.notify_all();
+    work(l);
+    done_.wait(l, [this] { return pending_ == 0; });
+    tasks_.clear();
+    next_ = 0;
+  }
+ private:
+  void work(std::unique_lock<std::mutex>& l) {
+    while (next_ < tasks_.size()) {
+      const CopyTask t = tasks_[next_++];
+      l.unlock();
+      std::memcpy(t.dst, t.src, t.bytes);
+      l.lock();
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    std::unique_lock<std::mutex> l(m_);
+    for (;;) {
+      cv_.wait(l, [this] { return stop_ || next_ < tasks_.size(); });
+      if (stop_) return;
+      work(l);
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  std::vector<CopyTask> tasks_;
+  size_t next_ = 0, pending_ = 0;
+  bool stop_ = false;
+  std::vector<std::thread> threads_;
+};
 
 struct pbh_ctx {
   int device = 0;
@@ -62,6 +122,11 @@ struct pbh_ctx {
   uint8_t* slot_buf[kSlots] = {};
   size_t slot_bytes = 0;
   uint64_t launches = 0;
+  uint8_t* slot_mirror[kSlots] = {};       // page-locked mirrors of slot_buf for pageable caller memory (allocated on first use)
+  bool slot_dirty[kSlots] = {};            // the slot's mirror is in use by copies in flight (sync before the slot is reused)
+  std::vector<CopyTask> slot_out[kSlots];  // copy-outs mirror -> caller memory, due once the slot's stream has drained
+  CopyPool* pool = nullptr;
+  int host_stage = 1;                      // PBH_OPT_HOST_STAGE: own staging of pageable memory (1) or the driver's (0)
   uint8_t* lane_buf[kSlots] = {};          // whole-batch staging of the asynchronous lanes (PBH_OPT_LANE_MODE 1 and 3)
   size_t lane_bytes[kSlots] = {};
   int lane_mode = 3;                       // PBH_OPT_LANE_MODE
@@ -91,6 +156,12 @@ struct pbh_ctx {
       (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
       return PBH_ERR_CUDA;                                                                       \
     }                                                                                            \
+  } while (0)
+
+#define PBH_TRY(expr)              \
+  do {                             \
+    int rc__ = (expr);             \
+    if (rc__ != PBH_OK) return rc__; \
   } while (0)
 
 static int device_numa_node(int device);
@@ -194,6 +265,10 @@ void pbh_ctx_destroy(pbh_ctx* ctx) {
   if (ctx->d_pairs) cudaFree(ctx->d_pairs);
   if (ctx->d_wtab) cudaFree(ctx->d_wtab);
   window_release(ctx);
+  delete ctx->pool;
+  ctx->pool = nullptr;
+  for (int s = 0; s < kSlots; s++)
+    if (ctx->slot_mirror[s]) { cudaFreeHost(ctx->slot_mirror[s]); ctx->slot_mirror[s] = nullptr; }
   if (ctx->d_tile_counters) cudaFree(ctx->d_tile_counters);
   delete ctx;
 }
@@ -226,6 +301,7 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
     ctx->lane_mode = value;
     return PBH_OK;
   }
+  if (option == PBH_OPT_HOST_STAGE) { ctx->host_stage = value != 0; return PBH_OK; }
   if (option == PBH_OPT_CHUNK_LOG2) {
     if (value < 8 || value > 20) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "chunk log2 must be in [8, 20]");
     ctx->chunk = (size_t)1 << value;
@@ -588,6 +664,7 @@ static int ensure_slots(pbh_ctx* ctx, size_t bytes_per_item) {
   if (ctx->slot_bytes >= need) return PBH_OK;
   for (int s = 0; s < kSlots; s++) {
     if (ctx->slot_buf[s]) { CUDA_TRY(ctx, cudaFree(ctx->slot_buf[s])); ctx->slot_buf[s] = nullptr; }
+    if (ctx->slot_mirror[s]) { CUDA_TRY(ctx, cudaFreeHost(ctx->slot_mirror[s])); ctx->slot_mirror[s] = nullptr; }
   }
   ctx->slot_bytes = 0;
   for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaMalloc(&ctx->slot_buf[s], need));
@@ -602,6 +679,78 @@ static int ensure_slots(pbh_ctx* ctx, size_t bytes_per_item) {
 // Every body lays its planes out inside kStagePlanes rows of C bytes; the static_asserts next to each body tie its
 // plane offsets to this budget.
 static constexpr size_t kStagePlanes = 128;
+static bool host_pinned(const uint8_t* p);
+static int slot_of(const pbh_ctx* ctx, const uint8_t* base) {
+  for (int s = 0; s < kSlots; s++)
+    if (ctx->slot_buf[s] && ctx->slot_buf[s] == base) return s;
+  return -1;
+}
+// the page-locked mirror of slot s (and the thread pool), created on first use
+static int ensure_mirror(pbh_ctx* ctx, int s) {
+  if (!ctx->slot_mirror[s]) CUDA_TRY(ctx, cudaHostAlloc(&ctx->slot_mirror[s], ctx->slot_bytes, cudaHostAllocDefault));
+  if (!ctx->pool) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    ctx->pool = new CopyPool((int)std::min(6u, std::max(1u, hw / 4)));
+  }
+  return PBH_OK;
+}
+static void row_tasks(std::vector<CopyTask>& out, uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, size_t width, size_t rows) {
+  constexpr size_t kSeg = (size_t)256 << 10;   // a row is cut into 256 KiB segments so that a single long row also spreads over the pool
+  for (size_t r = 0; r < rows; r++)
+    for (size_t o = 0; o < width; o += kSeg) out.push_back({dst + r * dpitch + o, src + r * spitch + o, std::min(kSeg, width - o)});
+}
+// `rows` rows of `width` bytes from caller memory (pitch hpitch) into the staging buffer `base` at dev (pitch dpitch), on st
+static int stage_h2d(pbh_ctx* ctx, uint8_t* base, cudaStream_t st, void* dev_, size_t dpitch, const void* host_, size_t hpitch, size_t width,
+                     size_t rows) {
+  uint8_t* dev = static_cast<uint8_t*>(dev_);
+  const uint8_t* host = static_cast<const uint8_t*>(host_);
+  if (rows == 1) dpitch = hpitch = width;
+  const int s = ctx->host_stage ? slot_of(ctx, base) : -1;
+  if (s < 0 || host_pinned(host)) {
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(dev, dpitch, host, hpitch, width, rows, cudaMemcpyHostToDevice, st));
+    return PBH_OK;
+  }
+  PBH_TRY(ensure_mirror(ctx, s));
+  uint8_t* mir = ctx->slot_mirror[s] + (dev - base);
+  std::vector<CopyTask> tasks;
+  row_tasks(tasks, mir, dpitch, host, hpitch, width, rows);
+  ctx->pool->run(tasks);
+  ctx->slot_dirty[s] = true;
+  CUDA_TRY(ctx, cudaMemcpy2DAsync(dev, dpitch, mir, dpitch, width, rows, cudaMemcpyHostToDevice, st));
+  return PBH_OK;
+}
+// the reverse: results at dev go to caller memory, directly (page-locked) or through the mirror (copied out by flush_slot)
+static int stage_d2h(pbh_ctx* ctx, uint8_t* base, cudaStream_t st, void* host_, size_t hpitch, const void* dev_, size_t dpitch, size_t width,
+                     size_t rows) {
+  const uint8_t* dev = static_cast<const uint8_t*>(dev_);
+  uint8_t* host = static_cast<uint8_t*>(host_);
+  if (rows == 1) dpitch = hpitch = width;
+  const int s = ctx->host_stage ? slot_of(ctx, base) : -1;
+  if (s < 0 || host_pinned(host)) {
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(host, hpitch, dev, dpitch, width, rows, cudaMemcpyDeviceToHost, st));
+    return PBH_OK;
+  }
+  PBH_TRY(ensure_mirror(ctx, s));
+  uint8_t* mir = ctx->slot_mirror[s] + (dev - base);
+  CUDA_TRY(ctx, cudaMemcpy2DAsync(mir, dpitch, dev, dpitch, width, rows, cudaMemcpyDeviceToHost, st));
+  row_tasks(ctx->slot_out[s], host, hpitch, mir, dpitch, width, rows);
+  ctx->slot_dirty[s] = true;
+  return PBH_OK;
+}
+// waits for slot s and delivers the outputs parked in its mirror
+static int flush_slot(pbh_ctx* ctx, int s) {
+  if (!ctx->slot_dirty[s]) return PBH_OK;
+  cudaError_t e = cudaStreamSynchronize(ctx->slot_stream[s]);
+  ctx->slot_dirty[s] = false;
+  if (e != cudaSuccess) {
+    ctx->slot_out[s].clear();
+    ctx->last_error = std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e);
+    return PBH_ERR_CUDA;
+  }
+  if (!ctx->slot_out[s].empty()) ctx->pool->run(ctx->slot_out[s]);
+  ctx->slot_out[s].clear();
+  return PBH_OK;
+}
 template <class Body>
 static int for_each_chunk(pbh_ctx* ctx, size_t n, Body body, bool wait = true) {
   int rc = ensure_slots(ctx, kStagePlanes);
@@ -610,7 +759,12 @@ static int for_each_chunk(pbh_ctx* ctx, size_t n, Body body, bool wait = true) {
   size_t k = 0;
   for (size_t lo = 0; lo < n && rc == PBH_OK; lo += C, k++) {
     const int s = (int)(k % kSlots);
-    rc = body(lo, std::min(C, n - lo), C, ctx->slot_buf[s], ctx->slot_stream[s]);
+    rc = flush_slot(ctx, s);          // the slot's mirror is about to be overwritten
+    if (rc == PBH_OK) rc = body(lo, std::min(C, n - lo), C, ctx->slot_buf[s], ctx->slot_stream[s]);
+  }
+  for (int s = 0; s < kSlots; s++) {
+    if (rc == PBH_OK) rc = flush_slot(ctx, s);
+    else { ctx->slot_out[s].clear(); }
   }
   // Also on failure: copies that read or write the caller's buffers may still be in flight, and the caller is free to
   // release them as soon as this call returns.
@@ -684,14 +838,14 @@ int pbh_prove_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pitch
   }
   return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
+    PBH_TRY(stage_h2d(ctx, base, st, d_wit, C, wit + lo, wit_pitch, m, 12));
+    PBH_TRY(stage_h2d(ctx, base, st, d_rnd, C, rnd + lo, rand_pitch, m, 9));
+    PBH_TRY(stage_h2d(ctx, base, st, d_chal, C, chal + lo, chal_pitch, m, 5));
     ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
     int rc = launch_prove(ctx, st, A);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
+    PBH_TRY(stage_d2h(ctx, base, st, proof + lo, proof_pitch, d_proof, C, m, 27));
+    PBH_TRY(stage_d2h(ctx, base, st, status + lo, 0, d_status, 0, m, 1));
     return PBH_OK;
   });
 }
@@ -718,14 +872,14 @@ int pbh_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t proof_
   }
   return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_proof = base, *d_chal = base + 27 * C, *d_u = base + 32 * C, *d_res = base + 33 * C, *d_gt = base + 34 * C;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
+    PBH_TRY(stage_h2d(ctx, base, st, d_proof, C, proof + lo, proof_pitch, m, 27));
+    PBH_TRY(stage_h2d(ctx, base, st, d_chal, C, chal + lo, chal_pitch, m, 5));
+    PBH_TRY(stage_h2d(ctx, base, st, d_u, 0, u + lo, 0, m, 1));
     VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, gt ? d_gt : nullptr, C, m, nullptr};
     int rc = launch_verify(ctx, st, A);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
-    if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, C, m, 4, cudaMemcpyDeviceToHost, st));
+    PBH_TRY(stage_d2h(ctx, base, st, result + lo, 0, d_res, 0, m, 1));
+    if (gt) PBH_TRY(stage_d2h(ctx, base, st, gt + lo, gt_pitch, d_gt, C, m, 4));
     return PBH_OK;
   });
 }
@@ -743,19 +897,19 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
   return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C,
             *d_u = base + 54 * C, *d_res = base + 55 * C;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_chal, C, chal + lo, chal_pitch, m, 5, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_u, u + lo, m, cudaMemcpyHostToDevice, st));
+    PBH_TRY(stage_h2d(ctx, base, st, d_wit, C, wit + lo, wit_pitch, m, 12));
+    PBH_TRY(stage_h2d(ctx, base, st, d_rnd, C, rnd + lo, rand_pitch, m, 9));
+    PBH_TRY(stage_h2d(ctx, base, st, d_chal, C, chal + lo, chal_pitch, m, 5));
+    PBH_TRY(stage_h2d(ctx, base, st, d_u, 0, u + lo, 0, m, 1));
     ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
     int rc = launch_prove(ctx, st, A);
     if (rc) return rc;
     VerifyArgs V{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
     rc = launch_verify(ctx, st, V);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
+    PBH_TRY(stage_d2h(ctx, base, st, proof + lo, proof_pitch, d_proof, C, m, 27));
+    PBH_TRY(stage_d2h(ctx, base, st, status + lo, 0, d_status, 0, m, 1));
+    PBH_TRY(stage_d2h(ctx, base, st, result + lo, 0, d_res, 0, m, 1));
     return PBH_OK;
   });
 }
@@ -1036,14 +1190,14 @@ int pbh_prove_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wit_pi
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_proof = base + 21 * C, *d_status = base + 48 * C, *d_chal = base + 49 * C;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_wit, C, wit + lo, wit_pitch, m, 12, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_rnd, C, rnd + lo, rand_pitch, m, 9, cudaMemcpyHostToDevice, st));
+    PBH_TRY(stage_h2d(ctx, base, st, d_wit, C, wit + lo, wit_pitch, m, 12));
+    PBH_TRY(stage_h2d(ctx, base, st, d_rnd, C, rnd + lo, rand_pitch, m, 9));
     ProveFsArgs F{{d_wit, C, d_rnd, C, nullptr, 0, d_proof, C, d_status, m}, chal_out ? d_chal : nullptr, C};
     int rc = launch_prove_fs(ctx, st, F);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(proof + lo, proof_pitch, d_proof, C, m, 27, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(status + lo, d_status, m, cudaMemcpyDeviceToHost, st));
-    if (chal_out) CUDA_TRY(ctx, cudaMemcpy2DAsync(chal_out + lo, chal_pitch, d_chal, C, m, 6, cudaMemcpyDeviceToHost, st));
+    PBH_TRY(stage_d2h(ctx, base, st, proof + lo, proof_pitch, d_proof, C, m, 27));
+    PBH_TRY(stage_d2h(ctx, base, st, status + lo, 0, d_status, 0, m, 1));
+    if (chal_out) PBH_TRY(stage_d2h(ctx, base, st, chal_out + lo, chal_pitch, d_chal, C, m, 6));
     return PBH_OK;
   });
 }
@@ -1056,13 +1210,13 @@ int pbh_verify_fs_batch(pbh_ctx* ctx, size_t n, const uint8_t* proof, size_t pro
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   return for_each_chunk(ctx, n, [&](size_t lo, size_t m, size_t C, uint8_t* base, cudaStream_t st) -> int {
     uint8_t *d_proof = base, *d_res = base + 27 * C, *d_chal = base + 28 * C, *d_gt = base + 34 * C;
-    CUDA_TRY(ctx, cudaMemcpy2DAsync(d_proof, C, proof + lo, proof_pitch, m, 27, cudaMemcpyHostToDevice, st));
+    PBH_TRY(stage_h2d(ctx, base, st, d_proof, C, proof + lo, proof_pitch, m, 27));
     VerifyFsArgs F{{d_proof, C, nullptr, 0, nullptr, d_res, gt ? d_gt : nullptr, C, m, nullptr}, chal_out ? d_chal : nullptr, C};
     int rc = launch_verify_fs(ctx, st, F);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
-    if (chal_out) CUDA_TRY(ctx, cudaMemcpy2DAsync(chal_out + lo, chal_pitch, d_chal, C, m, 6, cudaMemcpyDeviceToHost, st));
-    if (gt) CUDA_TRY(ctx, cudaMemcpy2DAsync(gt + lo, gt_pitch, d_gt, C, m, 4, cudaMemcpyDeviceToHost, st));
+    PBH_TRY(stage_d2h(ctx, base, st, result + lo, 0, d_res, 0, m, 1));
+    if (chal_out) PBH_TRY(stage_d2h(ctx, base, st, chal_out + lo, chal_pitch, d_chal, C, m, 6));
+    if (gt) PBH_TRY(stage_d2h(ctx, base, st, gt + lo, gt_pitch, d_gt, C, m, 4));
     return PBH_OK;
   });
 }
@@ -1116,7 +1270,7 @@ int pbh_prove_records(pbh_ctx* ctx, size_t n, const pbh_witness_record* in, pbh_
     uint8_t *d_wit = base, *d_rnd = base + 12 * C, *d_chal = base + 21 * C, *d_proof = base + 26 * C, *d_status = base + 53 * C;
     pbh_witness_record* d_in = reinterpret_cast<pbh_witness_record*>(base + 64 * C);
     pbh_proof_record* d_out = reinterpret_cast<pbh_proof_record*>(base + 96 * C);
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in + lo, m * sizeof(pbh_witness_record), cudaMemcpyHostToDevice, st));
+    PBH_TRY(stage_h2d(ctx, base, st, d_in, 0, in + lo, 0, m * sizeof(pbh_witness_record), 1));
     witness_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_in, d_wit, C, d_rnd, C, d_chal, C, nullptr);
     ctx->launches++;
     ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
@@ -1125,7 +1279,7 @@ int pbh_prove_records(pbh_ctx* ctx, size_t n, const pbh_witness_record* in, pbh_
     proof_planes_to_records_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_proof, C, d_status, d_out);
     ctx->launches++;
     CUDA_TRY(ctx, cudaGetLastError());
-    CUDA_TRY(ctx, cudaMemcpyAsync(out + lo, d_out, m * sizeof(pbh_proof_record), cudaMemcpyDeviceToHost, st));
+    PBH_TRY(stage_d2h(ctx, base, st, out + lo, 0, d_out, 0, m * sizeof(pbh_proof_record), 1));
     return PBH_OK;
   });
 }
@@ -1139,15 +1293,15 @@ int pbh_verify_records(pbh_ctx* ctx, size_t n, const pbh_proof_record* proofs, c
     uint8_t *d_proof = base, *d_chal = base + 27 * C, *d_u = base + 32 * C, *d_res = base + 33 * C;
     pbh_witness_record* d_par = reinterpret_cast<pbh_witness_record*>(base + 64 * C);
     pbh_proof_record* d_prf = reinterpret_cast<pbh_proof_record*>(base + 96 * C);
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_prf, proofs + lo, m * sizeof(pbh_proof_record), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_par, params + lo, m * sizeof(pbh_witness_record), cudaMemcpyHostToDevice, st));
+    PBH_TRY(stage_h2d(ctx, base, st, d_prf, 0, proofs + lo, 0, m * sizeof(pbh_proof_record), 1));
+    PBH_TRY(stage_h2d(ctx, base, st, d_par, 0, params + lo, 0, m * sizeof(pbh_witness_record), 1));
     proof_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_prf, d_proof, C, nullptr);
     witness_records_to_planes_kernel<<<grid_for(ctx, m, 8), kBlock, 0, st>>>(m, d_par, nullptr, 0, nullptr, 0, d_chal, C, d_u);
     ctx->launches += 2;
     VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
     int rc = launch_verify(ctx, st, A);
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpyAsync(result + lo, d_res, m, cudaMemcpyDeviceToHost, st));
+    PBH_TRY(stage_d2h(ctx, base, st, result + lo, 0, d_res, 0, m, 1));
     return PBH_OK;
   });
 }
@@ -1218,7 +1372,7 @@ static int packed_prove_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size_
           *d_u = base + 54 * C, *d_res = base + 55 * C;
   pbh_packed_witness* d_in = reinterpret_cast<pbh_packed_witness*>(base + 64 * C);
   pbh_packed_proof* d_out = reinterpret_cast<pbh_packed_proof*>(base + 80 * C);
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_in, in, m * sizeof(pbh_packed_witness), cudaMemcpyHostToDevice, st));
+  PBH_TRY(stage_h2d(ctx, base, st, d_in, 0, in, 0, m * sizeof(pbh_packed_witness), 1));
   int rc = launch_unpack_witness(ctx, st, m, d_in, d_wit, C, d_rnd, C, d_chal, C, result_host ? d_u : nullptr);
   if (rc) return rc;
   ProveArgs A{d_wit, C, d_rnd, C, d_chal, C, d_proof, C, d_status, m};
@@ -1231,8 +1385,8 @@ static int packed_prove_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size_
   }
   rc = launch_pack_proof(ctx, st, m, d_proof, C, d_status, d_out);
   if (rc) return rc;
-  CUDA_TRY(ctx, cudaMemcpyAsync(out, d_out, m * sizeof(pbh_packed_proof), cudaMemcpyDeviceToHost, st));
-  if (result_host) CUDA_TRY(ctx, cudaMemcpyAsync(result_host, d_res, m, cudaMemcpyDeviceToHost, st));
+  PBH_TRY(stage_d2h(ctx, base, st, out, 0, d_out, 0, m * sizeof(pbh_packed_proof), 1));
+  if (result_host) PBH_TRY(stage_d2h(ctx, base, st, result_host, 0, d_res, 0, m, 1));
   return PBH_OK;
 }
 static int packed_verify_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size_t C, size_t m, const pbh_packed_proof* proofs,
@@ -1240,14 +1394,14 @@ static int packed_verify_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size
   uint8_t *d_proof = base + 26 * C, *d_chal = base + 54 * C, *d_u = base + 59 * C, *d_res = base + 60 * C;
   pbh_packed_proof* d_prf = reinterpret_cast<pbh_packed_proof*>(base + 96 * C);
   uint32_t* d_cu = reinterpret_cast<uint32_t*>(base + 108 * C);
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_prf, proofs, m * sizeof(pbh_packed_proof), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(ctx, cudaMemcpyAsync(d_cu, chal_u, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  PBH_TRY(stage_h2d(ctx, base, st, d_prf, 0, proofs, 0, m * sizeof(pbh_packed_proof), 1));
+  PBH_TRY(stage_h2d(ctx, base, st, d_cu, 0, chal_u, 0, m * sizeof(uint32_t), 1));
   int rc = launch_unpack_proof(ctx, st, m, d_prf, d_cu, d_proof, C, nullptr, d_chal, C, d_u);
   if (rc) return rc;
   VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
   rc = launch_verify(ctx, st, A);
   if (rc) return rc;
-  CUDA_TRY(ctx, cudaMemcpyAsync(result, d_res, m, cudaMemcpyDeviceToHost, st));
+  PBH_TRY(stage_d2h(ctx, base, st, result, 0, d_res, 0, m, 1));
   return PBH_OK;
 }
 

@@ -391,3 +391,38 @@ def test_peer_window_replicates_the_summaries(gpu_ctx, oracle):
     finally:
         for c in ranks + [helper]:
             c.close()
+
+
+def test_pageable_staging_by_the_library_and_by_the_driver(gpu_ctx, oracle):
+    """PBH_OPT_HOST_STAGE: pageable caller memory staged through the library's page-locked mirrors + copy threads (1, default)
+    or by the driver (0) gives the same bytes, for byte planes with odd pitches, records and packed records, over several
+    staged chunks and slot reuse (chunk = 2^12 items -> more chunks than staging slots)."""
+    import pbh_b200
+    ctx = gpu_ctx["table"]
+    n = 9 * 4096 + 333
+    w, r, c, u, _ = oracle.generate_inputs(n, seed=123, dist=0, threads=8)
+    po, so = oracle.prove_batch(w, r, c, threads=8)
+    vo, go = oracle.verify_batch(po, c, u, threads=8)
+    wide = np.zeros((12, n + 37), np.uint8); wide[:, 5:5 + n] = w          # odd pitch and offset: pageable AND unaligned
+    ctx.set_option(pbh_b200.OPT_CHUNK_LOG2, 12)
+    try:
+        for stage in (1, 0, 1):
+            ctx.set_option(pbh_b200.OPT_HOST_STAGE, stage)
+            proof = np.full((27, n + 11), 0xEE, np.uint8)
+            status = np.full(n, 0xEE, np.uint8)
+            ctx.prove_batch(wide[:, 5:5 + n], r, c, proof=proof[:, 3:3 + n], status=status)
+            assert np.array_equal(proof[:, 3:3 + n], po) and np.array_equal(status, so), stage
+            assert (proof[:, :3] == 0xEE).all() and (proof[:, 3 + n:] == 0xEE).all()
+            res, gt = ctx.verify_batch(proof[:, 3:3 + n], c, u, want_gt=True)
+            assert np.array_equal(res, vo) and np.array_equal(gt, go), stage
+            p2, s2, r2 = ctx.prove_verify_batch(w, r, c, u)
+            assert np.array_equal(p2, po) and np.array_equal(s2, so) and np.array_equal(r2, vo), stage
+            pk = ctx.prove_packed(pbh_b200.pack_witness(w, r, c, u))
+            want = oracle.packed_pack_proofs(po, so)
+            assert np.array_equal(np.stack([pk["points_lo"], pk["points_hi"], pk["evals_status"]], axis=1), want), stage
+            assert np.array_equal(ctx.verify_packed(pk, pbh_b200.pack_chal_u(c, u)), vo), stage
+            recs = ctx.prove_records(pbh_b200.witness_records(w, r, c, u))
+            assert np.array_equal(pbh_b200.proof_planes(recs)[0], po), stage
+    finally:
+        ctx.set_option(pbh_b200.OPT_HOST_STAGE, 1)
+        ctx.set_option(pbh_b200.OPT_CHUNK_LOG2, 18)

@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--ring", type=int, default=8, help="distinct input/output batches cycled through (L2 defeat)")
     ap.add_argument("--cpu-sample", type=int, default=None)
     ap.add_argument("--e2e-steps", type=int, default=None)
+    ap.add_argument("--e2e-lanes", type=int, default=4, help="batches in flight on the packed end-to-end path (2..4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the full-batch oracle replay")
     ap.add_argument("--no-arith", action="store_true", help="skip timing the PBH_ALGO_ARITH kernels")
     ap.add_argument("--no-fs", action="store_true", help="skip timing the Fiat-Shamir kernels")
@@ -630,7 +631,8 @@ def main():
         # and 13 bytes down per proof + verification instead of 59 and 29
         packed_in0 = pbh_b200.pack_witness(*host_in)              # host-side format conversion, outside the timed region
         pk_sets = []
-        for _ in range(2):
+        L = max(2, min(4, args.e2e_lanes))               # batches in flight (PBH_LANES = 4)
+        for _ in range(L):
             d_ = dict(pin=ctx.host_alloc_as(n, pbh_b200.PACKED_WITNESS), out=ctx.host_alloc_as(n, pbh_b200.PACKED_PROOF),
                       cu=ctx.host_alloc_as(n, "<u4"), res=ctx.host_alloc_as(n, np.uint8))
             d_["pin"][...] = packed_in0
@@ -644,17 +646,17 @@ def main():
             ctx.verify_packed(pgk["out"], pgk["cu"], result=pgk["res"])
 
         def packed_lanes_step(i):
-            s_ = pk_sets[i % 2]
-            ctx.lane_sync(i % 2)
-            ctx.prove_packed_async(i % 2, s_["pin"], s_["out"])
-            ctx.verify_packed_async(i % 2, s_["out"], s_["cu"], s_["res"])
+            s_ = pk_sets[i % L]
+            ctx.lane_sync(i % L)
+            ctx.prove_packed_async(i % L, s_["pin"], s_["out"])
+            ctx.verify_packed_async(i % L, s_["out"], s_["cu"], s_["res"])
 
         def packed_fused_step(i):
             s_ = pk_sets[0]
             ctx.prove_verify_packed(s_["pin"], out=s_["out"], result=s_["res"])
 
         for fn in (lanes_step, pinned_step, pageable_step, fused_step, packed_lanes_step, packed_fused_step, pageable_packed_step):
-            for i in range(3):
+            for i in range(L + 1):
                 fn(i)
             ctx.sync()
         for s_ in sets:
@@ -662,6 +664,12 @@ def main():
         for s_ in pk_sets:
             s_["out"].view(np.uint8)[...] = 0xEE; s_["res"][...] = 0xEE
         dt_packed = timed(packed_lanes_step, ksteps)
+        ctx.set_option(pbh_b200.OPT_PROOF_RESIDENT, 0)      # the same two calls with the proofs uploaded again for the verifier
+        for i in range(L):
+            packed_lanes_step(i)
+        ctx.sync()
+        dt_packed_reupload = timed(packed_lanes_step, ksteps)
+        ctx.set_option(pbh_b200.OPT_PROOF_RESIDENT, 1)
         ref_packed = pbh_b200.pack_proofs(outs[0]["proof"].cpu().numpy(), outs[0]["status"].cpu().numpy())
         ref_result0 = outs[0]["result"].cpu().numpy()
         packed_equal = all(np.array_equal(s_["out"], ref_packed) and np.array_equal(s_["res"], ref_result0) for s_ in pk_sets)
@@ -693,12 +701,21 @@ def main():
         e2e_equal = e2e_equal and np.array_equal(pg["proof"], ref_proof) and np.array_equal(pg["result"], ref_result)
         dt_fused = timed(fused_step, ksteps)
         per = lambda dt, st: {"value": n * world * st / dt, "ms_per_step": 1e3 * dt / st}
-        e2e = {"value": n * world * ksteps / dt_packed, "unit": UNIT, "h2d_bytes_per_step": n * (16 + 12 + 4) * world,
-               "d2h_bytes_per_step": n * (12 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt_packed / ksteps,
-               "api": "pbh_prove_packed_async + pbh_verify_packed_async on two lanes (two batches in flight), pbh_lane_sync before a lane's buffers are reused; "
+        # Headline: every input of both calls is read from the host buffers (PBH_OPT_PROOF_RESIDENT 0), i.e. the proofs cross PCIe
+        # twice, down as prove's output and up again as verify's input.  The library's default (the verifier reads the device-resident
+        # copy of the proofs the prove call on the same lane has just produced) is reported beside it.
+        e2e = {"value": n * world * ksteps / dt_packed_reupload, "unit": UNIT, "h2d_bytes_per_step": n * (16 + 12 + 4) * world,
+               "d2h_bytes_per_step": n * (12 + 1) * world, "steps": ksteps, "ms_per_step": 1e3 * dt_packed_reupload / ksteps,
+               "api": f"pbh_prove_packed_async + pbh_verify_packed_async on {L} lanes ({L} batches in flight), pbh_lane_sync before a lane's buffers are reused; "
                       "the two reference calls, Plonk::prove then Plonk::verify, on the packed wire format",
-               "wire_format": "packed records (include/pbh_b200.h): prove 16 B in / 12 B out per item, verify 12 + 4 B in / 1 B out; the proof crosses PCIe "
-                              "twice (down from prove, up into verify) as with any two-call use; unpacking and packing run on the GPU inside the timed region",
+               "wire_format": "packed records (include/pbh_b200.h): prove 16 B in / 12 B out per item, verify 12 + 4 B in / 1 B out; the proofs cross PCIe twice "
+                              "(down from prove, up into verify: PBH_OPT_PROOF_RESIDENT 0 for this measurement); unpacking and packing run on the GPU inside "
+                              "the timed region",
+               "packed_lanes_proofs_resident": dict(per(dt_packed, ksteps), h2d_bytes_per_step=n * (16 + 4) * world, d2h_bytes_per_step=n * 13 * world,
+                                                    api="the same two calls with the library's default PBH_OPT_PROOF_RESIDENT 1: the verify call names the very buffer the prove "
+                                                        "call on the same lane is still filling (no synchronisation in between, so by the lane contract the caller cannot have "
+                                                        "touched it), and the verifier reads the device-resident copy of those proofs instead of uploading them again; the "
+                                                        "proofs still travel to the host as prove's output; results identical"),
                "host_memory": "page-locked (pbh_host_alloc), whole-batch copy-engine transfers both ways on the lane's stream",
                "numa_node_of_device": ctx.numa_node,
                "timing": "host wall clock around the C-ABI calls up to the final pbh_ctx_sync, max over ranks",

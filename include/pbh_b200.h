@@ -156,6 +156,13 @@ int pbh_ctx_get_algo(const pbh_ctx* ctx);
  * the staging buffers, which the copy engines then move asynchronously - (1, default) or left to the driver's own staging
  * of pageable copies, which runs on the calling thread at about 12 GB/s (0).  Page-locked memory never takes this path. */
 #define PBH_OPT_HOST_STAGE 9
+/* PBH_OPT_PROOF_RESIDENT: when pbh_verify_packed_async is called on a lane for the very `out` buffer (same pointer, same n) that the
+ * immediately preceding call on that lane, pbh_prove_packed_async, is still filling - no pbh_lane_sync / pbh_ctx_sync and no other
+ * call on the lane in between, so by the lane contract the caller cannot have touched the buffer and its contents will be exactly
+ * what the device holds - the verifier reads the device-resident copy of those proofs instead of uploading them again (1,
+ * default); the proofs still travel to the host as the prove call's output.  0 = always upload what the host buffer holds.
+ * Results are identical either way. */
+#define PBH_OPT_PROOF_RESIDENT 10
 int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value);
 int pbh_ctx_device(const pbh_ctx* ctx);
 int pbh_ctx_sync(pbh_ctx* ctx);                   /* wait for everything enqueued on the context    */

@@ -127,6 +127,11 @@ struct pbh_ctx {
   std::vector<CopyTask> slot_out[kSlots];  // copy-outs mirror -> caller memory, due once the slot's stream has drained
   CopyPool* pool = nullptr;
   int host_stage = 1;                      // PBH_OPT_HOST_STAGE: own staging of pageable memory (1) or the driver's (0)
+  // PBH_OPT_PROOF_RESIDENT: the packed proofs a lane's prove call has just produced are still on the device (as byte planes, rows
+  // 26..52 of the lane buffer) when the verify call for the SAME host buffer follows on the same lane
+  int proof_resident = 1;
+  const void* resident_host[kSlots] = {};
+  size_t resident_n[kSlots] = {};
   uint8_t* lane_buf[kSlots] = {};          // whole-batch staging of the asynchronous lanes (PBH_OPT_LANE_MODE 1 and 3)
   size_t lane_bytes[kSlots] = {};
   int lane_mode = 3;                       // PBH_OPT_LANE_MODE
@@ -302,6 +307,11 @@ int pbh_ctx_set_option(pbh_ctx* ctx, int option, int value) {
     return PBH_OK;
   }
   if (option == PBH_OPT_HOST_STAGE) { ctx->host_stage = value != 0; return PBH_OK; }
+  if (option == PBH_OPT_PROOF_RESIDENT) {
+    ctx->proof_resident = value != 0;
+    for (int s = 0; s < kSlots; s++) ctx->resident_host[s] = nullptr;
+    return PBH_OK;
+  }
   if (option == PBH_OPT_CHUNK_LOG2) {
     if (value < 8 || value > 20) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "chunk log2 must be in [8, 20]");
     ctx->chunk = (size_t)1 << value;
@@ -315,6 +325,7 @@ uint64_t pbh_ctx_launch_count(const pbh_ctx* ctx) { return ctx ? ctx->launches :
 
 int pbh_ctx_sync(pbh_ctx* ctx) {
   CTX_CHECK(ctx);
+  for (int s = 0; s < kSlots; s++) ctx->resident_host[s] = nullptr;
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->compute));
   for (int s = 0; s < kSlots; s++) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
@@ -933,6 +944,14 @@ static int lane_stream(pbh_ctx* ctx, int lane, cudaStream_t* st) {
   *st = ctx->slot_stream[lane];
   return PBH_OK;
 }
+// Whatever a lane call does next, the proof planes an earlier prove call left in the lane buffer stop being "the proofs the
+// caller's buffer will hold": every lane entry point and every synchronisation forgets them first.
+static const void* take_resident(pbh_ctx* ctx, int lane, size_t* n) {
+  const void* h = ctx->resident_host[lane];
+  *n = ctx->resident_n[lane];
+  ctx->resident_host[lane] = nullptr;
+  return h;
+}
 // page-locked (mapped or not): the copy engines can read and write it asynchronously
 static bool host_pinned(const uint8_t* p) {
   if (!p) return false;
@@ -957,6 +976,7 @@ int pbh_prove_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* wit, 
   cudaStream_t st;
   int rc = lane_stream(ctx, lane, &st);
   if (rc) return rc;
+  ctx->resident_host[lane] = nullptr;
   if (n == 0) return PBH_OK;
   if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
@@ -1008,6 +1028,7 @@ int pbh_verify_batch_async(pbh_ctx* ctx, int lane, size_t n, const uint8_t* proo
   cudaStream_t st;
   int rc = lane_stream(ctx, lane, &st);
   if (rc) return rc;
+  ctx->resident_host[lane] = nullptr;
   if (n == 0) return PBH_OK;
   if (!proof || !chal || !u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (proof_pitch < n || chal_pitch < n || (gt && gt_pitch < n)) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
@@ -1057,6 +1078,7 @@ int pbh_lane_sync(pbh_ctx* ctx, int lane) {
   cudaStream_t st;
   int rc = lane_stream(ctx, lane, &st);
   if (rc) return rc;
+  ctx->resident_host[lane] = nullptr;   // after a sync the caller may change its buffers
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
   CUDA_TRY(ctx, cudaStreamSynchronize(st));
   return PBH_OK;
@@ -1389,14 +1411,17 @@ static int packed_prove_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size_
   if (result_host) PBH_TRY(stage_d2h(ctx, base, st, result_host, 0, d_res, 0, m, 1));
   return PBH_OK;
 }
+// `resident`: the proof planes these packed proofs decode to are already at rows 26..52 of `base` - the prove call that produced
+// `proofs` on this lane left them there (packed_prove_body), and pack -> unpack is the identity on a prover's output - so neither
+// the upload of the proofs nor their decoding is repeated; only the challenge words travel.
 static int packed_verify_body(pbh_ctx* ctx, cudaStream_t st, uint8_t* base, size_t C, size_t m, const pbh_packed_proof* proofs,
-                              const uint32_t* chal_u, uint8_t* result) {
+                              const uint32_t* chal_u, uint8_t* result, bool resident = false) {
   uint8_t *d_proof = base + 26 * C, *d_chal = base + 54 * C, *d_u = base + 59 * C, *d_res = base + 60 * C;
   pbh_packed_proof* d_prf = reinterpret_cast<pbh_packed_proof*>(base + 96 * C);
   uint32_t* d_cu = reinterpret_cast<uint32_t*>(base + 108 * C);
-  PBH_TRY(stage_h2d(ctx, base, st, d_prf, 0, proofs, 0, m * sizeof(pbh_packed_proof), 1));
+  if (!resident) PBH_TRY(stage_h2d(ctx, base, st, d_prf, 0, proofs, 0, m * sizeof(pbh_packed_proof), 1));
   PBH_TRY(stage_h2d(ctx, base, st, d_cu, 0, chal_u, 0, m * sizeof(uint32_t), 1));
-  int rc = launch_unpack_proof(ctx, st, m, d_prf, d_cu, d_proof, C, nullptr, d_chal, C, d_u);
+  int rc = launch_unpack_proof(ctx, st, m, resident ? nullptr : d_prf, d_cu, d_proof, C, nullptr, d_chal, C, d_u);
   if (rc) return rc;
   VerifyArgs A{d_proof, C, d_chal, C, d_u, d_res, nullptr, 0, m, nullptr};
   rc = launch_verify(ctx, st, A);
@@ -1437,6 +1462,7 @@ int pbh_prove_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_wi
   cudaStream_t st;
   int rc = lane_stream(ctx, lane, &st);
   if (rc) return rc;
+  ctx->resident_host[lane] = nullptr;
   if (n == 0) return PBH_OK;
   if (!in || !out) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1444,7 +1470,9 @@ int pbh_prove_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_wi
     const size_t C = (n + kTile - 1) / kTile * kTile;
     rc = ensure_lane(ctx, lane, kStagePlanes * C);
     if (rc) return rc;
-    return packed_prove_body(ctx, st, ctx->lane_buf[lane], C, n, in, out, nullptr);
+    rc = packed_prove_body(ctx, st, ctx->lane_buf[lane], C, n, in, out, nullptr);
+    if (rc == PBH_OK && ctx->proof_resident) { ctx->resident_host[lane] = out; ctx->resident_n[lane] = n; }
+    return rc;
   }
   rc = pbh_ctx_sync(ctx);
   if (rc) return rc;
@@ -1455,6 +1483,8 @@ int pbh_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_p
   cudaStream_t st;
   int rc = lane_stream(ctx, lane, &st);
   if (rc) return rc;
+  size_t res_n = 0;
+  const void* res_host = take_resident(ctx, lane, &res_n);
   if (n == 0) return PBH_OK;
   if (!proofs || !chal_u || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1463,7 +1493,10 @@ int pbh_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_p
     const size_t C = (n + kTile - 1) / kTile * kTile;
     rc = ensure_lane(ctx, lane, kStagePlanes * C);
     if (rc) return rc;
-    return packed_verify_body(ctx, st, ctx->lane_buf[lane], C, n, proofs, chal_u, result);
+    // the very buffer the previous call on this lane is still filling, with no synchronisation in between (the caller may not
+    // touch it before pbh_lane_sync): its contents ARE the proofs resident in the lane buffer
+    const bool resident = ctx->proof_resident && res_host == static_cast<const void*>(proofs) && res_n == n;
+    return packed_verify_body(ctx, st, ctx->lane_buf[lane], C, n, proofs, chal_u, result, resident);
   }
   rc = pbh_ctx_sync(ctx);
   if (rc) return rc;

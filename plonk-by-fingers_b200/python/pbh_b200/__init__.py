@@ -27,7 +27,7 @@ ST_OK, ST_UNSATISFIED, ST_ACC_DIV0, ST_T_REMAINDER, ST_T_SLICE, ST_SRS_OOB, ST_B
 VR_ACCEPT, VR_REJECT_PAIRING, VR_NOT_ON_CURVE, VR_NOT_IN_FIELD, VR_PANIC_ZH0, VR_BAD_ENCODING = 1, 0, 2, 4, 0x10, 0x20
 ALGO_ARITH, ALGO_TABLE = 0, 1
 OPT_PROVER_FP32, OPT_PROVER_LAUNCH_SHAPE, OPT_TMA, OPT_CHUNK_LOG2, OPT_SPECIALISE, OPT_HOST_DIRECT, OPT_VERIFIER_FP32, OPT_LANE_MODE = 1, 2, 3, 4, 5, 6, 7, 8
-OPT_HOST_STAGE = 9
+OPT_HOST_STAGE, OPT_PROOF_RESIDENT = 9, 10
 DIST_UNIFORM, DIST_FULLPATH = 0, 1
 ERR = {0: "PBH_OK", -1: "PBH_ERR_BAD_ARGUMENT", -2: "PBH_ERR_SETUP_PANIC", -3: "PBH_ERR_CUDA", -4: "PBH_ERR_NO_DEVICE",
        -5: "PBH_ERR_UNSUPPORTED"}

@@ -188,6 +188,32 @@ def test_packed_lanes_and_device_conversions(gpu_ctx, oracle):
     ctx.sync()
     for (b, _), (pw, vo) in zip(sets, expect):
         assert np.array_equal(_words(b["out"]), pw) and np.array_equal(b["res"], vo)
+    # PBH_OPT_PROOF_RESIDENT: the calls above verified the device-resident copy of the proofs (same buffer, same lane, no sync in
+    # between).  After a synchronisation the caller may change its buffer, and the verifier must see the change: swap proofs
+    # between items, verify on the lane again, compare with the synchronous call on a pageable copy of the tampered buffer.
+    b0 = sets[0][0]
+    tampered = np.array(b0["out"])
+    tampered[:5000] = tampered[5000:10000]
+    b0["out"][...] = tampered
+    ctx.verify_packed_async(0, b0["out"], b0["cu"], b0["res"])
+    ctx.lane_sync(0)
+    want_t = ctx.verify_packed(tampered, np.array(b0["cu"]))
+    assert np.array_equal(b0["res"], want_t) and not np.array_equal(want_t, expect[0][1])
+    # prove, then verify a DIFFERENT buffer on the same lane: uploaded, not taken from the device
+    other = ctx.host_alloc_as(n, P.PACKED_PROOF)
+    other[...] = tampered
+    ctx.prove_packed_async(0, b0["pin"], b0["out"])
+    ctx.verify_packed_async(0, other, b0["cu"], b0["res"])
+    ctx.lane_sync(0)
+    assert np.array_equal(b0["res"], want_t) and np.array_equal(_words(b0["out"]), expect[0][0])
+    # the option off gives the same bytes as the resident path
+    ctx.set_option(P.OPT_PROOF_RESIDENT, 0)
+    ctx.prove_packed_async(0, b0["pin"], b0["out"])
+    ctx.verify_packed_async(0, b0["out"], b0["cu"], b0["res"])
+    ctx.lane_sync(0)
+    ctx.set_option(P.OPT_PROOF_RESIDENT, 1)
+    assert np.array_equal(b0["res"], expect[0][1]) and np.array_equal(_words(b0["out"]), expect[0][0])
+    ctx.host_free(other)
     # pageable arrays through the lane entry points: synchronous, same bytes
     b, (w, r, c, u) = sets[1]
     out = np.zeros(n, P.PACKED_PROOF); res = np.zeros(n, np.uint8)

@@ -869,6 +869,9 @@ def main():
                    "accepted": int((v2 == 1).sum().item()), "all_reached_pairing": int(((v2 != 0) & (v2 != 1)).sum().item()) == 0}
         del w2, r2, c2, u2, p2, s2, v2, v2a
         torch.cuda.empty_cache()
+        # the verifier against its ceilings at this size: a 2^20-item launch carries ~9 us of fixed cost (launch, first tile, tail)
+        kernels_rf.append(roofline_entry("verify_tma_kernel<TABLE> at 2^24 items (configs[2])", "verify_table", ms2, n2, 34, peaks, instr))
+        kernels_rf.append(roofline_entry("verify_tma_kernel<ARITH> at 2^24 items (configs[2])", "verify_arith", ms2a, n2, 34, peaks, instr))
     if world == 1 and not args.no_sweeps:
         import bench_sweeps
         sweeps = []

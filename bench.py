@@ -655,7 +655,12 @@ def main():
             s_ = pk_sets[0]
             ctx.prove_verify_packed(s_["pin"], out=s_["out"], result=s_["res"])
 
-        for fn in (lanes_step, pinned_step, pageable_step, fused_step, packed_lanes_step, packed_fused_step, pageable_packed_step):
+        def packed_fused_lanes_step(i):
+            s_ = pk_sets[i % L]
+            ctx.lane_sync(i % L)
+            ctx.prove_verify_packed_async(i % L, s_["pin"], s_["out"], s_["res"])
+
+        for fn in (lanes_step, pinned_step, pageable_step, fused_step, packed_lanes_step, packed_fused_step, pageable_packed_step, packed_fused_lanes_step):
             for i in range(L + 1):
                 fn(i)
             ctx.sync()
@@ -675,6 +680,10 @@ def main():
         packed_equal = all(np.array_equal(s_["out"], ref_packed) and np.array_equal(s_["res"], ref_result0) for s_ in pk_sets)
         dt_packed_fused = timed(packed_fused_step, ksteps)
         packed_equal = packed_equal and np.array_equal(pk_sets[0]["out"], ref_packed) and np.array_equal(pk_sets[0]["res"], ref_result0)
+        for s_ in pk_sets:
+            s_["out"].view(np.uint8)[...] = 0xEE; s_["res"][...] = 0xEE
+        dt_packed_fused_lanes = timed(packed_fused_lanes_step, ksteps)
+        packed_equal = packed_equal and all(np.array_equal(s_["out"], ref_packed) and np.array_equal(s_["res"], ref_result0) for s_ in pk_sets)
         dt_lanes = timed(lanes_step, ksteps)             # the library's default PBH_OPT_LANE_MODE
         lane_modes = {}
         for mode, what in ((0, "kernels read and write the host buffers in place"), (1, "copy-engine upload, in-place stores"),
@@ -725,6 +734,8 @@ def main():
                                         api="pbh_prove_batch_async + pbh_verify_batch_async on two lanes, one byte per field element (default PBH_OPT_LANE_MODE 3)"),
                "packed_fused_call": dict(per(dt_packed_fused, ksteps), h2d_bytes_per_step=n * 16 * world, d2h_bytes_per_step=n * 13 * world,
                                          api="pbh_prove_verify_packed (extension: the proof does not cross PCIe twice)"),
+               "packed_fused_call_lanes": dict(per(dt_packed_fused_lanes, ksteps), h2d_bytes_per_step=n * 16 * world, d2h_bytes_per_step=n * 13 * world,
+                                               api=f"pbh_prove_verify_packed_async on {L} lanes (extension)"),
                "lane_modes": lane_modes,
                "two_sync_calls_pinned": dict(per(dt_pinned, ksteps), api="pbh_prove_batch then pbh_verify_batch, page-locked buffers"),
                "two_sync_calls_pageable": dict(per(dt_pageable, max(3, ksteps // 2)), api="pbh_prove_batch then pbh_verify_batch, pageable numpy buffers (what a plain Vec<u8> is): "

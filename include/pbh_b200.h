@@ -325,6 +325,7 @@ int pbh_prove_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_wi
 int pbh_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result);
 /* Extension: prove, then verify the fresh proofs with the same record's challenges and u; the proof never re-crosses PCIe. */
 int pbh_prove_verify_packed(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out, uint8_t* result);
+int pbh_prove_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out, uint8_t* result);
 /* Device-side conversions between packed records and byte planes (device pointers; null plane pointers are skipped). */
 int pbh_unpack_witness_dev(pbh_ctx* ctx, size_t n, const pbh_packed_witness* in, uint8_t* wit, size_t wit_pitch, uint8_t* rand,
                            size_t rand_pitch, uint8_t* chal, size_t chal_pitch, uint8_t* u);

@@ -764,6 +764,12 @@ static int flush_slot(pbh_ctx* ctx, int s) {
 }
 template <class Body>
 static int for_each_chunk(pbh_ctx* ctx, size_t n, Body body, bool wait = true) {
+  // a synchronous call starts after everything the lanes (which share these streams) were given: it may read a buffer an
+  // asynchronous call is still filling
+  for (int s = 0; s < kSlots; s++) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->slot_stream[s]));
+    ctx->resident_host[s] = nullptr;
+  }
   int rc = ensure_slots(ctx, kStagePlanes);
   if (rc) return rc;
   const size_t C = ctx->chunk;
@@ -1477,6 +1483,25 @@ int pbh_prove_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_wi
   rc = pbh_ctx_sync(ctx);
   if (rc) return rc;
   return pbh_prove_packed(ctx, n, in, out);
+}
+int pbh_prove_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_witness* in, pbh_packed_proof* out, uint8_t* result) {
+  CTX_CHECK(ctx);
+  cudaStream_t st;
+  int rc = lane_stream(ctx, lane, &st);
+  if (rc) return rc;
+  ctx->resident_host[lane] = nullptr;
+  if (n == 0) return PBH_OK;
+  if (!in || !out || !result) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  if (n <= kLaneMaxItems && host_pinned(reinterpret_cast<const uint8_t*>(in)) && host_pinned(reinterpret_cast<const uint8_t*>(out)) && host_pinned(result)) {
+    const size_t C = (n + kTile - 1) / kTile * kTile;
+    rc = ensure_lane(ctx, lane, kStagePlanes * C);
+    if (rc) return rc;
+    return packed_prove_body(ctx, st, ctx->lane_buf[lane], C, n, in, out, result);
+  }
+  rc = pbh_ctx_sync(ctx);
+  if (rc) return rc;
+  return pbh_prove_verify_packed(ctx, n, in, out, result);
 }
 int pbh_verify_packed_async(pbh_ctx* ctx, int lane, size_t n, const pbh_packed_proof* proofs, const uint32_t* chal_u, uint8_t* result) {
   CTX_CHECK(ctx);

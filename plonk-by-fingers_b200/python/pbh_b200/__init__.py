@@ -53,7 +53,7 @@ pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_
 pbh_gt_mul_batch pbh_gt_pow600_batch pbh_poly_divrem_batch pbh_poly_addsub_ragged_batch
 pbh_prove_packed pbh_verify_packed pbh_prove_packed_async pbh_verify_packed_async pbh_prove_verify_packed pbh_unpack_witness_dev
 pbh_pack_proof_dev pbh_unpack_proof_dev pbh_pack_witness_host pbh_unpack_witness_host pbh_pack_chal_u_host pbh_pack_proofs_host
-pbh_unpack_proofs_host pbh_window_create pbh_window_attach pbh_window_attach_ptrs pbh_window_share pbh_window_destroy pbh_multi_prove_packed pbh_multi_verify_packed""".split()
+pbh_unpack_proofs_host pbh_window_create pbh_window_attach pbh_window_attach_ptrs pbh_window_share pbh_window_destroy pbh_multi_prove_packed pbh_multi_verify_packed pbh_prove_verify_packed_async""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -654,6 +654,14 @@ class Context:
             raise PbhError("proofs, chal_u and result must have the same length")
         self._check(self.lib.pbh_verify_packed_async(self.h, int(lane), C.c_size_t(prf.shape[0]), C.c_void_p(prf.ctypes.data),
                                                      C.c_void_p(cu.ctypes.data), C.c_void_p(res.ctypes.data)), "pbh_verify_packed_async")
+
+    def prove_verify_packed_async(self, lane, packed_in, out, result):
+        pin = self._packed(packed_in, PACKED_WITNESS, "packed_in"); o = self._packed(out, PACKED_PROOF, "out", True)
+        res = self._packed(result, np.dtype(np.uint8), "result", True)
+        if o.shape[0] != pin.shape[0] or res.shape[0] != pin.shape[0]:
+            raise PbhError("packed_in, out and result must have the same length")
+        self._check(self.lib.pbh_prove_verify_packed_async(self.h, int(lane), C.c_size_t(pin.shape[0]), C.c_void_p(pin.ctypes.data),
+                                                           C.c_void_p(o.ctypes.data), C.c_void_p(res.ctypes.data)), "pbh_prove_verify_packed_async")
 
     def host_alloc_as(self, n, dtype):
         """host_alloc viewed as n records of `dtype` (page-locked memory for the packed lane calls)."""

@@ -90,6 +90,8 @@ extern "C" {
     pub fn pbh_verify_packed_async(ctx: *mut pbh_ctx, lane: c_int, n: usize, proofs: *const PackedProof, chal_u: *const u32,
                                    result: *mut u8) -> c_int;
     pub fn pbh_prove_verify_packed(ctx: *mut pbh_ctx, n: usize, input: *const PackedWitness, out: *mut PackedProof, result: *mut u8) -> c_int;
+    pub fn pbh_prove_verify_packed_async(ctx: *mut pbh_ctx, lane: c_int, n: usize, input: *const PackedWitness, out: *mut PackedProof,
+                                         result: *mut u8) -> c_int;
     // host-side format conversion (CPU loops, no device): build packed records from byte planes and read proofs back
     pub fn pbh_pack_witness_host(n: usize, wit: *const u8, wit_pitch: usize, rand: *const u8, rand_pitch: usize, chal: *const u8,
                                  chal_pitch: usize, u: *const u8, out: *mut PackedWitness) -> c_int;

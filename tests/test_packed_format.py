@@ -188,6 +188,13 @@ def test_packed_lanes_and_device_conversions(gpu_ctx, oracle):
     ctx.sync()
     for (b, _), (pw, vo) in zip(sets, expect):
         assert np.array_equal(_words(b["out"]), pw) and np.array_equal(b["res"], vo)
+    # the fused call on the lanes: same proofs, same verdicts
+    for lane, (b, _) in enumerate(sets):
+        b["out"].view(np.uint8)[...] = 0xEE; b["res"][...] = 0xEE
+        ctx.prove_verify_packed_async(lane, b["pin"], b["out"], b["res"])
+    ctx.sync()
+    for (b, _), (pw, vo) in zip(sets, expect):
+        assert np.array_equal(_words(b["out"]), pw) and np.array_equal(b["res"], vo)
     # PBH_OPT_PROOF_RESIDENT: the calls above verified the device-resident copy of the proofs (same buffer, same lane, no sync in
     # between).  After a synchronisation the caller may change its buffer, and the verifier must see the change: swap proofs
     # between items, verify on the lane again, compare with the synchronous call on a pageable copy of the tampered buffer.

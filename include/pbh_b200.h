@@ -218,6 +218,9 @@ int pbh_lane_sync(pbh_ctx* ctx, int lane);
  * returns it, -1 otherwise) the pages are bound to that node before they are locked.  Freed by pbh_host_free or with the
  * context. */
 int pbh_host_alloc(pbh_ctx* ctx, size_t bytes, void** out);
+/* The same as write-combined memory, for INPUT buffers only (the host writes them sequentially, the device reads them): device
+ * reads need no snoop of the CPU caches.  CPU reads of such memory are uncached and slow. */
+int pbh_host_alloc_input(pbh_ctx* ctx, size_t bytes, void** out);
 int pbh_host_free(pbh_ctx* ctx, void* ptr);
 int pbh_ctx_numa_node(const pbh_ctx* ctx);
 

@@ -1137,6 +1137,19 @@ int pbh_host_alloc(pbh_ctx* ctx, size_t bytes, void** out) {
   *out = p;
   return PBH_OK;
 }
+// Page-locked WRITE-COMBINED memory for buffers the host only writes and the device only reads (inputs): the device's reads
+// of it need no snoop of the CPU caches.  CPU reads of such memory are uncached and very slow - never use it for outputs.
+int pbh_host_alloc_input(pbh_ctx* ctx, size_t bytes, void** out) {
+  CTX_CHECK(ctx);
+  if (!out || bytes == 0) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer or zero size");
+  *out = nullptr;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+  void* p = nullptr;
+  CUDA_TRY(ctx, cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocMapped | cudaHostAllocWriteCombined));
+  ctx->host_allocs[p] = {bytes, false};
+  *out = p;
+  return PBH_OK;
+}
 int pbh_host_free(pbh_ctx* ctx, void* p) {
   CTX_CHECK(ctx);
   if (!p) return PBH_OK;

@@ -53,7 +53,7 @@ pbh_multi_set_algo pbh_multi_prove_batch pbh_multi_verify_batch pbh_multi_prove_
 pbh_gt_mul_batch pbh_gt_pow600_batch pbh_poly_divrem_batch pbh_poly_addsub_ragged_batch
 pbh_prove_packed pbh_verify_packed pbh_prove_packed_async pbh_verify_packed_async pbh_prove_verify_packed pbh_unpack_witness_dev
 pbh_pack_proof_dev pbh_unpack_proof_dev pbh_pack_witness_host pbh_unpack_witness_host pbh_pack_chal_u_host pbh_pack_proofs_host
-pbh_unpack_proofs_host pbh_window_create pbh_window_attach pbh_window_attach_ptrs pbh_window_share pbh_window_destroy pbh_multi_prove_packed pbh_multi_verify_packed pbh_prove_verify_packed_async""".split()
+pbh_unpack_proofs_host pbh_window_create pbh_window_attach pbh_window_attach_ptrs pbh_window_share pbh_window_destroy pbh_multi_prove_packed pbh_multi_verify_packed pbh_prove_verify_packed_async pbh_host_alloc_input""".split()
 
 
 # 32-byte records of include/pbh_b200.h
@@ -216,6 +216,7 @@ def load_library():
         lib.pbh_multi_set_algo.argtypes = [C.c_void_p, C.c_int]
         lib.pbh_lane_sync.argtypes = [C.c_void_p, C.c_int]
         lib.pbh_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        lib.pbh_host_alloc_input.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         lib.pbh_host_free.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB
@@ -441,13 +442,15 @@ class Context:
     def numa_node(self):
         return int(self.lib.pbh_ctx_numa_node(self.h))
 
-    def host_alloc(self, shape):
+    def host_alloc(self, shape, write_combined=False):
         """uint8 numpy array over page-locked, mapped host memory (pbh_host_alloc): the host-pointer calls run in place
-        on it.  The memory lives until host_free(array) or the context closes."""
+        on it.  The memory lives until host_free(array) or the context closes.  write_combined: pbh_host_alloc_input
+        (input buffers only: the host writes, the device reads)."""
         shape = tuple(int(x) for x in (shape if isinstance(shape, (tuple, list)) else (shape,)))
         nbytes = max(1, int(np.prod(shape)))
         p = C.c_void_p()
-        self._check(self.lib.pbh_host_alloc(self.h, C.c_size_t(nbytes), C.byref(p)), "pbh_host_alloc")
+        fn = self.lib.pbh_host_alloc_input if write_combined else self.lib.pbh_host_alloc
+        self._check(fn(self.h, C.c_size_t(nbytes), C.byref(p)), "pbh_host_alloc")
         buf = (C.c_uint8 * nbytes).from_address(p.value)
         arr = np.frombuffer(buf, dtype=np.uint8, count=int(np.prod(shape))).reshape(shape)
         self._host_ptrs = getattr(self, "_host_ptrs", {})
@@ -663,10 +666,10 @@ class Context:
         self._check(self.lib.pbh_prove_verify_packed_async(self.h, int(lane), C.c_size_t(pin.shape[0]), C.c_void_p(pin.ctypes.data),
                                                            C.c_void_p(o.ctypes.data), C.c_void_p(res.ctypes.data)), "pbh_prove_verify_packed_async")
 
-    def host_alloc_as(self, n, dtype):
+    def host_alloc_as(self, n, dtype, write_combined=False):
         """host_alloc viewed as n records of `dtype` (page-locked memory for the packed lane calls)."""
         dtype = np.dtype(dtype)
-        raw = self.host_alloc(max(1, int(n)) * dtype.itemsize)
+        raw = self.host_alloc(max(1, int(n)) * dtype.itemsize, write_combined=write_combined)
         arr = raw[:int(n) * dtype.itemsize].view(dtype)
         self._host_ptrs[arr.ctypes.data] = self._host_ptrs[raw.ctypes.data]
         return arr

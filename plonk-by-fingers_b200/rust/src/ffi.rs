@@ -66,6 +66,7 @@ extern "C" {
                                   status: *mut u8, result: *mut u8) -> c_int;
     // asynchronous lanes over page-locked memory (two batches in flight keep both directions of the PCIe link busy)
     pub fn pbh_host_alloc(ctx: *mut pbh_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn pbh_host_alloc_input(ctx: *mut pbh_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn pbh_host_free(ctx: *mut pbh_ctx, ptr: *mut c_void) -> c_int;
     pub fn pbh_prove_batch_async(ctx: *mut pbh_ctx, lane: c_int, n: usize, wit: *const u8, wit_pitch: usize, rand: *const u8,
                                  rand_pitch: usize, chal: *const u8, chal_pitch: usize, proof: *mut u8, proof_pitch: usize,

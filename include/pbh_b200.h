@@ -239,6 +239,11 @@ int pbh_prove_verify_batch(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_t wi
  * handed the derived challenges, with the same status byte, and pbh_verify_fs_batch answers what pbh_verify_batch
  * answers for the derived challenges and u.
  *
+ * PARITY UNPINNED BY THE REFERENCE: the reference has no transcript, so no vector of its own pins these two entry points.  What
+ * is pinned: both SHA-256 implementations against hashlib, the oracle's challenges against a replay of this specification from the
+ * proof bytes alone, and - the part the reference does pin - that the proof / verdict equal Plonk::prove / Plonk::verify handed
+ * the derived challenges (tests/test_fiat_shamir.py).
+ *
  * Transcript.  A state is 32 bytes; state_{k+1} = SHA-256(state_k || message_k) (FIPS 180-4; every message is at most
  * 12 bytes, so each step is a single compression).  A G1 point is absorbed as the four bytes (x, y, infinite as 0/1, 0),
  * an evaluation as its byte.  A challenge is a big-endian 64-bit slice of the new state reduced mod 17.
@@ -311,7 +316,9 @@ int pbh_proof_planes_to_records_dev(pbh_ctx* ctx, size_t n, const uint8_t* proof
  *                       format cannot express: a point off the curve, a flagged identity with coordinates, an evaluation >= 17).
  *                       Both payload words are zero whenever the status code is not 0.
  *   chal_u              4 bytes per verification: alpha beta gamma z v u as six base-17 digits.
- * Semantics are those of the byte-plane entry points on the decoded values, bit for bit: pbh_prove_packed(in) = pack(
+ * PARITY UNPINNED BY THE REFERENCE as a format (the reference has no serialisation: src/plonk.rs:61); pinned by an independent
+ * restatement of this text (oracle/oracle.py packed_*, tests/test_packed_format.py).  The CONTENT is pinned: semantics are
+ * those of the byte-plane entry points on the decoded values, bit for bit: pbh_prove_packed(in) = pack(
  * pbh_prove_batch(unpack(in))), pbh_verify_packed(proofs, chal_u) = pbh_verify_batch(unpack(proofs), unpack(chal_u)).  A word
  * outside the format decodes to a byte outside the field (its top digit saturates at 255), hence PBH_ST_BAD_ENCODING /
  * PBH_VR_BAD_ENCODING / PBH_VR_NOT_IN_FIELD as for byte planes; a packed proof whose status code is not 0 decodes to the all-zero

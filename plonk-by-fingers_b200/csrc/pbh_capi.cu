@@ -15,6 +15,7 @@
 #include <vector>
 #include <cctype>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -36,7 +37,8 @@ void set_global_error(const std::string& e) { std::lock_guard<std::mutex> l(g_er
 // stream, so the H2D copy of chunk k+2, the kernel of chunk k+1 and the D2H copy of chunk k overlap (PCIe is full duplex).
 static constexpr size_t kChunkMax = (size_t)1 << 20;   // upper bound of the staged chunk (staging buffers are sized for it lazily)
 static constexpr int kSlots = 4;
-static constexpr uint32_t kCounterRing = 4096, kCounterGraphPool = 32768;   // tile-counter pairs (8 bytes each)
+static constexpr uint32_t kCounterRing = 4096, kCounterGraphPool = 32768;   // launch-local scheduler records
+static constexpr uint32_t kCounterWords = 4;   // {next tile, blocks done, 64-bit digest accumulator}: 16 bytes per launch
 
 // ---- pageable host buffers ----------------------------------------------------------------------------------------------
 // A copy between PAGEABLE host memory and the device is staged by the driver through its own page-locked buffer, on the
@@ -247,8 +249,8 @@ int pbh_ctx_create(const pbh_circuit* circuit, uint8_t srs_secret, uint32_t srs_
     for (int y = 0; y < 17; y++)
       for (int z = 0; z < 17; z++)
         if ((x * x + y * y) % 17 == (z * z) % 17) { wtab[3 * nw] = x; wtab[3 * nw + 1] = y; wtab[3 * nw + 2] = z; nw++; }
-  if ((ce = cudaMalloc(&ctx->d_tile_counters, (kCounterRing + kCounterGraphPool) * 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc(counters)", ce);
-  if ((ce = cudaMemset(ctx->d_tile_counters, 0, (kCounterRing + kCounterGraphPool) * 2 * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMemset(counters)", ce);
+  if ((ce = cudaMalloc(&ctx->d_tile_counters, (kCounterRing + kCounterGraphPool) * kCounterWords * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc(counters)", ce);
+  if ((ce = cudaMemset(ctx->d_tile_counters, 0, (kCounterRing + kCounterGraphPool) * kCounterWords * sizeof(unsigned int))) != cudaSuccess) return bail("cudaMemset(counters)", ce);
   if ((ce = cudaMalloc(&ctx->d_wtab, sizeof(wtab))) != cudaSuccess) return bail("cudaMalloc(wtab)", ce);
   if ((ce = cudaMemcpy(ctx->d_wtab, wtab, sizeof(wtab), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy(wtab)", ce);
   *out = ctx;
@@ -353,16 +355,16 @@ int pbh_ctx_get_verifier_constants(const pbh_ctx* ctx, uint8_t c[24]) {
   return PBH_OK;
 }
 
-// The {next tile, blocks done} pair of the launch about to be enqueued on `st`: launch-local, zero when the launch starts
-// (the last block of the previous holder reset it).  nullptr when a capturing stream has used up the graph pool.
+// The {next tile, blocks done, digest accumulator} record of the launch about to be enqueued on `st`: launch-local, zero when
+// the launch starts (the last block of the previous holder reset it).  nullptr when a capturing stream has used up the graph pool.
 static unsigned int* fresh_tile_counter(pbh_ctx* ctx, cudaStream_t st) {
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
   if (cap != cudaStreamCaptureStatusNone) {
     if (ctx->graph_counters_used >= kCounterGraphPool) return nullptr;
-    return ctx->d_tile_counters + (size_t)(kCounterRing + ctx->graph_counters_used++) * 2;
+    return ctx->d_tile_counters + (size_t)(kCounterRing + ctx->graph_counters_used++) * kCounterWords;
   }
-  return ctx->d_tile_counters + (size_t)(ctx->counter_seq++ % kCounterRing) * 2;
+  return ctx->d_tile_counters + (size_t)(ctx->counter_seq++ % kCounterRing) * kCounterWords;
 }
 
 // ---- TMA tensor maps --------------------------------------------------------------------------------------------
@@ -409,6 +411,8 @@ static int launch_digest(pbh_ctx* ctx, cudaStream_t st, size_t n, uint64_t first
 static PeerWindow peer_window_for(const pbh_ctx* ctx, const void* p, size_t bytes) {
   PeerWindow pw{};
   if (!ctx->win_attached || !p) return pw;
+  static const bool no_push = std::getenv("PBH_DEBUG_WINDOW_NO_PUSH") != nullptr;   // diagnostic: what do the remote stores cost?
+  if (no_push) return pw;
   const uint8_t* lo = ctx->win_base + (size_t)ctx->win_rank * ctx->win_bytes_per_rank;
   const uint8_t* q = static_cast<const uint8_t*>(p);
   if (q < lo || q + bytes > lo + ctx->win_bytes_per_rank) return pw;
@@ -472,7 +476,8 @@ static int launch_prove(pbh_ctx* ctx, cudaStream_t st, const ProveArgs& A, uint6
   else prove_kernel<ALGO_ARITH><<<grid, kBlock, 0, st>>>(ctx->hs.K, ctx->d_tables, A);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
-  if (digest) {   // not fused on this path
+  if (digest) {   // not fused on this path: the digest kernel accumulates into a zeroed word
+    CUDA_TRY(ctx, cudaMemsetAsync(digest, 0, sizeof(uint64_t), st));
     int rc = launch_digest(ctx, st, A.n, first_index, 27, A.proof, A.proof_pitch, digest);
     if (rc) return rc;
     return launch_publish(ctx, st, digest, sizeof(uint64_t), peer_window_for(ctx, digest, sizeof(uint64_t)));
@@ -650,8 +655,9 @@ int pbh_prove_digest_batch_dev(pbh_ctx* ctx, size_t n, const uint8_t* wit, size_
   CTX_CHECK(ctx);
   if (!digest) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-  CUDA_TRY(ctx, cudaMemsetAsync(digest, 0, sizeof(uint64_t), ctx->compute));
-  if (n == 0) return PBH_OK;
+  if (n == 0) { CUDA_TRY(ctx, cudaMemsetAsync(digest, 0, sizeof(uint64_t), ctx->compute)); return PBH_OK; }
+  // (no memset otherwise: the fused kernel's last block OVERWRITES *digest with the launch's total, so a captured step is two
+  // kernel nodes and nothing else; the unfused path zeroes the word itself)
   if (!wit || !rnd || !chal || !proof || !status) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "null pointer");
   if (wit_pitch < n || rand_pitch < n || chal_pitch < n || proof_pitch < n) return fail(ctx, PBH_ERR_BAD_ARGUMENT, "pitch < n");
   ProveArgs A{wit, wit_pitch, rnd, rand_pitch, chal, chal_pitch, proof, proof_pitch, status, n};

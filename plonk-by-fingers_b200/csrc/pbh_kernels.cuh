@@ -50,7 +50,7 @@ __device__ __forceinline__ void digest_flush(unsigned long long acc, unsigned lo
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 
-// Dynamic tile scheduler state: c[0] = next tile, c[1] = blocks finished.  The pair is launch-local (the host hands every
+// Dynamic tile scheduler state: c[0] = next tile, c[1] = blocks finished (c[2..3]: the prover's 64-bit digest accumulator).  The record is launch-local (the host hands every
 // launch its own, pbh_capi.cu: fresh_tile_counter) and zero when the launch starts: the last block to leave resets it, so
 // a launch recorded into a CUDA graph finds it zero again at every replay and no memset node is needed.
 // Returns true in thread 0 of the LAST block to leave (every other block's writes that preceded its own leave are then visible
@@ -356,18 +356,24 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
       unsigned long long sum = 0;
 #pragma unroll
       for (int k = 0; k < kTile / 32; k++) sum += S.digest_part[k];
-      atomicAdd(digest_out, sum);
+      // into the launch-local accumulator next to the tile counters (zero when the launch starts, like them): no memset of
+      // *digest_out is needed in front of the kernel
+      atomicAdd(reinterpret_cast<unsigned long long*>(tile_counter + 2), sum);
     }
   }
-  const bool replicate = PW.n != 0 && digest_out != nullptr;
   const bool last = tile_scheduler_leave(tile_counter);              // thread 0: its digest atomic precedes the fence in leave
-  if (replicate && last) {
-    // the launch's digest is complete: the last block pushes it to the same offset of every peer's window
+  if (last && digest_out != nullptr) {
+    // every block has added its share: the last one publishes the launch's digest (overwriting *digest_out), re-arms the
+    // accumulator for the next launch that is handed this record, and pushes the digest to every peer's window
     __threadfence();
-    const unsigned long long d = *reinterpret_cast<volatile unsigned long long*>(digest_out);
+    volatile unsigned long long* acc = reinterpret_cast<volatile unsigned long long*>(tile_counter + 2);
+    const unsigned long long d = *acc;
+    *acc = 0ull;
+    *digest_out = d;
 #pragma unroll
     for (uint32_t p = 0; p < 7; p++)     // fixed trip count: delta[] stays in the parameter bank (no local copy)
       if (p < PW.n) *reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(digest_out) + PW.delta[p]) = d;
+    __threadfence();
   }
 }
 

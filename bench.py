@@ -342,25 +342,30 @@ def main():
         `stream` at the end.  Cycle c (steps c*ring .. c*ring+ring-1, ring slots 0..) writes summary set c % 2; its ONE
         all-gather overlaps the kernels of cycle c + 1.  Used both directly and under stream capture."""
         gather_done = {}
+        verified = {}                                          # ring slot -> event: the verifier that last read the slot's proof
+        nccl_mode = world > 1 and window is None and not args.no_gather
         cycles = (steps + ring - 1) // ring
         for cyc in range(cycles):
             b = cyc % 2
-            if world > 1 and cyc >= 2 and not args.no_gather and window is None:
+            if nccl_mode and cyc >= 2:
                 stream.wait_event(gather_done[cyc - 2])       # the all-gather that read this summary set has finished
                 if vstream is not None:
                     vstream.wait_event(gather_done[cyc - 2])
-            if pstream1 is not None:
-                pstream1.wait_stream(stream)                  # everything `stream` waited for (previous cycle, gathers)
+            if pstream1 is not None and (nccl_mode or cyc == 0):
+                pstream1.wait_stream(stream)                  # fork; with NCCL also everything `stream` waited for (previous cycle, gathers)
             for slot in range(min(ring, steps - cyc * ring)):
                 w, rd, c, u, first = ins[slot]
                 o = outs[slot]
-                if pstream1 is not None and slot % 2 == 1:
+                pst = pstream1 if (pstream1 is not None and slot % 2 == 1) else stream
+                if slot in verified and not nccl_mode:
+                    # the only dependency between cycles: this slot's proof planes are rewritten, so the verifier that read them
+                    # a whole ring ago must be done (it is, long since: no stall, and no drain of the streams at the cycle's end)
+                    pst.wait_event(verified[slot])
+                if pst is pstream1:
                     with torch.cuda.stream(pstream1):
                         ctx_p1.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
-                    pst = pstream1
                 else:
                     ctx.prove_digest_batch(w, rd, c, o["proof"], o["status"], o["sets"][b]["digest"], first_index=first)
-                    pst = stream
                 if vstream is None:
                     ctx.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
                 else:
@@ -369,11 +374,14 @@ def main():
                     vstream.wait_event(proved)
                     with torch.cuda.stream(vstream):
                         ctx_v.verify_bitmap_batch(o["proof"], c, u, o["result"], o["sets"][b]["bitmap"])
-            if pstream1 is not None:
-                stream.wait_stream(pstream1)
-            if vstream is not None:
-                stream.wait_stream(vstream)
-            if world > 1 and not args.no_gather and window is None:
+                        verified[slot] = torch.cuda.Event()
+                        verified[slot].record(vstream)
+            if nccl_mode or cyc == cycles - 1:
+                if pstream1 is not None:
+                    stream.wait_stream(pstream1)
+                if vstream is not None:
+                    stream.wait_stream(vstream)
+            if nccl_mode:
                 ev_ = torch.cuda.Event()
                 ev_.record(stream)
                 comm_stream.wait_event(ev_)

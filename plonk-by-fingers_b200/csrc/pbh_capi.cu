@@ -499,10 +499,12 @@ static int launch_verify(pbh_ctx* ctx, cudaStream_t st, const VerifyArgs& A_in) 
       if (!tc) return fail(ctx, PBH_ERR_UNSUPPORTED, "too many launches captured into CUDA graphs from this context");
       if (ctx->algo == PBH_ALGO_TABLE) {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * 2 * ctx->grid_scale);
-        verify_tma_kernel<ALGO_TABLE, 4><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A, tc, A.bitmap ? pw : PeerWindow{});
+        if (A.bitmap && pw.n) verify_tma_kernel<ALGO_TABLE, 4, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A, tc, pw);
+        else verify_tma_kernel<ALGO_TABLE, 4, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, ctx->verifier_fp32 != 0, ctx->d_tables, A, tc, PeerWindow{});
       } else {
         int grid = (int)std::min<size_t>(tiles, (size_t)ctx->sm_count * (ctx->grid_scale == 2 ? 3 : 2));
-        verify_tma_kernel<ALGO_ARITH, 3><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A, tc, A.bitmap ? pw : PeerWindow{});
+        if (A.bitmap && pw.n) verify_tma_kernel<ALGO_ARITH, 3, true><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A, tc, pw);
+        else verify_tma_kernel<ALGO_ARITH, 3, false><<<grid, kTile, 0, st>>>(M, ctx->hs.K, ctx->hs.KF, false, ctx->d_tables, A, tc, PeerWindow{});
       }
       ctx->launches++;
       CUDA_TRY(ctx, cudaGetLastError());

@@ -216,7 +216,8 @@ def load_library():
         lib.pbh_multi_set_algo.argtypes = [C.c_void_p, C.c_int]
         lib.pbh_lane_sync.argtypes = [C.c_void_p, C.c_int]
         lib.pbh_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
-        lib.pbh_host_alloc_input.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        if hasattr(lib, "pbh_host_alloc_input"):
+            lib.pbh_host_alloc_input.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         lib.pbh_host_free.argtypes = [C.c_void_p, C.c_void_p]
         _LIB = lib
     return _LIB

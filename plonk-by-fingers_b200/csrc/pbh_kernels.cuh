@@ -242,17 +242,17 @@ __global__ void __launch_bounds__(kTile, 2) prove_f32_tma_kernel(const __grid_co
   // tiles, and there is no wave-quantisation tail.  The index is fetched two iterations ahead (`pending`), so the atomic's
   // round trip is never waited for.  (A static first tile - the block index, loads issued before the tables are staged - was
   // measured: nothing gained at 2^20 items, 1.4 % (TABLE) to 4.5 % (ARITH) lost at 2^24.)
-  stage_tables(S.T, gT);
+  // The two atomics leave first and fly while the whole block stages the tables; their results are not needed before that.
+  uint32_t pending = 0, t0 = 0;
   if (tid == 0) {
+    t0 = atomicAdd(tile_counter, 1u);
+    pending = atomicAdd(tile_counter, 1u);
     tma::mbar_init(&S.full[0], 1);
     tma::mbar_init(&S.full[1], 1);
     tma::fence_mbar_init();
   }
-  __syncthreads();
-  uint32_t pending = 0;
+  stage_tables(S.T, gT);                                      // ends with a block barrier
   if (tid == 0) {
-    const uint32_t t0 = atomicAdd(tile_counter, 1u);
-    pending = atomicAdd(tile_counter, 1u);
     S.tile_of_stage[0] = t0;
     if (t0 < tiles) issue(t0, 0);
   }
@@ -467,21 +467,6 @@ struct VerifyTmaSmem {
   alignas(32) uint32_t ballot[2][8];        // the tile's eight verdict words, kept for the peer-window stores
   Tables T;
 };
-// The tile's 32 bitmap bytes go to every peer as one 32-byte store of eight lanes (lane = word index).  Out of line: this is
-// the rare path, the tile loop stays compact.
-__device__ __noinline__ void push_tile_bitmap(uint8_t* bitmap, size_t n, size_t tile, uint32_t word, const PeerWindow& PW) {
-  const size_t w0 = tile * kTile + (size_t)threadIdx.x * 32;
-  if (w0 >= n) return;
-#pragma unroll 1
-  for (uint32_t p = 0; p < PW.n; p++) {
-    uint8_t* dst = bitmap + w0 / 8 + PW.delta[p];
-    if (w0 + 32 <= n) {
-      *reinterpret_cast<uint32_t*>(dst) = word;
-    } else {
-      for (size_t b = 0; b < (n - w0 + 7) / 8; b++) dst[b] = (uint8_t)(word >> (8 * b));
-    }
-  }
-}
 // PEERS: the instantiation that also stores every tile's bitmap bytes into the peers' windows.  A separate instantiation, not
 // a run-time branch: the branch alone made the plain verifier 6 % slower at 2^24 items (measured; the compiler emits the tile
 // loop twice and schedules both copies worse).
@@ -500,17 +485,16 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
     tma::load_2d(&S.in[stage][27][0], &M.chal, &S.full[stage], c0, 0);
     tma::load_2d(&S.in[stage][32][0], &M.u, &S.full[stage], c0, 0);
   };
-  stage_tables(S.T, gT);
+  uint32_t pending = 0, t0 = 0;                               // dynamic tile scheduler, see prove_f32_tma_kernel
   if (tid == 0) {
+    t0 = atomicAdd(tile_counter, 1u);
+    pending = atomicAdd(tile_counter, 1u);
     tma::mbar_init(&S.full[0], 1);
     tma::mbar_init(&S.full[1], 1);
     tma::fence_mbar_init();
   }
-  __syncthreads();
-  uint32_t pending = 0;
-  if (tid == 0) {                                             // dynamic tile scheduler, see prove_f32_tma_kernel
-    const uint32_t t0 = atomicAdd(tile_counter, 1u);
-    pending = atomicAdd(tile_counter, 1u);
+  stage_tables(S.T, gT);
+  if (tid == 0) {
     S.tile_of_stage[0] = t0;
     if (t0 < tiles) issue(t0, 0);
   }
@@ -562,7 +546,25 @@ __global__ void __launch_bounds__(kTile, MIN_BLOCKS) verify_tma_kernel(const __g
       if (PEERS && (tid & 31) == 0) S.ballot[stage][tid >> 5] = bits;
     }
     __syncthreads();   // every thread has read in[stage]; it may be refilled by the prefetch of the iteration after next
-    if (PEERS && A.bitmap != nullptr && tid < 8) push_tile_bitmap(A.bitmap, A.n, tile, S.ballot[stage][tid], PW);
+    if (PEERS && A.bitmap != nullptr && tid < 8) {
+      // the tile's 32 bitmap bytes go to every peer as one 32-byte store of eight lanes (ballot[stage] is rewritten two
+      // iterations from now, behind another block barrier); inline, with the deltas read from the parameter bank: as an
+      // out-of-line call taking the window by reference the same stores cost 1.5-2 us per step at N = 2 and 8
+      const size_t w0 = tile * kTile + (size_t)tid * 32;
+      if (w0 < A.n) {
+        const uint32_t word = S.ballot[stage][tid];
+#pragma unroll
+        for (uint32_t p = 0; p < 7; p++) {
+          if (p >= PW.n) continue;
+          uint8_t* dst = A.bitmap + w0 / 8 + PW.delta[p];
+          if (w0 + 32 <= A.n) {
+            *reinterpret_cast<uint32_t*>(dst) = word;
+          } else {
+            for (size_t b = 0; b < (A.n - w0 + 7) / 8; b++) dst[b] = (uint8_t)(word >> (8 * b));
+          }
+        }
+      }
+    }
   }
   tile_scheduler_leave(tile_counter);
 }

@@ -125,6 +125,17 @@ def cpu_leg(sample_items, threads):
     return sample_items / dt, dt
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return None
+
+
 def np_slice(a, n):
     import numpy as np
     return np.ascontiguousarray(a[..., :n])
@@ -158,7 +169,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8 (F_17 / F_101 residues, u64 arithmetic)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(), "nproc": os.cpu_count(),
                          "sample": f"{sample} D_fullpath items per step, prove then verify, C++ restatement of the reference, {threads} threads"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -920,7 +931,7 @@ def main():
                                    np.array_equal(g_c, h_c[:, :4096]) and np.array_equal(g_u, h_u[:4096]))
         if world == 1:
             v1, dt1 = cpu_leg(20000, 1)
-            cpu = {"value": n / dt_full, "unit": UNIT, "cores": threads, "kind": "port",
+            cpu = {"value": n / dt_full, "unit": UNIT, "cores": threads, "kind": "port", "cpu_model": cpu_model(), "nproc": os.cpu_count(),
                    "sample": f"the whole 2^20-item D_fullpath batch of ring slot 0 (the batch the GPU is checked against), prove then verify, C++ restatement of the reference (oracle/), {threads} threads, {dt_full:.1f} s",
                    "single_thread": {"value": v1, "cores": 1, "sample": f"20000 items, {dt1:.1f} s"}}
 

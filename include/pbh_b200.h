@@ -40,7 +40,8 @@
 extern "C" {
 #endif
 
-#define PBH_ABI_VERSION 1
+/* 2: round 2 added entry points only (lanes, packed records, peer windows, multi-device, sweeps); every round-1 signature is unchanged */
+#define PBH_ABI_VERSION 2
 
 /* ---- errors (return values) ---------------------------------------------------------------- */
 typedef enum pbh_error {
